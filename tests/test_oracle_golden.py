@@ -1,0 +1,123 @@
+"""Pin the numpy oracle (oracle/hdpo_oracle.py) against outputs of the unmodified reference.
+
+The fixtures were produced by tests/golden/make_golden.py running the reference's own Scenario /
+Simulator / Trainer.simulate_batch / autograd on CPU (fp32 and fp64). Tolerances:
+  * integer index tables (allocation_shift): bit-exact
+  * single-step outputs and gradients: fp64 run 1e-12, fp32 run 2e-6 relative
+  * rollout per-scenario per-period costs: fp64 1e-9; fp32 1e-5 relative (north-star bar)
+  * rollout parameter gradients: fp64 1e-8 relative L2; fp32 within max(1e-5, 3x the reference's own
+    fp32-vs-fp64 error) (the wide nets' fp32 noise floor is ~4e-5)
+"""
+import numpy as np
+import pytest
+
+from oracle import hdpo_oracle as O
+import golden_util as G
+
+
+@pytest.mark.parametrize("name", G.step_cases())
+@pytest.mark.parametrize("tag,dtype,tol", [("ref64", np.float64, 1e-12), ("ref", np.float32, 2e-6)])
+def test_single_step_matches_reference(name, tag, dtype, tol):
+    meta, g = G.load("step", name)
+    pb = G.problem_from_meta(meta)
+    data = G.cast(g["data"], dtype)
+    action = G.cast(g["action"], dtype)
+    up = G.cast(g["up"], dtype)
+    ref = g[tag]
+    state = O._initial_state(pb, data)
+    B = data["demands"].shape[0]
+    # integer tables: bit-exact (environment.py:77-101)
+    if tag == "ref":
+        for key, inv in (("allocation_shift", "store"), ("warehouse_allocation_shift", "wh"),
+                         ("echelon_allocation_shift", "ech")):
+            if key in ref:
+                n, L = state[inv].shape[1:]
+                got = O.allocation_shift(B, n, L)
+                assert got.dtype == np.int64 and np.array_equal(got, ref[key])
+    new, reward, esaved = O.env_step(pb, state, action, data, meta["period"])
+    assert G.rel_l2(reward, ref["reward"]) < tol
+    names = {"store": "store_inventories", "wh": "warehouse_inventories", "ech": "echelon_inventories"}
+    for k, v in new.items():
+        np.testing.assert_allclose(v, ref[f"new/{names[k]}"], rtol=tol, atol=tol)
+    # adjoint with the same upstream: loss = sum(reward*r_b) + sum(new*up); r_bar is per-scenario here
+    g_new = {k: up[names[k]] for k in new}
+    r_bar = up["reward"]
+    # (a [B,1] r_bar broadcasts where the trainer's scalar 1/(B*T*S) would)
+    g_state, g_act = O.env_step_adjoint(pb, state, action, data, esaved, g_new, r_bar[:, None])
+    inv_names = {"store": "initial_inventories", "wh": "initial_warehouse_inventories",
+                 "ech": "initial_echelon_inventories"}
+    for k, v in g_state.items():
+        np.testing.assert_allclose(v, ref[f"grad/{inv_names[k]}"], rtol=10 * tol, atol=10 * tol)
+    for k, v in g_act.items():
+        np.testing.assert_allclose(v, ref[f"grad/action_{k}"], rtol=10 * tol, atol=10 * tol)
+
+
+@pytest.mark.parametrize("name", G.rollout_cases())
+def test_rollout_fp64_matches_reference_fp64(name):
+    meta, g = G.load("rollout", name)
+    pb = G.problem_from_meta(meta)
+    pol = G.policy_from_golden(meta, g["param"], np.float64)
+    data = G.cast(g["data"], np.float64)
+    fwd, grads = O.rollout_grad(pol, pb, data, meta["T"])
+    ref = g["ref64"]
+    np.testing.assert_allclose(fwd["reward_tb"], ref["reward_tb"], rtol=1e-9, atol=1e-9)
+    assert abs(fwd["total"] - ref["total"]) <= 1e-10 * abs(ref["total"])
+    rep = fwd["reward_tb"][meta["ignore_periods"]:].sum()
+    assert abs(rep - ref["report"]) <= 1e-10 * abs(ref["report"])
+    flat = O.flatten_grads(pol, grads)
+    for k, v in flat.items():
+        assert G.rel_l2(v, ref[f"grad/{k}"]) < 1e-8, k
+
+
+@pytest.mark.parametrize("name", G.rollout_cases())
+def test_rollout_fp32_matches_reference_fp32(name):
+    meta, g = G.load("rollout", name)
+    pb = G.problem_from_meta(meta)
+    pol = G.policy_from_golden(meta, g["param"], np.float32)
+    data = G.cast(g["data"], np.float32)
+    fwd, grads = O.rollout_grad(pol, pb, data, meta["T"])
+    ref, ref64 = g["ref"], g["ref64"]
+    assert fwd["reward_tb"].dtype == np.float32
+    # per-scenario (summed over periods) costs: the north-star 1e-5 relative bar
+    # gate against the float64 truth; allowance = max(1e-5, 3x the reference's own fp32 error to that truth)
+    cost_b = fwd["reward_tb"].astype(np.float64).sum(0)
+    ref_b = ref["reward_tb"].astype(np.float64).sum(0)
+    true_b = ref64["reward_tb"].sum(0)
+    cfloor = np.abs(ref_b / true_b - 1).max()
+    assert np.abs(cost_b / true_b - 1).max() <= max(1e-5, 3 * cfloor), (np.abs(cost_b / true_b - 1).max(), cfloor)
+    assert abs(float(fwd["total"]) - float(ref64["total"])) <= max(1e-5, 3 * cfloor) * abs(float(ref64["total"]))
+    flat = O.flatten_grads(pol, grads)
+    mine = np.concatenate([flat[k].ravel() for k in sorted(flat)])
+    r32 = np.concatenate([ref[f"grad/{k}"].ravel() for k in sorted(flat)])
+    r64 = np.concatenate([ref64[f"grad/{k}"].ravel() for k in sorted(flat)])
+    floor = G.rel_l2(r32, r64)
+    assert G.rel_l2(mine, r64) <= max(1e-5, 3 * floor), (G.rel_l2(mine, r64), floor)
+
+
+def test_final_state_and_first_action():
+    for name in G.rollout_cases():
+        meta, g = G.load("rollout", name)
+        pb = G.problem_from_meta(meta)
+        pol = G.policy_from_golden(meta, g["param"], np.float64)
+        data = G.cast(g["data"], np.float64)
+        state = O._initial_state(pb, data)
+        action, _ = O.policy_forward(pol, pb, state, data)
+        for k, v in action.items():
+            np.testing.assert_allclose(v, g["ref"][f"action0/{k}"], rtol=2e-4, atol=2e-5)  # fp32 reference action
+        fwd = O.rollout_forward(pol, pb, data, meta["T"])
+        names = {"store": "store_inventories", "wh": "warehouse_inventories", "ech": "echelon_inventories"}
+        for k, v in fwd["final"].items():
+            ref = g["ref"][f"final/{names[k]}"]
+            assert v.shape == ref.shape
+            scale = max(1.0, np.abs(ref).max())
+            assert np.abs(v - ref).max() <= 2e-3 * scale, (name, k)  # fp32 reference vs fp64 oracle after T periods
+
+
+def test_discrete_allocation_rounds_half_to_even():
+    meta, g = G.load("rollout", "one_store_lost")
+    pb = G.problem_from_meta(meta)
+    pol = G.policy_from_golden(meta, g["param"], np.float32)
+    data = G.cast(g["data"], np.float32)
+    fwd = O.rollout_forward(pol, pb, data, 5, discrete=True, keep_tape=True)
+    for _, action, _, _ in fwd["tape"]:
+        assert np.array_equal(action["stores"], np.rint(action["stores"]))
