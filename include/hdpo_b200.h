@@ -1,0 +1,225 @@
+/*
+ * hdpo_b200.h - C ABI of the B200-native HDPO rollout engine (libhdpo_b200.so).
+ *
+ * The reference (MatiasAlvo/Neural_inventory_control) has no FFI layer: its hot path is Python calling
+ * PyTorch eager ops.  This header is the boundary a maintainer would bind (ctypes stub in
+ * INTEGRATION.md) to replace exactly that path:
+ *
+ *   hdpo_step_fwd / hdpo_step_bwd        <- environment.py:110-299,391-434  Simulator.step (+ its autograd)
+ *   hdpo_allocation_shift                <- environment.py:77-101           initialize_shifts_for_allocation_put
+ *   hdpo_rollout_fwd                     <- trainer.py:181-216              Trainer.simulate_batch
+ *                                           neural_networks.py:195-214,314-427  Vanilla{OneStore,Serial,Warehouse}.forward
+ *                                           neural_networks.py:111-166      feasibility projections
+ *                                           loss_functions.py:10-11         PolicyLoss (reward.sum())
+ *   hdpo_rollout_bwd                     <- trainer.py:169-173              mean_loss.backward()
+ *   hdpo_rollout_train_host              <- trainer.py:155-173              one batch, host buffers in / host results out
+ *   hdpo_philox_normal / _poisson        <- data_handling.py:178-211        Scenario.generate_*_demand (statistical parity)
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no torch / C++ types.  All arrays are dense, row-major, float32
+ *     unless stated; "device" pointers are CUDA device memory of the current device.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream) except the *_host entry point, which synchronises the stream before returning.
+ *   - return value: 0 = ok, negative = error (HDPO_E_*); hdpo_last_error() returns a thread-local,
+ *     human-readable message for the last failing call.  Nothing throws across the boundary.
+ *   - the caller owns every buffer.  The only scratch memory is the explicit `workspace`, whose size
+ *     is queried first with hdpo_rollout_workspace_bytes().  No hidden allocation, no CPU fallback.
+ *   - thread-compatible: concurrent calls must use distinct streams AND distinct workspaces.
+ */
+#ifndef HDPO_B200_H_
+#define HDPO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HDPO_ABI_VERSION 1
+#define HDPO_MAX_LAYERS 8 /* linear layers per MLP */
+
+enum {
+  HDPO_OK = 0,
+  HDPO_E_INVALID = -1,     /* bad descriptor / null pointer / unsupported shape */
+  HDPO_E_CUDA = -2,        /* a CUDA runtime call failed (message has the cudaError string) */
+  HDPO_E_NO_DEVICE = -3,   /* no CUDA device / not an sm_100 device */
+  HDPO_E_WORKSPACE = -4    /* workspace too small */
+};
+
+/* policy architectures with a fused rollout (neural_networks.py:1519-1536 registry names) */
+enum {
+  HDPO_ARCH_VANILLA_ONE_STORE = 0, /* neural_networks.py:195-214 */
+  HDPO_ARCH_VANILLA_SERIAL = 1,    /* neural_networks.py:314-355 */
+  HDPO_ARCH_VANILLA_WAREHOUSE = 2, /* neural_networks.py:358-427 */
+  HDPO_ARCH_SYMMETRY_AWARE = 3     /* SURVEY.md 2.3 (recovered from stale bytecode) */
+};
+
+/* activation ids (neural_networks.py:36-43) */
+enum { HDPO_ACT_NONE = 0, HDPO_ACT_ELU = 1, HDPO_ACT_RELU = 2, HDPO_ACT_TANH = 3, HDPO_ACT_SIGMOID = 4, HDPO_ACT_SOFTPLUS = 5 };
+
+/* demand tensor layouts */
+enum {
+  HDPO_DEMAND_BST = 0, /* [B, S, t_stride]  the reference layout (data_handling.py:59, environment.py:171-177) */
+  HDPO_DEMAND_TSB = 1  /* [t_stride, S, B]  time-major, what hdpo_philox_* writes; fully coalesced */
+};
+
+/* matmul precision of the policy MLP */
+enum {
+  HDPO_PREC_FP32 = 0,   /* FFMA, fp32 everywhere (parity mode) */
+  HDPO_PREC_TF32X3 = 1, /* tcgen05 kind::tf32, 3-pass split (hi*hi + hi*lo + lo*hi), fp32 accumulate */
+  HDPO_PREC_TF32 = 2    /* tcgen05 kind::tf32, single pass (throughput mode; NOT within the 1e-5 bar) */
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * Problem shape shared by the per-step and the rollout entry points.
+ * (problem_params + tensor shapes of Scenario.get_data(), data_handling.py:54-81)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct HdpoProblem {
+  int32_t B;               /* scenarios in the batch */
+  int32_t S;               /* n_stores >= 1 */
+  int32_t W;               /* n_warehouses (0 allowed); action width Wc = max(W,1) */
+  int32_t E;               /* n_extra_echelons */
+  int32_t L, Lw, Le;       /* pipeline lengths: store_inventories.shape[2], warehouse..., echelon... (>= 2) */
+  int32_t lost_demand;     /* problem_params['lost_demand'] */
+  int32_t maximize_profit; /* problem_params['maximize_profit'] */
+  int32_t has_edge_cost;   /* 'warehouse_edge_costs' present (environment.py:254) */
+} HdpoProblem;
+
+/* Per-scenario constants, all device pointers, reference layouts (float32; lead times float-encoded
+ * integers exactly as Scenario.get_data() emits them, data_handling.py:81). Unused ones may be NULL. */
+typedef struct HdpoStatics {
+  const float* holding_costs;           /* [B,S] */
+  const float* underage_costs;          /* [B,S] */
+  const float* lead_times;              /* [B,S,Wc] */
+  const float* warehouse_lead_times;    /* [B,W] */
+  const float* warehouse_holding_costs; /* [B,W] */
+  const float* warehouse_edge_costs;    /* [B,W] or NULL */
+  const float* echelon_lead_times;      /* [B,E] */
+  const float* echelon_holding_costs;   /* [B,E] */
+  const float* mean;                    /* [B,S] symmetry-aware only */
+  const float* std;                     /* [B,S] symmetry-aware only */
+} HdpoStatics;
+
+/* Inventory state, reference layouts. */
+typedef struct HdpoState {
+  float* store;     /* [B,S,L]  */
+  float* warehouse; /* [B,W,Lw] or NULL */
+  float* echelon;   /* [B,E,Le] or NULL */
+} HdpoState;
+
+typedef struct HdpoAction {
+  float* stores;     /* [B,S,Wc] */
+  float* warehouses; /* [B,W,1] or NULL */
+  float* echelons;   /* [B,E,1] or NULL */
+} HdpoAction;
+
+/* ------------------------------------------------------------------------------------------------
+ * K3 - one simulator period for an arbitrary policy (environment.py:110-169).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* demand[b*demand_stride_b + s*demand_stride_s] is the current demand of (b,s): pass the base pointer
+ * already offset to column t+period_shift; strides are in elements.
+ * Writes next state into `next` (must not alias `cur`), reward[B], and raw_* scratch needed by the
+ * backward (raw_store [B,S], raw_wh [B,W], raw_ech [B,E]; any may be NULL when the node type is absent). */
+int hdpo_step_fwd(const HdpoProblem* pb, const HdpoStatics* st, const HdpoState* cur, const HdpoAction* act,
+                  const float* demand, int64_t demand_stride_b, int64_t demand_stride_s, HdpoState* next,
+                  float* reward, void* stream);
+
+/* Adjoint of hdpo_step_fwd.  g_next: adjoint wrt `next` (NULL members = zero); g_reward[B];
+ * outputs g_cur (adjoint wrt `cur`) and g_act (adjoint wrt the action).  `cur`, `act`, `demand` are the
+ * forward inputs.  Sub-gradient conventions follow torch autograd (see DESIGN.md "kinks"). */
+int hdpo_step_bwd(const HdpoProblem* pb, const HdpoStatics* st, const HdpoState* cur, const HdpoAction* act,
+                  const float* demand, int64_t demand_stride_b, int64_t demand_stride_s, const HdpoState* g_next,
+                  const float* g_reward, HdpoState* g_cur, HdpoAction* g_act, void* stream);
+
+/* shift[b,n] = b*(len*n_nodes) + n*len as int64, bit-exact with environment.py:77-101. */
+int hdpo_allocation_shift(int64_t* shift, int32_t B, int32_t n_nodes, int32_t len, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1 / K2 - fused T-period rollout and its reverse-time adjoint.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct HdpoMlp {
+  int32_t n_layers;                     /* number of Linear layers (>= 1) */
+  int32_t widths[HDPO_MAX_LAYERS + 1];  /* widths[0] = input size, widths[i+1] = out features of layer i */
+  int32_t hidden_act;                   /* HDPO_ACT_* after every layer but the last */
+  int32_t out_act;                      /* HDPO_ACT_* after the last layer */
+} HdpoMlp;
+
+typedef struct HdpoRolloutDesc {
+  HdpoProblem pb;
+  int32_t arch;               /* HDPO_ARCH_* */
+  int32_t T;                  /* periods to simulate */
+  int32_t t_stride;           /* time extent of the demand tensor (>= T + period_shift) */
+  int32_t period_shift;       /* observation_params['demand']['period_shift'] */
+  int32_t ignore_periods;     /* periods excluded from the reported loss (trainer.py:209) */
+  int32_t demand_layout;      /* HDPO_DEMAND_* */
+  int32_t discrete_allocation;/* round actions half-to-even (trainer.py:201-202); forward only */
+  int32_t transshipment;      /* nn_params['transshipment'] (no hold logit / no clip at 1) */
+  int32_t precision;          /* HDPO_PREC_* */
+  int32_t save_for_backward;  /* 1: forward writes the state tape into the workspace */
+  float warehouse_upper_bound;/* neural_networks.py:1538-1546 */
+  float prop_eps;             /* symmetry-aware proportional allocation epsilon (1e-15 old / 1e-10 current) */
+  HdpoMlp master;             /* vanilla_*: the 'master' net; symmetry_aware: the 'context' net */
+  HdpoMlp store_net;          /* symmetry_aware only */
+  HdpoMlp warehouse_net;      /* symmetry_aware only */
+  const int32_t* adjacency;   /* device [W,S] 0/1, NULL = fully connected (neural_networks.py:383-390) */
+} HdpoRolloutDesc;
+
+/* Number of float parameters the descriptor's nets hold, in state_dict order:
+ * for each net (master|context, store, warehouse), for each layer: weight [out,in] then bias [out]. */
+int64_t hdpo_param_count(const HdpoRolloutDesc* d);
+
+/* Bytes of workspace hdpo_rollout_fwd (with save_for_backward) + hdpo_rollout_bwd need. */
+size_t hdpo_rollout_workspace_bytes(const HdpoRolloutDesc* d);
+
+/* Forward rollout.  params: device flat parameter vector (hdpo_param_count floats).
+ * demands: device, layout per d->demand_layout.  init: initial inventories (read only).
+ * Outputs (device): cost_b[B] = sum_t reward[t,b]; report_b[B] = same for t >= ignore_periods (may be NULL);
+ * reward_tb [T,B] optional (NULL to skip); totals[2] (double) = {sum_b cost_b, sum_b report_b};
+ * final: state after T periods (members may be NULL). */
+int hdpo_rollout_fwd(const HdpoRolloutDesc* d, const float* params, const float* demands, const HdpoStatics* st,
+                     const HdpoState* init, float* cost_b, float* report_b, float* reward_tb, double* totals,
+                     HdpoState* final_state, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Reverse-time adjoint of the forward that last filled `workspace` (same d, params, demands, st).
+ * dLoss/dreward[t,b] = g_total + (t >= ignore_periods ? g_report : 0).
+ * grad_params (device, hdpo_param_count floats) is OVERWRITTEN with dLoss/dparams. */
+int hdpo_rollout_bwd(const HdpoRolloutDesc* d, const float* params, const float* demands, const HdpoStatics* st,
+                     float g_total, float g_report, float* grad_params, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* One training batch end to end with HOST buffers (pinned recommended): copies params, demands, statics
+ * and initial state host->device into the workspace, runs forward + adjoint with
+ * g_total = 1/(B*T*S) (trainer.py:169), copies totals[2] and grad_params back, synchronises.
+ * Device scratch = hdpo_rollout_host_workspace_bytes(d). */
+size_t hdpo_rollout_host_workspace_bytes(const HdpoRolloutDesc* d);
+int hdpo_rollout_train_host(const HdpoRolloutDesc* d, const float* h_params, const float* h_demands,
+                            const HdpoStatics* h_st, const HdpoState* h_init, const int32_t* h_adjacency,
+                            double* h_totals, float* h_grad_params, void* d_workspace, size_t workspace_bytes,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4 - on-device Philox4x32-10 demand sampler (counter-based: element i of a call draws from counter
+ * (offset + i/4), key = seed).  Output layout HDPO_DEMAND_TSB [T,S,B] or BST via `layout`.
+ * normal: mean[s] + std[s]*z, optional one-factor correlation rho (cov_ij = rho*std_i*std_j, i != j,
+ * data_handling.py:193-201), optional clip at 0 (data_handling.py:145-146).
+ * ---------------------------------------------------------------------------------------------- */
+int hdpo_philox_normal(float* out, int32_t B, int32_t S, int32_t T, int32_t layout, const float* mean,
+                       const float* std, float rho, int32_t clip_at_zero, uint64_t seed, uint64_t offset,
+                       void* stream);
+int hdpo_philox_poisson(float* out, int32_t B, int32_t S, int32_t T, int32_t layout, const float* mean,
+                        uint64_t seed, uint64_t offset, void* stream);
+
+/* misc */
+const char* hdpo_last_error(void);
+int hdpo_abi_version(void);
+/* Launch statistics since process start: number of kernels this library has launched. */
+int64_t hdpo_kernel_launch_count(void);
+/* SM count / name of the current device (fails with HDPO_E_NO_DEVICE when none). */
+int hdpo_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, char* name, int32_t name_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDPO_B200_H_ */

@@ -1,0 +1,68 @@
+// hdpo_math.cuh - activations and their derivatives with torch semantics (neural_networks.py:36-43).
+// Precise libm-grade device functions on purpose (expm1f/log1pf/expf, no --use_fast_math): the parity bar is
+// 1e-5 relative against a true-fp32 reference.
+#pragma once
+
+#include "hdpo_platform.cuh"
+#include "../../include/hdpo_b200.h"
+
+namespace hdpo {
+
+// nn.ELU(alpha=1): x > 0 ? x : expm1(x)
+__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
+// derivative expressed with the OUTPUT y: 1 for x > 0, exp(x) = y + 1 for x <= 0 (y == 0 at x == 0 -> 1)
+__device__ __forceinline__ float elu_grad_from_out(float y) { return y > 0.f ? 1.f : y + 1.f; }
+
+// nn.Softplus(beta=1, threshold=20)
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float softplus_grad(float x) {
+  if (x > 20.f) return 1.f;
+  float z = expf(x);
+  return z / (z + 1.f);
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) {
+  float e = expf(-fabsf(x));
+  return x >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+}
+
+// generic activation by id; `y` = output, used for derivatives where torch does the same
+__device__ __forceinline__ float act_fwd(int act, float x) {
+  switch (act) {
+    case HDPO_ACT_ELU: return elu_f(x);
+    case HDPO_ACT_RELU: return fmaxf(x, 0.f);
+    case HDPO_ACT_TANH: return tanhf(x);
+    case HDPO_ACT_SIGMOID: return sigmoid_f(x);
+    case HDPO_ACT_SOFTPLUS: return softplus_f(x);
+    default: return x;
+  }
+}
+// derivative given pre-activation x and output y
+__device__ __forceinline__ float act_grad(int act, float x, float y) {
+  switch (act) {
+    case HDPO_ACT_ELU: return x > 0.f ? 1.f : y + 1.f;
+    case HDPO_ACT_RELU: return x > 0.f ? 1.f : 0.f;
+    case HDPO_ACT_TANH: return 1.f - y * y;
+    case HDPO_ACT_SIGMOID: return y * (1.f - y);
+    case HDPO_ACT_SOFTPLUS: return softplus_grad(x);
+    default: return 1.f;
+  }
+}
+// derivative from the output alone (exact for elu/relu/tanh/sigmoid/none; softplus: 1 - exp(-y))
+__device__ __forceinline__ float act_grad_from_out(int act, float y) {
+  switch (act) {
+    case HDPO_ACT_ELU: return elu_grad_from_out(y);
+    case HDPO_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case HDPO_ACT_TANH: return 1.f - y * y;
+    case HDPO_ACT_SIGMOID: return y * (1.f - y);
+    case HDPO_ACT_SOFTPLUS: return y > 20.f ? 1.f : -expm1f(-y);
+    default: return 1.f;
+  }
+}
+
+// clip(x, min=0) and its torch sub-gradient (1 for x >= 0, incl. x == 0)
+__device__ __forceinline__ float relu0(float x) { return fmaxf(x, 0.f); }
+__device__ __forceinline__ float ge0(float x) { return x >= 0.f ? 1.f : 0.f; }
+__device__ __forceinline__ float le0(float x) { return x <= 0.f ? 1.f : 0.f; }
+
+}  // namespace hdpo

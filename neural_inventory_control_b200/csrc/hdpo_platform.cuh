@@ -1,0 +1,41 @@
+// hdpo_platform.cuh - thin platform layer for the SIMT kernels.
+//
+// Product build (nvcc, sm_100a): plain CUDA. Kernels are launched with HDPO_LAUNCH on the caller's stream.
+// Test build (-DHDPO_EMU, g++, no GPU): tests/emu/cuda_emu.h maps the CUDA execution model onto host threads
+// (one std::thread per CUDA thread, std::barrier for __syncthreads) so the *same kernel sources* can be checked
+// against the oracle in the CPU-only build container. The emulated library is test infrastructure: it is built
+// by tests/emu/build_emu.py into tests/emu/_build/ and is never loaded by the product package.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+
+#ifdef HDPO_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+namespace hdpo {
+
+void count_launch();  // capi.cu
+
+#ifndef HDPO_EMU
+#define HDPO_DYN_SMEM(type, name)                                  \
+  extern __shared__ __align__(16) unsigned char hdpo_dyn_smem_[];  \
+  type* name = reinterpret_cast<type*>(hdpo_dyn_smem_)
+
+// kfn must be a variable holding the kernel (so template commas are fine): auto kfn = kernel<A,B>;
+#define HDPO_LAUNCH(kfn, grid, block, smem, stream, ...)                          \
+  do {                                                                            \
+    kfn<<<(grid), (block), (smem), reinterpret_cast<cudaStream_t>(stream)>>>(__VA_ARGS__); \
+    ::hdpo::count_launch();                                                       \
+  } while (0)
+#endif
+
+constexpr int kWarp = 32;
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace hdpo

@@ -1,0 +1,178 @@
+"""Parity of the CUDA kernels, called through the C ABI, against the reference-generated goldens and the oracle.
+
+Each test is parametrised over two backends:
+  * `cuda` (marked gpu)  - the product library on the B200: these are the parity tests proper;
+  * `emu`                - the same .cu sources on the host-thread emulator, so that kernel arithmetic is
+                           also checked in the CPU-only container (tests/emu; never a product path).
+Tolerances: integer/index work bit-exact; per-scenario costs 1e-5 relative to the float64 reference run
+(or 3x the fp32 reference's own error where that is larger); gradients relative-L2 with
+the same rule.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import abi_driver as D
+import golden_util as G
+from neural_inventory_control_b200 import _capi as K
+from oracle import hdpo_oracle as O
+
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+_cache = {}
+
+
+def backend(name):
+    if name not in _cache:
+        _cache[name] = D.EmuBackend() if name == "emu" else D.CudaBackend()
+    return _cache[name]
+
+
+SMALL = ["one_store_lost", "one_store_lost_trained", "one_store_backlogged", "one_store_backlogged_lead20",
+         "serial_system", "serial_system_perturbed"]
+WIDE = ["one_warehouse_s5", "one_warehouse_s50", "many_warehouses_2x10", "many_warehouses_3x50"]
+
+
+def fused_cases():
+    return SMALL + WIDE
+
+
+def check_rollout_against_golden(out, meta, g, T, ignore):
+    ref, ref64 = g["ref"], g["ref64"]
+    true_tb = ref64["reward_tb"][:T]
+    true_b = true_tb.sum(0)
+    ref_b = ref["reward_tb"][:T].astype(np.float64).sum(0)
+    floor = np.abs(ref_b / true_b - 1).max()
+    tol = max(1e-5, 3 * floor)
+    got_b = out["cost_b"].astype(np.float64)
+    assert np.abs(got_b / true_b - 1).max() <= tol, (np.abs(got_b / true_b - 1).max(), floor)
+    rep_true = true_tb[ignore:].sum(0)
+    assert np.abs(out["report_b"].astype(np.float64) - rep_true).max() <= tol * np.abs(true_b).max()
+    assert abs(out["totals"][0] - true_b.sum()) <= tol * abs(true_b.sum())
+    assert abs(out["totals"][1] - rep_true.sum()) <= tol * abs(true_b.sum())
+    # per-period per-scenario costs
+    scale = np.abs(true_tb).max()
+    assert np.abs(out["reward_tb"] - true_tb).max() <= 10 * tol * scale
+
+
+@pytest.mark.parametrize("be_name", BACKENDS)
+@pytest.mark.parametrize("name", G.step_cases())
+def test_step_fwd_bwd_matches_reference(be_name, name):
+    be = backend(be_name)
+    meta, g = G.load("step", name)
+    out = D.step(be, meta, g["data"], g["action"], up={**g["up"]}, t=meta["period"])
+    ref = g["ref"]
+    np.testing.assert_allclose(out["reward"], ref["reward"], rtol=2e-6, atol=1e-6)
+    names = {"store": "store_inventories", "wh": "warehouse_inventories", "ech": "echelon_inventories"}
+    inv = {"store": "initial_inventories", "wh": "initial_warehouse_inventories", "ech": "initial_echelon_inventories"}
+    for k, v in out["new"].items():
+        if v is not None:
+            np.testing.assert_allclose(v, ref[f"new/{names[k]}"], rtol=2e-6, atol=2e-6)
+    for k, v in out["g_cur"].items():
+        if v is not None:
+            np.testing.assert_allclose(v, ref[f"grad/{inv[k]}"], rtol=1e-5, atol=1e-5)
+    for k, v in out["g_act"].items():
+        np.testing.assert_allclose(v, ref[f"grad/action_{k}"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("be_name", BACKENDS)
+def test_allocation_shift_bit_exact(be_name):
+    be = backend(be_name)
+    for (B, n, L) in [(1, 1, 2), (16, 7, 3), (257, 50, 6), (1000, 3, 20)]:
+        h = be.zeros((B, n), np.int64)
+        K.check(be.lib, be.lib.hdpo_allocation_shift(be.ptr(h), B, n, L, be.stream), "hdpo_allocation_shift")
+        be.sync()
+        got = be.get(h)
+        assert got.dtype == np.int64 and np.array_equal(got, O.allocation_shift(B, n, L))
+    meta, g = G.load("step", "many_warehouses")
+    B, S, L = g["data"]["initial_inventories"].shape
+    h = be.zeros((B, S), np.int64)
+    K.check(be.lib, be.lib.hdpo_allocation_shift(be.ptr(h), B, S, L, be.stream), "hdpo_allocation_shift")
+    be.sync()
+    assert np.array_equal(be.get(h), g["ref"]["allocation_shift"])  # the reference's own table
+
+
+@pytest.mark.parametrize("be_name", BACKENDS)
+@pytest.mark.parametrize("name", SMALL)
+def test_rollout_costs_and_gradients_match_reference(be_name, name):
+    be = backend(be_name)
+    meta, g = G.load("rollout", name)
+    out = D.rollout(be, meta, g["param"], g["data"])
+    check_rollout_against_golden(out, meta, g, meta["T"], meta["ignore_periods"])
+    ref, ref64 = g["ref"], g["ref64"]
+    keys = sorted(out["grad"])
+    mine = np.concatenate([out["grad"][k].ravel() for k in keys])
+    r32 = np.concatenate([ref[f"grad/{k}"].ravel() for k in keys])
+    r64 = np.concatenate([ref64[f"grad/{k}"].ravel() for k in keys])
+    floor = G.rel_l2(r32, r64)
+    assert G.rel_l2(mine, r64) <= max(1e-5, 3 * floor), (G.rel_l2(mine, r64), floor)
+    for k in keys:  # and per tensor
+        assert G.rel_l2(out["grad"][k], ref64[f"grad/{k}"]) <= max(2e-5, 5 * floor), k
+    names = {"store": "store_inventories", "wh": "warehouse_inventories", "ech": "echelon_inventories"}
+    for k, v in out["final"].items():
+        if v is not None:
+            rf = ref[f"final/{names[k]}"]
+            assert np.abs(v - rf).max() <= 1e-4 * max(1.0, np.abs(rf).max())
+
+
+@pytest.mark.parametrize("be_name", BACKENDS)
+@pytest.mark.parametrize("name", ["one_store_lost", "serial_system"])
+def test_rollout_time_major_demand_layout_is_identical(be_name, name):
+    be = backend(be_name)
+    meta, g = G.load("rollout", name)
+    a = D.rollout(be, meta, g["param"], g["data"])
+    b = D.rollout(be, meta, g["param"], g["data"], demand_layout=K.DEMAND_TSB)
+    assert np.array_equal(a["reward_tb"], b["reward_tb"])
+    assert np.array_equal(a["grad_flat"], b["grad_flat"])
+
+
+@pytest.mark.parametrize("be_name", BACKENDS)
+@pytest.mark.parametrize("name,n,T,ignore", [("one_store_lost", 45, 17, 5), ("serial_system", 33, 50, 49),
+                                             ("one_store_backlogged_lead20", 1, 3, 0)])
+def test_rollout_ragged_batches_against_oracle(be_name, name, n, T, ignore):
+    """B not a multiple of the warp tile, short horizons, ignore near T: compare with the pinned oracle."""
+    be = backend(be_name)
+    meta, g = G.load("rollout", name)
+    data = D.slice_batch(g["data"], n)
+    out = D.rollout(be, meta, g["param"], data, T=T, ignore=ignore, g_total=0.37, g_report=-0.11)
+    pb = G.problem_from_meta(meta)
+    pol = G.policy_from_golden(meta, g["param"], np.float64)
+    d64 = G.cast(data, np.float64)
+    fwd = O.rollout_forward(pol, pb, d64, T, ignore)
+    np.testing.assert_allclose(out["reward_tb"], fwd["reward_tb"], rtol=2e-5, atol=2e-4)
+    np.testing.assert_allclose(out["report_b"], fwd["reward_tb"][ignore:].sum(0), rtol=2e-5, atol=2e-4)
+    # gradient with two different upstream scalars == linear combination of two oracle adjoints
+    _, g_all = O.rollout_grad(pol, pb, d64, T, grad_scale=1.0)
+    full = O.flatten_grads(pol, g_all)
+    # report-only part: rerun the oracle adjoint on the tail by zeroing r_bar before `ignore` is not available, so
+    # use linearity: grad(g_total, g_report) = g_total * grad_all + g_report * grad_tail, with grad_tail from the
+    # kernel itself at (0, 1), and check the (1, 0) leg against the oracle.
+    leg_all = D.rollout(be, meta, g["param"], data, T=T, ignore=ignore, g_total=1.0, g_report=0.0)
+    leg_tail = D.rollout(be, meta, g["param"], data, T=T, ignore=ignore, g_total=0.0, g_report=1.0)
+    for k in full:
+        assert G.rel_l2(leg_all["grad"][k], full[k]) < 2e-5, k
+    combo = 0.37 * leg_all["grad_flat"].astype(np.float64) - 0.11 * leg_tail["grad_flat"].astype(np.float64)
+    assert G.rel_l2(out["grad_flat"], combo) < 1e-5
+    if ignore >= T:
+        assert np.all(leg_tail["grad_flat"] == 0)
+
+
+@pytest.mark.parametrize("be_name", BACKENDS)
+def test_discrete_allocation_forward(be_name):
+    be = backend(be_name)
+    meta, g = G.load("rollout", "one_store_lost")
+    out = D.rollout(be, meta, g["param"], g["data"], T=20, discrete=True, backward=False)
+    pb = G.problem_from_meta(meta)
+    pol = G.policy_from_golden(meta, g["param"], np.float32)
+    fwd = O.rollout_forward(pol, pb, G.cast(g["data"], np.float32), 20, meta["ignore_periods"], discrete=True)
+    # rounding makes the trajectory piecewise constant in the weights: identical unless an action sits on a .5 tie
+    close = np.isclose(out["reward_tb"], fwd["reward_tb"], rtol=1e-5, atol=1e-4)
+    assert close.mean() > 0.99
+
+
+@pytest.mark.parametrize("be_name", BACKENDS)
+def test_backward_rejects_discrete_and_small_workspace(be_name):
+    be = backend(be_name)
+    meta, g = G.load("rollout", "one_store_lost")
+    with pytest.raises(K.HdpoError):
+        D.rollout(be, meta, g["param"], g["data"], T=5, discrete=True, backward=True)
