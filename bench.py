@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py - train scenario-periods/s (forward + adjoint rollout) of the HDPO hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" = one fused forward rollout + reverse-time adjoint over one batch of synthetic demand that is already
+resident in HBM (plus, for N > 1, the policy-gradient all-reduce over NCCL). Scenario batches are sharded across
+ranks with a fixed per-GPU batch (weak scaling). Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement").
+`--impl reference` times the CPU port of the reference's own path (oracle/torch_port.py, PyTorch eager on the
+host cores, all threads) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_WORKLOAD = "one_store_backlogged_lead20"
+METRIC = "train scenario-periods/sec (fwd+bwd)"
+UNIT = "scenario-periods/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_setup(workload, B, T, seed=0):
+    """The same synthetic workload on the host, as inputs of the PyTorch-eager port (oracle/torch_port.py)."""
+    import torch
+    from neural_inventory_control_b200 import workloads as WL
+    pspec, pp, data, widths = WL.WORKLOADS[workload]("cpu", B=B, T=T)
+    g = torch.Generator().manual_seed(seed)
+    flat = WL.init_flat_params(widths, g, "cpu")
+    layers, o = [], 0
+    for i in range(len(widths) - 1):
+        n = widths[i + 1] * widths[i]
+        w = flat[o:o + n].view(widths[i + 1], widths[i]).clone().requires_grad_(True)
+        o += n
+        b = flat[o:o + widths[i + 1]].clone().requires_grad_(True)
+        o += widths[i + 1]
+        layers.append((w, b))
+    pol = {"arch": pspec.arch, "layers": layers, "hidden_act": pspec.master[1], "out_act": pspec.master[2],
+           "wub": torch.tensor([pspec.warehouse_upper_bound]), "adjacency": None, "transshipment": pspec.transshipment}
+    pb = dict(pp, period_shift=0)
+    return pol, pb, data
+
+
+def time_cpu_port(workload, B, T, steps, warmup):
+    import torch
+    from oracle import torch_port as TP
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pol, pb, data = cpu_port_setup(workload, B, T)
+    for _ in range(warmup):
+        TP.train_step(pol, pb, data, T)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        TP.train_step(pol, pb, data, T)
+    dt = (time.perf_counter() - t0) / steps
+    return B * T / dt, dt, cores
+
+
+def cpu_sample_size(workload):
+    return {"one_store_backlogged_lead20": 16384, "one_store_lost": 16384, "serial_system": 8192}.get(workload, 1024)
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (PyTorch-eager port), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Bc, T = cpu_sample_size(args.workload), 50
+    value, dt, cores = time_cpu_port(args.workload, Bc, T, args.steps, args.warmup)
+    sample = f"{Bc} scenarios x {T} periods per step (bounded sample of the workload), PyTorch-eager port, {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "periods": T, "scenarios_per_step": Bc, "device": "host cpu"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--batch", type=int, default=None, help="scenarios per GPU (default: the workload's)")
+    ap.add_argument("--periods", type=int, default=50)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from neural_inventory_control_b200 import _capi as K
+    from neural_inventory_control_b200 import engine as EN
+    from neural_inventory_control_b200 import workloads as WL
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the HDPO engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    kw = {"T": args.periods}
+    if args.batch:
+        kw["B"] = args.batch
+    pspec, pp, data, widths = WL.WORKLOADS[args.workload](dev, seed=57 + rank, **kw)
+    B, S, T = data["demands"].shape[0], pp["n_stores"], args.periods
+    gen = torch.Generator(device=dev).manual_seed(0)  # identical weights on every rank
+    flat = WL.init_flat_params(widths, gen, dev)
+    eng = EN.FusedRollout(pspec, pp, data, T, ignore_periods=30)
+    grad = torch.zeros_like(flat)
+    lib = eng.lib
+    g_total = 1.0 / (world * B * T * S)
+
+    def step():
+        eng.forward(flat, data)
+        eng.backward(g_total, 0.0, out=grad)
+        if world > 1:
+            dist.all_reduce(grad)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.hdpo_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = lib.hdpo_kernel_launch_count() - l0
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = world * B * T / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel alone (the adjoint), CUDA events on the launching stream
+    def time_region(fn, n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    n_k = max(3, min(args.steps, 10))
+    fwd_ms = time_region(lambda: eng.forward(flat, data), n_k)
+    bwd_ms = time_region(lambda: eng.backward(g_total, 0.0, out=grad), n_k)
+    peaks = load_peaks()
+    macs = sum(widths[i] * widths[i + 1] for i in range(len(widths) - 1))
+    detached = pspec.arch == "vanilla_serial"
+    flops_step = WL.flops_per_scenario_period(widths, first_layer_dgrad=not detached)
+    flops_bwd = flops_step - 2 * macs  # dgrad + wgrad; the adjoint kernel's recompute is not counted
+    tf32_peak = peaks["bf16_tflops"] / 2.0
+    achieved = flops_bwd * B * T / (bwd_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": "small_bwd_kernel (reverse-time adjoint, SIMT fp32 parity mode)",
+        "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": None,
+        "peak_source": f"{peaks['source']}: tf32 taken as bf16_tflops/2 (burst, kernel timed alone)",
+        "kernel_ms": bwd_ms, "fwd_kernel_ms": fwd_ms,
+        "step_frac": flops_step * B * T / (ms_per_step * 1e-3) / 1e12 / (peaks["bf16_tflops_sustained"] / 2.0),
+        "hbm_frac": 8.0 * S * B * T / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
+    }
+
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D of the batch + D2H of loss and gradient
+    e2e = None
+    if not args.no_e2e:
+        host = {k: v.cpu().pin_memory() for k, v in data.items()}
+        h_flat = flat.cpu().pin_memory()
+        h_grad = torch.empty_like(h_flat).pin_memory()
+        h_tot = torch.zeros(2, dtype=torch.float64).pin_memory()
+        desc = eng.desc
+        ws_bytes = int(lib.hdpo_rollout_host_workspace_bytes(C.byref(desc)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        hp = lambda k: host[k].data_ptr() if k in host else None  # noqa: E731
+        h_st = K.Statics(hp("holding_costs"), hp("underage_costs"), hp("lead_times"), hp("warehouse_lead_times"),
+                         hp("warehouse_holding_costs"), hp("warehouse_edge_costs"), hp("echelon_lead_times"),
+                         hp("echelon_holding_costs"), hp("mean"), hp("std"))
+        h_init = K.State(hp("initial_inventories"), hp("initial_warehouse_inventories"),
+                         hp("initial_echelon_inventories"))
+        stream = EN.current_stream_ptr(dev)
+
+        def host_step():
+            rc = lib.hdpo_rollout_train_host(C.byref(desc), h_flat.data_ptr(), host["demands"].data_ptr(),
+                                             C.byref(h_st), C.byref(h_init), None, h_tot.data_ptr(), h_grad.data_ptr(),
+                                             ws.data_ptr(), ws_bytes, stream)
+            K.check(lib, rc, "hdpo_rollout_train_host")
+
+        for _ in range(2):
+            host_step()
+        n_e = max(3, min(args.steps, 5))
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e):
+            host_step()  # synchronises the stream before returning
+        dt = (time.perf_counter() - t0) / n_e
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = sum(v.numel() * 4 for v in host.values()) + h_flat.numel() * 4
+        e2e = {"value": world * B * T / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 16 + h_grad.numel() * 4, "ms_per_step": dt * 1e3,
+               "api": "hdpo_rollout_train_host (C ABI, pinned host buffers)"}
+        del ws
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        Bc = cpu_sample_size(args.workload)
+        v, dt, cores = time_cpu_port(args.workload, Bc, T, 3, 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{Bc} scenarios x {T} periods, 1 warm-up + 3 timed steps, PyTorch-eager port of the "
+                                  f"reference path on {cores} host threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "scenarios_per_gpu": B, "periods": T, "stores": S,
+                       "policy_widths": widths, "l2": "inputs larger than L2 (demand + state tape per step)"
+                       if B * T * 4 * (1 + widths[0]) > 126e6 else "working set below L2 size; no flush",
+                       "parallelism": f"dp{world} (scenario shards, gradient all-reduce)" if world > 1 else "single GPU"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,92 @@
+"""Synthetic instances of the BASELINE.json configurations, generated on the device.
+
+Each builder returns (pspec, problem_params, data dict of CUDA tensors in the reference layouts, layer shapes).
+Values follow the shipped YAMLs (one_store_backlogged.yml, serial_system.yml, ...); only the demand traces are
+synthetic draws of the same distributions (no dataset files are involved).
+"""
+import math
+
+import torch
+
+from .engine import PolicySpec
+
+WORKLOADS = {}
+
+
+def register(name):
+    def deco(fn):
+        WORKLOADS[name] = fn
+        return fn
+    return deco
+
+
+def init_flat_params(widths, gen, device):
+    """torch.nn.Linear default init (U(+-1/sqrt(fan_in)) for weight and bias), flattened in state_dict order."""
+    chunks = []
+    for i in range(len(widths) - 1):
+        k = 1.0 / math.sqrt(widths[i])
+        chunks.append((torch.rand(widths[i + 1] * widths[i], generator=gen, device=device) * 2 - 1) * k)
+        chunks.append((torch.rand(widths[i + 1], generator=gen, device=device) * 2 - 1) * k)
+    return torch.cat(chunks).contiguous()
+
+
+def _one_store(B, T, L, lead, dist, lost, device, seed):
+    g = torch.Generator(device=device).manual_seed(seed)
+    if dist == "poisson":
+        dem = torch.poisson(torch.full((B, 1, T), 5.0, device=device), generator=g)
+    else:
+        dem = (torch.randn(B, 1, T, generator=g, device=device) * 1.6 + 5.0).clamp_(min=0)
+    data = {
+        "demands": dem,
+        "initial_inventories": 5.0 * torch.rand(B, 1, L, generator=g, device=device),
+        "holding_costs": torch.ones(B, 1, device=device),
+        "underage_costs": torch.full((B, 1), 9.0, device=device),
+        "lead_times": torch.full((B, 1, 1), float(lead), device=device),
+    }
+    pp = {"n_stores": 1, "n_warehouses": 0, "n_extra_echelons": 0, "lost_demand": lost, "maximize_profit": False}
+    widths = [L, 32, 32, 32, 1]
+    return PolicySpec("vanilla_one_store", (widths, "elu", None)), pp, data, widths
+
+
+@register("one_store_lost")
+def one_store_lost(device, B=8192, T=50, seed=57):
+    """cfg 1: one_store_lost.yml + vanilla_one_store.yml (Poisson(5), lead 4, p=9, h=1)."""
+    return _one_store(B, T, 4, 4, "poisson", True, device, seed)
+
+
+@register("one_store_backlogged_lead20")
+def one_store_backlogged_lead20(device, B=1 << 20, T=50, seed=57):
+    """cfg 2: one_store_backlogged.yml with the longest tested lead time (20), N(5,1.6) clipped at 0."""
+    return _one_store(B, T, 20, 20, "normal", False, device, seed)
+
+
+@register("serial_system")
+def serial_system(device, B=1 << 20, T=50, seed=57):
+    """cfg 3: serial_system.yml + vanilla_serial.yml (4 stages: 2 extra echelons, warehouse, store)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    dem = (torch.randn(B, 1, T, generator=g, device=device) * 2.0 + 5.0).clamp_(min=0)
+    data = {
+        "demands": dem,
+        "initial_inventories": 5.0 * torch.rand(B, 1, 4, generator=g, device=device),
+        "holding_costs": torch.ones(B, 1, device=device),
+        "underage_costs": torch.full((B, 1), 9.0, device=device),
+        "lead_times": torch.full((B, 1, 1), 4.0, device=device),
+        "initial_warehouse_inventories": torch.zeros(B, 1, 3, device=device),
+        "warehouse_lead_times": torch.full((B, 1), 3.0, device=device),
+        "warehouse_holding_costs": torch.full((B, 1), 0.5, device=device),
+        "initial_echelon_inventories": torch.zeros(B, 2, 4, device=device),
+        "echelon_lead_times": torch.tensor([2.0, 4.0], device=device).expand(B, 2).contiguous(),
+        "echelon_holding_costs": torch.tensor([0.1, 0.2], device=device).expand(B, 2).contiguous(),
+    }
+    pp = {"n_stores": 1, "n_warehouses": 1, "n_extra_echelons": 2, "lost_demand": False, "maximize_profit": False}
+    widths = [15, 32, 32, 4]
+    return PolicySpec("vanilla_serial", (widths, "elu", None), warehouse_upper_bound=20.0), pp, data, widths
+
+
+def flops_per_scenario_period(widths, first_layer_dgrad=True):
+    """Algorithmic FLOPs: 2*3*MACs_fwd (forward + dgrad + wgrad); recompute is not counted."""
+    macs = sum(widths[i] * widths[i + 1] for i in range(len(widths) - 1))
+    f = 2 * 3 * macs
+    if not first_layer_dgrad:
+        f -= 2 * widths[0] * widths[1]
+    return f

@@ -121,3 +121,34 @@ def test_discrete_allocation_rounds_half_to_even():
     fwd = O.rollout_forward(pol, pb, data, 5, discrete=True, keep_tape=True)
     for _, action, _, _ in fwd["tape"]:
         assert np.array_equal(action["stores"], np.rint(action["stores"]))
+
+
+# ---- the PyTorch-eager CPU port used as the reported CPU baseline (oracle/torch_port.py) ----
+def _torch_policy(meta, params, dtype):
+    import torch
+    idxs = sorted({int(k.split(".")[2]) for k in params if k.endswith(".weight")})
+    layers = [(torch.tensor(params[f"net.master.{i}.weight"], dtype=dtype, requires_grad=True),
+               torch.tensor(params[f"net.master.{i}.bias"], dtype=dtype, requires_grad=True)) for i in idxs]
+    adj = meta["problem_params"].get("warehouse_store_adjacency")
+    return {"arch": meta["nn_name"], "layers": layers, "hidden_act": meta["inner_layer_activations"]["master"],
+            "out_act": meta["output_layer_activation"]["master"],
+            "wub": torch.tensor([meta["warehouse_upper_bound"]], dtype=dtype),
+            "adjacency": None if adj is None else torch.tensor(adj), "transshipment": meta.get("transshipment", False)}
+
+
+@pytest.mark.parametrize("name", G.rollout_cases())
+def test_torch_port_matches_reference_fp64(name):
+    import torch
+    from oracle import torch_port as TP
+    meta, g = G.load("rollout", name)
+    pol = _torch_policy(meta, g["param"], torch.float64)
+    pb = dict(meta["problem_params"], period_shift=meta.get("period_shift", 0))
+    data = {k: torch.tensor(v, dtype=torch.float64) for k, v in g["data"].items()}
+    total, report, grads = TP.train_step(pol, pb, data, meta["T"], meta["ignore_periods"])
+    ref = g["ref64"]
+    assert abs(total - ref["total"]) <= 1e-10 * abs(ref["total"])
+    assert abs(report - ref["report"]) <= 1e-10 * abs(ref["report"])
+    idxs = sorted({int(k.split(".")[2]) for k in g["param"] if k.endswith(".weight")})
+    names = [f"net.master.{i}.{wb}" for i in idxs for wb in ("weight", "bias")]
+    for n, gr in zip(names, grads):
+        assert G.rel_l2(gr.numpy(), ref[f"grad/{n}"]) < 1e-8, n
