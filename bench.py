@@ -101,7 +101,9 @@ def cpu_port_setup(workload, B, T, seed=0):
         o += widths[i + 1]
         layers.append((w, b))
     pol = {"arch": pspec.arch, "layers": layers, "hidden_act": pspec.master[1], "out_act": pspec.master[2],
-           "wub": torch.tensor([pspec.warehouse_upper_bound]), "adjacency": None, "transshipment": pspec.transshipment}
+           "wub": torch.tensor([pspec.warehouse_upper_bound]),
+           "adjacency": None if pspec.adjacency is None else torch.tensor(pspec.adjacency),
+           "transshipment": pspec.transshipment}
     pb = dict(pp, period_shift=0)
     return pol, pb, data
 
@@ -122,7 +124,8 @@ def time_cpu_port(workload, B, T, steps, warmup):
 
 
 def cpu_sample_size(workload):
-    return {"one_store_backlogged_lead20": 16384, "one_store_lost": 16384, "serial_system": 8192}.get(workload, 1024)
+    return {"one_store_backlogged_lead20": 16384, "one_store_lost": 16384, "serial_system": 8192,
+            "one_warehouse_lost_demand": 256, "many_warehouses_lost_demand": 256}.get(workload, 1024)
 
 
 def run_reference(args):
@@ -243,8 +246,11 @@ def main():
     flops_bwd = flops_step - 2 * macs  # dgrad + wgrad; the adjoint kernel's recompute is not counted
     tf32_peak = peaks["bf16_tflops"] / 2.0
     achieved = flops_bwd * B * T / (bwd_ms * 1e-3) / 1e12
+    small = pspec.arch in ("vanilla_one_store", "vanilla_serial")
     roofline = {
-        "bound": "tensor", "kernel": "small_bwd_kernel (reverse-time adjoint, SIMT fp32 parity mode)",
+        "bound": "tensor",
+        "kernel": ("small_bwd_kernel (reverse-time adjoint, SIMT fp32 parity mode)" if small else
+                   "adjoint sweep: sgemm_kernel dgrad+wgrad tiles (SIMT fp32 parity mode) + warehouse_head_bwd"),
         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": None,
         "peak_source": f"{peaks['source']}: tf32 taken as bf16_tflops/2 (burst, kernel timed alone)",
         "kernel_ms": bwd_ms, "fwd_kernel_ms": fwd_ms,
@@ -269,10 +275,15 @@ def main():
         h_init = K.State(hp("initial_inventories"), hp("initial_warehouse_inventories"),
                          hp("initial_echelon_inventories"))
         stream = EN.current_stream_ptr(dev)
+        h_adj = None
+        if pspec.adjacency is not None:
+            h_adj = torch.tensor(pspec.adjacency, dtype=torch.int32).contiguous().pin_memory()
 
         def host_step():
             rc = lib.hdpo_rollout_train_host(C.byref(desc), h_flat.data_ptr(), host["demands"].data_ptr(),
-                                             C.byref(h_st), C.byref(h_init), None, h_tot.data_ptr(), h_grad.data_ptr(),
+                                             C.byref(h_st), C.byref(h_init),
+                                             h_adj.data_ptr() if h_adj is not None else None, h_tot.data_ptr(),
+                                             h_grad.data_ptr(),
                                              ws.data_ptr(), ws_bytes, stream)
             K.check(lib, rc, "hdpo_rollout_train_host")
 

@@ -1,0 +1,6 @@
+"""Root-level module with the reference's name, so `from trainer import *` / user notebooks keep working.
+The implementation lives in neural_inventory_control_b200.environment (star-import chain as in the reference)."""
+from shared_imports import *  # noqa: F401,F403
+from data_handling import *  # noqa: F401,F403
+from neural_networks import *  # noqa: F401,F403
+from neural_inventory_control_b200.environment import *  # noqa: F401,F403

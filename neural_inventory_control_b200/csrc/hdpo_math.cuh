@@ -3,13 +3,29 @@
 // 1e-5 relative against a true-fp32 reference.
 #pragma once
 
+#include <type_traits>
+
 #include "hdpo_platform.cuh"
 #include "../../include/hdpo_b200.h"
 
 namespace hdpo {
 
+// expm1(x) for x <= 0 in ~10 instructions at <= 2 ulp: degree-7 Taylor/Horner near zero (|x| <= 0.35, truncation
+// 1.6e-8 relative), expf(x) - 1 below that (result magnitude >= 0.29, so the absolute error of expf dominates).
+// libm's expm1f is ~25 instructions; with 96 ELUs per scenario-period that cost as much as the FFMAs themselves.
+__device__ __forceinline__ float expm1_nonpos(float x) {
+  float p = fmaf(x, 1.f / 5040.f, 1.f / 720.f);
+  p = fmaf(x, p, 1.f / 120.f);
+  p = fmaf(x, p, 1.f / 24.f);
+  p = fmaf(x, p, 1.f / 6.f);
+  p = fmaf(x, p, 0.5f);
+  p = fmaf(x, p, 1.f);
+  p = x * p;
+  return x > -0.35f ? p : expf(x) - 1.f;
+}
+
 // nn.ELU(alpha=1): x > 0 ? x : expm1(x)
-__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1_nonpos(x); }
 // derivative expressed with the OUTPUT y: 1 for x > 0, exp(x) = y + 1 for x <= 0 (y == 0 at x == 0 -> 1)
 __device__ __forceinline__ float elu_grad_from_out(float y) { return y > 0.f ? 1.f : y + 1.f; }
 
@@ -57,6 +73,40 @@ __device__ __forceinline__ float act_grad_from_out(int act, float y) {
     case HDPO_ACT_SIGMOID: return y * (1.f - y);
     case HDPO_ACT_SOFTPLUS: return y > 20.f ? 1.f : -expm1f(-y);
     default: return 1.f;
+  }
+}
+
+// Compile-time activation variants + a row-level dispatcher. Applying the runtime switch PER ELEMENT inside unrolled
+// loops inlines all six activations (tanhf / log1pf / division slow paths) 32x per row and blew the kernels up to
+// 300 KB of SASS (instruction-cache thrash, ncu "no_instruction" stalls); dispatching once per row keeps the hot
+// loop to the one activation actually in use.
+template <int ACT>
+__device__ __forceinline__ float act_fwd_t(float x) {
+  if (ACT == HDPO_ACT_ELU) return elu_f(x);
+  if (ACT == HDPO_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == HDPO_ACT_TANH) return tanhf(x);
+  if (ACT == HDPO_ACT_SIGMOID) return sigmoid_f(x);
+  if (ACT == HDPO_ACT_SOFTPLUS) return softplus_f(x);
+  return x;
+}
+template <int ACT>
+__device__ __forceinline__ float act_grad_out_t(float y) {
+  if (ACT == HDPO_ACT_ELU) return elu_grad_from_out(y);
+  if (ACT == HDPO_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (ACT == HDPO_ACT_TANH) return 1.f - y * y;
+  if (ACT == HDPO_ACT_SIGMOID) return y * (1.f - y);
+  if (ACT == HDPO_ACT_SOFTPLUS) return y > 20.f ? 1.f : -expm1f(-y);
+  return 1.f;
+}
+template <class F>
+__device__ __forceinline__ void dispatch_act(int act, F&& f) {
+  switch (act) {
+    case HDPO_ACT_ELU: f(std::integral_constant<int, HDPO_ACT_ELU>{}); break;
+    case HDPO_ACT_RELU: f(std::integral_constant<int, HDPO_ACT_RELU>{}); break;
+    case HDPO_ACT_TANH: f(std::integral_constant<int, HDPO_ACT_TANH>{}); break;
+    case HDPO_ACT_SIGMOID: f(std::integral_constant<int, HDPO_ACT_SIGMOID>{}); break;
+    case HDPO_ACT_SOFTPLUS: f(std::integral_constant<int, HDPO_ACT_SOFTPLUS>{}); break;
+    default: f(std::integral_constant<int, HDPO_ACT_NONE>{}); break;
   }
 }
 

@@ -1,20 +1,820 @@
-// rollout_wide.cu - placeholder until the tile-GEMM pipeline lands (next milestone).
+// rollout_wide.cu - K1/K2 for wide policy nets over many stores (VanillaWarehouse: one or many warehouses).
+//
+// Replaces trainer.py:181-216 + neural_networks.py:369-427 + environment.py:110-270 and their autograd for a whole
+// batch. Unlike the small-net path the policy MLP here is a real GEMM (153->512->512->512->51 per scenario), so the
+// rollout is a pipeline of tile kernels per period instead of one persistent kernel:
+//
+//   forward, period t :  X_t --[gemm+bias+act] x n_layers--> Y_t --[warehouse_head_fwd: masked softmax x on-hand,
+//                        sigmoid x bound, store / warehouse dynamics, cost]--> X_{t+1}
+//   adjoint, period t :  gX_{t+1} --[warehouse_head_bwd]--> gY_t, gX_t(direct) --[dgrad gemm (x act') ...]--> gX_t
+//   after the sweep   :  dW_l = sum_t gz_{l,t}^T h_{l-1,t} as ONE split-K GEMM per layer over all T*B rows
+//
+// HBM layout (180 GB part): everything the adjoint needs is SAVED, not recomputed - the state tape X[T+1][Bp][w0],
+// every layer output ACT_l[T][Bp][w_{l+1}] and every pre-activation adjoint GZ_l[T][Bp][w_{l+1}] (cfg 4 at
+// B = 8192: ~5.6 GB). Rows are scenarios (padded to 128), columns padded to 64, so all tiles are full and all
+// float4 accesses aligned; weights are re-packed into zero-padded [N][K] slabs once per call.
+//
+// This file holds the fp32 SIMT tile GEMM (parity mode). The tcgen05 3xTF32 GEMM replaces `sgemm` call sites
+// one-for-one (same operand layouts) - see gemm_tc.cuh.
 #include "rollout_wide.cuh"
 
 namespace hdpo {
 namespace wide {
 
-bool supported(const HdpoRolloutDesc*) { return false; }
-size_t workspace_bytes(const HdpoRolloutDesc*) { return 0; }
-int forward(const HdpoRolloutDesc*, const float*, const float*, const HdpoStatics*, const HdpoState*, float*, float*,
-            float*, double*, HdpoState*, void*, size_t, void*) {
-  set_error("wide rollout not built");
-  return HDPO_E_INVALID;
+constexpr int kRowPad = 128;   // scenarios padded to the GEMM M tile
+constexpr int kColPad = 64;    // layer widths padded to the GEMM N tile
+constexpr int kMaxStoresPerWarp = 256;
+constexpr int kSplitK = 16;
+
+static inline int pad_to(int x, int q) { return (x + q - 1) / q * q; }
+static inline size_t a256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+bool supported(const HdpoRolloutDesc* d) {
+  if (d->arch != HDPO_ARCH_VANILLA_WAREHOUSE) return false;
+  if (d->precision != HDPO_PREC_FP32) return false;
+  const HdpoProblem& pb = d->pb;
+  if (pb.W < 1 || pb.E != 0 || pb.W > 8) return false;
+  if (pb.S * pb.W > 1024 || pb.S > kMaxStoresPerWarp) return false;
+  const HdpoMlp& m = d->master;
+  if (m.widths[0] != pb.S * pb.L + pb.W * pb.Lw) return false;
+  if (m.widths[m.n_layers] != pb.S * pb.W + pb.W) return false;
+  if (m.out_act != HDPO_ACT_NONE) return false;
+  return true;
 }
-int backward(const HdpoRolloutDesc*, const float*, const float*, const HdpoStatics*, float, float, float*, void*, size_t,
-             void*) {
-  set_error("wide rollout not built");
-  return HDPO_E_INVALID;
+
+// ------------------------------------------------------------------------------------------------------------
+// workspace plan
+// ------------------------------------------------------------------------------------------------------------
+struct Plan {
+  int n, B, Bp, T, save;
+  int w[HDPO_MAX_LAYERS + 1], wp[HDPO_MAX_LAYERS + 1];
+  int gw[HDPO_MAX_LAYERS], gb[HDPO_MAX_LAYERS];  // offsets in the flat (state_dict) parameter vector
+  int P;
+  size_t o_W[HDPO_MAX_LAYERS], o_b[HDPO_MAX_LAYERS];       // packed weights / biases
+  size_t o_X, o_act[HDPO_MAX_LAYERS], o_gz[HDPO_MAX_LAYERS];  // tapes
+  size_t o_gx, o_part, o_bpart, total;                      // state adjoint, split-K partials
+  size_t x_stride, act_stride[HDPO_MAX_LAYERS];              // floats per period
+  int max_wk;
+};
+
+static Plan make_plan(const HdpoRolloutDesc* d) {
+  Plan p;
+  const HdpoMlp& m = d->master;
+  p.n = m.n_layers;
+  p.B = d->pb.B;
+  p.Bp = pad_to(p.B > 0 ? p.B : 1, kRowPad);
+  p.T = d->T;
+  p.save = d->save_for_backward;
+  int off = 0;
+  for (int i = 0; i <= p.n; ++i) {
+    p.w[i] = m.widths[i];
+    p.wp[i] = pad_to(m.widths[i], kColPad);
+  }
+  for (int l = 0; l < p.n; ++l) {
+    p.gw[l] = off;
+    off += p.w[l + 1] * p.w[l];
+    p.gb[l] = off;
+    off += p.w[l + 1];
+  }
+  p.P = off;
+  const size_t f = sizeof(float);
+  size_t o = 0;
+  auto take = [&](size_t n_floats) {
+    size_t at = o;
+    o += a256(n_floats * f);
+    return at;
+  };
+  p.max_wk = 0;
+  for (int l = 0; l < p.n; ++l) {
+    p.o_W[l] = take(static_cast<size_t>(p.wp[l + 1]) * p.wp[l]);
+    p.o_b[l] = take(p.wp[l + 1]);
+    int wk = p.wp[l + 1] * p.wp[l];
+    if (wk > p.max_wk) p.max_wk = wk;
+  }
+  const size_t tslots = p.save ? static_cast<size_t>(p.T) : 1;
+  p.x_stride = static_cast<size_t>(p.Bp) * p.wp[0];
+  p.o_X = take((p.save ? tslots + 1 : 2) * p.x_stride);
+  for (int l = 0; l < p.n; ++l) {
+    p.act_stride[l] = static_cast<size_t>(p.Bp) * p.wp[l + 1];
+    p.o_act[l] = take(tslots * p.act_stride[l]);
+  }
+  for (int l = 0; l < p.n; ++l) p.o_gz[l] = p.save ? take(tslots * p.act_stride[l]) : 0;
+  p.o_gx = p.save ? take(p.x_stride) : 0;
+  p.o_part = p.save ? take(static_cast<size_t>(kSplitK) * p.max_wk) : 0;
+  int max_wp = 0;
+  for (int i = 0; i <= p.n; ++i) max_wp = p.wp[i] > max_wp ? p.wp[i] : max_wp;
+  p.o_bpart = p.save ? take(static_cast<size_t>(128) * max_wp) : 0;
+  p.total = o + 256;
+  return p;
+}
+
+size_t workspace_bytes(const HdpoRolloutDesc* d) { return make_plan(d).total; }
+
+// ------------------------------------------------------------------------------------------------------------
+// fp32 SIMT tile GEMM:  C[M,N] = epi( sum_k A(m,k) * B(k,n) ),  all dims multiples of the tile, ld* multiples of 4
+//   A_T = false: A(m,k) = A[m*lda + k]      A_T = true: A(m,k) = A[k*lda + m]
+//   B_T = false: B(k,n) = B[k*ldb + n]      B_T = true: B(k,n) = B[n*ldb + k]
+// ------------------------------------------------------------------------------------------------------------
+enum { EPI_BIAS_ACT = 0, EPI_MUL_ACTGRAD = 1, EPI_ACCUM = 2, EPI_SPLITK = 3 };
+
+constexpr int BN = 64, BK = 16, GEMM_THREADS = 256;
+
+struct GemmArgs {
+  const float* A;
+  const float* B;
+  float* C;
+  int M, N, K;          // K = contraction length handled by ONE z-slice
+  int lda, ldb, ldc;
+  const float* bias;    // EPI_BIAS_ACT
+  const float* aux;     // EPI_MUL_ACTGRAD: saved layer output, same shape/ld as C
+  int act;
+  size_t c_slice;       // EPI_SPLITK: floats between z-slices of C
+  size_t a_kslice, b_kslice;  // element offset added per z-slice to A / B (k origin of the slice)
+};
+
+template <int BM, bool A_T, bool B_T, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(GemmArgs g) {
+  constexpr int TM = BM / 16;  // rows per thread (8 or 4)
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const float* __restrict__ A = g.A + blockIdx.z * g.a_kslice;
+  const float* __restrict__ Bm = g.B + blockIdx.z * g.b_kslice;
+
+  // global -> register staging. A tile: BM x BK floats = BM*4 float4; B tile: 64 x 16 floats = 256 float4.
+  constexpr int A_F4 = BM * BK / 4 / GEMM_THREADS;  // 2 (BM=128) or 1 (BM=64)
+  float4 ra[A_F4], rb;
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < A_F4; ++i) {
+      const int idx = tid + i * GEMM_THREADS;
+      if (A_T) {  // contiguous along m: idx -> (k = idx / (BM/4), mq = idx % (BM/4))
+        const int k = idx / (BM / 4), mq = idx % (BM / 4);
+        ra[i] = *reinterpret_cast<const float4*>(A + static_cast<size_t>(k0 + k) * g.lda + m0 + 4 * mq);
+      } else {    // contiguous along k: idx -> (m = idx % BM, kq = idx / BM)
+        const int m = idx % BM, kq = idx / BM;
+        ra[i] = *reinterpret_cast<const float4*>(A + static_cast<size_t>(m0 + m) * g.lda + k0 + 4 * kq);
+      }
+    }
+    if (B_T) {    // B[n*ldb + k], contiguous along k: tid -> (n = tid % 64, kq = tid / 64)
+      const int n = tid % BN, kq = tid / BN;
+      rb = *reinterpret_cast<const float4*>(Bm + static_cast<size_t>(n0 + n) * g.ldb + k0 + 4 * kq);
+    } else {      // B[k*ldb + n], contiguous along n: tid -> (k = tid / 16, nq = tid % 16)
+      const int k = tid / (BN / 4), nq = tid % (BN / 4);
+      rb = *reinterpret_cast<const float4*>(Bm + static_cast<size_t>(k0 + k) * g.ldb + n0 + 4 * nq);
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_F4; ++i) {
+      const int idx = tid + i * GEMM_THREADS;
+      if (A_T) {
+        const int k = idx / (BM / 4), mq = idx % (BM / 4);
+        *reinterpret_cast<float4*>(&As[buf][k][4 * mq]) = ra[i];
+      } else {
+        const int m = idx % BM, kq = idx / BM;
+        As[buf][4 * kq + 0][m] = ra[i].x;
+        As[buf][4 * kq + 1][m] = ra[i].y;
+        As[buf][4 * kq + 2][m] = ra[i].z;
+        As[buf][4 * kq + 3][m] = ra[i].w;
+      }
+    }
+    if (B_T) {
+      const int n = tid % BN, kq = tid / BN;
+      Bs[buf][4 * kq + 0][n] = rb.x;
+      Bs[buf][4 * kq + 1][n] = rb.y;
+      Bs[buf][4 * kq + 2][n] = rb.z;
+      Bs[buf][4 * kq + 3][n] = rb.w;
+    } else {
+      const int k = tid / (BN / 4), nq = tid % (BN / 4);
+      *reinterpret_cast<float4*>(&Bs[buf][k][4 * nq]) = rb;
+    }
+  };
+
+  float acc[TM][4];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  const int n_k = g.K / BK;
+  for (int kt = 0; kt < n_k; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < n_k) load_tiles((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM];
+#pragma unroll
+      for (int q = 0; q < TM / 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + 4 * q]);
+        a[4 * q + 0] = v.x;
+        a[4 * q + 1] = v.y;
+        a[4 * q + 2] = v.z;
+        a[4 * q + 3] = v.w;
+      }
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        acc[i][0] = fmaf(a[i], b.x, acc[i][0]);
+        acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(a[i], b.z, acc[i][2]);
+        acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+      }
+    }
+    if (kt + 1 < n_k) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue: thread owns rows m0 + ty*TM + i, columns n0 + tx*4 .. +3
+  const int n = n0 + tx * 4;
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (EPI == EPI_BIAS_ACT) bias4 = *reinterpret_cast<const float4*>(g.bias + n);
+  float* Cz = g.C + (EPI == EPI_SPLITK ? blockIdx.z * g.c_slice : 0);
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    float4* dst = reinterpret_cast<float4*>(Cz + static_cast<size_t>(m) * g.ldc + n);
+    float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    if (EPI == EPI_BIAS_ACT) {
+      v.x += bias4.x;
+      v.y += bias4.y;
+      v.z += bias4.z;
+      v.w += bias4.w;
+      dispatch_act(g.act, [&](auto tag) {
+        constexpr int ACT = decltype(tag)::value;
+        v.x = act_fwd_t<ACT>(v.x);
+        v.y = act_fwd_t<ACT>(v.y);
+        v.z = act_fwd_t<ACT>(v.z);
+        v.w = act_fwd_t<ACT>(v.w);
+      });
+    } else if (EPI == EPI_MUL_ACTGRAD) {
+      const float4 h = *reinterpret_cast<const float4*>(g.aux + static_cast<size_t>(m) * g.ldc + n);
+      dispatch_act(g.act, [&](auto tag) {
+        constexpr int ACT = decltype(tag)::value;
+        v.x *= act_grad_out_t<ACT>(h.x);
+        v.y *= act_grad_out_t<ACT>(h.y);
+        v.z *= act_grad_out_t<ACT>(h.z);
+        v.w *= act_grad_out_t<ACT>(h.w);
+      });
+    } else if (EPI == EPI_ACCUM) {
+      const float4 c0 = *dst;
+      v.x += c0.x;
+      v.y += c0.y;
+      v.z += c0.z;
+      v.w += c0.w;
+    }
+    *dst = v;
+  }
+}
+
+template <bool A_T, bool B_T, int EPI>
+static int sgemm(const GemmArgs& g, int splits, void* stream) {
+  // BM = 128 when that still yields >= ~1 wave of CTAs, else 64 (small batches / weight-gradient tiles)
+  const bool big = (g.M % 128 == 0) && (static_cast<long long>(g.M / 128) * (g.N / BN) * splits >= 148);
+  if (big) {
+    auto k = sgemm_kernel<128, A_T, B_T, EPI>;
+    HDPO_LAUNCH(k, dim3(g.N / BN, g.M / 128, splits), GEMM_THREADS, 0, stream, g);
+  } else {
+    auto k = sgemm_kernel<64, A_T, B_T, EPI>;
+    HDPO_LAUNCH(k, dim3(g.N / BN, g.M / 64, splits), GEMM_THREADS, 0, stream, g);
+  }
+  HDPO_LAUNCH_OK();
+  return HDPO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small helper kernels
+// ------------------------------------------------------------------------------------------------------------
+
+// flat state_dict parameters -> zero-padded [Np][Kp] weight slab + [Np] bias
+__global__ void __launch_bounds__(256) pack_layer_kernel(const float* __restrict__ params, int gw, int gb, int N, int K,
+                                                         int Np, int Kp, float* __restrict__ Wp, float* __restrict__ bp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Np * Kp) {
+    const int n = i / Kp, k = i % Kp;
+    Wp[i] = (n < N && k < K) ? params[gw + n * K + k] : 0.f;
+  }
+  if (i < Np) bp[i] = i < N ? params[gb + i] : 0.f;
+}
+
+// initial state rows X_0[b] = [store inventories flat | warehouse inventories flat | 0 pad]; padded rows = 0
+__global__ void __launch_bounds__(256) init_state_kernel(const float* __restrict__ store, const float* __restrict__ wh,
+                                                         int B, int Bp, int nS, int nW, int ldx, float* __restrict__ X,
+                                                         float* __restrict__ cost_b, float* __restrict__ report_b) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < static_cast<size_t>(Bp) * ldx) {
+    const int b = static_cast<int>(i / ldx), k = static_cast<int>(i % ldx);
+    float v = 0.f;
+    if (b < B) {
+      if (k < nS) v = store[static_cast<size_t>(b) * nS + k];
+      else if (k < nS + nW) v = wh[static_cast<size_t>(b) * nW + (k - nS)];
+    }
+    X[i] = v;
+  }
+  if (i < static_cast<size_t>(B)) {
+    cost_b[i] = 0.f;
+    if (report_b) report_b[i] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) zero_kernel(float* __restrict__ p, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
+}
+
+// final state rows -> reference layouts
+__global__ void __launch_bounds__(256) export_state_kernel(const float* __restrict__ X, int B, int nS, int nW, int ldx,
+                                                           float* __restrict__ store, float* __restrict__ wh) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * (nS + nW)) return;
+  const int b = static_cast<int>(i / (nS + nW)), k = static_cast<int>(i % (nS + nW));
+  const float v = X[static_cast<size_t>(b) * ldx + k];
+  if (k < nS) {
+    if (store) store[static_cast<size_t>(b) * nS + k] = v;
+  } else if (wh) {
+    wh[static_cast<size_t>(b) * nW + (k - nS)] = v;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// warehouse policy head + simulator period: one WARP per scenario, lanes over stores
+// ------------------------------------------------------------------------------------------------------------
+struct HeadArgs {
+  int B, S, W, L, Lw, T_stride, tt;  // tt = t + period_shift (demand column)
+  int ldx, ldy, demand_layout;
+  int lost, profit, has_edge, transshipment, discrete, in_report;
+  float wub;
+  const int32_t* adjacency;  // [W][S] or null
+  const float* demands;
+  HdpoStatics st;
+};
+
+constexpr int HEAD_WARPS = 4;
+
+__device__ __forceinline__ float demand_of(const HeadArgs& a, int b, int s) {
+  if (a.demand_layout == HDPO_DEMAND_TSB) return __ldg(a.demands + (static_cast<size_t>(a.tt) * a.S + s) * a.B + b);
+  return __ldg(a.demands + (static_cast<size_t>(b) * a.S + s) * a.T_stride + a.tt);
+}
+
+// softmax shares p[s*W+w] of warehouse w over its connected stores (+ constant hold logit 1.0 unless transshipment)
+// written to `share` (shared memory scratch of this warp). neural_networks.py:140-166, 399-419.
+__device__ __forceinline__ void softmax_shares(const HeadArgs& a, const float* __restrict__ y, float* __restrict__ share,
+                                               int lane) {
+  for (int w = 0; w < a.W; ++w) {
+    float mx = a.transshipment ? -INFINITY : 1.f;
+    for (int s = lane; s < a.S; s += 32) {
+      const bool conn = !a.adjacency || a.adjacency[w * a.S + s] != 0;
+      if (conn) mx = fmaxf(mx, y[s * a.W + w]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int s = lane; s < a.S; s += 32) {
+      const bool conn = !a.adjacency || a.adjacency[w * a.S + s] != 0;
+      const float e = conn ? expf(y[s * a.W + w] - mx) : 0.f;
+      share[s * a.W + w] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    if (!a.transshipment) sum += expf(1.f - mx);
+    const float inv = 1.f / sum;
+    for (int s = lane; s < a.S; s += 32) share[s * a.W + w] *= inv;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(HEAD_WARPS * 32)
+warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ Xn,
+                          float* __restrict__ cost_b, float* __restrict__ report_b, float* __restrict__ reward_t) {
+  HDPO_DYN_SMEM(float, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * HEAD_WARPS + warp;
+  if (b >= a.B) return;
+  const int SW = a.S * a.W;
+  float* share = smem + warp * (SW + 32);  // alloc[s*W+w]; tail: per-warehouse scratch
+  const float* x = X + static_cast<size_t>(b) * a.ldx;
+  const float* y = Y + static_cast<size_t>(b) * a.ldy;
+  float* xn = Xn + static_cast<size_t>(b) * a.ldx;
+  const int nS = a.S * a.L;
+  softmax_shares(a, y, share, lane);
+  // allocations = share * warehouse on-hand (optionally rounded half-to-even)
+  for (int i = lane; i < SW; i += 32) {
+    const int w = i % a.W;
+    float al = share[i] * x[nS + w * a.Lw];
+    if (a.discrete) al = rintf(al);
+    share[i] = al;
+  }
+  __syncwarp();
+  // ---- stores
+  float cost = 0.f;
+  for (int s = lane; s < a.S; s += 32) {
+    const float* xs = x + s * a.L;
+    float* xo = xn + s * a.L;
+    const int bs = b * a.S + s;
+    const float on_hand = xs[0];
+    const float d = demand_of(a, b, s);
+    const float raw = on_hand - d;
+    const float h = a.st.holding_costs[bs], p = a.st.underage_costs[bs];
+    cost += a.profit ? (-p * fminf(on_hand, d) + h * relu0(raw)) : (p * relu0(-raw) + h * relu0(raw));
+    const float post = a.lost ? relu0(raw) : raw;
+    xo[0] = post + xs[1];
+    for (int k = 1; k < a.L - 1; ++k) xo[k] = xs[k + 1];
+    xo[a.L - 1] = 0.f;
+    for (int w = 0; w < a.W; ++w) {
+      const float al = share[s * a.W + w];
+      if (al != 0.f) {
+        const int slot = static_cast<int>(a.st.lead_times[static_cast<size_t>(bs) * a.W + w]) - 1;
+        if (slot >= 0 && slot < a.L) xo[slot] += al;
+      }
+    }
+  }
+  // ---- warehouses: lane w
+  if (lane < a.W) {
+    const int w = lane;
+    const int bw = b * a.W + w;
+    float drawn = 0.f;
+    for (int s = 0; s < a.S; ++s) drawn += share[s * a.W + w];
+    const float* xw = x + nS + w * a.Lw;
+    float* xo = xn + nS + w * a.Lw;
+    const float raw = xw[0] - drawn;
+    float aw = sigmoid_f(y[SW + w]) * a.wub;
+    if (a.discrete) aw = rintf(aw);
+    float cw = a.st.warehouse_holding_costs[bw] * relu0(raw);
+    if (a.has_edge) cw += a.st.warehouse_edge_costs[bw] * aw;
+    cost += cw;
+    xo[0] = raw + xw[1];
+    for (int k = 1; k < a.Lw - 1; ++k) xo[k] = xw[k + 1];
+    xo[a.Lw - 1] = 0.f;
+    if (aw != 0.f) {
+      const int slot = static_cast<int>(a.st.warehouse_lead_times[bw]) - 1;
+      if (slot >= 0 && slot < a.Lw) xo[slot] += aw;
+    }
+  }
+  // padding columns of the next state row stay zero
+  for (int k = nS + a.W * a.Lw + lane; k < a.ldx; k += 32) xn[k] = 0.f;
+  cost = warp_sum(cost);
+  if (lane == 0) {
+    cost_b[b] += cost;
+    if (report_b && a.in_report) report_b[b] += cost;
+    if (reward_t) reward_t[b] = cost;
+  }
+}
+
+// Adjoint of the head + period. gX: on entry adjoint wrt X_{t+1} row, on exit the direct part of the adjoint wrt X_t.
+__global__ void __launch_bounds__(HEAD_WARPS * 32)
+warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ gX,
+                          float* __restrict__ gY, float rb) {
+  HDPO_DYN_SMEM(float, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * HEAD_WARPS + warp;
+  if (b >= a.B) return;
+  const int SW = a.S * a.W;
+  float* share = smem + warp * (2 * SW + 64);  // p[s*W+w]
+  float* galloc = share + SW;                  // adjoint of the allocations
+  float* wscr = galloc + SW;                   // [0..W): g_raw_w, [W..2W): on-hand W0, [2W..3W): sum_s g_p*p
+  const float* x = X + static_cast<size_t>(b) * a.ldx;
+  const float* y = Y + static_cast<size_t>(b) * a.ldy;
+  float* g = gX + static_cast<size_t>(b) * a.ldx;
+  float* gy = gY + static_cast<size_t>(b) * a.ldy;
+  const int nS = a.S * a.L;
+  softmax_shares(a, y, share, lane);
+  // ---- warehouses first (lane w): g_raw_w feeds the store-allocation adjoints
+  if (lane < a.W) {
+    const int w = lane;
+    const int bw = b * a.W + w;
+    const float W0 = x[nS + w * a.Lw];
+    float drawn = 0.f;
+    for (int s = 0; s < a.S; ++s) drawn += share[s * a.W + w] * W0;
+    const float raw = W0 - drawn;
+    float* gw = g + nS + w * a.Lw;
+    const float sg = sigmoid_f(y[SW + w]);
+    const float aw = sg * a.wub;
+    float gaw = 0.f;
+    if (aw != 0.f) {
+      const int slot = static_cast<int>(a.st.warehouse_lead_times[bw]) - 1;
+      if (slot >= 0 && slot < a.Lw) gaw = gw[slot];
+    }
+    if (a.has_edge) gaw += rb * a.st.warehouse_edge_costs[bw];
+    const float gn0 = gw[0];
+    const float g_raw = rb * a.st.warehouse_holding_costs[bw] * ge0(raw) + gn0;
+    for (int k = a.Lw - 1; k >= 2; --k) gw[k] = gw[k - 1];
+    gw[1] = gn0;
+    gw[0] = g_raw;
+    wscr[w] = g_raw;
+    wscr[a.W + w] = W0;
+    gy[SW + w] = gaw * a.wub * sg * (1.f - sg);
+  }
+  __syncwarp();
+  // ---- stores (lane s): dynamics adjoint + allocation adjoints
+  for (int s = lane; s < a.S; s += 32) {
+    const float* xs = x + s * a.L;
+    float* gs = g + s * a.L;
+    const int bs = b * a.S + s;
+    const float on_hand = xs[0];
+    const float d = demand_of(a, b, s);
+    const float raw = on_hand - d;
+    const float h = a.st.holding_costs[bs], p = a.st.underage_costs[bs];
+    for (int w = 0; w < a.W; ++w) {
+      const float al = share[s * a.W + w] * wscr[a.W + w];
+      float ga = 0.f;
+      if (al != 0.f) {
+        const int slot = static_cast<int>(a.st.lead_times[static_cast<size_t>(bs) * a.W + w]) - 1;
+        if (slot >= 0 && slot < a.L) ga = gs[slot];
+      }
+      galloc[s * a.W + w] = ga - wscr[w];
+    }
+    float g0;
+    if (a.profit) {
+      const float tie = on_hand < d ? 1.f : (on_hand == d ? 0.5f : 0.f);
+      g0 = rb * (-p * tie + h * ge0(raw));
+    } else {
+      g0 = rb * (-p * le0(raw) + h * ge0(raw));
+    }
+    const float gn0 = gs[0];
+    g0 += a.lost ? gn0 * ge0(raw) : gn0;
+    for (int k = a.L - 1; k >= 2; --k) gs[k] = gs[k - 1];
+    gs[1] = gn0;
+    gs[0] = g0;
+  }
+  __syncwarp();
+  // ---- policy head adjoint: alloc = p * W0 ; softmax backward over the connected set
+  for (int w = 0; w < a.W; ++w) {
+    const float W0 = wscr[a.W + w];
+    float dot = 0.f;  // sum_s g_alloc * p   (= adjoint of W0, and with W0 the softmax inner product)
+    for (int s = lane; s < a.S; s += 32) dot += galloc[s * a.W + w] * share[s * a.W + w];
+    dot = warp_sum(dot);
+    if (lane == 0) g[nS + w * a.Lw] += dot;
+    for (int s = lane; s < a.S; s += 32) {
+      const float pw = share[s * a.W + w];
+      gy[s * a.W + w] = pw * (galloc[s * a.W + w] * W0 - dot * W0);
+    }
+  }
+  for (int k = SW + a.W + lane; k < a.ldy; k += 32) gy[k] = 0.f;
+}
+
+// column sums of a [rows][ld] matrix (bias gradients), two deterministic stages
+__global__ void __launch_bounds__(256) colsum_stage1_kernel(const float* __restrict__ G, size_t rows, int ld, int n_chunks,
+                                                            float* __restrict__ part) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = blockIdx.y;
+  if (col >= ld) return;
+  const size_t per = (rows + n_chunks - 1) / n_chunks;
+  const size_t r0 = chunk * per, r1 = (r0 + per < rows) ? r0 + per : rows;
+  float s = 0.f;
+  for (size_t r = r0; r < r1; ++r) s += G[r * ld + col];
+  part[static_cast<size_t>(chunk) * ld + col] = s;
+}
+
+// grad[gw + n*K + k] = sum_z part[z][n][k] ; grad[gb + n] = sum_chunks bpart[chunk][n]
+__global__ void __launch_bounds__(256) unpack_grad_kernel(const float* __restrict__ part, int splits, size_t slice, int Kp,
+                                                          int N, int K, const float* __restrict__ bpart, int n_chunks,
+                                                          int ldb, int gw, int gb, float* __restrict__ grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N * K) {
+    const int n = i / K, k = i % K;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[z * slice + static_cast<size_t>(n) * Kp + k];
+    grad[gw + i] = s;
+  }
+  if (i < N) {
+    float s = 0.f;
+    for (int c = 0; c < n_chunks; ++c) s += bpart[static_cast<size_t>(c) * ldb + i];
+    grad[gb + i] = s;
+  }
+}
+
+__global__ void __launch_bounds__(1024) totals_kernel(const float* __restrict__ cost_b, const float* __restrict__ report_b,
+                                                      int B, double* __restrict__ totals) {
+  __shared__ double s0[1024];
+  __shared__ double s1[1024];
+  double a = 0.0, r = 0.0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    a += static_cast<double>(cost_b[i]);
+    if (report_b) r += static_cast<double>(report_b[i]);
+  }
+  s0[threadIdx.x] = a;
+  s1[threadIdx.x] = r;
+  __syncthreads();
+  for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+    if (static_cast<int>(threadIdx.x) < w) {
+      s0[threadIdx.x] += s0[threadIdx.x + w];
+      s1[threadIdx.x] += s1[threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    totals[0] = s0[0];
+    totals[1] = s1[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------------------
+static HeadArgs head_args(const HdpoRolloutDesc* d, const Plan& p, const float* demands, const HdpoStatics* st, int t) {
+  HeadArgs a;
+  a.B = p.B;
+  a.S = d->pb.S;
+  a.W = d->pb.W;
+  a.L = d->pb.L;
+  a.Lw = d->pb.Lw;
+  a.T_stride = d->t_stride;
+  a.tt = t + d->period_shift;
+  a.ldx = p.wp[0];
+  a.ldy = p.wp[p.n];
+  a.demand_layout = d->demand_layout;
+  a.lost = d->pb.lost_demand;
+  a.profit = d->pb.maximize_profit;
+  a.has_edge = d->pb.has_edge_cost;
+  a.transshipment = d->transshipment;
+  a.discrete = d->discrete_allocation;
+  a.in_report = t >= d->ignore_periods;
+  a.wub = d->warehouse_upper_bound;
+  a.adjacency = d->pb.W > 1 ? d->adjacency : nullptr;
+  a.demands = demands;
+  a.st = *st;
+  return a;
+}
+
+static float* wsf(void* ws, size_t off) { return reinterpret_cast<float*>(static_cast<char*>(ws) + off); }
+
+int forward(const HdpoRolloutDesc* d, const float* params, const float* demands, const HdpoStatics* st,
+            const HdpoState* init, float* cost_b, float* report_b, float* reward_tb, double* totals,
+            HdpoState* final_state, void* ws, size_t ws_bytes, void* stream) {
+  const Plan p = make_plan(d);
+  HDPO_REQUIRE(ws != nullptr, "the wide rollout needs its workspace (hdpo_rollout_workspace_bytes)");
+  if (ws_bytes < p.total) {
+    set_error("workspace too small: %zu < %zu", ws_bytes, p.total);
+    return HDPO_E_WORKSPACE;
+  }
+  HDPO_REQUIRE(d->pb.W == 1 || d->adjacency != nullptr, "warehouse_store_adjacency required for n_warehouses > 1");
+  const HdpoProblem& pb = d->pb;
+  const int nS = pb.S * pb.L, nW = pb.W * pb.Lw;
+  // pack weights
+  for (int l = 0; l < p.n; ++l) {
+    const int cnt = p.wp[l + 1] * p.wp[l];
+    auto k = pack_layer_kernel;
+    HDPO_LAUNCH(k, ceil_div(cnt, 256), 256, 0, stream, params, p.gw[l], p.gb[l], p.w[l + 1], p.w[l], p.wp[l + 1],
+                p.wp[l], wsf(ws, p.o_W[l]), wsf(ws, p.o_b[l]));
+    HDPO_LAUNCH_OK();
+  }
+  {
+    auto k = init_state_kernel;
+    const size_t cnt = static_cast<size_t>(p.Bp) * p.wp[0];
+    HDPO_LAUNCH(k, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream, init->store, init->warehouse, p.B, p.Bp,
+                nS, nW, p.wp[0], wsf(ws, p.o_X), cost_b, report_b);
+    HDPO_LAUNCH_OK();
+  }
+  const size_t head_smem = static_cast<size_t>(HEAD_WARPS) * (pb.S * pb.W + 32) * sizeof(float);
+  for (int t = 0; t < p.T; ++t) {
+    const size_t xs = p.save ? static_cast<size_t>(t) : static_cast<size_t>(t & 1);
+    const size_t xn = p.save ? static_cast<size_t>(t + 1) : static_cast<size_t>((t + 1) & 1);
+    const size_t as = p.save ? static_cast<size_t>(t) : 0;
+    const float* X = wsf(ws, p.o_X) + xs * p.x_stride;
+    float* Xn = wsf(ws, p.o_X) + xn * p.x_stride;
+    const float* in = X;
+    for (int l = 0; l < p.n; ++l) {
+      GemmArgs g{};
+      g.A = in;
+      g.B = wsf(ws, p.o_W[l]);
+      g.C = wsf(ws, p.o_act[l]) + as * p.act_stride[l];
+      g.M = p.Bp;
+      g.N = p.wp[l + 1];
+      g.K = p.wp[l];
+      g.lda = p.wp[l];
+      g.ldb = p.wp[l];
+      g.ldc = p.wp[l + 1];
+      g.bias = wsf(ws, p.o_b[l]);
+      g.act = (l + 1 < p.n) ? d->master.hidden_act : d->master.out_act;
+      int rc = sgemm<false, true, EPI_BIAS_ACT>(g, 1, stream);
+      if (rc) return rc;
+      in = g.C;
+    }
+    HeadArgs a = head_args(d, p, demands, st, t);
+    auto k = warehouse_head_fwd_kernel;
+    HDPO_LAUNCH(k, ceil_div(p.B, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, in, Xn, cost_b, report_b,
+                reward_tb ? reward_tb + static_cast<size_t>(t) * p.B : static_cast<float*>(nullptr));
+    HDPO_LAUNCH_OK();
+  }
+  if (final_state && (final_state->store || final_state->warehouse)) {
+    const size_t xf = p.save ? static_cast<size_t>(p.T) : static_cast<size_t>(p.T & 1);
+    auto k = export_state_kernel;
+    const size_t cnt = static_cast<size_t>(p.B) * (nS + nW);
+    HDPO_LAUNCH(k, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream,
+                static_cast<const float*>(wsf(ws, p.o_X) + xf * p.x_stride), p.B, nS, nW, p.wp[0], final_state->store,
+                final_state->warehouse);
+    HDPO_LAUNCH_OK();
+  }
+  if (totals) {
+    auto k = totals_kernel;
+    HDPO_LAUNCH(k, 1, 1024, 0, stream, static_cast<const float*>(cost_b), static_cast<const float*>(report_b), p.B,
+                totals);
+    HDPO_LAUNCH_OK();
+  }
+  return HDPO_OK;
+}
+
+int backward(const HdpoRolloutDesc* d, const float* params, const float* demands, const HdpoStatics* st, float g_total,
+             float g_report, float* grad_params, void* ws, size_t ws_bytes, void* stream) {
+  (void)params;
+  const Plan p = make_plan(d);
+  HDPO_REQUIRE(ws != nullptr && p.save, "backward needs the workspace of a forward run with save_for_backward = 1");
+  if (ws_bytes < p.total) {
+    set_error("workspace too small: %zu < %zu", ws_bytes, p.total);
+    return HDPO_E_WORKSPACE;
+  }
+  const HdpoProblem& pb = d->pb;
+  float* gX = wsf(ws, p.o_gx);
+  {
+    auto k = zero_kernel;
+    HDPO_LAUNCH(k, static_cast<unsigned>(ceil_div64(p.x_stride, 256)), 256, 0, stream, gX, p.x_stride);
+    HDPO_LAUNCH_OK();
+  }
+  const size_t head_smem = static_cast<size_t>(HEAD_WARPS) * (2 * pb.S * pb.W + 64) * sizeof(float);
+  const int last = p.n - 1;
+  for (int t = p.T - 1; t >= 0; --t) {
+    const float* X = wsf(ws, p.o_X) + static_cast<size_t>(t) * p.x_stride;
+    const float* Y = wsf(ws, p.o_act[last]) + static_cast<size_t>(t) * p.act_stride[last];
+    float* gY = wsf(ws, p.o_gz[last]) + static_cast<size_t>(t) * p.act_stride[last];
+    HeadArgs a = head_args(d, p, demands, st, t);
+    const float rb = g_total + (t >= d->ignore_periods ? g_report : 0.f);
+    auto k = warehouse_head_bwd_kernel;
+    HDPO_LAUNCH(k, ceil_div(p.B, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, Y, gX, gY, rb);
+    HDPO_LAUNCH_OK();
+    // dgrad chain: gz_{l-1} = (gz_l W_l) * act'(h_{l-1});  finally gX += gz_0 W_0
+    for (int l = last; l >= 0; --l) {
+      GemmArgs g{};
+      g.A = wsf(ws, p.o_gz[l]) + static_cast<size_t>(t) * p.act_stride[l];
+      g.B = wsf(ws, p.o_W[l]);
+      g.M = p.Bp;
+      g.N = p.wp[l];
+      g.K = p.wp[l + 1];
+      g.lda = p.wp[l + 1];
+      g.ldb = p.wp[l];
+      g.ldc = p.wp[l];
+      g.act = d->master.hidden_act;
+      int rc;
+      if (l > 0) {
+        g.C = wsf(ws, p.o_gz[l - 1]) + static_cast<size_t>(t) * p.act_stride[l - 1];
+        g.aux = wsf(ws, p.o_act[l - 1]) + static_cast<size_t>(t) * p.act_stride[l - 1];
+        rc = sgemm<false, false, EPI_MUL_ACTGRAD>(g, 1, stream);
+      } else {
+        g.C = gX;
+        rc = sgemm<false, false, EPI_ACCUM>(g, 1, stream);
+      }
+      if (rc) return rc;
+    }
+  }
+  // weight gradients: dW_l[n][k] = sum over all (t, b) rows of gz_l[row][n] * in_l[row][k], split-K over the rows
+  const size_t rows = static_cast<size_t>(p.T) * p.Bp;
+  int splits = kSplitK;
+  while (splits > 1 && (rows / splits) % BK != 0) splits >>= 1;
+  const size_t rows_per = rows / splits;
+  for (int l = 0; l < p.n; ++l) {
+    GemmArgs g{};
+    g.A = wsf(ws, p.o_gz[l]);                                   // [rows][wp[l+1]] used transposed
+    g.B = (l == 0) ? wsf(ws, p.o_X) : wsf(ws, p.o_act[l - 1]);  // [rows][wp[l]]  (X tape: first T blocks)
+    g.C = wsf(ws, p.o_part);
+    g.M = p.wp[l + 1];
+    g.N = p.wp[l];
+    g.K = static_cast<int>(rows_per);
+    g.lda = p.wp[l + 1];
+    g.ldb = p.wp[l];
+    g.ldc = p.wp[l];
+    g.c_slice = static_cast<size_t>(p.wp[l + 1]) * p.wp[l];
+    g.a_kslice = rows_per * p.wp[l + 1];
+    g.b_kslice = rows_per * p.wp[l];
+    int rc = sgemm<true, false, EPI_SPLITK>(g, splits, stream);
+    if (rc) return rc;
+    const int n_chunks = 128;
+    auto k1 = colsum_stage1_kernel;
+    HDPO_LAUNCH(k1, dim3(ceil_div(p.wp[l + 1], 256), n_chunks), 256, 0, stream, static_cast<const float*>(g.A), rows,
+                p.wp[l + 1], n_chunks, wsf(ws, p.o_bpart));
+    HDPO_LAUNCH_OK();
+    auto k2 = unpack_grad_kernel;
+    HDPO_LAUNCH(k2, ceil_div(p.w[l + 1] * p.w[l], 256), 256, 0, stream, static_cast<const float*>(g.C), splits, g.c_slice,
+                p.wp[l], p.w[l + 1], p.w[l], static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1],
+                p.gw[l], p.gb[l], grad_params);
+    HDPO_LAUNCH_OK();
+  }
+  return HDPO_OK;
 }
 
 }  // namespace wide

@@ -1,0 +1,272 @@
+"""Trainer with the reference's interface (trainer.py:5-324); `simulate_batch` is the drop-in boundary.
+
+`simulate_batch(loss_function, simulator, model, periods, problem_params, data_batch, observation_params,
+ignore_periods=0, discrete_allocation=False) -> (batch_reward, reward_to_report)` returns two 0-d tensors that
+carry an autograd graph, exactly like the reference - but for fusable policies (+ PolicyLoss) the graph is ONE
+node: the whole T-period rollout ran in the fused forward kernel and `mean_loss.backward()` triggers the
+reverse-time adjoint kernel. Everything else in `do_one_epoch` / `train` / `test` (optimizer step, gradient
+clipping, best-model tracking, early stopping, checkpoints) is the reference's own control flow.
+"""
+import copy
+import datetime
+import os
+
+import numpy as np
+import torch
+
+from . import engine as EN
+from .loss_functions import PolicyLoss
+
+_FUSED_MODULE_ORDER = ("master", "context", "store", "warehouse")
+
+
+class Trainer:
+    def __init__(self, device="cpu"):
+        self.all_train_losses = []
+        self.all_dev_losses = []
+        self.all_test_losses = []
+        self.device = device
+        self.time_stamp = self.get_time_stamp()
+        self.best_performance_data = {"train_loss": np.inf, "dev_loss": np.inf, "last_epoch_saved": -1000,
+                                      "model_params_to_save": None}
+        self.best_epoch = 0
+        self.use_fused = os.environ.get("HDPO_DISABLE_FUSED", "0") != "1"
+        self._engines = {}
+        self.last_path = None  # "fused" | "generic": which path the last simulate_batch took (for tests/logging)
+
+    def reset(self):
+        self.all_train_losses, self.all_dev_losses, self.all_test_losses = [], [], []
+
+    # ------------------------------------------------------------------ epoch loops (reference control flow)
+    def train(self, epochs, loss_function, simulator, model, data_loaders, optimizer, problem_params,
+              observation_params, params_by_dataset, trainer_params):
+        for epoch in range(epochs):
+            tr = params_by_dataset["train"]
+            _, train_report = self.do_one_epoch(optimizer, data_loaders["train"], loss_function, simulator, model,
+                                                tr["periods"], problem_params, observation_params, train=True,
+                                                ignore_periods=tr["ignore_periods"])
+            self.all_train_losses.append(train_report)
+            if epoch % trainer_params["do_dev_every_n_epochs"] == 0:
+                dv = params_by_dataset["dev"]
+                _, dev_report = self.do_one_epoch(optimizer, data_loaders["dev"], loss_function, simulator, model,
+                                                  dv["periods"], problem_params, observation_params, train=False,
+                                                  ignore_periods=dv["ignore_periods"])
+                self.all_dev_losses.append(dev_report)
+                self.update_best_params_and_save(epoch, train_report, dev_report, trainer_params, model, optimizer)
+                patience = trainer_params.get("early_stopping_patience_epochs", None)
+                if patience is not None and (epoch - self.best_epoch) >= patience:
+                    print(f"\nEarly stopping triggered at epoch {epoch + 1}")
+                    print(f"No improvement for {epoch - self.best_epoch} epochs")
+                    print(f"Best model was at epoch {self.best_epoch + 1} with dev loss: "
+                          f"{self.best_performance_data['dev_loss']}")
+                    break
+            else:
+                dev_report = 0
+                self.all_dev_losses.append(self.all_dev_losses[-1])
+            if epoch % trainer_params["print_results_every_n_epochs"] == 0:
+                print(f"epoch: {epoch + 1}")
+                print(f"Average per-period train loss: {train_report}")
+                print(f"Average per-period dev loss: {dev_report}")
+                print(f"Best per-period dev loss: {self.best_performance_data['dev_loss']}")
+
+    def test(self, loss_function, simulator, model, data_loaders, optimizer, problem_params, observation_params,
+             params_by_dataset, discrete_allocation=False):
+        if model.trainable and self.best_performance_data["model_params_to_save"] is not None:
+            model.load_state_dict(self.best_performance_data["model_params_to_save"])
+        ts = params_by_dataset["test"]
+        return self.do_one_epoch(optimizer, data_loaders["test"], loss_function, simulator, model, ts["periods"],
+                                 problem_params, observation_params, train=False,
+                                 ignore_periods=ts["ignore_periods"], discrete_allocation=discrete_allocation)
+
+    def do_one_epoch(self, optimizer, data_loader, loss_function, simulator, model, periods, problem_params,
+                     observation_params, train=True, ignore_periods=0, discrete_allocation=False):
+        epoch_loss = 0
+        epoch_loss_to_report = 0
+        total_samples = len(data_loader.dataset)
+        n_stores = problem_params["n_stores"]
+        with torch.no_grad() if not train else torch.enable_grad():
+            for data_batch in data_loader:
+                data_batch = self.move_batch_to_device(data_batch)
+                if train:
+                    optimizer.zero_grad()
+                total_reward, reward_to_report = self.simulate_batch(
+                    loss_function, simulator, model, periods, problem_params, data_batch, observation_params,
+                    ignore_periods, discrete_allocation)
+                epoch_loss += total_reward.item()
+                epoch_loss_to_report += reward_to_report.item()
+                mean_loss = total_reward / (len(data_batch["demands"]) * periods * n_stores)
+                if train and model.trainable:
+                    mean_loss.backward()
+                    clip = getattr(model, "gradient_clipping_norm_value", None)
+                    if clip is not None:
+                        torch.nn.utils.clip_grad_norm_(model.parameters(), clip)
+                    optimizer.step()
+        return (epoch_loss / (total_samples * periods * n_stores),
+                epoch_loss_to_report / (total_samples * (periods - ignore_periods) * n_stores))
+
+    # ------------------------------------------------------------------ the hot path
+    def simulate_batch(self, loss_function, simulator, model, periods, problem_params, data_batch, observation_params,
+                       ignore_periods=0, discrete_allocation=False):
+        pspec = self._fusable_spec(loss_function, simulator, model, periods, problem_params, data_batch,
+                                   observation_params)
+        if pspec is not None:
+            try:
+                out = self._simulate_batch_fused(pspec, simulator, model, periods, problem_params, data_batch,
+                                                 observation_params, ignore_periods, discrete_allocation)
+                self.last_path = "fused"
+                return out
+            except EN.K.HdpoError as e:
+                if "no fused rollout" not in str(e):
+                    raise
+        self.last_path = "generic"
+        return self._simulate_batch_generic(loss_function, simulator, model, periods, problem_params, data_batch,
+                                            observation_params, ignore_periods, discrete_allocation)
+
+    def _simulate_batch_generic(self, loss_function, simulator, model, periods, problem_params, data_batch,
+                                observation_params, ignore_periods, discrete_allocation):
+        """Any torch policy: policy(obs) in torch, one K3 kernel per period (trainer.py:181-216 semantics)."""
+        batch_reward = 0
+        reward_to_report = 0
+        observation, _ = simulator.reset(periods, problem_params, data_batch, observation_params)
+        for t in range(periods):
+            obs_and_internal = dict(observation)
+            obs_and_internal["internal_data"] = simulator._internal_data  # for non-admissible benchmark policies
+            action = model(obs_and_internal)
+            if discrete_allocation:
+                action = {key: val.round() for key, val in action.items()}
+            observation, reward, terminated, _, _ = simulator.step(action)
+            total_reward = loss_function(None, action, reward)
+            batch_reward += total_reward
+            if t >= ignore_periods:
+                reward_to_report += total_reward
+            if terminated:
+                break
+        return batch_reward, reward_to_report
+
+    def _fusable_spec(self, loss_function, simulator, model, periods, problem_params, data_batch, observation_params):
+        if not self.use_fused or type(loss_function) is not PolicyLoss or not hasattr(model, "fusable_spec"):
+            return None
+        if not data_batch["initial_inventories"].is_cuda:
+            return None
+        pspec = model.fusable_spec()
+        if pspec is None and any(isinstance(m, torch.nn.modules.lazy.LazyModuleMixin) for m in model.modules()):
+            # materialise the LazyLinear layers with one throw-away single-scenario forward (initialisation only)
+            one = {k: v[:1] for k, v in data_batch.items()}
+            with torch.no_grad():
+                obs, _ = simulator.reset(periods, problem_params, one, observation_params)
+                obs = dict(obs)
+                obs["internal_data"] = simulator._internal_data
+                model(obs)
+            pspec = model.fusable_spec()
+        return pspec
+
+    def _flat_params(self, model, pspec):
+        names = [m for m in _FUSED_MODULE_ORDER if m in model.net]
+        params = [p for m in names for p in model.net[m].parameters()]
+        if len(params) == 1:
+            return params[0].reshape(-1)
+        return torch.cat([p.reshape(-1) for p in params])
+
+    def _simulate_batch_fused(self, pspec, simulator, model, periods, problem_params, data_batch, observation_params,
+                              ignore_periods, discrete_allocation):
+        need_grad = torch.is_grad_enabled() and model.trainable and not discrete_allocation
+        shift = observation_params["demand"]["period_shift"]
+        B = data_batch["initial_inventories"].shape[0]
+        key = (id(model), B, periods, data_batch["demands"].shape[2], ignore_periods, bool(discrete_allocation),
+               need_grad, shift, pspec.warehouse_upper_bound)
+        eng = self._engines.get(key)
+        if eng is None:
+            if len(self._engines) > 8:
+                self._engines.clear()
+            eng = EN.FusedRollout(pspec, problem_params, data_batch, periods, ignore_periods=ignore_periods,
+                                  period_shift=shift, discrete_allocation=discrete_allocation,
+                                  save_for_backward=need_grad)
+            self._engines[key] = eng
+        # keep the simulator's visible state coherent with what a per-period run would leave behind
+        simulator.reset(periods, problem_params, data_batch, observation_params)
+        flat = self._flat_params(model, pspec)
+        if need_grad:
+            total, report = EN.rollout(eng, data_batch, flat)
+        else:
+            totals = eng.forward(flat.detach(), data_batch).to(torch.float32)
+            total, report = totals[0], totals[1]
+        simulator.observation["current_period"] += periods
+        return total, report
+
+    # ------------------------------------------------------------------ checkpoints / bookkeeping
+    def save_model(self, epoch, model, optimizer, trainer_params):
+        path = self.create_many_folders_if_not_exist_and_return_path(trainer_params["base_dir"],
+                                                                     trainer_params["save_model_folders"])
+        # key names (incl. the reference's mislabelled ones, trainer.py:227-229) are kept for file compatibility
+        torch.save({
+            "epoch": epoch,
+            "model_state_dict": self.best_performance_data["model_params_to_save"],
+            "optimizer_state_dict": optimizer.state_dict(),
+            "best_train_loss": self.best_performance_data["dev_loss"],
+            "best_dev_loss": self.all_train_losses,
+            "all_train_losses": self.all_train_losses,
+            "all_dev_losses": self.all_dev_losses,
+            "all_test_losses": self.all_test_losses,
+            "warehouse_upper_bound": model.warehouse_upper_bound,
+        }, f"{path}/{trainer_params['save_model_filename']}.pt")
+
+    def create_folder_if_not_exists(self, folder):
+        if not os.path.isdir(folder):
+            os.mkdir(folder)
+
+    def create_many_folders_if_not_exist_and_return_path(self, base_dir, intermediate_folder_strings):
+        path = base_dir
+        for part in intermediate_folder_strings:
+            path += f"/{part}"
+            self.create_folder_if_not_exists(path)
+        return path
+
+    def update_best_params_and_save(self, epoch, train_loss, dev_loss, trainer_params, model, optimizer):
+        current = {"train_loss": train_loss, "dev_loss": dev_loss}
+        metric = trainer_params["choose_best_model_on"]
+        if current[metric] < self.best_performance_data[metric]:
+            self.best_performance_data["train_loss"] = train_loss
+            self.best_performance_data["dev_loss"] = dev_loss
+            if model.trainable:
+                self.best_performance_data["model_params_to_save"] = copy.deepcopy(model.state_dict())
+            self.best_performance_data["update"] = True
+            self.best_epoch = epoch
+        if trainer_params["save_model"] and model.trainable:
+            due = self.best_performance_data["last_epoch_saved"] + trainer_params["epochs_between_save"] <= epoch
+            if due and self.best_performance_data["update"]:
+                self.best_performance_data["last_epoch_saved"] = epoch
+                self.best_performance_data["update"] = False
+                self.save_model(epoch, model, optimizer, trainer_params)
+
+    def plot_losses(self, ymin=None, ymax=None):
+        from .shared_imports import plt
+        if plt is None:
+            raise RuntimeError("matplotlib is not installed")
+        plt.plot(self.all_train_losses, label="Train loss")
+        plt.plot(self.all_dev_losses, label="Dev loss")
+        plt.legend()
+        if ymin is not None and ymax is not None:
+            plt.ylim(ymin, ymax)
+        plt.xlabel("Epoch")
+        plt.ylabel("Loss")
+        plt.show()
+
+    def move_batch_to_device(self, data_batch):
+        return {k: v.to(self.device, non_blocking=True) for k, v in data_batch.items()}
+
+    def load_model(self, model, optimizer, model_path):
+        checkpoint = torch.load(model_path, map_location=self.device, weights_only=False)
+        model.load_state_dict(checkpoint["model_state_dict"])
+        optimizer.load_state_dict(checkpoint["optimizer_state_dict"])
+        self.all_train_losses = checkpoint["all_train_losses"]
+        self.all_dev_losses = checkpoint["all_dev_losses"]
+        self.all_test_losses = checkpoint["all_test_losses"]
+        model.warehouse_upper_bound = checkpoint["warehouse_upper_bound"]
+        return model, optimizer
+
+    def get_time_stamp(self):
+        return int(datetime.datetime.now().timestamp())
+
+    def get_year_month_day(self):
+        now = datetime.datetime.now()
+        return f"{now.year}_{now.month:02d}_{now.day:02d}"

@@ -90,3 +90,62 @@ def flops_per_scenario_period(widths, first_layer_dgrad=True):
     if not first_layer_dgrad:
         f -= 2 * widths[0] * widths[1]
     return f
+
+
+def _many_stores(device, B, T, S, W, seed, adjacency=None, lead=None, wh_holding=(0.3,), wh_edge=None, hidden=512):
+    """Shared builder of the warehouse settings (one_warehouse_lost_demand.yml / many_warehouses_lost_demand.yml):
+    per-store means U[2.5,7.5], cv U[.25,.5], one-factor correlation 0.5, holding U[.7,1.3], underage U[6.3,11.7]."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    u = lambda lo, hi, *shape: lo + (hi - lo) * torch.rand(*shape, generator=g, device=device)  # noqa: E731
+    mean = u(2.5, 7.5, S)
+    std = mean * u(0.25, 0.5, S)
+    rho = 0.5
+    z0 = torch.randn(B, 1, T, generator=g, device=device)
+    zs = torch.randn(B, S, T, generator=g, device=device)
+    dem = (mean[None, :, None] + std[None, :, None] * (rho ** 0.5 * z0 + (1 - rho) ** 0.5 * zs)).clamp_(min=0)
+    if lead is None:
+        lead = torch.randint(2, 4, (S, 1), generator=g, device=device).float().expand(S, W)
+    L = int(max(3, lead.max().item()))
+    data = {
+        "demands": dem.contiguous(),
+        "initial_inventories": (mean[None, :, None] * torch.rand(B, S, L, generator=g, device=device)).contiguous(),
+        "holding_costs": u(0.7, 1.3, S).expand(B, S).contiguous(),
+        "underage_costs": u(6.3, 11.7, S).expand(B, S).contiguous(),
+        "lead_times": lead.float().expand(B, S, W).contiguous(),
+        "mean": mean.expand(B, S).contiguous(),
+        "std": std.expand(B, S).contiguous(),
+        "initial_warehouse_inventories": torch.zeros(B, W, 3, device=device),
+        "warehouse_lead_times": torch.full((B, W), 3.0, device=device),
+        "warehouse_holding_costs": torch.tensor(list(wh_holding), device=device).expand(B, W).contiguous(),
+    }
+    if wh_edge is not None:
+        data["warehouse_edge_costs"] = torch.tensor(list(wh_edge), device=device).expand(B, W).contiguous()
+    pp = {"n_stores": S, "n_warehouses": W, "n_extra_echelons": 0, "lost_demand": True, "maximize_profit": False}
+    if adjacency is not None:
+        pp["warehouse_store_adjacency"] = adjacency
+    out = S * W + W
+    widths = [S * L + W * 3, hidden, hidden, hidden, out]
+    wub = 4.0 * float(mean.sum())
+    pspec = PolicySpec("vanilla_warehouse", (widths, "elu", None), warehouse_upper_bound=wub, adjacency=adjacency)
+    return pspec, pp, data, widths
+
+
+@register("one_warehouse_lost_demand")
+def one_warehouse_lost_demand(device, B=8192, T=50, seed=57):
+    """cfg 4: one_warehouse_lost_demand.yml at 50 stores + vanilla_warehouse.yml (153 -> 512^3 -> 51)."""
+    return _many_stores(device, B, T, 50, 1, seed)
+
+
+@register("many_warehouses_lost_demand")
+def many_warehouses_lost_demand(device, B=1024, T=50, seed=57):
+    """cfg 5: 3 warehouses x 50 stores, Bernoulli(0.7) adjacency with every store connected, leads in [1,7)
+    (SURVEY.md 8d), 1024 scenarios per GPU (8192 over 8 GPUs)."""
+    S, W = 50, 3
+    g = torch.Generator().manual_seed(7)
+    adj = (torch.rand(W, S, generator=g) < 0.7).int()
+    for s in range(S):
+        if adj[:, s].sum() == 0:
+            adj[int(torch.randint(W, (1,), generator=g)), s] = 1
+    lead = (torch.randint(1, 7, (S, W), generator=g) * adj.t()).float().to(device)
+    return _many_stores(device, B, T, S, W, seed, adjacency=adj.tolist(), lead=lead, wh_holding=(0.3, 0.4, 0.2),
+                        wh_edge=(0.5, 1.5, 0.7))

@@ -25,7 +25,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __grid_constant__
 
 struct dim3 {

@@ -176,3 +176,53 @@ def test_backward_rejects_discrete_and_small_workspace(be_name):
     meta, g = G.load("rollout", "one_store_lost")
     with pytest.raises(K.HdpoError):
         D.rollout(be, meta, g["param"], g["data"], T=5, discrete=True, backward=True)
+
+
+# ---- wide path (VanillaWarehouse: tile-GEMM pipeline + warehouse head kernels) ----
+def _grad_check_vs_golden(out, g, floor_mult=3):
+    ref, ref64 = g["ref"], g["ref64"]
+    keys = sorted(out["grad"])
+    mine = np.concatenate([out["grad"][k].ravel() for k in keys])
+    r32 = np.concatenate([ref[f"grad/{k}"].ravel() for k in keys])
+    r64 = np.concatenate([ref64[f"grad/{k}"].ravel() for k in keys])
+    floor = G.rel_l2(r32, r64)
+    assert G.rel_l2(mine, r64) <= max(1e-5, floor_mult * floor), (G.rel_l2(mine, r64), floor)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", WIDE)
+def test_wide_rollout_costs_and_gradients_match_reference(name):
+    """Full 50-period goldens of the warehouse settings (GPU only: the emulator needs ~30 s per case)."""
+    be = backend("cuda")
+    meta, g = G.load("rollout", name)
+    out = D.rollout(be, meta, g["param"], g["data"])
+    check_rollout_against_golden(out, meta, g, meta["T"], meta["ignore_periods"])
+    _grad_check_vs_golden(out, g)
+    names = {"store": "store_inventories", "wh": "warehouse_inventories"}
+    for k, rk in names.items():
+        rf = g["ref"][f"final/{rk}"]
+        assert np.abs(out["final"][k] - rf).max() <= 2e-3 * max(1.0, np.abs(rf).max())
+
+
+@pytest.mark.parametrize("be_name", BACKENDS)
+@pytest.mark.parametrize("name,n,T,ignore", [("one_warehouse_s5", 32, 6, 2), ("many_warehouses_2x10", 19, 7, 3),
+                                             ("many_warehouses_3x50", 5, 4, 0)])
+def test_wide_rollout_short_horizon_against_oracle(be_name, name, n, T, ignore):
+    """Short horizons (before the chaotic regime) against the pinned float64 oracle: tight tolerances."""
+    be = backend(be_name)
+    meta, g = G.load("rollout", name)
+    data = D.slice_batch(g["data"], n)
+    out = D.rollout(be, meta, g["param"], data, T=T, ignore=ignore)
+    pb = G.problem_from_meta(meta)
+    pol = G.policy_from_golden(meta, g["param"], np.float64)
+    fwd, grads = O.rollout_grad(pol, pb, G.cast(data, np.float64), T)
+    scale = np.abs(fwd["reward_tb"]).max()
+    assert np.abs(out["reward_tb"] - fwd["reward_tb"]).max() <= 1e-5 * scale
+    np.testing.assert_allclose(out["cost_b"], fwd["reward_tb"].sum(0), rtol=1e-5)
+    np.testing.assert_allclose(out["report_b"], fwd["reward_tb"][ignore:].sum(0), rtol=1e-5, atol=1e-5 * scale)
+    flat = O.flatten_grads(pol, grads)
+    mine = np.concatenate([out["grad"][k].ravel() for k in sorted(flat)])
+    want = np.concatenate([flat[k].ravel() for k in sorted(flat)])
+    assert G.rel_l2(mine, want) <= 2e-5, G.rel_l2(mine, want)
+    for k in ("store", "wh"):
+        np.testing.assert_allclose(out["final"][k], fwd["final"][k], rtol=1e-4, atol=1e-4)
