@@ -120,8 +120,8 @@ typedef struct HdpoAction {
 
 /* demand[b*demand_stride_b + s*demand_stride_s] is the current demand of (b,s): pass the base pointer
  * already offset to column t+period_shift; strides are in elements.
- * Writes next state into `next` (must not alias `cur`), reward[B], and raw_* scratch needed by the
- * backward (raw_store [B,S], raw_wh [B,W], raw_ech [B,E]; any may be NULL when the node type is absent). */
+ * Writes the next state into `next` (must not alias `cur`) and reward[B]. Precondition (as in the reference's
+ * flat put, environment.py:422): every NON-ZERO allocation has 1 <= lead time <= pipeline length. */
 int hdpo_step_fwd(const HdpoProblem* pb, const HdpoStatics* st, const HdpoState* cur, const HdpoAction* act,
                   const float* demand, int64_t demand_stride_b, int64_t demand_stride_s, HdpoState* next,
                   float* reward, void* stream);
@@ -210,6 +210,9 @@ int hdpo_philox_normal(float* out, int32_t B, int32_t S, int32_t T, int32_t layo
                        void* stream);
 int hdpo_philox_poisson(float* out, int32_t B, int32_t S, int32_t T, int32_t layout, const float* mean,
                         uint64_t seed, uint64_t offset, void* stream);
+/* The raw stream: out[4*g .. 4*g+3] = Philox4x32-10(counter = offset + g, key = seed), g < n_groups.
+ * Bit-exact with the Random123 known-answer vectors. */
+int hdpo_philox_raw(uint32_t* out, uint64_t n_groups, uint64_t seed, uint64_t offset, void* stream);
 
 /* misc */
 const char* hdpo_last_error(void);

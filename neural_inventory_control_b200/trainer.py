@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import engine as EN
+from . import parallel as PL
 from .loss_functions import PolicyLoss
 
 _FUSED_MODULE_ORDER = ("master", "context", "store", "warehouse")
@@ -84,19 +85,28 @@ class Trainer:
         epoch_loss_to_report = 0
         total_samples = len(data_loader.dataset)
         n_stores = problem_params["n_stores"]
+        rank, world = PL.world_info()  # (0, 1) unless launched under torchrun with an initialised process group
         with torch.no_grad() if not train else torch.enable_grad():
             for data_batch in data_loader:
-                data_batch = self.move_batch_to_device(data_batch)
+                n_global = len(data_batch["demands"])
+                # scenario-parallel: every rank sees the same batch order (same sampler seed) and keeps its shard
+                data_batch = self.move_batch_to_device(PL.shard_batch(data_batch, rank, world))
                 if train:
                     optimizer.zero_grad()
                 total_reward, reward_to_report = self.simulate_batch(
                     loss_function, simulator, model, periods, problem_params, data_batch, observation_params,
                     ignore_periods, discrete_allocation)
+                mean_loss = total_reward / (n_global * periods * n_stores)
+                do_step = train and model.trainable
+                if do_step:
+                    mean_loss.backward()
+                if world > 1:  # ONE collective per batch: flat gradient + the two loss scalars
+                    total_reward, reward_to_report = total_reward.detach().clone(), reward_to_report.detach().clone()
+                    PL.allreduce_sum_(([p.grad for p in model.parameters() if p.grad is not None] if do_step else [])
+                                      + [total_reward, reward_to_report])
                 epoch_loss += total_reward.item()
                 epoch_loss_to_report += reward_to_report.item()
-                mean_loss = total_reward / (len(data_batch["demands"]) * periods * n_stores)
-                if train and model.trainable:
-                    mean_loss.backward()
+                if do_step:
                     clip = getattr(model, "gradient_clipping_norm_value", None)
                     if clip is not None:
                         torch.nn.utils.clip_grad_norm_(model.parameters(), clip)

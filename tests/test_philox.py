@@ -1,0 +1,114 @@
+"""K4 sampler: the raw Philox4x32-10 stream is bit-exact (known-answer vectors + numpy restatement); normal and
+Poisson demand are checked element-wise against the numpy transforms and statistically against the target
+distributions (mean / std / correlation / Poisson pmf), in both output layouts."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import abi_driver as D
+from neural_inventory_control_b200 import _capi as K
+from oracle import philox_oracle as PO
+
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+_cache = {}
+
+
+def backend(name):
+    if name not in _cache:
+        _cache[name] = D.EmuBackend() if name == "emu" else D.CudaBackend()
+    return _cache[name]
+
+
+def test_oracle_known_answer_vectors():
+    for ctr, key, want in PO.KAT:
+        got = PO.philox4x32_10(*[np.array([c], np.uint64) for c in ctr], key[0], key[1])
+        assert tuple(int(g[0]) for g in got) == want
+
+
+@pytest.mark.parametrize("be_name", BACKENDS)
+def test_raw_stream_bit_exact(be_name):
+    be = backend(be_name)
+    for seed, offset, n in [(0, 0, 1), (0xDEADBEEFCAFEF00D, 12345678901, 1000), (57, (1 << 32) - 3, 64)]:
+        h = be.zeros((n, 4), np.int32)
+        K.check(be.lib, be.lib.hdpo_philox_raw(be.ptr(h), n, seed, offset, be.stream), "hdpo_philox_raw")
+        be.sync()
+        got = be.get(h).view(np.uint32)
+        assert np.array_equal(got, PO.raw_stream(n, seed, offset))
+    # counter 0 / key 0 is the first Random123 known-answer vector
+    h = be.zeros((1, 4), np.int32)
+    K.check(be.lib, be.lib.hdpo_philox_raw(be.ptr(h), 1, 0, 0, be.stream), "hdpo_philox_raw")
+    be.sync()
+    assert tuple(int(x) for x in be.get(h).view(np.uint32)[0]) == PO.KAT[0][2]
+
+
+def _normal(be, B, S, T, layout, mean, std, rho, clip, seed, offset):
+    out = be.zeros((T, S, B) if layout == K.DEMAND_TSB else (B, S, T))
+    m, s = be.put(np.asarray(mean, np.float32)), be.put(np.asarray(std, np.float32))
+    rc = be.lib.hdpo_philox_normal(be.ptr(out), B, S, T, layout, be.ptr(m), be.ptr(s), rho, int(clip), seed, offset,
+                                   be.stream)
+    K.check(be.lib, rc, "hdpo_philox_normal")
+    be.sync()
+    return be.get(out)
+
+
+@pytest.mark.parametrize("be_name", BACKENDS)
+def test_normal_demand_matches_numpy_transform_and_layouts(be_name):
+    be = backend(be_name)
+    B, S, T = 37, 3, 11
+    mean, std = [5.0, 2.5, 7.0], [1.6, 0.8, 3.0]
+    for rho in (0.0, 0.5):
+        tsb = _normal(be, B, S, T, K.DEMAND_TSB, mean, std, rho, True, 99, 1000)
+        bst = _normal(be, B, S, T, K.DEMAND_BST, mean, std, rho, True, 99, 1000)
+        assert np.array_equal(bst, tsb.transpose(2, 1, 0))
+        want = PO.normal_demand(B, S, T, mean, std, rho, True, 99, 1000)
+        np.testing.assert_allclose(tsb, want, rtol=2e-5, atol=2e-5)
+        assert (tsb >= 0).all()
+
+
+@pytest.mark.parametrize("be_name", BACKENDS)
+def test_normal_demand_statistics(be_name):
+    be = backend(be_name)
+    B, S, T = 4096, 4, 16
+    mean, std = [5.0, 2.5, 7.5, 6.0], [1.6, 1.0, 3.0, 2.0]
+    d = _normal(be, B, S, T, K.DEMAND_TSB, mean, std, 0.5, False, 2024, 0).astype(np.float64)
+    n = B * T
+    for s in range(S):
+        x = d[:, s, :].ravel()
+        assert abs(x.mean() - mean[s]) < 5 * std[s] / np.sqrt(n)
+        assert abs(x.std() / std[s] - 1) < 0.02
+    flat = d.transpose(1, 0, 2).reshape(S, -1)
+    corr = np.corrcoef(flat)
+    off = corr[~np.eye(S, dtype=bool)]
+    assert np.all(np.abs(off - 0.5) < 0.03), corr
+    # independence across time / scenarios: lag-1 autocorrelation ~ 0
+    x = d[:, 0, :]
+    assert abs(np.corrcoef(x[:-1].ravel(), x[1:].ravel())[0, 1]) < 0.03  # the common factor is drawn per (t,b)
+    y = _normal(be, B, 1, T, K.DEMAND_TSB, [5.0], [1.6], 0.0, False, 7, 0).astype(np.float64)[:, 0, :]
+    assert abs(np.corrcoef(y[:-1].ravel(), y[1:].ravel())[0, 1]) < 0.02
+    # normality: skewness and excess kurtosis near zero
+    z = (y.ravel() - 5.0) / 1.6
+    assert abs((z ** 3).mean()) < 0.03 and abs((z ** 4).mean() - 3.0) < 0.08
+
+
+@pytest.mark.parametrize("be_name", BACKENDS)
+def test_poisson_demand_statistics(be_name):
+    from math import exp, factorial
+    be = backend(be_name)
+    B, S, T = 8192, 2, 8
+    lam = [5.0, 0.7]
+    out = be.zeros((T, S, B))
+    m = be.put(np.asarray(lam, np.float32))
+    K.check(be.lib, be.lib.hdpo_philox_poisson(be.ptr(out), B, S, T, K.DEMAND_TSB, be.ptr(m), 11, 0, be.stream),
+            "hdpo_philox_poisson")
+    be.sync()
+    d = be.get(out)
+    assert np.array_equal(d, np.rint(d)) and (d >= 0).all()
+    n = B * T
+    for s in range(S):
+        x = d[:, s, :].ravel()
+        assert abs(x.mean() - lam[s]) < 5 * np.sqrt(lam[s] / n)
+        assert abs(x.var() / lam[s] - 1) < 0.05
+        for k in range(0, 12):
+            pk = exp(-lam[s]) * lam[s] ** k / factorial(k)
+            assert abs((x == k).mean() - pk) < 5 * np.sqrt(pk * (1 - pk) / n) + 1e-4

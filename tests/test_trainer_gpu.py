@@ -1,0 +1,170 @@
+"""GPU tests of the reference-facing Python layer (Trainer.simulate_batch / Simulator.step / policies) against the
+reference-generated goldens: the same state_dict and the same Scenario tensors go through
+  (a) the FUSED path  (one forward kernel + one adjoint kernel per batch), and
+  (b) the GENERIC path (torch policy + one K3 kernel per period, torch autograd across periods),
+and both must reproduce the reference's totals and parameter gradients."""
+import copy
+import os
+from collections import defaultdict
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+import golden_util as G
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cfg(kind, name):
+    with open(os.path.join(ROOT, "config_files", kind, f"{name}.yml")) as f:
+        return yaml.safe_load(f)
+
+
+class _FakeScenario:
+    def __init__(self, problem_params, store_params):
+        self.problem_params, self.store_params = problem_params, store_params
+
+
+def _build(meta, g, device):
+    """Model from this repo's NeuralNetworkCreator carrying the golden weights, plus the golden batch on device."""
+    from neural_inventory_control_b200.neural_networks import NeuralNetworkCreator
+    p = copy.deepcopy(_cfg("policies_and_hyperparams", meta["policy"]))
+    nn_params = p["nn_params"]
+    nn_params["neurons_per_hidden_layer"] = meta["neurons_per_hidden_layer"]
+    pp = meta["problem_params"]
+    scen = _FakeScenario(pp, {"demand": {"mean": [meta["warehouse_upper_bound"] / max(nn_params.get(
+        "warehouse_upper_bound_mult", 1), 1)]}})
+    model = NeuralNetworkCreator().create_neural_network(scen, nn_params, device=device)
+    data = {k: torch.tensor(v, device=device) for k, v in g["data"].items()}
+    return model, data, pp
+
+
+def _obs_params(meta):
+    s = _cfg("settings", meta["setting"])
+    return defaultdict(lambda: None, s["observation_params"])
+
+
+def _run(meta, g, fused, device="cuda:0"):
+    from neural_inventory_control_b200.environment import Simulator
+    from neural_inventory_control_b200.loss_functions import PolicyLoss
+    from neural_inventory_control_b200.trainer import Trainer
+    model, data, pp = _build(meta, g, device)
+    tr = Trainer(device=device)
+    tr.use_fused = fused
+    sim = Simulator(device=device)
+    obs_params = _obs_params(meta)
+    # materialise lazily-shaped layers, then load the golden weights
+    with torch.no_grad():
+        tr.simulate_batch(PolicyLoss(), sim, model, 1, pp, {k: v[:2] for k, v in data.items()}, obs_params)
+    model.load_state_dict({k: torch.tensor(v) for k, v in g["param"].items()})
+    total, report = tr.simulate_batch(PolicyLoss(), sim, model, meta["T"], pp, data, obs_params,
+                                      meta["ignore_periods"])
+    B = data["demands"].shape[0]
+    (total / (B * meta["T"] * pp["n_stores"])).backward()
+    grads = {k: v.grad.detach().cpu().numpy() for k, v in model.named_parameters()}
+    return tr.last_path, float(total), float(report), grads, sim
+
+
+CASES = ["one_store_lost", "one_store_backlogged_lead20", "serial_system", "one_warehouse_s5", "many_warehouses_2x10"]
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "generic"])
+def test_simulate_batch_matches_reference(name, fused):
+    meta, g = G.load("rollout", name)
+    path, total, report, grads, sim = _run(meta, g, fused)
+    assert path == ("fused" if fused else "generic")
+    ref, ref64 = g["ref"], g["ref64"]
+    floor_c = abs(float(ref["total"]) / float(ref64["total"]) - 1)
+    tol = max(1e-5, 3 * floor_c)
+    assert abs(total / float(ref64["total"]) - 1) <= tol
+    assert abs(report / float(ref64["report"]) - 1) <= tol
+    keys = sorted(grads)
+    mine = np.concatenate([grads[k].ravel() for k in keys])
+    r32 = np.concatenate([ref[f"grad/{k}"].ravel() for k in keys])
+    r64 = np.concatenate([ref64[f"grad/{k}"].ravel() for k in keys])
+    floor = G.rel_l2(r32, r64)
+    assert G.rel_l2(mine, r64) <= max(1e-5, 3 * floor), (G.rel_l2(mine, r64), floor)
+    assert int(sim.observation["current_period"]) == meta["T"]
+
+
+def test_generic_step_observation_contract():
+    """Simulator.reset/step keep the reference's observation dict, int64 shift tables and period bookkeeping."""
+    from neural_inventory_control_b200.environment import Simulator
+    meta, g = G.load("step", "many_warehouses")
+    dev = "cuda:0"
+    data = {k: torch.tensor(v, device=dev) for k, v in g["data"].items()}
+    obs_params = defaultdict(lambda: None, {
+        "include_warehouse_inventory": True,
+        "include_static_features": {"holding_costs": True, "underage_costs": True, "lead_times": True},
+        "demand": {"past_periods": 0, "period_shift": 1}})
+    sim = Simulator(device=dev)
+    obs, info = sim.reset(2, meta["problem_params"], data, obs_params)
+    assert info is None
+    for k in ("store_inventories", "warehouse_inventories", "warehouse_lead_times", "warehouse_holding_costs",
+              "warehouse_edge_costs", "holding_costs", "underage_costs", "lead_times", "current_period"):
+        assert k in obs, k
+    assert obs["current_period"].device.type == "cpu"
+    shift = sim._internal_data["allocation_shift"]
+    assert shift.dtype == torch.int64 and np.array_equal(shift.cpu().numpy(), g["ref"]["allocation_shift"])
+    assert np.array_equal(sim._internal_data["warehouse_allocation_shift"].cpu().numpy(),
+                          g["ref"]["warehouse_allocation_shift"])
+    action = {k: torch.tensor(v, device=dev, requires_grad=True) for k, v in g["action"].items()}
+    obs, reward, terminated, _, _ = sim.step(action)
+    np.testing.assert_allclose(reward.detach().cpu().numpy(), g["ref"]["reward"], rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(obs["store_inventories"].detach().cpu().numpy(), g["ref"]["new/store_inventories"],
+                               rtol=2e-6, atol=2e-6)
+    assert not bool(terminated)
+    up = g["up"]
+    loss = (reward * torch.tensor(up["reward"], device=dev)).sum() \
+        + (obs["store_inventories"] * torch.tensor(up["store_inventories"], device=dev)).sum() \
+        + (obs["warehouse_inventories"] * torch.tensor(up["warehouse_inventories"], device=dev)).sum()
+    loss.backward()
+    for k, v in action.items():
+        np.testing.assert_allclose(v.grad.cpu().numpy(), g["ref"][f"grad/action_{k}"], rtol=1e-5, atol=1e-5)
+    obs, reward, terminated, _, _ = sim.step({k: v.detach() for k, v in action.items()})
+    assert bool(terminated) and int(obs["current_period"]) == 2
+
+
+def test_training_loop_reduces_loss_and_eval_modes_run():
+    """A few epochs of `Trainer.train` through the fused path on the shipped one-store setting (reduced sample
+    counts): the reported train loss must go down; dev (no_grad) and test (discrete allocation) epochs must run."""
+    from torch.utils.data import DataLoader
+    from neural_inventory_control_b200.data_handling import DatasetCreator, Scenario
+    from neural_inventory_control_b200.environment import Simulator
+    from neural_inventory_control_b200.loss_functions import PolicyLoss
+    from neural_inventory_control_b200.neural_networks import NeuralNetworkCreator
+    from neural_inventory_control_b200.trainer import Trainer
+    dev = "cuda:0"
+    s = copy.deepcopy(_cfg("settings", "one_store_lost"))
+    p = copy.deepcopy(_cfg("policies_and_hyperparams", "vanilla_one_store"))
+    obs_params = defaultdict(lambda: None, s["observation_params"])
+    pbd = s["params_by_dataset"]
+    pbd["train"].update(n_samples=2048, batch_size=512)
+    pbd["dev"].update(n_samples=512, batch_size=512, periods=60, ignore_periods=30)
+    pbd["test"].update(n_samples=256, batch_size=256, periods=80, ignore_periods=40)
+    common = (s["problem_params"], s["store_params"], s["warehouse_params"], s["echelon_params"])
+    sc = Scenario(60, *common, 2048 + 512, obs_params, s["seeds"])
+    train, devset = DatasetCreator().create_datasets(sc, split=True, by_sample_indexes=True, sample_index_for_split=512)
+    sc_test = Scenario(80, *common, 256, obs_params, s["test_seeds"])
+    test = DatasetCreator().create_datasets(sc_test, split=False)
+    loaders = {"train": DataLoader(train, batch_size=512, shuffle=True),
+               "dev": DataLoader(devset, batch_size=512, shuffle=False),
+               "test": DataLoader(test, batch_size=256, shuffle=False)}
+    torch.manual_seed(0)
+    model = NeuralNetworkCreator().create_neural_network(sc_test, p["nn_params"], device=dev)
+    opt = torch.optim.Adam(model.parameters(), lr=p["optimizer_params"]["learning_rate"])
+    tr, sim = Trainer(device=dev), Simulator(device=dev)
+    tp = p["trainer_params"]
+    tp.update(epochs=12, do_dev_every_n_epochs=4, print_results_every_n_epochs=100, save_model=False)
+    tr.train(12, PolicyLoss(), sim, model, loaders, opt, s["problem_params"], obs_params, pbd, tp)
+    assert tr.last_path == "fused"
+    assert len(tr.all_train_losses) == 12 and len(tr.all_dev_losses) == 12
+    assert tr.all_train_losses[-1] < 0.8 * tr.all_train_losses[0]
+    assert tr.best_performance_data["model_params_to_save"] is not None
+    loss, report = tr.test(PolicyLoss(), sim, model, loaders, opt, s["problem_params"], obs_params, pbd,
+                           discrete_allocation=True)
+    assert np.isfinite(loss) and np.isfinite(report) and report > 0
