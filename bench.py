@@ -157,6 +157,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--batch", type=int, default=None, help="scenarios per GPU (default: the workload's)")
     ap.add_argument("--periods", type=int, default=50)
+    ap.add_argument("--precision", default=None, choices=["fp32", "tf32x3", "tf32"],
+                    help="policy-MLP matmul mode (default: tf32x3 = parity-grade tcgen05 where available, else fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -187,7 +189,9 @@ def main():
     B, S, T = data["demands"].shape[0], pp["n_stores"], args.periods
     gen = torch.Generator(device=dev).manual_seed(0)  # identical weights on every rank
     flat = WL.init_flat_params(widths, gen, dev)
-    eng = EN.FusedRollout(pspec, pp, data, T, ignore_periods=30)
+    small = pspec.arch in ("vanilla_one_store", "vanilla_serial")
+    precision = args.precision or ("fp32" if small else "tf32x3")
+    eng = EN.FusedRollout(pspec, pp, data, T, ignore_periods=30, precision=precision)
     grad = torch.zeros_like(flat)
     lib = eng.lib
     g_total = 1.0 / (world * B * T * S)
@@ -246,11 +250,13 @@ def main():
     flops_bwd = flops_step - 2 * macs  # dgrad + wgrad; the adjoint kernel's recompute is not counted
     tf32_peak = peaks["bf16_tflops"] / 2.0
     achieved = flops_bwd * B * T / (bwd_ms * 1e-3) / 1e12
-    small = pspec.arch in ("vanilla_one_store", "vanilla_serial")
     roofline = {
         "bound": "tensor",
         "kernel": ("small_bwd_kernel (reverse-time adjoint, SIMT fp32 parity mode)" if small else
+                   f"adjoint sweep ({precision}): gemm_tc_kernel dgrad tiles (tcgen05) + sgemm_kernel wgrad (SIMT) + "
+                   "warehouse_head_bwd" if precision != "fp32" else
                    "adjoint sweep: sgemm_kernel dgrad+wgrad tiles (SIMT fp32 parity mode) + warehouse_head_bwd"),
+        "precision": precision,
         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": None,
         "peak_source": f"{peaks['source']}: tf32 taken as bf16_tflops/2 (burst, kernel timed alone)",
         "kernel_ms": bwd_ms, "fwd_kernel_ms": fwd_ms,
@@ -318,7 +324,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32" if precision == "fp32" else ("tf32x3 (fp32-grade split, fp32 accumulate)" if precision == "tf32x3"
+                                                         else "tf32"),
+            "data": "synthetic",
             "config": {"workload": args.workload, "scenarios_per_gpu": B, "periods": T, "stores": S,
                        "policy_widths": widths, "l2": "inputs larger than L2 (demand + state tape per step)"
                        if B * T * 4 * (1 + widths[0]) > 126e6 else "working set below L2 size; no flush",

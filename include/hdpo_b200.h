@@ -214,6 +214,11 @@ int hdpo_philox_poisson(float* out, int32_t B, int32_t S, int32_t T, int32_t lay
  * Bit-exact with the Random123 known-answer vectors. */
 int hdpo_philox_raw(uint32_t* out, uint64_t n_groups, uint64_t seed, uint64_t offset, void* stream);
 
+/* Test hook for the tcgen05 tile GEMM: C[M,N] = A[M,K] * B[N,K]^T (n_pass 3 = 3xTF32, 1 = TF32); dense row-major
+ * device arrays, M % 128 == 0, N % 64 == 0, K % 32 == 0; scratch = 2*(M*K + N*K) floats of device memory. */
+int hdpo_debug_gemm_tc(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t n_pass,
+                       float* scratch, void* stream);
+
 /* misc */
 const char* hdpo_last_error(void);
 int hdpo_abi_version(void);

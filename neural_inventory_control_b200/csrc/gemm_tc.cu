@@ -1,0 +1,446 @@
+// gemm_tc.cu - tcgen05 / TMEM / TMA tile GEMM (see gemm_tc.cuh). Inline PTX only; no CUTLASS dependency.
+#include "gemm_tc.cuh"
+
+#ifndef HDPO_EMU
+
+namespace hdpo {
+namespace tc {
+
+// ------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 32 floats (128 B), 8-row atoms 1024 B apart.
+// bits: [0,14) addr>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 | [46,48) version=1 | [61,64) 2=SW128
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// kernel: 6 warps = TMA producer | MMA issuer (+TMEM owner) | 4 epilogue warps (128 rows of the tile)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kThreads = 192;
+constexpr int kBK = 32;  // floats per K block = one 128-byte swizzle row
+// Accumulator splitting. The tensor core adds each K=8 product block into the fp32 accumulator with truncation, so
+// the error of ONE accumulator grows linearly with the number of tcgen05.mma issued into it (measured: 4e-6
+// relative at K = 512, 192 MMAs). We therefore keep 4 accumulators in TMEM: [0] collects the small cross terms
+// (lo*hi, hi*lo; 2^-11 of the magnitude, their truncation is negligible) and [1..3] each take one third of the K
+// range of the hi*hi term; the epilogue adds the four in fp32 with round-to-nearest. 4 x 128 columns = all of TMEM.
+constexpr int kAccums = 4;
+constexpr int kHiChunks = kAccums - 1;
+
+template <int BN>
+struct SmemPlan {
+  static constexpr int kStages = (BN == 128) ? 3 : 4;
+  static constexpr int kABytes = 128 * kBK * 4;
+  static constexpr int kBBytes = BN * kBK * 4;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, GemmTcArgs g) {
+  using P = SmemPlan<BN>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + ((1024 - (raw_addr & 1023)) & 1023);  // SW128 needs 1024-byte aligned tiles
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P::kStages * P::kStageBytes);
+  uint64_t* empty_bar = full_bar + P::kStages;
+  uint64_t* accum_bar = empty_bar + P::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * BN;
+  const int n_kb = g.K / kBK;
+  const bool three = g.n_pass == 3;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a_hi);
+    prefetch_tmap(&tm_b_hi);
+    if (three) {
+      prefetch_tmap(&tm_a_lo);
+      prefetch_tmap(&tm_b_lo);
+    }
+    for (int s = 0; s < P::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  // TMEM: kAccums accumulators of BN fp32 columns each (see "accumulator splitting" at the MMA loop)
+  if (warp == 1) tmem_alloc(tmem_slot, kAccums * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const uint32_t tx = three ? P::kStageBytes : (P::kABytes + P::kBBytes);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int s = kb % P::kStages;
+        const uint32_t ph = (kb / P::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        unsigned char* st = smem + s * P::kStageBytes;
+        mbar_expect_tx(&full_bar[s], tx);
+        tma_load_2d(st, &tm_a_hi, &full_bar[s], kb * kBK, g.a_row0 + m0);
+        tma_load_2d(st + 2 * P::kABytes, &tm_b_hi, &full_bar[s], kb * kBK, g.b_row0 + n0);
+        if (three) {
+          tma_load_2d(st + P::kABytes, &tm_a_lo, &full_bar[s], kb * kBK, g.a_row0 + m0);
+          tma_load_2d(st + 2 * P::kABytes + P::kBBytes, &tm_b_lo, &full_bar[s], kb * kBK, g.b_row0 + n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                             (static_cast<uint32_t>(128 >> 4) << 24);
+      const int nch = n_kb < kHiChunks ? n_kb : kHiChunks;
+      uint32_t started = 0;  // bit i: accumulator i already holds data
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int s = kb % P::kStages;
+        const uint32_t ph = (kb / P::kStages) & 1;
+        const int chunk = 1 + (kb * nch) / n_kb;
+        const uint32_t d_hi = tmem_d + static_cast<uint32_t>(chunk * BN);
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * P::kStageBytes);
+        const uint64_t a_hi = make_kmajor_desc(st), a_lo = make_kmajor_desc(st + P::kABytes);
+        const uint64_t b_hi = make_kmajor_desc(st + 2 * P::kABytes),
+                       b_lo = make_kmajor_desc(st + 2 * P::kABytes + P::kBBytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 8; ++k) {
+          const uint64_t adv = static_cast<uint64_t>((k * 8 * 4) >> 4);  // 32 bytes per K=8 step inside the swizzle row
+          umma_tf32(d_hi, a_hi + adv, b_hi + adv, idesc, (started >> chunk) & 1u);
+          started |= 1u << chunk;
+          if (three) {
+            umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, started & 1u);
+            umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+            started |= 1u;
+          }
+        }
+        umma_commit(&empty_bar[s]);  // frees the ring slot once these MMAs have read it
+      }
+      umma_commit(accum_bar);        // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warp q = warp % 4 owns TMEM lanes [32q, 32q+32) = tile rows =====
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const size_t rbase = static_cast<size_t>(row) * g.ldc;
+#pragma unroll 1
+    const int nch = n_kb < kHiChunks ? n_kb : kHiChunks;
+    const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      float v[16];
+      tmem_ld16(lane_base + BN + c0, r);  // hi*hi, first K chunk
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+      for (int c = 1; c < nch; ++c) {
+        tmem_ld16(lane_base + (1 + c) * BN + c0, r);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
+      }
+      if (three) {
+        tmem_ld16(lane_base + c0, r);  // cross terms
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
+      }
+      const int n = n0 + c0;
+      if (EPI == EPI_FWD_HIDDEN || EPI == EPI_FWD_OUT) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(g.bias + n + 4 * j4);
+          v[4 * j4 + 0] += b4.x;
+          v[4 * j4 + 1] += b4.y;
+          v[4 * j4 + 2] += b4.z;
+          v[4 * j4 + 3] += b4.w;
+        }
+        dispatch_act(g.act, [&](auto tag) {
+          constexpr int ACT = decltype(tag)::value;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = act_fwd_t<ACT>(v[j]);
+        });
+      } else if (EPI == EPI_DGRAD_HIDDEN) {
+        float h[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 a = *reinterpret_cast<const float4*>(g.aux_hi + rbase + n + 4 * j4);
+          const float4 b = *reinterpret_cast<const float4*>(g.aux_lo + rbase + n + 4 * j4);
+          h[4 * j4 + 0] = a.x + b.x;
+          h[4 * j4 + 1] = a.y + b.y;
+          h[4 * j4 + 2] = a.z + b.z;
+          h[4 * j4 + 3] = a.w + b.w;
+        }
+        dispatch_act(g.act, [&](auto tag) {
+          constexpr int ACT = decltype(tag)::value;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= act_grad_out_t<ACT>(h[j]);
+        });
+      } else if (EPI == EPI_DGRAD_ACCUM) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 c = *reinterpret_cast<const float4*>(g.c_full + rbase + n + 4 * j4);
+          v[4 * j4 + 0] += c.x;
+          v[4 * j4 + 1] += c.y;
+          v[4 * j4 + 2] += c.z;
+          v[4 * j4 + 3] += c.w;
+        }
+      }
+      if (EPI == EPI_FWD_HIDDEN || EPI == EPI_DGRAD_HIDDEN) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          float4 hi, lo;
+          hi.x = tf32_hi(v[4 * j4 + 0]);
+          hi.y = tf32_hi(v[4 * j4 + 1]);
+          hi.z = tf32_hi(v[4 * j4 + 2]);
+          hi.w = tf32_hi(v[4 * j4 + 3]);
+          // the remainder is rounded (not left to the tensor core's truncation) so that its error is unbiased
+          lo.x = tf32_hi(v[4 * j4 + 0] - hi.x);
+          lo.y = tf32_hi(v[4 * j4 + 1] - hi.y);
+          lo.z = tf32_hi(v[4 * j4 + 2] - hi.z);
+          lo.w = tf32_hi(v[4 * j4 + 3] - hi.w);
+          *reinterpret_cast<float4*>(g.c_hi + rbase + n + 4 * j4) = hi;
+          *reinterpret_cast<float4*>(g.c_lo + rbase + n + 4 * j4) = lo;
+        }
+      } else {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          *reinterpret_cast<float4*>(g.c_full + rbase + n + 4 * j4) =
+              make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, kAccums * BN);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  HDPO_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  HDPO_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 4) % 16 == 0, "TMA needs 16-byte aligned rows");
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {ld * sizeof(float)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box_rows=%u)", static_cast<int>(r),
+              static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols),
+              static_cast<unsigned long long>(ld), box_rows);
+    return HDPO_E_CUDA;
+  }
+  return HDPO_OK;
+}
+
+template <int BN, int EPI>
+static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                  const GemmTcArgs& g, void* stream) {
+  auto k = gemm_tc_kernel<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlan<BN>::kTotal));
+    configured = true;
+  }
+  k<<<dim3(g.N / BN, g.M / 128), kThreads, SmemPlan<BN>::kTotal, static_cast<cudaStream_t>(stream)>>>(a_hi, a_lo, b_hi,
+                                                                                                      b_lo, g);
+  count_launch();
+  HDPO_LAUNCH_OK();
+  return HDPO_OK;
+}
+
+template <int BN>
+static int launch_epi(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                      const GemmTcArgs& g, int epi, void* stream) {
+  switch (epi) {
+    case EPI_FWD_HIDDEN: return launch<BN, EPI_FWD_HIDDEN>(a_hi, a_lo, b_hi, b_lo, g, stream);
+    case EPI_FWD_OUT: return launch<BN, EPI_FWD_OUT>(a_hi, a_lo, b_hi, b_lo, g, stream);
+    case EPI_DGRAD_HIDDEN: return launch<BN, EPI_DGRAD_HIDDEN>(a_hi, a_lo, b_hi, b_lo, g, stream);
+    case EPI_DGRAD_ACCUM: return launch<BN, EPI_DGRAD_ACCUM>(a_hi, a_lo, b_hi, b_lo, g, stream);
+    case EPI_STORE: return launch<BN, EPI_STORE>(a_hi, a_lo, b_hi, b_lo, g, stream);
+  }
+  set_error("bad epilogue %d", epi);
+  return HDPO_E_INVALID;
+}
+
+int gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+         const GemmTcArgs& g, int epi, int bn, void* stream) {
+  HDPO_REQUIRE(g.M % 128 == 0 && g.N % bn == 0 && g.K % kBK == 0 && g.K > 0, "tcgen05 GEMM shape %dx%dx%d not tileable",
+               g.M, g.N, g.K);
+  HDPO_REQUIRE(g.n_pass == 1 || g.n_pass == 3, "n_pass must be 1 or 3");
+  if (bn == 128) return launch_epi<128>(a_hi, a_lo, b_hi, b_lo, g, epi, stream);
+  if (bn == 64) return launch_epi<64>(a_hi, a_lo, b_hi, b_lo, g, epi, stream);
+  set_error("unsupported BN %d", bn);
+  return HDPO_E_INVALID;
+}
+
+// split fp32 -> (tf32 hi, exact remainder lo)
+__global__ void __launch_bounds__(256) split_hi_lo_kernel(const float* __restrict__ x, float* __restrict__ hi,
+                                                          float* __restrict__ lo, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  const float h = tf32_hi(v);
+  hi[i] = h;
+  lo[i] = tf32_hi(v - h);
+}
+
+}  // namespace tc
+}  // namespace hdpo
+
+using namespace hdpo;
+
+// Test hook: C[M,N] = A[M,K] * B[N,K]^T on the tcgen05 path (n_pass = 3: 3xTF32, 1: TF32). A, B, C dense row-major
+// device arrays with M % 128 == 0, N % 64 == 0, K % 32 == 0; scratch = 2*(M*K + N*K) floats of device memory.
+extern "C" int hdpo_debug_gemm_tc(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
+                                  int32_t n_pass, float* scratch, void* stream) {
+  HDPO_REQUIRE(A && B && C && scratch, "null argument");
+  HDPO_REQUIRE(M % 128 == 0 && N % 64 == 0 && K % 32 == 0 && M > 0 && N > 0 && K > 0, "shape not tileable");
+  float* a_hi = scratch;
+  float* a_lo = a_hi + static_cast<size_t>(M) * K;
+  float* b_hi = a_lo + static_cast<size_t>(M) * K;
+  float* b_lo = b_hi + static_cast<size_t>(N) * K;
+  const size_t na = static_cast<size_t>(M) * K, nb = static_cast<size_t>(N) * K;
+  tc::split_hi_lo_kernel<<<static_cast<unsigned>((na + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(A, a_hi, a_lo, na);
+  tc::split_hi_lo_kernel<<<static_cast<unsigned>((nb + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(B, b_hi, b_lo, nb);
+  count_launch();
+  count_launch();
+  HDPO_LAUNCH_OK();
+  const int bn = tc::pick_bn(N);
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = tc::make_tensor_map(&ma_hi, a_hi, M, K, K, 128))) return rc;
+  if ((rc = tc::make_tensor_map(&ma_lo, a_lo, M, K, K, 128))) return rc;
+  if ((rc = tc::make_tensor_map(&mb_hi, b_hi, N, K, K, bn))) return rc;
+  if ((rc = tc::make_tensor_map(&mb_lo, b_lo, N, K, K, bn))) return rc;
+  tc::GemmTcArgs g{};
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.n_pass = n_pass;
+  g.ldc = N;
+  g.c_full = C;
+  return tc::gemm(ma_hi, ma_lo, mb_hi, mb_lo, g, tc::EPI_STORE, bn, stream);
+}
+
+#else  // HDPO_EMU: tensor cores cannot be emulated; the entry point exists and refuses.
+
+extern "C" int hdpo_debug_gemm_tc(const float*, const float*, float*, int32_t, int32_t, int32_t, int32_t, float*, void*) {
+  hdpo::set_error("tcgen05 path is not available in the host-thread emulator");
+  return HDPO_E_INVALID;
+}
+
+#endif

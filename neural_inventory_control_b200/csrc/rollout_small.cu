@@ -36,7 +36,7 @@ static int pad_in(int in) {
 
 bool supported(const HdpoRolloutDesc* d) {
   if (d->arch != HDPO_ARCH_VANILLA_ONE_STORE && d->arch != HDPO_ARCH_VANILLA_SERIAL) return false;
-  if (d->precision != HDPO_PREC_FP32) return false;
+  // any precision request is honoured with fp32 FFMA here (the small nets have no tensor-core variant yet)
   const HdpoProblem& pb = d->pb;
   if (pb.S != 1) return false;
   const HdpoMlp& m = d->master;

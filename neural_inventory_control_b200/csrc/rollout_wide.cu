@@ -17,6 +17,7 @@
 // This file holds the fp32 SIMT tile GEMM (parity mode). The tcgen05 3xTF32 GEMM replaces `sgemm` call sites
 // one-for-one (same operand layouts) - see gemm_tc.cuh.
 #include "rollout_wide.cuh"
+#include "gemm_tc.cuh"
 
 namespace hdpo {
 namespace wide {
@@ -31,7 +32,9 @@ static inline size_t a256(size_t x) { return (x + 255) & ~static_cast<size_t>(25
 
 bool supported(const HdpoRolloutDesc* d) {
   if (d->arch != HDPO_ARCH_VANILLA_WAREHOUSE) return false;
-  if (d->precision != HDPO_PREC_FP32) return false;
+#ifdef HDPO_EMU
+  if (d->precision != HDPO_PREC_FP32) return false;  // tensor cores cannot be emulated
+#endif
   const HdpoProblem& pb = d->pb;
   if (pb.W < 1 || pb.E != 0 || pb.W > 8) return false;
   if (pb.S * pb.W > 1024 || pb.S > kMaxStoresPerWarp) return false;
@@ -47,12 +50,16 @@ bool supported(const HdpoRolloutDesc* d) {
 // ------------------------------------------------------------------------------------------------------------
 struct Plan {
   int n, B, Bp, T, save;
+  int tc, n_pass;  // tensor-core mode: every GEMM operand is kept as a (tf32 hi, remainder lo) pair
   int w[HDPO_MAX_LAYERS + 1], wp[HDPO_MAX_LAYERS + 1];
   int gw[HDPO_MAX_LAYERS], gb[HDPO_MAX_LAYERS];  // offsets in the flat (state_dict) parameter vector
   int P;
   size_t o_W[HDPO_MAX_LAYERS], o_b[HDPO_MAX_LAYERS];       // packed weights / biases
   size_t o_X, o_act[HDPO_MAX_LAYERS], o_gz[HDPO_MAX_LAYERS];  // tapes
   size_t o_gx, o_part, o_bpart, total;                      // state adjoint, split-K partials
+  // tensor-core mode extras: lo halves, transposed weights (dgrad B operand), split state tape
+  size_t o_W_lo[HDPO_MAX_LAYERS], o_WT[HDPO_MAX_LAYERS], o_WT_lo[HDPO_MAX_LAYERS];
+  size_t o_X_hi, o_X_lo, o_act_lo[HDPO_MAX_LAYERS], o_gz_lo[HDPO_MAX_LAYERS];
   size_t x_stride, act_stride[HDPO_MAX_LAYERS];              // floats per period
   int max_wk;
 };
@@ -65,6 +72,8 @@ static Plan make_plan(const HdpoRolloutDesc* d) {
   p.Bp = pad_to(p.B > 0 ? p.B : 1, kRowPad);
   p.T = d->T;
   p.save = d->save_for_backward;
+  p.tc = d->precision != HDPO_PREC_FP32;
+  p.n_pass = d->precision == HDPO_PREC_TF32 ? 1 : 3;
   int off = 0;
   for (int i = 0; i <= p.n; ++i) {
     p.w[i] = m.widths[i];
@@ -88,17 +97,26 @@ static Plan make_plan(const HdpoRolloutDesc* d) {
   for (int l = 0; l < p.n; ++l) {
     p.o_W[l] = take(static_cast<size_t>(p.wp[l + 1]) * p.wp[l]);
     p.o_b[l] = take(p.wp[l + 1]);
+    p.o_W_lo[l] = p.tc ? take(static_cast<size_t>(p.wp[l + 1]) * p.wp[l]) : 0;
+    p.o_WT[l] = p.tc ? take(static_cast<size_t>(p.wp[l + 1]) * p.wp[l]) : 0;
+    p.o_WT_lo[l] = p.tc ? take(static_cast<size_t>(p.wp[l + 1]) * p.wp[l]) : 0;
     int wk = p.wp[l + 1] * p.wp[l];
     if (wk > p.max_wk) p.max_wk = wk;
   }
   const size_t tslots = p.save ? static_cast<size_t>(p.T) : 1;
   p.x_stride = static_cast<size_t>(p.Bp) * p.wp[0];
   p.o_X = take((p.save ? tslots + 1 : 2) * p.x_stride);
+  p.o_X_hi = p.tc ? take(tslots * p.x_stride) : 0;
+  p.o_X_lo = p.tc ? take(tslots * p.x_stride) : 0;
   for (int l = 0; l < p.n; ++l) {
     p.act_stride[l] = static_cast<size_t>(p.Bp) * p.wp[l + 1];
-    p.o_act[l] = take(tslots * p.act_stride[l]);
+    p.o_act[l] = take(tslots * p.act_stride[l]);  // tc: hi half for hidden layers, full fp32 for the output layer
+    p.o_act_lo[l] = (p.tc && l + 1 < p.n) ? take(tslots * p.act_stride[l]) : 0;
   }
-  for (int l = 0; l < p.n; ++l) p.o_gz[l] = p.save ? take(tslots * p.act_stride[l]) : 0;
+  for (int l = 0; l < p.n; ++l) {
+    p.o_gz[l] = p.save ? take(tslots * p.act_stride[l]) : 0;
+    p.o_gz_lo[l] = (p.save && p.tc) ? take(tslots * p.act_stride[l]) : 0;
+  }
   p.o_gx = p.save ? take(p.x_stride) : 0;
   p.o_part = p.save ? take(static_cast<size_t>(kSplitK) * p.max_wk) : 0;
   int max_wp = 0;
@@ -122,6 +140,8 @@ constexpr int BN = 64, BK = 16, GEMM_THREADS = 256;
 struct GemmArgs {
   const float* A;
   const float* B;
+  const float* A2;      // optional: operand is A + A2 (hi/lo pairs of the tensor-core mode)
+  const float* B2;
   float* C;
   int M, N, K;          // K = contraction length handled by ONE z-slice
   int lda, ldb, ldc;
@@ -142,6 +162,19 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(GemmArgs g) {
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const float* __restrict__ A = g.A + blockIdx.z * g.a_kslice;
   const float* __restrict__ Bm = g.B + blockIdx.z * g.b_kslice;
+  const float* __restrict__ A2 = g.A2 ? g.A2 + blockIdx.z * g.a_kslice : nullptr;
+  const float* __restrict__ B2 = g.B2 ? g.B2 + blockIdx.z * g.b_kslice : nullptr;
+  auto ld4 = [](const float* p0, const float* p1, size_t off) {
+    float4 v = *reinterpret_cast<const float4*>(p0 + off);
+    if (p1) {
+      const float4 w = *reinterpret_cast<const float4*>(p1 + off);
+      v.x += w.x;
+      v.y += w.y;
+      v.z += w.z;
+      v.w += w.w;
+    }
+    return v;
+  };
 
   // global -> register staging. A tile: BM x BK floats = BM*4 float4; B tile: 64 x 16 floats = 256 float4.
   constexpr int A_F4 = BM * BK / 4 / GEMM_THREADS;  // 2 (BM=128) or 1 (BM=64)
@@ -152,18 +185,18 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(GemmArgs g) {
       const int idx = tid + i * GEMM_THREADS;
       if (A_T) {  // contiguous along m: idx -> (k = idx / (BM/4), mq = idx % (BM/4))
         const int k = idx / (BM / 4), mq = idx % (BM / 4);
-        ra[i] = *reinterpret_cast<const float4*>(A + static_cast<size_t>(k0 + k) * g.lda + m0 + 4 * mq);
+        ra[i] = ld4(A, A2, static_cast<size_t>(k0 + k) * g.lda + m0 + 4 * mq);
       } else {    // contiguous along k: idx -> (m = idx % BM, kq = idx / BM)
         const int m = idx % BM, kq = idx / BM;
-        ra[i] = *reinterpret_cast<const float4*>(A + static_cast<size_t>(m0 + m) * g.lda + k0 + 4 * kq);
+        ra[i] = ld4(A, A2, static_cast<size_t>(m0 + m) * g.lda + k0 + 4 * kq);
       }
     }
     if (B_T) {    // B[n*ldb + k], contiguous along k: tid -> (n = tid % 64, kq = tid / 64)
       const int n = tid % BN, kq = tid / BN;
-      rb = *reinterpret_cast<const float4*>(Bm + static_cast<size_t>(n0 + n) * g.ldb + k0 + 4 * kq);
+      rb = ld4(Bm, B2, static_cast<size_t>(n0 + n) * g.ldb + k0 + 4 * kq);
     } else {      // B[k*ldb + n], contiguous along n: tid -> (k = tid / 16, nq = tid % 16)
       const int k = tid / (BN / 4), nq = tid % (BN / 4);
-      rb = *reinterpret_cast<const float4*>(Bm + static_cast<size_t>(k0 + k) * g.ldb + n0 + 4 * nq);
+      rb = ld4(Bm, B2, static_cast<size_t>(k0 + k) * g.ldb + n0 + 4 * nq);
     }
   };
   auto store_tiles = [&](int buf) {
@@ -294,14 +327,46 @@ static int sgemm(const GemmArgs& g, int splits, void* stream) {
 // ------------------------------------------------------------------------------------------------------------
 
 // flat state_dict parameters -> zero-padded [Np][Kp] weight slab + [Np] bias
+__device__ __forceinline__ float tf32_round(float x) {
+#ifdef HDPO_EMU
+  return x;
+#else
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+#endif
+}
+
+// tensor-core mode: W_lo, WT (transposed [Kp][Np]) and WT_lo are non-null and Wp receives the hi half
 __global__ void __launch_bounds__(256) pack_layer_kernel(const float* __restrict__ params, int gw, int gb, int N, int K,
-                                                         int Np, int Kp, float* __restrict__ Wp, float* __restrict__ bp) {
+                                                         int Np, int Kp, float* __restrict__ Wp, float* __restrict__ bp,
+                                                         float* __restrict__ W_lo, float* __restrict__ WT,
+                                                         float* __restrict__ WT_lo) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Np * Kp) {
     const int n = i / Kp, k = i % Kp;
-    Wp[i] = (n < N && k < K) ? params[gw + n * K + k] : 0.f;
+    const float w = (n < N && k < K) ? params[gw + n * K + k] : 0.f;
+    if (W_lo) {
+      const float hi = tf32_round(w), lo = tf32_round(w - hi);
+      Wp[i] = hi;
+      W_lo[i] = lo;
+      WT[static_cast<size_t>(k) * Np + n] = hi;
+      WT_lo[static_cast<size_t>(k) * Np + n] = lo;
+    } else {
+      Wp[i] = w;
+    }
   }
   if (i < Np) bp[i] = i < N ? params[gb + i] : 0.f;
+}
+
+// row-wise split of a [rows][ld] fp32 array into (hi, lo)
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, float* __restrict__ hi,
+                                                         float* __restrict__ lo, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i], h = tf32_round(v);
+  hi[i] = h;
+  lo[i] = tf32_round(v - h);
 }
 
 // initial state rows X_0[b] = [store inventories flat | warehouse inventories flat | 0 pad]; padded rows = 0
@@ -322,6 +387,11 @@ __global__ void __launch_bounds__(256) init_state_kernel(const float* __restrict
     cost_b[i] = 0.f;
     if (report_b) report_b[i] = 0.f;
   }
+}
+
+__global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += b[i];
 }
 
 __global__ void __launch_bounds__(256) zero_kernel(float* __restrict__ p, size_t n) {
@@ -358,7 +428,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // warehouse policy head + simulator period: one WARP per scenario, lanes over stores
 // ------------------------------------------------------------------------------------------------------------
 struct HeadArgs {
-  int B, S, W, L, Lw, T_stride, tt;  // tt = t + period_shift (demand column)
+  int B, Bp, S, W, L, Lw, T_stride, tt;  // tt = t + period_shift (demand column); Bp = rows incl. tile padding
   int ldx, ldy, demand_layout;
   int lost, profit, has_edge, transshipment, discrete, in_report;
   float wub;
@@ -402,11 +472,22 @@ __device__ __forceinline__ void softmax_shares(const HeadArgs& a, const float* _
 
 __global__ void __launch_bounds__(HEAD_WARPS * 32)
 warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ Xn,
-                          float* __restrict__ cost_b, float* __restrict__ report_b, float* __restrict__ reward_t) {
+                          float* __restrict__ cost_b, float* __restrict__ report_b, float* __restrict__ reward_t,
+                          float* __restrict__ Xn_hi, float* __restrict__ Xn_lo) {
   HDPO_DYN_SMEM(float, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * HEAD_WARPS + warp;
-  if (b >= a.B) return;
+  if (b >= a.Bp) return;
+  if (b >= a.B) {  // tile-padding rows stay exactly zero so that they never contribute to a weight gradient
+    for (int k = lane; k < a.ldx; k += 32) {
+      Xn[static_cast<size_t>(b) * a.ldx + k] = 0.f;
+      if (Xn_hi) {
+        Xn_hi[static_cast<size_t>(b) * a.ldx + k] = 0.f;
+        Xn_lo[static_cast<size_t>(b) * a.ldx + k] = 0.f;
+      }
+    }
+    return;
+  }
   const int SW = a.S * a.W;
   float* share = smem + warp * (SW + 32);  // alloc[s*W+w]; tail: per-warehouse scratch
   const float* x = X + static_cast<size_t>(b) * a.ldx;
@@ -469,6 +550,16 @@ warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
   }
   // padding columns of the next state row stay zero
   for (int k = nS + a.W * a.Lw + lane; k < a.ldx; k += 32) xn[k] = 0.f;
+  if (Xn_hi) {  // tensor-core mode: the next period's layer-0 GEMM reads the state as a (hi, lo) pair
+    __syncwarp();
+    float* xh = Xn_hi + static_cast<size_t>(b) * a.ldx;
+    float* xl = Xn_lo + static_cast<size_t>(b) * a.ldx;
+    for (int k = lane; k < a.ldx; k += 32) {
+      const float v = xn[k], h = tf32_round(v);
+      xh[k] = h;
+      xl[k] = tf32_round(v - h);
+    }
+  }
   cost = warp_sum(cost);
   if (lane == 0) {
     cost_b[b] += cost;
@@ -480,11 +571,18 @@ warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
 // Adjoint of the head + period. gX: on entry adjoint wrt X_{t+1} row, on exit the direct part of the adjoint wrt X_t.
 __global__ void __launch_bounds__(HEAD_WARPS * 32)
 warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ gX,
-                          float* __restrict__ gY, float rb) {
+                          float* __restrict__ gY, float rb, float* __restrict__ gY_lo) {
   HDPO_DYN_SMEM(float, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * HEAD_WARPS + warp;
-  if (b >= a.B) return;
+  if (b >= a.Bp) return;
+  if (b >= a.B) {
+    for (int k = lane; k < a.ldy; k += 32) {
+      gY[static_cast<size_t>(b) * a.ldy + k] = 0.f;
+      if (gY_lo) gY_lo[static_cast<size_t>(b) * a.ldy + k] = 0.f;
+    }
+    return;
+  }
   const int SW = a.S * a.W;
   float* share = smem + warp * (2 * SW + 64);  // p[s*W+w]
   float* galloc = share + SW;                  // adjoint of the allocations
@@ -567,6 +665,15 @@ warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
     }
   }
   for (int k = SW + a.W + lane; k < a.ldy; k += 32) gy[k] = 0.f;
+  if (gY_lo) {  // tensor-core mode: gY (in place) becomes the hi half, gY_lo the remainder
+    __syncwarp();
+    float* gl = gY_lo + static_cast<size_t>(b) * a.ldy;
+    for (int k = lane; k < a.ldy; k += 32) {
+      const float v = gy[k], h = tf32_round(v);
+      gy[k] = h;
+      gl[k] = tf32_round(v - h);
+    }
+  }
 }
 
 // column sums of a [rows][ld] matrix (bias gradients), two deterministic stages
@@ -631,6 +738,7 @@ __global__ void __launch_bounds__(1024) totals_kernel(const float* __restrict__ 
 static HeadArgs head_args(const HdpoRolloutDesc* d, const Plan& p, const float* demands, const HdpoStatics* st, int t) {
   HeadArgs a;
   a.B = p.B;
+  a.Bp = p.Bp;
   a.S = d->pb.S;
   a.W = d->pb.W;
   a.L = d->pb.L;
@@ -655,6 +763,18 @@ static HeadArgs head_args(const HdpoRolloutDesc* d, const Plan& p, const float* 
 
 static float* wsf(void* ws, size_t off) { return reinterpret_cast<float*>(static_cast<char*>(ws) + off); }
 
+#ifndef HDPO_EMU
+// tensor maps of one (hi, lo) operand pair
+struct MapPair {
+  CUtensorMap hi, lo;
+};
+static int make_pair(MapPair* m, const float* hi, const float* lo, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  int rc = tc::make_tensor_map(&m->hi, hi, rows, cols, cols, box_rows);
+  if (rc) return rc;
+  return tc::make_tensor_map(&m->lo, lo, rows, cols, cols, box_rows);
+}
+#endif
+
 int forward(const HdpoRolloutDesc* d, const float* params, const float* demands, const HdpoStatics* st,
             const HdpoState* init, float* cost_b, float* report_b, float* reward_tb, double* totals,
             HdpoState* final_state, void* ws, size_t ws_bytes, void* stream) {
@@ -667,12 +787,15 @@ int forward(const HdpoRolloutDesc* d, const float* params, const float* demands,
   HDPO_REQUIRE(d->pb.W == 1 || d->adjacency != nullptr, "warehouse_store_adjacency required for n_warehouses > 1");
   const HdpoProblem& pb = d->pb;
   const int nS = pb.S * pb.L, nW = pb.W * pb.Lw;
-  // pack weights
+  const size_t tslots = p.save ? static_cast<size_t>(p.T) : 1;
+  // pack weights (tensor-core mode: hi/lo halves and their transposes)
   for (int l = 0; l < p.n; ++l) {
     const int cnt = p.wp[l + 1] * p.wp[l];
     auto k = pack_layer_kernel;
     HDPO_LAUNCH(k, ceil_div(cnt, 256), 256, 0, stream, params, p.gw[l], p.gb[l], p.w[l + 1], p.w[l], p.wp[l + 1],
-                p.wp[l], wsf(ws, p.o_W[l]), wsf(ws, p.o_b[l]));
+                p.wp[l], wsf(ws, p.o_W[l]), wsf(ws, p.o_b[l]), p.tc ? wsf(ws, p.o_W_lo[l]) : static_cast<float*>(nullptr),
+                p.tc ? wsf(ws, p.o_WT[l]) : static_cast<float*>(nullptr),
+                p.tc ? wsf(ws, p.o_WT_lo[l]) : static_cast<float*>(nullptr));
     HDPO_LAUNCH_OK();
   }
   {
@@ -681,7 +804,26 @@ int forward(const HdpoRolloutDesc* d, const float* params, const float* demands,
     HDPO_LAUNCH(k, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream, init->store, init->warehouse, p.B, p.Bp,
                 nS, nW, p.wp[0], wsf(ws, p.o_X), cost_b, report_b);
     HDPO_LAUNCH_OK();
+    if (p.tc) {
+      auto ks = split_rows_kernel;
+      HDPO_LAUNCH(ks, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream,
+                  static_cast<const float*>(wsf(ws, p.o_X)), wsf(ws, p.o_X_hi), wsf(ws, p.o_X_lo), cnt);
+      HDPO_LAUNCH_OK();
+    }
   }
+#ifndef HDPO_EMU
+  MapPair mA[HDPO_MAX_LAYERS], mB[HDPO_MAX_LAYERS];
+  if (p.tc) {
+    for (int l = 0; l < p.n; ++l) {
+      const float* a_hi = (l == 0) ? wsf(ws, p.o_X_hi) : wsf(ws, p.o_act[l - 1]);
+      const float* a_lo = (l == 0) ? wsf(ws, p.o_X_lo) : wsf(ws, p.o_act_lo[l - 1]);
+      int rc = make_pair(&mA[l], a_hi, a_lo, tslots * p.Bp, p.wp[l], tc::kBoxRowsA);
+      if (rc) return rc;
+      rc = make_pair(&mB[l], wsf(ws, p.o_W[l]), wsf(ws, p.o_W_lo[l]), p.wp[l + 1], p.wp[l], tc::pick_bn(p.wp[l + 1]));
+      if (rc) return rc;
+    }
+  }
+#endif
   const size_t head_smem = static_cast<size_t>(HEAD_WARPS) * (pb.S * pb.W + 32) * sizeof(float);
   for (int t = 0; t < p.T; ++t) {
     const size_t xs = p.save ? static_cast<size_t>(t) : static_cast<size_t>(t & 1);
@@ -691,26 +833,60 @@ int forward(const HdpoRolloutDesc* d, const float* params, const float* demands,
     float* Xn = wsf(ws, p.o_X) + xn * p.x_stride;
     const float* in = X;
     for (int l = 0; l < p.n; ++l) {
-      GemmArgs g{};
-      g.A = in;
-      g.B = wsf(ws, p.o_W[l]);
-      g.C = wsf(ws, p.o_act[l]) + as * p.act_stride[l];
-      g.M = p.Bp;
-      g.N = p.wp[l + 1];
-      g.K = p.wp[l];
-      g.lda = p.wp[l];
-      g.ldb = p.wp[l];
-      g.ldc = p.wp[l + 1];
-      g.bias = wsf(ws, p.o_b[l]);
-      g.act = (l + 1 < p.n) ? d->master.hidden_act : d->master.out_act;
-      int rc = sgemm<false, true, EPI_BIAS_ACT>(g, 1, stream);
+      float* out = wsf(ws, p.o_act[l]) + as * p.act_stride[l];
+      const int act = (l + 1 < p.n) ? d->master.hidden_act : d->master.out_act;
+      int rc;
+      if (!p.tc) {
+        GemmArgs g{};
+        g.A = in;
+        g.B = wsf(ws, p.o_W[l]);
+        g.C = out;
+        g.M = p.Bp;
+        g.N = p.wp[l + 1];
+        g.K = p.wp[l];
+        g.lda = p.wp[l];
+        g.ldb = p.wp[l];
+        g.ldc = p.wp[l + 1];
+        g.bias = wsf(ws, p.o_b[l]);
+        g.act = act;
+        rc = sgemm<false, true, EPI_BIAS_ACT>(g, 1, stream);
+      } else {
+#ifndef HDPO_EMU
+        tc::GemmTcArgs g{};
+        g.M = p.Bp;
+        g.N = p.wp[l + 1];
+        g.K = p.wp[l];
+        g.n_pass = p.n_pass;
+        g.a_row0 = static_cast<int>(as * p.Bp);
+        g.b_row0 = 0;
+        g.ldc = p.wp[l + 1];
+        g.act = act;
+        g.bias = wsf(ws, p.o_b[l]);
+        const bool hidden = l + 1 < p.n;
+        g.c_full = out;
+        g.c_hi = out;
+        g.c_lo = hidden ? wsf(ws, p.o_act_lo[l]) + as * p.act_stride[l] : nullptr;
+        rc = tc::gemm(mA[l].hi, mA[l].lo, mB[l].hi, mB[l].lo, g, hidden ? tc::EPI_FWD_HIDDEN : tc::EPI_FWD_OUT,
+                      tc::pick_bn(p.wp[l + 1]), stream);
+#else
+        rc = HDPO_E_INVALID;
+#endif
+      }
       if (rc) return rc;
-      in = g.C;
+      in = out;
     }
     HeadArgs a = head_args(d, p, demands, st, t);
+    // tensor-core mode: the state written for period t+1 is also split into the (hi, lo) tape slot t+1
+    float* xn_hi = nullptr;
+    float* xn_lo = nullptr;
+    if (p.tc && (t + 1 < p.T)) {
+      const size_t slot = p.save ? static_cast<size_t>(t + 1) : 0;
+      xn_hi = wsf(ws, p.o_X_hi) + slot * p.x_stride;
+      xn_lo = wsf(ws, p.o_X_lo) + slot * p.x_stride;
+    }
     auto k = warehouse_head_fwd_kernel;
-    HDPO_LAUNCH(k, ceil_div(p.B, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, in, Xn, cost_b, report_b,
-                reward_tb ? reward_tb + static_cast<size_t>(t) * p.B : static_cast<float*>(nullptr));
+    HDPO_LAUNCH(k, ceil_div(p.Bp, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, in, Xn, cost_b, report_b,
+                reward_tb ? reward_tb + static_cast<size_t>(t) * p.B : static_cast<float*>(nullptr), xn_hi, xn_lo);
     HDPO_LAUNCH_OK();
   }
   if (final_state && (final_state->store || final_state->warehouse)) {
@@ -747,37 +923,77 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
     HDPO_LAUNCH(k, static_cast<unsigned>(ceil_div64(p.x_stride, 256)), 256, 0, stream, gX, p.x_stride);
     HDPO_LAUNCH_OK();
   }
+#ifndef HDPO_EMU
+  MapPair mA[HDPO_MAX_LAYERS], mB[HDPO_MAX_LAYERS];
+  if (p.tc) {
+    for (int l = 0; l < p.n; ++l) {  // dgrad of layer l: A = gz_l [rows][wp[l+1]], B = W_l^T [wp[l]][wp[l+1]]
+      int rc = make_pair(&mA[l], wsf(ws, p.o_gz[l]), wsf(ws, p.o_gz_lo[l]), static_cast<uint64_t>(p.T) * p.Bp,
+                         p.wp[l + 1], tc::kBoxRowsA);
+      if (rc) return rc;
+      rc = make_pair(&mB[l], wsf(ws, p.o_WT[l]), wsf(ws, p.o_WT_lo[l]), p.wp[l], p.wp[l + 1], tc::pick_bn(p.wp[l]));
+      if (rc) return rc;
+    }
+  }
+#endif
   const size_t head_smem = static_cast<size_t>(HEAD_WARPS) * (2 * pb.S * pb.W + 64) * sizeof(float);
   const int last = p.n - 1;
   for (int t = p.T - 1; t >= 0; --t) {
     const float* X = wsf(ws, p.o_X) + static_cast<size_t>(t) * p.x_stride;
     const float* Y = wsf(ws, p.o_act[last]) + static_cast<size_t>(t) * p.act_stride[last];
     float* gY = wsf(ws, p.o_gz[last]) + static_cast<size_t>(t) * p.act_stride[last];
+    float* gY_lo = p.tc ? wsf(ws, p.o_gz_lo[last]) + static_cast<size_t>(t) * p.act_stride[last] : nullptr;
     HeadArgs a = head_args(d, p, demands, st, t);
     const float rb = g_total + (t >= d->ignore_periods ? g_report : 0.f);
     auto k = warehouse_head_bwd_kernel;
-    HDPO_LAUNCH(k, ceil_div(p.B, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, Y, gX, gY, rb);
+    HDPO_LAUNCH(k, ceil_div(p.Bp, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, Y, gX, gY, rb, gY_lo);
     HDPO_LAUNCH_OK();
     // dgrad chain: gz_{l-1} = (gz_l W_l) * act'(h_{l-1});  finally gX += gz_0 W_0
     for (int l = last; l >= 0; --l) {
-      GemmArgs g{};
-      g.A = wsf(ws, p.o_gz[l]) + static_cast<size_t>(t) * p.act_stride[l];
-      g.B = wsf(ws, p.o_W[l]);
-      g.M = p.Bp;
-      g.N = p.wp[l];
-      g.K = p.wp[l + 1];
-      g.lda = p.wp[l + 1];
-      g.ldb = p.wp[l];
-      g.ldc = p.wp[l];
-      g.act = d->master.hidden_act;
       int rc;
-      if (l > 0) {
-        g.C = wsf(ws, p.o_gz[l - 1]) + static_cast<size_t>(t) * p.act_stride[l - 1];
-        g.aux = wsf(ws, p.o_act[l - 1]) + static_cast<size_t>(t) * p.act_stride[l - 1];
-        rc = sgemm<false, false, EPI_MUL_ACTGRAD>(g, 1, stream);
+      if (!p.tc) {
+        GemmArgs g{};
+        g.A = wsf(ws, p.o_gz[l]) + static_cast<size_t>(t) * p.act_stride[l];
+        g.B = wsf(ws, p.o_W[l]);
+        g.M = p.Bp;
+        g.N = p.wp[l];
+        g.K = p.wp[l + 1];
+        g.lda = p.wp[l + 1];
+        g.ldb = p.wp[l];
+        g.ldc = p.wp[l];
+        g.act = d->master.hidden_act;
+        if (l > 0) {
+          g.C = wsf(ws, p.o_gz[l - 1]) + static_cast<size_t>(t) * p.act_stride[l - 1];
+          g.aux = wsf(ws, p.o_act[l - 1]) + static_cast<size_t>(t) * p.act_stride[l - 1];
+          rc = sgemm<false, false, EPI_MUL_ACTGRAD>(g, 1, stream);
+        } else {
+          g.C = gX;
+          rc = sgemm<false, false, EPI_ACCUM>(g, 1, stream);
+        }
       } else {
-        g.C = gX;
-        rc = sgemm<false, false, EPI_ACCUM>(g, 1, stream);
+#ifndef HDPO_EMU
+        tc::GemmTcArgs g{};
+        g.M = p.Bp;
+        g.N = p.wp[l];
+        g.K = p.wp[l + 1];
+        g.n_pass = p.n_pass;
+        g.a_row0 = t * p.Bp;
+        g.b_row0 = 0;
+        g.ldc = p.wp[l];
+        g.act = d->master.hidden_act;
+        if (l > 0) {
+          const size_t off = static_cast<size_t>(t) * p.act_stride[l - 1];
+          g.c_hi = wsf(ws, p.o_gz[l - 1]) + off;
+          g.c_lo = wsf(ws, p.o_gz_lo[l - 1]) + off;
+          g.aux_hi = wsf(ws, p.o_act[l - 1]) + off;
+          g.aux_lo = wsf(ws, p.o_act_lo[l - 1]) + off;
+          rc = tc::gemm(mA[l].hi, mA[l].lo, mB[l].hi, mB[l].lo, g, tc::EPI_DGRAD_HIDDEN, tc::pick_bn(p.wp[l]), stream);
+        } else {
+          g.c_full = gX;
+          rc = tc::gemm(mA[l].hi, mA[l].lo, mB[l].hi, mB[l].lo, g, tc::EPI_DGRAD_ACCUM, tc::pick_bn(p.wp[l]), stream);
+        }
+#else
+        rc = HDPO_E_INVALID;
+#endif
       }
       if (rc) return rc;
     }
@@ -790,7 +1006,9 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
   for (int l = 0; l < p.n; ++l) {
     GemmArgs g{};
     g.A = wsf(ws, p.o_gz[l]);                                   // [rows][wp[l+1]] used transposed
-    g.B = (l == 0) ? wsf(ws, p.o_X) : wsf(ws, p.o_act[l - 1]);  // [rows][wp[l]]  (X tape: first T blocks)
+    g.A2 = p.tc ? wsf(ws, p.o_gz_lo[l]) : nullptr;
+    g.B = (l == 0) ? wsf(ws, p.o_X) : wsf(ws, p.o_act[l - 1]);  // [rows][wp[l]]  (X tape: first T blocks, full fp32)
+    g.B2 = (p.tc && l > 0) ? wsf(ws, p.o_act_lo[l - 1]) : nullptr;
     g.C = wsf(ws, p.o_part);
     g.M = p.wp[l + 1];
     g.N = p.wp[l];
@@ -804,6 +1022,13 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
     int rc = sgemm<true, false, EPI_SPLITK>(g, splits, stream);
     if (rc) return rc;
     const int n_chunks = 128;
+    if (p.tc) {  // bias gradient needs hi + lo: fold lo into hi in place first (gz tapes are dead after this layer)
+      auto ka = add_inplace_kernel;
+      const size_t cnt = rows * p.wp[l + 1];
+      HDPO_LAUNCH(ka, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream, wsf(ws, p.o_gz[l]),
+                  static_cast<const float*>(wsf(ws, p.o_gz_lo[l])), cnt);
+      HDPO_LAUNCH_OK();
+    }
     auto k1 = colsum_stage1_kernel;
     HDPO_LAUNCH(k1, dim3(ceil_div(p.wp[l + 1], 256), n_chunks), 256, 0, stream, static_cast<const float*>(g.A), rows,
                 p.wp[l + 1], n_chunks, wsf(ws, p.o_bpart));

@@ -32,6 +32,9 @@ class Trainer:
                                       "model_params_to_save": None}
         self.best_epoch = 0
         self.use_fused = os.environ.get("HDPO_DISABLE_FUSED", "0") != "1"
+        # matmul precision request for policies with a tensor-core rollout (the wide MLPs): "tf32x3" is the
+        # parity-grade tcgen05 mode, "fp32" the SIMT FFMA mode, "tf32" single-pass (throughput, not parity-grade)
+        self.precision = os.environ.get("HDPO_PRECISION", "tf32x3")
         self._engines = {}
         self.last_path = None  # "fused" | "generic": which path the last simulate_batch took (for tests/logging)
 
@@ -190,7 +193,7 @@ class Trainer:
                 self._engines.clear()
             eng = EN.FusedRollout(pspec, problem_params, data_batch, periods, ignore_periods=ignore_periods,
                                   period_shift=shift, discrete_allocation=discrete_allocation,
-                                  save_for_backward=need_grad)
+                                  save_for_backward=need_grad, precision=self.precision)
             self._engines[key] = eng
         # keep the simulator's visible state coherent with what a per-period run would leave behind
         simulator.reset(periods, problem_params, data_batch, observation_params)

@@ -151,6 +151,8 @@ def rollout(be, meta, params, data, T=None, ignore=None, demand_layout=K.DEMAND_
     ws_bytes = L.hdpo_rollout_workspace_bytes(C.byref(desc))
     assert ws_bytes > 0, L.hdpo_last_error()
     ws = be.zeros(ws_bytes, np.uint8)
+    if hasattr(be, "torch"):  # a dirty workspace: the kernels must not rely on zero-initialised scratch
+        ws.view(be.torch.float32)[: (ws_bytes // 4)].fill_(float("nan"))
     B = bt.B
     p = be.ptr
     flat_h = be.put(flat)

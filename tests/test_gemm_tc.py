@@ -1,0 +1,42 @@
+"""tcgen05 / TMEM / TMA tile GEMM (csrc/gemm_tc.cu) against a float64 numpy product. GPU only (tensor cores cannot
+be emulated). 3xTF32 must be fp32-grade (1e-5 bar of the parity mode); single-pass TF32 is checked at its own
+10-bit-mantissa accuracy so that a silently wrong descriptor / swizzle cannot hide behind a loose tolerance."""
+import numpy as np
+import pytest
+
+import abi_driver as D
+from neural_inventory_control_b200 import _capi as K
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,Kd", [(128, 64, 32), (128, 128, 64), (256, 192, 96), (384, 512, 512), (1024, 64, 512),
+                                    (2048, 512, 192)])
+def test_gemm_tc_matches_float64(M, N, Kd):
+    be = D.CudaBackend()
+    rng = np.random.RandomState(M + N + Kd)
+    A = rng.randn(M, Kd).astype(np.float32)
+    B = (rng.randn(N, Kd) / np.sqrt(Kd)).astype(np.float32)
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+    scale = np.abs(want).max()
+    a, b = be.put(A), be.put(B)
+    scratch = be.zeros(2 * (M * Kd + N * Kd))
+    fp32_err = np.abs((A @ B.T).astype(np.float64) - want).max() / scale  # what a true-fp32 GEMM achieves here
+    for n_pass, tol in ((3, max(2e-6, 4 * fp32_err)), (1, 2e-3)):
+        c = be.zeros((M, N))
+        rc = be.lib.hdpo_debug_gemm_tc(be.ptr(a), be.ptr(b), be.ptr(c), M, N, Kd, n_pass, be.ptr(scratch), be.stream)
+        K.check(be.lib, rc, "hdpo_debug_gemm_tc")
+        be.sync()
+        got = be.get(c).astype(np.float64)
+        err = np.abs(got - want).max() / scale
+        print(f"gemm_tc {M}x{N}x{Kd} n_pass={n_pass}: max err/scale {err:.3e} (fp32 numpy: {fp32_err:.3e})")
+        assert err < tol, (n_pass, err)
+        if n_pass == 1:
+            assert err > 1e-6  # it really is the single-pass path
+
+
+def test_gemm_tc_rejects_untileable_shapes():
+    be = D.CudaBackend()
+    z = be.zeros(16)
+    assert be.lib.hdpo_debug_gemm_tc(be.ptr(z), be.ptr(z), be.ptr(z), 100, 64, 32, 3, be.ptr(z), be.stream) != 0
+    assert b"tileable" in be.lib.hdpo_last_error()

@@ -190,12 +190,14 @@ def _grad_check_vs_golden(out, g, floor_mult=3):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("name", WIDE)
-def test_wide_rollout_costs_and_gradients_match_reference(name):
-    """Full 50-period goldens of the warehouse settings (GPU only: the emulator needs ~30 s per case)."""
+def test_wide_rollout_costs_and_gradients_match_reference(name, precision):
+    """Full 50-period goldens of the warehouse settings (GPU only: the emulator needs ~30 s per case), through the
+    fp32 SIMT GEMM and through the tcgen05 3xTF32 GEMM - both are parity modes and must meet the same bar."""
     be = backend("cuda")
     meta, g = G.load("rollout", name)
-    out = D.rollout(be, meta, g["param"], g["data"])
+    out = D.rollout(be, meta, g["param"], g["data"], precision=precision)
     check_rollout_against_golden(out, meta, g, meta["T"], meta["ignore_periods"])
     _grad_check_vs_golden(out, g)
     names = {"store": "store_inventories", "wh": "warehouse_inventories"}
@@ -204,15 +206,20 @@ def test_wide_rollout_costs_and_gradients_match_reference(name):
         assert np.abs(out["final"][k] - rf).max() <= 2e-3 * max(1.0, np.abs(rf).max())
 
 
-@pytest.mark.parametrize("be_name", BACKENDS)
+WIDE_MODES = [pytest.param("emu", "fp32", id="emu-fp32"),
+              pytest.param("cuda", "fp32", id="cuda-fp32", marks=pytest.mark.gpu),
+              pytest.param("cuda", "tf32x3", id="cuda-tf32x3", marks=pytest.mark.gpu)]
+
+
+@pytest.mark.parametrize("be_name,precision", WIDE_MODES)
 @pytest.mark.parametrize("name,n,T,ignore", [("one_warehouse_s5", 32, 6, 2), ("many_warehouses_2x10", 19, 7, 3),
                                              ("many_warehouses_3x50", 5, 4, 0)])
-def test_wide_rollout_short_horizon_against_oracle(be_name, name, n, T, ignore):
+def test_wide_rollout_short_horizon_against_oracle(be_name, precision, name, n, T, ignore):
     """Short horizons (before the chaotic regime) against the pinned float64 oracle: tight tolerances."""
     be = backend(be_name)
     meta, g = G.load("rollout", name)
     data = D.slice_batch(g["data"], n)
-    out = D.rollout(be, meta, g["param"], data, T=T, ignore=ignore)
+    out = D.rollout(be, meta, g["param"], data, T=T, ignore=ignore, precision=precision)
     pb = G.problem_from_meta(meta)
     pol = G.policy_from_golden(meta, g["param"], np.float64)
     fwd, grads = O.rollout_grad(pol, pb, G.cast(data, np.float64), T)
@@ -226,3 +233,40 @@ def test_wide_rollout_short_horizon_against_oracle(be_name, name, n, T, ignore):
     assert G.rel_l2(mine, want) <= 2e-5, G.rel_l2(mine, want)
     for k in ("store", "wh"):
         np.testing.assert_allclose(out["final"][k], fwd["final"][k], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_wide_rollout_single_pass_tf32_is_close_but_not_parity_grade():
+    """HDPO_PREC_TF32 (throughput mode) runs the same pipeline with one tensor pass: 10-bit-mantissa accuracy."""
+    be = backend("cuda")
+    meta, g = G.load("rollout", "many_warehouses_2x10")
+    data = D.slice_batch(g["data"], 32)
+    fast = D.rollout(be, meta, g["param"], data, T=8, ignore=0, precision="tf32")
+    exact = D.rollout(be, meta, g["param"], data, T=8, ignore=0, precision="fp32")
+    rel = np.abs(fast["cost_b"] / exact["cost_b"] - 1).max()
+    assert 1e-7 < rel < 2e-2, rel
+    assert G.rel_l2(fast["grad_flat"], exact["grad_flat"]) < 5e-2
+
+
+@pytest.mark.gpu
+def test_wide_rollout_large_batch_tc_vs_simt_and_padding_rows():
+    """B not a multiple of the 128-row tile and a dirty workspace: tile-padding rows must not leak into the weight
+    gradient; tcgen05 3xTF32 and fp32 SIMT agree at fp32 level on a 512-wide net (K = 512 accumulations)."""
+    import torch
+    be = backend("cuda")
+    meta, g = G.load("rollout", "one_warehouse_s50")
+    rng = np.random.RandomState(0)
+    params = {}
+    widths = [153, 512, 512, 51]
+    for i in range(3):
+        k = 1 / np.sqrt(widths[i])
+        params[f"net.master.{2 * i}.weight"] = rng.uniform(-k, k, (widths[i + 1], widths[i])).astype(np.float32)
+        params[f"net.master.{2 * i}.bias"] = rng.uniform(-k, k, (widths[i + 1],)).astype(np.float32)
+    data = {k: np.concatenate([v] * 13, 0)[:200] for k, v in g["data"].items()}  # 200 scenarios -> 56 padding rows
+    junk = torch.full((64 << 20,), float("nan"), device="cuda")  # poison freshly freed memory
+    del junk
+    a = D.rollout(be, meta, params, data, T=5, ignore=1, precision="fp32")
+    b = D.rollout(be, meta, params, data, T=5, ignore=1, precision="tf32x3")
+    assert np.isfinite(a["grad_flat"]).all() and np.isfinite(b["grad_flat"]).all()
+    np.testing.assert_allclose(b["cost_b"], a["cost_b"], rtol=2e-6)
+    assert G.rel_l2(b["grad_flat"], a["grad_flat"]) < 5e-6
