@@ -218,6 +218,10 @@ int hdpo_philox_raw(uint32_t* out, uint64_t n_groups, uint64_t seed, uint64_t of
  * device arrays, M % 128 == 0, N % 64 == 0, K % 32 == 0; scratch = 2*(M*K + N*K) floats of device memory. */
 int hdpo_debug_gemm_tc(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t n_pass,
                        float* scratch, void* stream);
+/* Same for the weight-gradient (MN-major) form: C[M,N] = A[K,M]^T * B[K,N], A / B row-major [K][M] / [K][N];
+ * K % k_per_split == 0, k_per_split % 32 == 0; scratch = 2*(K*M + K*N) + (K/k_per_split)*M*N floats. */
+int hdpo_debug_gemm_tc_wgrad(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
+                             int32_t k_per_split, int32_t n_pass, float* scratch, void* stream);
 
 /* misc */
 const char* hdpo_last_error(void);

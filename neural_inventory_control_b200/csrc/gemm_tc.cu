@@ -98,6 +98,21 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand tile as TMA lays it down from a row-major [k][mn] array with a {32 mn, BK k} box. For 32-bit
+// (tf32) MN-major operands the tensor core only accepts the "128B swizzle with 32-byte atoms" layout
+// (UMMA layout type 1 = SWIZZLE_128B_BASE32B, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): each k row is 128 B
+// (32 mn elements) whose four 32-byte chunks are XOR-swizzled with (k mod 4); 4 k rows = one 512-byte atom
+// (SBO: next group of 4 k); the next 32 mn elements are the next TMA box, BK*128 bytes further (LBO).
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(1) << 61;
+  return d;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // kernel: 6 warps = TMA producer | MMA issuer (+TMEM owner) | 4 epilogue warps (128 rows of the tile)
 // ------------------------------------------------------------------------------------------------------------
@@ -120,7 +135,11 @@ struct SmemPlan {
   static constexpr int kTotal = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int EPI>
+// MN = false: D[M,N] = A[M,K] B[N,K]^T, operands K-major (rows = m / n, contiguous k).
+// MN = true : D[M,N] = sum_k A[k][m] B[k][n], operands MN-major (rows = k, contiguous m / n): the weight-gradient
+//             form dW = gz^T h straight from the [row][feature] tapes; blockIdx.z selects a K range of k_per_split rows
+//             and writes its own partial slice (short ranges keep the truncating accumulation fp32-grade).
+template <int BN, int EPI, bool MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, GemmTcArgs g) {
@@ -135,7 +154,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * 128, n0 = blockIdx.x * BN;
-  const int n_kb = g.K / kBK;
+  const int n_kb = (MN ? g.k_per_split : g.K) / kBK;
+  const int k_begin = MN ? static_cast<int>(blockIdx.z) * g.k_per_split : 0;
   const bool three = g.n_pass == 3;
 
   if (warp == 0 && lane == 0) {
@@ -169,11 +189,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         mbar_wait(&empty_bar[s], ph ^ 1);
         unsigned char* st = smem + s * P::kStageBytes;
         mbar_expect_tx(&full_bar[s], tx);
-        tma_load_2d(st, &tm_a_hi, &full_bar[s], kb * kBK, g.a_row0 + m0);
-        tma_load_2d(st + 2 * P::kABytes, &tm_b_hi, &full_bar[s], kb * kBK, g.b_row0 + n0);
-        if (three) {
-          tma_load_2d(st + P::kABytes, &tm_a_lo, &full_bar[s], kb * kBK, g.a_row0 + m0);
-          tma_load_2d(st + 2 * P::kABytes + P::kBBytes, &tm_b_lo, &full_bar[s], kb * kBK, g.b_row0 + n0);
+        if (!MN) {
+          tma_load_2d(st, &tm_a_hi, &full_bar[s], kb * kBK, g.a_row0 + m0);
+          tma_load_2d(st + 2 * P::kABytes, &tm_b_hi, &full_bar[s], kb * kBK, g.b_row0 + n0);
+          if (three) {
+            tma_load_2d(st + P::kABytes, &tm_a_lo, &full_bar[s], kb * kBK, g.a_row0 + m0);
+            tma_load_2d(st + 2 * P::kABytes + P::kBBytes, &tm_b_lo, &full_bar[s], kb * kBK, g.b_row0 + n0);
+          }
+        } else {
+          constexpr int kBox = kBK * 128;  // bytes of one {32 mn, BK k} box
+          const int krow = k_begin + kb * kBK;
+          for (int i = 0; i < 128 / 32; ++i) {
+            tma_load_2d(st + i * kBox, &tm_a_hi, &full_bar[s], m0 + 32 * i, g.a_row0 + krow);
+            if (three) tma_load_2d(st + P::kABytes + i * kBox, &tm_a_lo, &full_bar[s], m0 + 32 * i, g.a_row0 + krow);
+          }
+          for (int i = 0; i < BN / 32; ++i) {
+            tma_load_2d(st + 2 * P::kABytes + i * kBox, &tm_b_hi, &full_bar[s], n0 + 32 * i, g.b_row0 + krow);
+            if (three)
+              tma_load_2d(st + 2 * P::kABytes + P::kBBytes + i * kBox, &tm_b_lo, &full_bar[s], n0 + 32 * i,
+                          g.b_row0 + krow);
+          }
         }
       }
     }
@@ -182,7 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (lane == 0) {
       // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
-                             (static_cast<uint32_t>(128 >> 4) << 24);
+                             (static_cast<uint32_t>(128 >> 4) << 24) | (MN ? ((1u << 15) | (1u << 16)) : 0u);
       const int nch = n_kb < kHiChunks ? n_kb : kHiChunks;
       uint32_t started = 0;  // bit i: accumulator i already holds data
       for (int kb = 0; kb < n_kb; ++kb) {
@@ -193,12 +228,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + s * P::kStageBytes);
-        const uint64_t a_hi = make_kmajor_desc(st), a_lo = make_kmajor_desc(st + P::kABytes);
-        const uint64_t b_hi = make_kmajor_desc(st + 2 * P::kABytes),
-                       b_lo = make_kmajor_desc(st + 2 * P::kABytes + P::kBBytes);
+        constexpr uint32_t kLbo = kBK * 128;
+        const uint64_t a_hi = MN ? make_mnmajor_desc(st, kLbo) : make_kmajor_desc(st);
+        const uint64_t a_lo = MN ? make_mnmajor_desc(st + P::kABytes, kLbo) : make_kmajor_desc(st + P::kABytes);
+        const uint64_t b_hi = MN ? make_mnmajor_desc(st + 2 * P::kABytes, kLbo) : make_kmajor_desc(st + 2 * P::kABytes);
+        const uint64_t b_lo = MN ? make_mnmajor_desc(st + 2 * P::kABytes + P::kBBytes, kLbo)
+                                 : make_kmajor_desc(st + 2 * P::kABytes + P::kBBytes);
 #pragma unroll
         for (int k = 0; k < kBK / 8; ++k) {
-          const uint64_t adv = static_cast<uint64_t>((k * 8 * 4) >> 4);  // 32 bytes per K=8 step inside the swizzle row
+          // K-major: 32 bytes per K=8 step inside the swizzle row; MN-major: one 1024-byte atom (8 k rows) per step
+          const uint64_t adv = static_cast<uint64_t>((MN ? k * 1024 : k * 8 * 4) >> 4);
           umma_tf32(d_hi, a_hi + adv, b_hi + adv, idesc, (started >> chunk) & 1u);
           started |= 1u << chunk;
           if (three) {
@@ -217,7 +256,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int row = m0 + q * 32 + lane;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const size_t rbase = static_cast<size_t>(row) * g.ldc;
+    const size_t rbase = static_cast<size_t>(row) * g.ldc + (MN ? static_cast<size_t>(blockIdx.z) * g.c_slice : 0);
 #pragma unroll 1
     const int nch = n_kb < kHiChunks ? n_kb : kHiChunks;
     const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
@@ -326,7 +365,8 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+int make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    bool mn_major) {
   EncodeTiledFn fn = encode_fn();
   HDPO_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   HDPO_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 4) % 16 == 0, "TMA needs 16-byte aligned rows");
@@ -335,7 +375,9 @@ int make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box_rows=%u)", static_cast<int>(r),
@@ -346,17 +388,18 @@ int make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t
   return HDPO_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool MN = false>
 static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                   const GemmTcArgs& g, void* stream) {
-  auto k = gemm_tc_kernel<BN, EPI>;
+  auto k = gemm_tc_kernel<BN, EPI, MN>;
   static bool configured = false;
   if (!configured) {
     HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlan<BN>::kTotal));
     configured = true;
   }
-  k<<<dim3(g.N / BN, g.M / 128), kThreads, SmemPlan<BN>::kTotal, static_cast<cudaStream_t>(stream)>>>(a_hi, a_lo, b_hi,
-                                                                                                      b_lo, g);
+  const unsigned nz = MN ? static_cast<unsigned>(g.K / g.k_per_split) : 1u;
+  k<<<dim3(g.N / BN, g.M / 128, nz), kThreads, SmemPlan<BN>::kTotal, static_cast<cudaStream_t>(stream)>>>(a_hi, a_lo,
+                                                                                                          b_hi, b_lo, g);
   count_launch();
   HDPO_LAUNCH_OK();
   return HDPO_OK;
@@ -383,6 +426,18 @@ int gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_
   HDPO_REQUIRE(g.n_pass == 1 || g.n_pass == 3, "n_pass must be 1 or 3");
   if (bn == 128) return launch_epi<128>(a_hi, a_lo, b_hi, b_lo, g, epi, stream);
   if (bn == 64) return launch_epi<64>(a_hi, a_lo, b_hi, b_lo, g, epi, stream);
+  set_error("unsupported BN %d", bn);
+  return HDPO_E_INVALID;
+}
+
+int gemm_wgrad(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+               const GemmTcArgs& g, int bn, void* stream) {
+  HDPO_REQUIRE(g.M % 128 == 0 && g.N % bn == 0 && g.k_per_split % kBK == 0 && g.k_per_split > 0 &&
+                   g.K % g.k_per_split == 0,
+               "tcgen05 weight-gradient GEMM shape %dx%dx%d (k_per_split %d) not tileable", g.M, g.N, g.K, g.k_per_split);
+  HDPO_REQUIRE(g.n_pass == 1 || g.n_pass == 3, "n_pass must be 1 or 3");
+  if (bn == 128) return launch<128, EPI_STORE, true>(a_hi, a_lo, b_hi, b_lo, g, stream);
+  if (bn == 64) return launch<64, EPI_STORE, true>(a_hi, a_lo, b_hi, b_lo, g, stream);
   set_error("unsupported BN %d", bn);
   return HDPO_E_INVALID;
 }
@@ -436,7 +491,67 @@ extern "C" int hdpo_debug_gemm_tc(const float* A, const float* B, float* C, int3
   return tc::gemm(ma_hi, ma_lo, mb_hi, mb_lo, g, tc::EPI_STORE, bn, stream);
 }
 
+// sum of the K-slice partials: C[i] = sum_z part[z*slice + i] (double accumulation)
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, int nz, size_t slice,
+                                                           float* __restrict__ C) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= slice) return;
+  double s = 0.0;
+  for (int z = 0; z < nz; ++z) s += static_cast<double>(part[z * slice + i]);
+  C[i] = static_cast<float>(s);
+}
+
+// Test hook (weight-gradient form): C[M,N] = A[K,M]^T * B[K,N] with A, B row-major [K][M] / [K][N] device arrays,
+// M % 128 == 0, N % 64 == 0, K % k_per_split == 0, k_per_split % 32 == 0.
+// scratch = 2*(K*M + K*N) + (K/k_per_split)*M*N floats.
+extern "C" int hdpo_debug_gemm_tc_wgrad(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
+                                        int32_t k_per_split, int32_t n_pass, float* scratch, void* stream) {
+  HDPO_REQUIRE(A && B && C && scratch, "null argument");
+  HDPO_REQUIRE(M % 128 == 0 && N % 64 == 0 && k_per_split > 0 && k_per_split % 32 == 0 && K % k_per_split == 0,
+               "shape not tileable");
+  const size_t na = static_cast<size_t>(K) * M, nb = static_cast<size_t>(K) * N;
+  float* a_hi = scratch;
+  float* a_lo = a_hi + na;
+  float* b_hi = a_lo + na;
+  float* b_lo = b_hi + nb;
+  float* part = b_lo + nb;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  tc::split_hi_lo_kernel<<<static_cast<unsigned>((na + 255) / 256), 256, 0, st>>>(A, a_hi, a_lo, na);
+  tc::split_hi_lo_kernel<<<static_cast<unsigned>((nb + 255) / 256), 256, 0, st>>>(B, b_hi, b_lo, nb);
+  count_launch();
+  count_launch();
+  HDPO_LAUNCH_OK();
+  const int bn = tc::pick_bn(N);
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = tc::make_tensor_map(&ma_hi, a_hi, K, M, M, 32, true))) return rc;
+  if ((rc = tc::make_tensor_map(&ma_lo, a_lo, K, M, M, 32, true))) return rc;
+  if ((rc = tc::make_tensor_map(&mb_hi, b_hi, K, N, N, 32, true))) return rc;
+  if ((rc = tc::make_tensor_map(&mb_lo, b_lo, K, N, N, 32, true))) return rc;
+  tc::GemmTcArgs g{};
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.k_per_split = k_per_split;
+  g.c_slice = static_cast<size_t>(M) * N;
+  g.n_pass = n_pass;
+  g.ldc = N;
+  g.c_full = part;
+  if ((rc = tc::gemm_wgrad(ma_hi, ma_lo, mb_hi, mb_lo, g, bn, stream))) return rc;
+  const size_t slice = static_cast<size_t>(M) * N;
+  sum_partials_kernel<<<static_cast<unsigned>((slice + 255) / 256), 256, 0, st>>>(part, K / k_per_split, slice, C);
+  count_launch();
+  HDPO_LAUNCH_OK();
+  return HDPO_OK;
+}
+
 #else  // HDPO_EMU: tensor cores cannot be emulated; the entry point exists and refuses.
+
+extern "C" int hdpo_debug_gemm_tc_wgrad(const float*, const float*, float*, int32_t, int32_t, int32_t, int32_t, int32_t,
+                                        float*, void*) {
+  hdpo::set_error("tcgen05 path is not available in the host-thread emulator");
+  return HDPO_E_INVALID;
+}
 
 extern "C" int hdpo_debug_gemm_tc(const float*, const float*, float*, int32_t, int32_t, int32_t, int32_t, float*, void*) {
   hdpo::set_error("tcgen05 path is not available in the host-thread emulator");

@@ -25,6 +25,8 @@ enum { EPI_FWD_HIDDEN = 0, EPI_FWD_OUT = 1, EPI_DGRAD_HIDDEN = 2, EPI_DGRAD_ACCU
 
 struct GemmTcArgs {
   int M, N, K;          // M % 128 == 0, N % BN == 0, K % 32 == 0
+  int k_per_split;      // weight-gradient form only: contraction rows handled by one blockIdx.z slice
+  size_t c_slice;       // weight-gradient form only: floats between the partial outputs of consecutive slices
   int n_pass;           // 3 = 3xTF32, 1 = single-pass TF32
   int a_row0, b_row0;   // row origin of this GEMM inside the A / B tensor maps (e.g. t * Bp for tapes)
   int ldc;              // leading dimension (floats) of every output / aux array
@@ -37,8 +39,15 @@ struct GemmTcArgs {
   const float* aux_lo;
 };
 
-// one 2-D fp32 tensor map over a row-major [rows][ld] array, box = [box_rows][32 floats], 128B swizzle
-int make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+// one 2-D fp32 tensor map over a row-major [rows][ld] array, box = [box_rows][32 floats]; 128B swizzle for K-major
+// operands, 128B swizzle with 32-byte atoms for the MN-major (weight-gradient) operands
+int make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    bool mn_major = false);
+
+// weight-gradient form: D[M,N] (per K slice) = sum_k A[k][m] * B[k][n] with A = [K][M], B = [K][N] row-major arrays
+// (tensor maps with box_rows = 32); partial slice z is written at c_full + z * c_slice.
+int gemm_wgrad(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+               const GemmTcArgs& g, int bn, void* stream);
 
 int gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
          const GemmTcArgs& g, int epi, int bn, void* stream);

@@ -51,6 +51,7 @@ bool supported(const HdpoRolloutDesc* d) {
 struct Plan {
   int n, B, Bp, T, save;
   int tc, n_pass;  // tensor-core mode: every GEMM operand is kept as a (tf32 hi, remainder lo) pair
+  int wg_kps, wg_splits;  // tensor-core weight gradient: contraction rows per partial slice, number of slices
   int w[HDPO_MAX_LAYERS + 1], wp[HDPO_MAX_LAYERS + 1];
   int gw[HDPO_MAX_LAYERS], gb[HDPO_MAX_LAYERS];  // offsets in the flat (state_dict) parameter vector
   int P;
@@ -118,7 +119,13 @@ static Plan make_plan(const HdpoRolloutDesc* d) {
     p.o_gz_lo[l] = (p.save && p.tc) ? take(tslots * p.act_stride[l]) : 0;
   }
   p.o_gx = p.save ? take(p.x_stride) : 0;
-  p.o_part = p.save ? take(static_cast<size_t>(kSplitK) * p.max_wk) : 0;
+  {
+    // short K slices keep the tensor core's truncating accumulation fp32-grade (see gemm_tc.cu)
+    const size_t rows = static_cast<size_t>(p.T) * p.Bp;
+    p.wg_kps = rows % 512 == 0 ? 512 : (rows % 256 == 0 ? 256 : 128);
+    p.wg_splits = static_cast<int>(rows / p.wg_kps);
+  }
+  p.o_part = p.save ? take(static_cast<size_t>(p.tc ? (p.wg_splits > kSplitK ? p.wg_splits : kSplitK) : kSplitK) * p.max_wk) : 0;
   int max_wp = 0;
   for (int i = 0; i <= p.n; ++i) max_wp = p.wp[i] > max_wp ? p.wp[i] : max_wp;
   p.o_bpart = p.save ? take(static_cast<size_t>(128) * max_wp) : 0;
@@ -387,11 +394,6 @@ __global__ void __launch_bounds__(256) init_state_kernel(const float* __restrict
     cost_b[i] = 0.f;
     if (report_b) report_b[i] = 0.f;
   }
-}
-
-__global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, size_t n) {
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) a[i] += b[i];
 }
 
 __global__ void __launch_bounds__(256) zero_kernel(float* __restrict__ p, size_t n) {
@@ -677,7 +679,8 @@ warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
 }
 
 // column sums of a [rows][ld] matrix (bias gradients), two deterministic stages
-__global__ void __launch_bounds__(256) colsum_stage1_kernel(const float* __restrict__ G, size_t rows, int ld, int n_chunks,
+__global__ void __launch_bounds__(256) colsum_stage1_kernel(const float* __restrict__ G, const float* __restrict__ G2,
+                                                            size_t rows, int ld, int n_chunks,
                                                             float* __restrict__ part) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int chunk = blockIdx.y;
@@ -685,20 +688,27 @@ __global__ void __launch_bounds__(256) colsum_stage1_kernel(const float* __restr
   const size_t per = (rows + n_chunks - 1) / n_chunks;
   const size_t r0 = chunk * per, r1 = (r0 + per < rows) ? r0 + per : rows;
   float s = 0.f;
-  for (size_t r = r0; r < r1; ++r) s += G[r * ld + col];
+  if (G2) {
+    for (size_t r = r0; r < r1; ++r) s += G[r * ld + col] + G2[r * ld + col];
+  } else {
+    for (size_t r = r0; r < r1; ++r) s += G[r * ld + col];
+  }
   part[static_cast<size_t>(chunk) * ld + col] = s;
 }
 
 // grad[gw + n*K + k] = sum_z part[z][n][k] ; grad[gb + n] = sum_chunks bpart[chunk][n]
-__global__ void __launch_bounds__(256) unpack_grad_kernel(const float* __restrict__ part, int splits, size_t slice, int Kp,
-                                                          int N, int K, const float* __restrict__ bpart, int n_chunks,
-                                                          int ldb, int gw, int gb, float* __restrict__ grad) {
+// `transposed`: the partial slices hold dW^T ([Kp rows][Np cols], leading dimension ldp = Np) instead of dW ([..][Kp])
+__global__ void __launch_bounds__(256) unpack_grad_kernel(const float* __restrict__ part, int splits, size_t slice, int ldp,
+                                                          int transposed, int N, int K, const float* __restrict__ bpart,
+                                                          int n_chunks, int ldb, int gw, int gb,
+                                                          float* __restrict__ grad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N * K) {
     const int n = i / K, k = i % K;
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[z * slice + static_cast<size_t>(n) * Kp + k];
-    grad[gw + i] = s;
+    const size_t at = transposed ? static_cast<size_t>(k) * ldp + n : static_cast<size_t>(n) * ldp + k;
+    double s = 0.0;  // hundreds of partial slices: accumulate in double so the reduction adds no fp32 error
+    for (int z = 0; z < splits; ++z) s += static_cast<double>(part[z * slice + at]);
+    grad[gw + i] = static_cast<float>(s);
   }
   if (i < N) {
     float s = 0.f;
@@ -1004,39 +1014,69 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
   while (splits > 1 && (rows / splits) % BK != 0) splits >>= 1;
   const size_t rows_per = rows / splits;
   for (int l = 0; l < p.n; ++l) {
-    GemmArgs g{};
-    g.A = wsf(ws, p.o_gz[l]);                                   // [rows][wp[l+1]] used transposed
-    g.A2 = p.tc ? wsf(ws, p.o_gz_lo[l]) : nullptr;
-    g.B = (l == 0) ? wsf(ws, p.o_X) : wsf(ws, p.o_act[l - 1]);  // [rows][wp[l]]  (X tape: first T blocks, full fp32)
-    g.B2 = (p.tc && l > 0) ? wsf(ws, p.o_act_lo[l - 1]) : nullptr;
-    g.C = wsf(ws, p.o_part);
-    g.M = p.wp[l + 1];
-    g.N = p.wp[l];
-    g.K = static_cast<int>(rows_per);
-    g.lda = p.wp[l + 1];
-    g.ldb = p.wp[l];
-    g.ldc = p.wp[l];
-    g.c_slice = static_cast<size_t>(p.wp[l + 1]) * p.wp[l];
-    g.a_kslice = rows_per * p.wp[l + 1];
-    g.b_kslice = rows_per * p.wp[l];
-    int rc = sgemm<true, false, EPI_SPLITK>(g, splits, stream);
-    if (rc) return rc;
-    const int n_chunks = 128;
-    if (p.tc) {  // bias gradient needs hi + lo: fold lo into hi in place first (gz tapes are dead after this layer)
-      auto ka = add_inplace_kernel;
-      const size_t cnt = rows * p.wp[l + 1];
-      HDPO_LAUNCH(ka, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream, wsf(ws, p.o_gz[l]),
-                  static_cast<const float*>(wsf(ws, p.o_gz_lo[l])), cnt);
-      HDPO_LAUNCH_OK();
+    const float* gz_hi = wsf(ws, p.o_gz[l]);
+    const float* gz_lo = p.tc ? wsf(ws, p.o_gz_lo[l]) : nullptr;
+    int used_splits = splits, transposed = 0, ldp = p.wp[l];
+    const size_t c_slice = static_cast<size_t>(p.wp[l + 1]) * p.wp[l];
+    bool done = false;
+#ifndef HDPO_EMU
+    if (p.tc && (p.wp[l + 1] % 128 == 0 || p.wp[l] % 128 == 0)) {
+      // tcgen05 MN-major form straight from the tapes; when the output width is not a multiple of the 128-row MMA
+      // tile (e.g. the 64-padded last layer) compute dW^T = in^T gz instead and transpose while unpacking.
+      transposed = p.wp[l + 1] % 128 != 0;
+      const float* in_hi = (l == 0) ? wsf(ws, p.o_X_hi) : wsf(ws, p.o_act[l - 1]);
+      const float* in_lo = (l == 0) ? wsf(ws, p.o_X_lo) : wsf(ws, p.o_act_lo[l - 1]);
+      MapPair mg, mi;
+      int rc = tc::make_tensor_map(&mg.hi, gz_hi, rows, p.wp[l + 1], p.wp[l + 1], 32, true);
+      if (!rc) rc = tc::make_tensor_map(&mg.lo, gz_lo, rows, p.wp[l + 1], p.wp[l + 1], 32, true);
+      if (!rc) rc = tc::make_tensor_map(&mi.hi, in_hi, rows, p.wp[l], p.wp[l], 32, true);
+      if (!rc) rc = tc::make_tensor_map(&mi.lo, in_lo, rows, p.wp[l], p.wp[l], 32, true);
+      if (rc) return rc;
+      tc::GemmTcArgs g{};
+      g.M = transposed ? p.wp[l] : p.wp[l + 1];
+      g.N = transposed ? p.wp[l + 1] : p.wp[l];
+      g.K = static_cast<int>(rows);
+      g.k_per_split = p.wg_kps;
+      g.c_slice = c_slice;
+      g.n_pass = p.n_pass;
+      g.ldc = g.N;
+      g.c_full = wsf(ws, p.o_part);
+      rc = transposed ? tc::gemm_wgrad(mi.hi, mi.lo, mg.hi, mg.lo, g, tc::pick_bn(g.N), stream)
+                      : tc::gemm_wgrad(mg.hi, mg.lo, mi.hi, mi.lo, g, tc::pick_bn(g.N), stream);
+      if (rc) return rc;
+      used_splits = p.wg_splits;
+      ldp = g.N;
+      done = true;
     }
+#endif
+    if (!done) {
+      GemmArgs g{};
+      g.A = gz_hi;  // [rows][wp[l+1]] used transposed
+      g.A2 = gz_lo;
+      g.B = (l == 0) ? wsf(ws, p.o_X) : wsf(ws, p.o_act[l - 1]);  // [rows][wp[l]]  (X tape: first T blocks, full fp32)
+      g.B2 = (p.tc && l > 0) ? wsf(ws, p.o_act_lo[l - 1]) : nullptr;
+      g.C = wsf(ws, p.o_part);
+      g.M = p.wp[l + 1];
+      g.N = p.wp[l];
+      g.K = static_cast<int>(rows_per);
+      g.lda = p.wp[l + 1];
+      g.ldb = p.wp[l];
+      g.ldc = p.wp[l];
+      g.c_slice = c_slice;
+      g.a_kslice = rows_per * p.wp[l + 1];
+      g.b_kslice = rows_per * p.wp[l];
+      int rc = sgemm<true, false, EPI_SPLITK>(g, splits, stream);
+      if (rc) return rc;
+    }
+    const int n_chunks = 128;
     auto k1 = colsum_stage1_kernel;
-    HDPO_LAUNCH(k1, dim3(ceil_div(p.wp[l + 1], 256), n_chunks), 256, 0, stream, static_cast<const float*>(g.A), rows,
-                p.wp[l + 1], n_chunks, wsf(ws, p.o_bpart));
+    HDPO_LAUNCH(k1, dim3(ceil_div(p.wp[l + 1], 256), n_chunks), 256, 0, stream, gz_hi, gz_lo, rows, p.wp[l + 1], n_chunks,
+                wsf(ws, p.o_bpart));
     HDPO_LAUNCH_OK();
     auto k2 = unpack_grad_kernel;
-    HDPO_LAUNCH(k2, ceil_div(p.w[l + 1] * p.w[l], 256), 256, 0, stream, static_cast<const float*>(g.C), splits, g.c_slice,
-                p.wp[l], p.w[l + 1], p.w[l], static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1],
-                p.gw[l], p.gb[l], grad_params);
+    HDPO_LAUNCH(k2, ceil_div(p.w[l + 1] * p.w[l], 256), 256, 0, stream, static_cast<const float*>(wsf(ws, p.o_part)),
+                used_splits, c_slice, ldp, transposed, p.w[l + 1], p.w[l],
+                static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1], p.gw[l], p.gb[l], grad_params);
     HDPO_LAUNCH_OK();
   }
   return HDPO_OK;

@@ -40,3 +40,27 @@ def test_gemm_tc_rejects_untileable_shapes():
     z = be.zeros(16)
     assert be.lib.hdpo_debug_gemm_tc(be.ptr(z), be.ptr(z), be.ptr(z), 100, 64, 32, 3, be.ptr(z), be.stream) != 0
     assert b"tileable" in be.lib.hdpo_last_error()
+
+
+@pytest.mark.parametrize("M,N,Kd,kps", [(128, 64, 64, 32), (128, 128, 256, 128), (256, 192, 1024, 256),
+                                        (512, 512, 4096, 1024), (64 * 2, 64, 2048, 1024)])
+def test_gemm_tc_weight_gradient_form(M, N, Kd, kps):
+    """MN-major operands straight from [row][feature] tapes: C = A^T B with split-K partial slices."""
+    be = D.CudaBackend()
+    rng = np.random.RandomState(M + N + Kd)
+    A = rng.randn(Kd, M).astype(np.float32)
+    B = (rng.randn(Kd, N) / np.sqrt(Kd)).astype(np.float32)
+    want = A.astype(np.float64).T @ B.astype(np.float64)
+    scale = np.abs(want).max()
+    fp32_err = np.abs((A.T @ B).astype(np.float64) - want).max() / scale
+    a, b = be.put(A), be.put(B)
+    scratch = be.zeros(2 * (Kd * M + Kd * N) + (Kd // kps) * M * N)
+    for n_pass, tol in ((3, max(2e-6, 4 * fp32_err)), (1, 2e-3)):
+        c = be.zeros((M, N))
+        rc = be.lib.hdpo_debug_gemm_tc_wgrad(be.ptr(a), be.ptr(b), be.ptr(c), M, N, Kd, kps, n_pass, be.ptr(scratch),
+                                             be.stream)
+        K.check(be.lib, rc, "hdpo_debug_gemm_tc_wgrad")
+        be.sync()
+        err = np.abs(be.get(c).astype(np.float64) - want).max() / scale
+        print(f"gemm_tc wgrad {M}x{N}x{Kd}/{kps} n_pass={n_pass}: max err/scale {err:.3e} (fp32 numpy: {fp32_err:.3e})")
+        assert err < tol, (n_pass, err)
