@@ -128,7 +128,11 @@ constexpr int kHiChunks = kAccums - 1;
 
 template <int BN>
 struct SmemPlan {
+#ifdef HDPO_TC_BN64_EXPERIMENT
+  static constexpr int kStages = (BN == 128) ? 3 : 2;   // 2 x 48 KB: two CTAs per SM overlap mainloop and epilogue
+#else
   static constexpr int kStages = (BN == 128) ? 3 : 4;
+#endif
   static constexpr int kABytes = 128 * kBK * 4;
   static constexpr int kBBytes = BN * kBK * 4;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
@@ -139,8 +143,13 @@ struct SmemPlan {
 // MN = true : D[M,N] = sum_k A[k][m] B[k][n], operands MN-major (rows = k, contiguous m / n): the weight-gradient
 //             form dW = gz^T h straight from the [row][feature] tapes; blockIdx.z selects a K range of k_per_split rows
 //             and writes its own partial slice (short ranges keep the truncating accumulation fp32-grade).
+#ifdef HDPO_TC_BN64_EXPERIMENT
+#define HDPO_TC_MIN_CTAS(BN) ((BN) == 64 ? 2 : 1)
+#else
+#define HDPO_TC_MIN_CTAS(BN) 1
+#endif
 template <int BN, int EPI, bool MN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, HDPO_TC_MIN_CTAS(BN))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, GemmTcArgs g) {
   using P = SmemPlan<BN>;

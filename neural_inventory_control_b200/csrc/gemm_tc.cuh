@@ -53,7 +53,11 @@ int gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_
          const GemmTcArgs& g, int epi, int bn, void* stream);
 
 constexpr int kBoxRowsA = 128;
+#ifdef HDPO_TC_BN64_EXPERIMENT
+inline int pick_bn(int) { return 64; }
+#else
 inline int pick_bn(int N) { return (N % 128 == 0) ? 128 : 64; }
+#endif
 
 }  // namespace tc
 }  // namespace hdpo

@@ -152,3 +152,51 @@ def test_torch_port_matches_reference_fp64(name):
     names = [f"net.master.{i}.{wb}" for i in idxs for wb in ("weight", "bias")]
     for n, gr in zip(names, grads):
         assert G.rel_l2(gr.numpy(), ref[f"grad/{n}"]) < 1e-8, n
+
+
+def test_symmetry_aware_oracle_adjoint_matches_torch_autograd():
+    """SymmetryAware has no executable reference (recovered from stale bytecode), so the explicit
+    adjoint of the oracle restatement is cross-checked against torch autograd through this repo's torch policy
+    class + the pinned torch port of the simulator, in float64 (parity 'restatement vs restatement')."""
+    import copy
+    import os
+    import torch
+    import yaml
+    from neural_inventory_control_b200.neural_networks import NeuralNetworkCreator
+    from oracle import torch_port as TP
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    meta, g = G.load("rollout", "one_warehouse_s5")
+    p = yaml.safe_load(open(os.path.join(root, "config_files/policies_and_hyperparams/symmetry_aware.yml")))
+    p["nn_params"]["neurons_per_hidden_layer"] = {"context": [24], "store": [16, 16], "warehouse": [8, 8]}
+    p["nn_params"]["output_sizes"]["context"] = 12
+
+    class Scen:
+        problem_params = meta["problem_params"]
+        store_params = {"demand": {"mean": [meta["warehouse_upper_bound"] / 4]}}
+    torch.manual_seed(3)
+    model = NeuralNetworkCreator().create_neural_network(Scen(), p["nn_params"], device="cpu")
+    data = {k: torch.tensor(v[:16]).double() for k, v in g["data"].items()}
+
+    def obs_of(state):
+        return {"store_inventories": state["store"], "warehouse_inventories": state["wh"], "mean": data["mean"],
+                "std": data["std"], "underage_costs": data["underage_costs"], "lead_times": data["lead_times"]}
+    state = {"store": data["initial_inventories"], "wh": data["initial_warehouse_inventories"]}
+    model({k: v.float() for k, v in obs_of(state).items()})  # materialise the lazy layers
+    model = model.double()
+    model.warehouse_upper_bound = model.warehouse_upper_bound.double()
+    pb = dict(meta["problem_params"], period_shift=0)
+    T, total = 10, 0
+    for t in range(T):
+        state, r = TP.env_step(pb, state, model(obs_of(state)), data, t)
+        total = total + r.sum()
+    (total / (16 * T * pb["n_stores"])).backward()
+    sd = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+    a = p["nn_params"]
+    nets = {m: O.mlp_from_state_dict(sd, m, a["inner_layer_activations"][m], a["output_layer_activation"][m])
+            for m in ("context", "store", "warehouse")}
+    pol = O.Policy("symmetry_aware", nets, float(model.warehouse_upper_bound[0]), prop_eps=1e-15)
+    fwd, grads = O.rollout_grad(pol, G.problem_from_meta(meta), {k: v.numpy() for k, v in data.items()}, T)
+    assert abs(float(total.detach()) / fwd["total"] - 1) < 1e-12
+    flat = O.flatten_grads(pol, grads)
+    for k, v in model.named_parameters():
+        assert G.rel_l2(v.grad.numpy(), flat[k]) < 1e-10, k

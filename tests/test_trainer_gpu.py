@@ -168,3 +168,45 @@ def test_training_loop_reduces_loss_and_eval_modes_run():
     loss, report = tr.test(PolicyLoss(), sim, model, loaders, opt, s["problem_params"], obs_params, pbd,
                            discrete_allocation=True)
     assert np.isfinite(loss) and np.isfinite(report) and report > 0
+
+
+def test_symmetry_aware_generic_path_matches_oracle():
+    """The re-created SymmetryAware policy (absent from the reference snapshot's sources) through the
+    GENERIC path (torch policy + K3 step kernels + torch autograd) against the float64 oracle restatement of the same
+    recovered forward: costs and all three nets' gradients."""
+    from neural_inventory_control_b200.environment import Simulator
+    from neural_inventory_control_b200.loss_functions import PolicyLoss
+    from neural_inventory_control_b200.neural_networks import NeuralNetworkCreator
+    from neural_inventory_control_b200.trainer import Trainer
+    from oracle import hdpo_oracle as O
+    dev = "cuda:0"
+    meta, g = G.load("rollout", "one_warehouse_s5")
+    p = copy.deepcopy(_cfg("policies_and_hyperparams", "symmetry_aware"))
+    p["nn_params"]["neurons_per_hidden_layer"] = {"context": [24], "store": [16, 16], "warehouse": [8, 8]}
+    p["nn_params"]["output_sizes"]["context"] = 12
+    pp = meta["problem_params"]
+    wub = meta["warehouse_upper_bound"]
+    scen = _FakeScenario(pp, {"demand": {"mean": [wub / 4]}})
+    torch.manual_seed(3)
+    model = NeuralNetworkCreator().create_neural_network(scen, p["nn_params"], device=dev)
+    data = {k: torch.tensor(v[:16], device=dev) for k, v in g["data"].items()}
+    obs_params = _obs_params(meta)
+    tr, sim = Trainer(device=dev), Simulator(device=dev)
+    tr.use_fused = False
+    T = 10
+    total, report = tr.simulate_batch(PolicyLoss(), sim, model, T, pp, data, obs_params, 3)
+    assert tr.last_path == "generic"
+    B = 16
+    (total / (B * T * pp["n_stores"])).backward()
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    acts = p["nn_params"]
+    nets = {m: O.mlp_from_state_dict(sd, m, acts["inner_layer_activations"][m], acts["output_layer_activation"][m]
+                                     ).astype(np.float64) for m in ("context", "store", "warehouse")}
+    pol = O.Policy("symmetry_aware", nets, float(model.warehouse_upper_bound[0]), prop_eps=1e-15)
+    d64 = {k: v[:16].astype(np.float64) for k, v in g["data"].items()}
+    fwd, grads = O.rollout_grad(pol, G.problem_from_meta(meta), d64, T)
+    assert abs(float(total) / fwd["total"] - 1) < 1e-5
+    assert abs(float(report) / fwd["reward_tb"][3:].sum() - 1) < 1e-5
+    flat = O.flatten_grads(pol, grads)
+    for k, v in model.named_parameters():
+        assert G.rel_l2(v.grad.cpu().numpy(), flat[k]) < 5e-5, k
