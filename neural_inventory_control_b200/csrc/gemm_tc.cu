@@ -71,15 +71,19 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+// asynchronous TMEM load of 16 columns of this warp's 32 lanes; results are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
       "[%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// programmatic dependent launch: wait for the producing grid's memory / allow the dependent grid's prologue to start
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ float tf32_hi(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -114,9 +118,10 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// kernel: 6 warps = TMA producer | MMA issuer (+TMEM owner) | 4 epilogue warps (128 rows of the tile)
+// kernel: 10 warps = TMA producer | MMA issuer (+TMEM owner) | 8 epilogue warps (128 rows x 2 column halves)
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                  // two warps per TMEM lane quadrant, each takes half of the tile's columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA producer warp + MMA warp + epilogue warps
 constexpr int kBK = 32;  // floats per K block = one 128-byte swizzle row
 // Accumulator splitting. The tensor core adds each K=8 product block into the fp32 accumulator with truncation, so
 // the error of ONE accumulator grows linearly with the number of tcgen05.mma issued into it (measured: 4e-6
@@ -187,6 +192,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  // everything above overlapped the tail of the previous kernel in the stream (PDL); from here on we read its output
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -261,29 +269,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
   } else {
     // ===== epilogue: warp q = warp % 4 owns TMEM lanes [32q, 32q+32) = tile rows =====
-    const int q = warp & 3;
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;       // which half of the tile's columns this warp drains
     const int row = m0 + q * 32 + lane;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const size_t rbase = static_cast<size_t>(row) * g.ldc + (MN ? static_cast<size_t>(blockIdx.z) * g.c_slice : 0);
-#pragma unroll 1
     const int nch = n_kb < kHiChunks ? n_kb : kHiChunks;
     const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t r[16];
+#pragma unroll 1
+    for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
+      uint32_t r0[16], r1[16], r2[16], r3[16];
       float v[16];
-      tmem_ld16(lane_base + BN + c0, r);  // hi*hi, first K chunk
+      // issue every accumulator's load for this column chunk, then wait once
+      tmem_ld16_async(lane_base + BN + c0, r0);  // hi*hi, first K chunk
+      if (nch > 1) tmem_ld16_async(lane_base + 2 * BN + c0, r1);
+      if (nch > 2) tmem_ld16_async(lane_base + 3 * BN + c0, r2);
+      if (three) tmem_ld16_async(lane_base + c0, r3);  // cross terms
+      tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-      for (int c = 1; c < nch; ++c) {
-        tmem_ld16(lane_base + (1 + c) * BN + c0, r);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
-      }
-      if (three) {
-        tmem_ld16(lane_base + c0, r);  // cross terms
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
+      for (int j = 0; j < 16; ++j) {
+        float a = __uint_as_float(r0[j]);
+        if (nch > 1) a += __uint_as_float(r1[j]);
+        if (nch > 2) a += __uint_as_float(r2[j]);
+        if (three) a += __uint_as_float(r3[j]);
+        v[j] = a;
       }
       const int n = n0 + c0;
       if (EPI == EPI_FWD_HIDDEN || EPI == EPI_FWD_OUT) {
@@ -407,8 +417,17 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtens
     configured = true;
   }
   const unsigned nz = MN ? static_cast<unsigned>(g.K / g.k_per_split) : 1u;
-  k<<<dim3(g.N / BN, g.M / 128, nz), kThreads, SmemPlan<BN>::kTotal, static_cast<cudaStream_t>(stream)>>>(a_hi, a_lo,
-                                                                                                          b_hi, b_lo, g);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(g.N / BN, g.M / 128, nz);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = SmemPlan<BN>::kTotal;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: prologue overlaps the previous kernel's tail
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  HDPO_CUDA_OK(cudaLaunchKernelEx(&cfg, k, a_hi, a_lo, b_hi, b_lo, g));
   count_launch();
   HDPO_LAUNCH_OK();
   return HDPO_OK;
