@@ -110,6 +110,22 @@ __device__ __forceinline__ void dispatch_act(int act, F&& f) {
   }
 }
 
+// Packed fp32 FMA (Blackwell: fma.rn.f32x2 -> SASS FFMA2): two independent round-to-nearest FMAs per issued
+// instruction, bit-identical to two fmaf() calls. The small-net kernels are issue-bound (FMA ~50 % of the issued
+// instructions), so halving the FMA instruction count is a direct win.
+__device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
+#ifdef HDPO_EMU
+  d.x = fmaf(a.x, b.x, d.x);
+  d.y = fmaf(a.y, b.y, d.y);
+#else
+  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+  const unsigned long long aa = *reinterpret_cast<const unsigned long long*>(&a);
+  const unsigned long long bb = *reinterpret_cast<const unsigned long long*>(&b);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+  d = *reinterpret_cast<float2*>(&dd);
+#endif
+}
+
 // clip(x, min=0) and its torch sub-gradient (1 for x >= 0, incl. x == 0)
 __device__ __forceinline__ float relu0(float x) { return fmaxf(x, 0.f); }
 __device__ __forceinline__ float ge0(float x) { return x >= 0.f ? 1.f : 0.f; }

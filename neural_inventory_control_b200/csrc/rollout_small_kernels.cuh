@@ -74,19 +74,18 @@ static __device__ void stage_weights(const Cfg& c, const float* __restrict__ par
 
 __device__ __forceinline__ float f4c(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
-// acc[j][n] = bias[n] + sum_k Wt[k][n] * in_j[k]   for NS scenario rows handled by this lane
+// acc[j][n] = bias[n] + sum_k Wt[k][n] * in_j[k]   for NS scenario rows handled by this lane.
+// Accumulators are float2 pairs (n even, n odd) fed by packed FFMA2: per k and scenario 16 FFMA2 + one (x,x) pack.
 template <int NS>
 __device__ __forceinline__ void layer_fwd(const float* __restrict__ Wt, const float* __restrict__ bias, int K4,
-                                          const float* const (&in)[NS], float (&acc)[NS][H]) {
+                                          const float* const (&in)[NS], float2 (&acc)[NS][H / 2]) {
 #pragma unroll
   for (int n4 = 0; n4 < H / 4; ++n4) {
     const float4 bv = reinterpret_cast<const float4*>(bias)[n4];
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-      acc[j][4 * n4 + 0] = bv.x;
-      acc[j][4 * n4 + 1] = bv.y;
-      acc[j][4 * n4 + 2] = bv.z;
-      acc[j][4 * n4 + 3] = bv.w;
+      acc[j][2 * n4 + 0] = make_float2(bv.x, bv.y);
+      acc[j][2 * n4 + 1] = make_float2(bv.z, bv.w);
     }
   }
   for (int k4 = 0; k4 < K4; ++k4) {
@@ -96,16 +95,20 @@ __device__ __forceinline__ void layer_fwd(const float* __restrict__ Wt, const fl
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const float4* w = reinterpret_cast<const float4*>(Wt + (4 * k4 + kk) * H);
+      float2 xx[NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const float xk = f4c(xv[j], kk);
+        xx[j] = make_float2(xk, xk);
+      }
 #pragma unroll
       for (int n4 = 0; n4 < H / 4; ++n4) {
         const float4 wv = w[n4];
+        const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-          const float xk = f4c(xv[j], kk);
-          acc[j][4 * n4 + 0] = fmaf(wv.x, xk, acc[j][4 * n4 + 0]);
-          acc[j][4 * n4 + 1] = fmaf(wv.y, xk, acc[j][4 * n4 + 1]);
-          acc[j][4 * n4 + 2] = fmaf(wv.z, xk, acc[j][4 * n4 + 2]);
-          acc[j][4 * n4 + 3] = fmaf(wv.w, xk, acc[j][4 * n4 + 3]);
+          ffma2(acc[j][2 * n4 + 0], w01, xx[j]);
+          ffma2(acc[j][2 * n4 + 1], w23, xx[j]);
         }
       }
     }
@@ -113,16 +116,16 @@ __device__ __forceinline__ void layer_fwd(const float* __restrict__ Wt, const fl
 }
 
 // apply the hidden activation and store the row
-__device__ __forceinline__ void act_store_row(int act, const float (&acc)[H], float* __restrict__ row) {
+__device__ __forceinline__ void act_store_row(int act, const float2 (&acc)[H / 2], float* __restrict__ row) {
   dispatch_act(act, [&](auto tag) {
     constexpr int ACT = decltype(tag)::value;
 #pragma unroll
     for (int n4 = 0; n4 < H / 4; ++n4) {
       float4 v;
-      v.x = act_fwd_t<ACT>(acc[4 * n4 + 0]);
-      v.y = act_fwd_t<ACT>(acc[4 * n4 + 1]);
-      v.z = act_fwd_t<ACT>(acc[4 * n4 + 2]);
-      v.w = act_fwd_t<ACT>(acc[4 * n4 + 3]);
+      v.x = act_fwd_t<ACT>(acc[2 * n4 + 0].x);
+      v.y = act_fwd_t<ACT>(acc[2 * n4 + 0].y);
+      v.z = act_fwd_t<ACT>(acc[2 * n4 + 1].x);
+      v.w = act_fwd_t<ACT>(acc[2 * n4 + 1].y);
       reinterpret_cast<float4*>(row)[n4] = v;
     }
   });
@@ -156,7 +159,7 @@ __device__ __forceinline__ void out_layer_fwd(const Cfg& c, const float* __restr
 template <int NS>
 __device__ __forceinline__ void mlp_fwd(const Cfg& c, const float* __restrict__ Ws, const float* const (&xrow)[NS],
                                         float* const (&hrow)[NS], int h_layer_stride, float (&y)[NS][kMaxOut]) {
-  float acc[NS][H];
+  float2 acc[NS][H / 2];
   layer_fwd<NS>(Ws + c.s_wt0, Ws + c.s_b0, c.IN4 / 4, xrow, acc);
 #pragma unroll
   for (int j = 0; j < NS; ++j) act_store_row(c.hidden_act, acc[j], hrow[j]);
@@ -479,11 +482,34 @@ static __global__ void __launch_bounds__(1024) totals_kernel(const float* __rest
 // K2: reverse-time adjoint
 // ------------------------------------------------------------------------------------------------------------
 
-// lane tile of an [H x (4*KQ)] weight gradient: rows 4*ni..4*ni+3, columns ki*KQ..ki*KQ+KQ-1
+// lane tile of an [H x (4*KQ)] weight gradient: rows 4*ni..4*ni+3, columns ki*KQ..ki*KQ+KQ-1.
+// Column pairs are accumulated with packed FFMA2 ((g_i, g_i) x (x_q, x_q+1)); an odd KQ keeps one scalar tail column.
+template <int KQ>
+struct WgradAcc {            // per-lane 4 x KQ tile of dW kept in registers for the whole kernel
+  static constexpr int KP = KQ / 2;
+  float2 pair[4][KP > 0 ? KP : 1];
+  float tail[4];             // last column when KQ is odd
+  float bias[4];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int q = 0; q < (KP > 0 ? KP : 1); ++q) pair[i][q] = make_float2(0.f, 0.f);
+      tail[i] = 0.f;
+      bias[i] = 0.f;
+    }
+  }
+  __device__ __forceinline__ float at(int i, int q) const {
+    if ((KQ & 1) && q == KQ - 1) return tail[i];
+    return (q & 1) ? pair[i][q >> 1].y : pair[i][q >> 1].x;
+  }
+};
+
 template <int KQ>
 __device__ __forceinline__ void wgrad_tile(const float* __restrict__ G, int gs, const float* __restrict__ X, int xs,
-                                           int lane, float (&acc)[4][KQ], float (&bacc)[4]) {
+                                           int lane, WgradAcc<KQ>& a) {
   const int ni = lane >> 2, ki = lane & 3;
+  constexpr int KP = KQ / 2;
   for (int cidx = 0; cidx < 32; ++cidx) {
     const float4 g = *reinterpret_cast<const float4*>(G + cidx * gs + 4 * ni);
     float xv[KQ];
@@ -500,33 +526,40 @@ __device__ __forceinline__ void wgrad_tile(const float* __restrict__ G, int gs, 
 #pragma unroll
       for (int q = 0; q < KQ; ++q) xv[q] = X[cidx * xs + ki * KQ + q];
     }
+    const float2 g0 = make_float2(g.x, g.x), g1 = make_float2(g.y, g.y), g2 = make_float2(g.z, g.z),
+                 g3 = make_float2(g.w, g.w);
 #pragma unroll
-    for (int q = 0; q < KQ; ++q) {
-      acc[0][q] = fmaf(g.x, xv[q], acc[0][q]);
-      acc[1][q] = fmaf(g.y, xv[q], acc[1][q]);
-      acc[2][q] = fmaf(g.z, xv[q], acc[2][q]);
-      acc[3][q] = fmaf(g.w, xv[q], acc[3][q]);
+    for (int q = 0; q < KP; ++q) {
+      const float2 x2 = make_float2(xv[2 * q], xv[2 * q + 1]);
+      ffma2(a.pair[0][q], g0, x2);
+      ffma2(a.pair[1][q], g1, x2);
+      ffma2(a.pair[2][q], g2, x2);
+      ffma2(a.pair[3][q], g3, x2);
     }
-    bacc[0] += g.x;
-    bacc[1] += g.y;
-    bacc[2] += g.z;
-    bacc[3] += g.w;
+    if (KQ & 1) {
+      a.tail[0] = fmaf(g.x, xv[KQ - 1], a.tail[0]);
+      a.tail[1] = fmaf(g.y, xv[KQ - 1], a.tail[1]);
+      a.tail[2] = fmaf(g.z, xv[KQ - 1], a.tail[2]);
+      a.tail[3] = fmaf(g.w, xv[KQ - 1], a.tail[3]);
+    }
+    a.bias[0] += g.x;
+    a.bias[1] += g.y;
+    a.bias[2] += g.z;
+    a.bias[3] += g.w;
   }
 }
 
-// g_in[k] = sum_n Wt[k][n] * gz[n]  (thread-local dgrad), k = 0..K-1
-__device__ __forceinline__ float dgrad_dot(const float* __restrict__ Wt_row, const float (&gz)[H]) {
+// g_in[k] = sum_n Wt[k][n] * gz[n]  (thread-local dgrad), k = 0..K-1; gz held as float2 pairs, packed FFMA2
+__device__ __forceinline__ float dgrad_dot(const float* __restrict__ Wt_row, const float2 (&gz)[H / 2]) {
   const float4* w = reinterpret_cast<const float4*>(Wt_row);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int n4 = 0; n4 < H / 4; ++n4) {
     const float4 wv = w[n4];
-    s0 = fmaf(wv.x, gz[4 * n4 + 0], s0);
-    s1 = fmaf(wv.y, gz[4 * n4 + 1], s1);
-    s2 = fmaf(wv.z, gz[4 * n4 + 2], s2);
-    s3 = fmaf(wv.w, gz[4 * n4 + 3], s3);
+    ffma2(s01, make_float2(wv.x, wv.y), gz[2 * n4 + 0]);
+    ffma2(s23, make_float2(wv.z, wv.w), gz[2 * n4 + 1]);
   }
-  return (s0 + s1) + (s2 + s3);
+  return (s01.x + s01.y) + (s23.x + s23.y);
 }
 
 template <int ARCH, int KQ0, int NHH>
@@ -550,21 +583,12 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
   constexpr int HL = 32 * HS;  // layer stride inside Hb
 
   // register-resident parameter-gradient tiles
-  float a0[4][KQ0], b0[4];
-  float ah[NHH > 0 ? NHH : 1][4][8], bh[NHH > 0 ? NHH : 1][4];
+  WgradAcc<KQ0> a0;
+  WgradAcc<8> ah[NHH > 0 ? NHH : 1];
   float ao[kMaxOut], bo = 0.f;  // lane = k for ao; lane = o for bo
+  a0.clear();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    b0[i] = 0.f;
-#pragma unroll
-    for (int q = 0; q < KQ0; ++q) a0[i][q] = 0.f;
-#pragma unroll
-    for (int l = 0; l < (NHH > 0 ? NHH : 1); ++l) {
-      bh[l][i] = 0.f;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) ah[l][i][q] = 0.f;
-    }
-  }
+  for (int l = 0; l < (NHH > 0 ? NHH : 1); ++l) ah[l].clear();
 #pragma unroll
   for (int o = 0; o < kMaxOut; ++o) ao[o] = 0.f;
 
@@ -626,7 +650,7 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
       }
       __syncwarp();
       // thread-local: g_h_last[k] = sum_o Wo[o][k] gy[o]; gz = g_h * act'(h) -> overwrite the activation row
-      float gz[H];
+      float2 gz[H / 2];
       {
         float* hl = hrow + NHH * HL;
         dispatch_act(c.hidden_act, [&](auto tag) {
@@ -645,11 +669,10 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
               }
             }
             const float4 hv = reinterpret_cast<const float4*>(hl)[k4];
-            gz[4 * k4 + 0] = acc4.x * act_grad_out_t<ACT>(hv.x);
-            gz[4 * k4 + 1] = acc4.y * act_grad_out_t<ACT>(hv.y);
-            gz[4 * k4 + 2] = acc4.z * act_grad_out_t<ACT>(hv.z);
-            gz[4 * k4 + 3] = acc4.w * act_grad_out_t<ACT>(hv.w);
-            reinterpret_cast<float4*>(hl)[k4] = make_float4(gz[4 * k4], gz[4 * k4 + 1], gz[4 * k4 + 2], gz[4 * k4 + 3]);
+            gz[2 * k4 + 0] = make_float2(acc4.x * act_grad_out_t<ACT>(hv.x), acc4.y * act_grad_out_t<ACT>(hv.y));
+            gz[2 * k4 + 1] = make_float2(acc4.z * act_grad_out_t<ACT>(hv.z), acc4.w * act_grad_out_t<ACT>(hv.w));
+            reinterpret_cast<float4*>(hl)[k4] =
+                make_float4(gz[2 * k4].x, gz[2 * k4].y, gz[2 * k4 + 1].x, gz[2 * k4 + 1].y);
           }
         });
       }
@@ -657,7 +680,7 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
 #pragma unroll
       for (int l = NHH - 1; l >= 0; --l) {
         __syncwarp();
-        wgrad_tile<8>(Hb + (l + 1) * HL, HS, Hb + l * HL, HS, lane, ah[l], bh[l]);
+        wgrad_tile<8>(Hb + (l + 1) * HL, HS, Hb + l * HL, HS, lane, ah[l]);
         __syncwarp();
         float* hp = hrow + l * HL;
         const float* Wt = Ws + c.s_wth[l];
@@ -678,15 +701,13 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
 #pragma unroll
         for (int k4 = 0; k4 < H / 4; ++k4) {
           const float4 v = reinterpret_cast<const float4*>(hp)[k4];
-          gz[4 * k4 + 0] = v.x;
-          gz[4 * k4 + 1] = v.y;
-          gz[4 * k4 + 2] = v.z;
-          gz[4 * k4 + 3] = v.w;
+          gz[2 * k4 + 0] = make_float2(v.x, v.y);
+          gz[2 * k4 + 1] = make_float2(v.z, v.w);
         }
       }
       // F. layer 0: dW0 += gz0^T x ; state adjoint += W0^T gz0 unless the input was detached
       __syncwarp();
-      wgrad_tile<KQ0>(Hb, HS, Xw, c.XS, lane, a0, b0);
+      wgrad_tile<KQ0>(Hb, HS, Xw, c.XS, lane, a0);
       __syncwarp();
       if (!c.detach_input) {
         const float* Wt0 = Ws + c.s_wt0;
@@ -706,9 +727,9 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
 #pragma unroll
         for (int q = 0; q < KQ0; ++q) {
           const int k = ki * KQ0 + q;
-          if (k < c.IN) out[c.gw[0] + n * c.IN + k] = a0[i][q];
+          if (k < c.IN) out[c.gw[0] + n * c.IN + k] = a0.at(i, q);
         }
-        if (ki == 0) out[c.gb[0] + n] = b0[i];
+        if (ki == 0) out[c.gb[0] + n] = a0.bias[i];
       }
     }
   }
@@ -722,9 +743,9 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int k = ki * 8 + q;
-          if (k < n_in) out[c.gw[l + 1] + n * n_in + k] = ah[l][i][q];
+          if (k < n_in) out[c.gw[l + 1] + n * n_in + k] = ah[l].at(i, q);
         }
-        if (ki == 0) out[c.gb[l + 1] + n] = bh[l][i];
+        if (ki == 0) out[c.gb[l + 1] + n] = ah[l].bias[i];
       }
     }
   }
