@@ -136,6 +136,12 @@ int hdpo_step_bwd(const HdpoProblem* pb, const HdpoStatics* st, const HdpoState*
 /* shift[b,n] = b*(len*n_nodes) + n*len as int64, bit-exact with environment.py:77-101. */
 int hdpo_allocation_shift(int64_t* shift, int32_t B, int32_t n_nodes, int32_t len, void* stream);
 
+/* Batch assembly on the device: dst[i][0..row_floats) = src[idx[i]][0..row_floats) for i < n_rows (idx int64).
+ * Replaces the DataLoader's per-sample collate + per-batch H2D copy (data_handling.py:385-395, trainer.py:155-156)
+ * once the dataset is resident in HBM. */
+int hdpo_gather_rows(float* dst, const float* src, const int64_t* idx, int64_t n_rows, int64_t row_floats,
+                     void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K1 / K2 - fused T-period rollout and its reverse-time adjoint.
  * ---------------------------------------------------------------------------------------------- */

@@ -61,7 +61,7 @@ def make_mlp(widths, hidden_act, out_act):
 
 
 EXPORTS = [
-    "hdpo_step_fwd", "hdpo_step_bwd", "hdpo_allocation_shift", "hdpo_param_count", "hdpo_rollout_workspace_bytes",
+    "hdpo_step_fwd", "hdpo_step_bwd", "hdpo_allocation_shift", "hdpo_gather_rows", "hdpo_param_count", "hdpo_rollout_workspace_bytes",
     "hdpo_rollout_fwd", "hdpo_rollout_bwd", "hdpo_rollout_host_workspace_bytes", "hdpo_rollout_train_host",
     "hdpo_philox_normal", "hdpo_philox_poisson", "hdpo_philox_raw", "hdpo_debug_gemm_tc", "hdpo_debug_gemm_tc_wgrad", "hdpo_last_error", "hdpo_abi_version", "hdpo_kernel_launch_count",
     "hdpo_device_info",
@@ -74,6 +74,7 @@ def bind(lib):
     lib.hdpo_step_bwd.argtypes = [P(Problem), P(Statics), P(State), P(Action), p, C.c_int64, C.c_int64, P(State), p,
                                   P(State), P(Action), p]
     lib.hdpo_allocation_shift.argtypes = [p, C.c_int32, C.c_int32, C.c_int32, p]
+    lib.hdpo_gather_rows.argtypes = [p, p, p, C.c_int64, C.c_int64, p]
     lib.hdpo_param_count.argtypes = [P(RolloutDesc)]
     lib.hdpo_param_count.restype = C.c_int64
     lib.hdpo_rollout_workspace_bytes.argtypes = [P(RolloutDesc)]

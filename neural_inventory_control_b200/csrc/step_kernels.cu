@@ -196,6 +196,23 @@ __global__ void allocation_shift_kernel(int64_t* __restrict__ shift, int B, int 
   shift[i] = b * (static_cast<int64_t>(len) * n) + s * len;
 }
 
+// dst[i][:] = src[idx[i]][:]  (batch assembly on the device: replaces DataLoader's per-sample collate + H2D copy)
+__global__ void __launch_bounds__(256) gather_rows_kernel(float* __restrict__ dst, const float* __restrict__ src,
+                                                          const int64_t* __restrict__ idx, int64_t n_rows,
+                                                          int64_t row_floats, int vec4) {
+  const int64_t per_row = vec4 ? row_floats / 4 : row_floats;
+  const int64_t total = n_rows * per_row;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / per_row, c = i % per_row;
+    const int64_t s = idx[r];
+    if (vec4)
+      reinterpret_cast<float4*>(dst)[r * per_row + c] = reinterpret_cast<const float4*>(src)[s * per_row + c];
+    else
+      dst[r * per_row + c] = src[s * per_row + c];
+  }
+}
+
 int validate_problem(const HdpoProblem* pb) {
   HDPO_REQUIRE(pb != nullptr, "null HdpoProblem");
   HDPO_REQUIRE(pb->B >= 0 && pb->S >= 1, "bad B=%d / S=%d", pb->B, pb->S);
@@ -271,6 +288,20 @@ extern "C" int hdpo_allocation_shift(int64_t* shift, int32_t B, int32_t n_nodes,
   const int64_t n = static_cast<int64_t>(B) * n_nodes;
   auto k = allocation_shift_kernel;
   HDPO_LAUNCH(k, static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, stream, shift, B, n_nodes, len);
+  HDPO_LAUNCH_OK();
+  return HDPO_OK;
+}
+
+extern "C" int hdpo_gather_rows(float* dst, const float* src, const int64_t* idx, int64_t n_rows, int64_t row_floats,
+                                void* stream) {
+  HDPO_REQUIRE(dst && src && idx && n_rows >= 0 && row_floats >= 1, "bad arguments");
+  if (n_rows == 0) return HDPO_OK;
+  const int vec4 = (row_floats % 4 == 0) && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) % 16 == 0);
+  const int64_t total = n_rows * (vec4 ? row_floats / 4 : row_floats);
+  int64_t blocks = ceil_div64(total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  auto k = gather_rows_kernel;
+  HDPO_LAUNCH(k, static_cast<unsigned>(blocks), 256, 0, stream, dst, src, idx, n_rows, row_floats, vec4);
   HDPO_LAUNCH_OK();
   return HDPO_OK;
 }

@@ -14,6 +14,7 @@ import os
 import numpy as np
 import torch
 
+from . import device_dataset as DD
 from . import engine as EN
 from . import parallel as PL
 from .loss_functions import PolicyLoss
@@ -36,6 +37,9 @@ class Trainer:
         # parity-grade tcgen05 mode, "fp32" the SIMT FFMA mode, "tf32" single-pass (throughput, not parity-grade)
         self.precision = os.environ.get("HDPO_PRECISION", "tf32x3")
         self._engines = {}
+        # keep datasets resident in HBM and assemble batches with a gather kernel instead of per-sample collate
+        self.use_device_dataset = os.environ.get("HDPO_DEVICE_DATASET", "1") != "0"
+        self._device_loaders = {}
         self.last_path = None  # "fused" | "generic": which path the last simulate_batch took (for tests/logging)
 
     def reset(self):
@@ -89,6 +93,7 @@ class Trainer:
         total_samples = len(data_loader.dataset)
         n_stores = problem_params["n_stores"]
         rank, world = PL.world_info()  # (0, 1) unless launched under torchrun with an initialised process group
+        data_loader = self._maybe_device_loader(data_loader)
         with torch.no_grad() if not train else torch.enable_grad():
             for data_batch in data_loader:
                 n_global = len(data_batch["demands"])
@@ -116,6 +121,14 @@ class Trainer:
                     optimizer.step()
         return (epoch_loss / (total_samples * periods * n_stores),
                 epoch_loss_to_report / (total_samples * (periods - ignore_periods) * n_stores))
+
+    def _maybe_device_loader(self, data_loader):
+        if not self.use_device_dataset or not str(self.device).startswith("cuda") or not DD.eligible(data_loader):
+            return data_loader
+        key = id(data_loader)
+        if key not in self._device_loaders:
+            self._device_loaders[key] = DD.DeviceBatches(data_loader, self.device)
+        return self._device_loaders[key]
 
     # ------------------------------------------------------------------ the hot path
     def simulate_batch(self, loss_function, simulator, model, periods, problem_params, data_batch, observation_params,

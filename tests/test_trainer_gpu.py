@@ -210,3 +210,39 @@ def test_symmetry_aware_generic_path_matches_oracle():
     flat = O.flatten_grads(pol, grads)
     for k, v in model.named_parameters():
         assert G.rel_l2(v.grad.cpu().numpy(), flat[k]) < 5e-5, k
+
+
+def test_device_resident_batches_match_dataloader_semantics():
+    """DeviceBatches: same batch sizes / last partial batch / coverage as the torch DataLoader it stands in for; a
+    shuffled epoch is a permutation of the dataset; gathered rows are bit-identical to the source rows."""
+    from torch.utils.data import DataLoader
+    from neural_inventory_control_b200.data_handling import MyDataset
+    from neural_inventory_control_b200.device_dataset import DeviceBatches, eligible
+    n = 1000
+    g = torch.Generator().manual_seed(0)
+    data = {"demands": torch.rand(n, 3, 17, generator=g), "initial_inventories": torch.rand(n, 3, 4, generator=g),
+            "holding_costs": torch.rand(n, 3, generator=g), "tag": torch.arange(n).float()}
+    ds = MyDataset(n, data)
+    for shuffle in (False, True):
+        loader = DataLoader(ds, batch_size=256, shuffle=shuffle)
+        assert eligible(loader)
+        db = DeviceBatches(loader, "cuda:0")
+        assert len(db) == len(loader) == 4 and len(db.dataset) == n
+        seen = []
+        for batch in db:
+            assert set(batch) == set(data)
+            tags = batch["tag"].long().cpu()
+            seen.append(tags)
+            for k in data:
+                assert torch.equal(batch[k].cpu(), data[k][tags])
+        sizes = [len(t) for t in seen]
+        assert sizes == [256, 256, 256, 232]
+        allt = torch.cat(seen)
+        assert torch.equal(allt.sort().values, torch.arange(n))
+        if shuffle:
+            assert not torch.equal(allt, torch.arange(n))
+            again = torch.cat([b["tag"].long().cpu() for b in db])
+            assert not torch.equal(again, allt)  # fresh permutation per epoch
+        else:
+            assert torch.equal(allt, torch.arange(n))
+    assert len(DeviceBatches(DataLoader(ds, batch_size=256, shuffle=True, drop_last=True), "cuda:0")) == 3
