@@ -10,6 +10,7 @@ import os
 from . import _capi as K
 
 _LIB = None
+_DEVICE_OK = False  # cudaGetDeviceProperties costs ~2.5 ms: check once, not per call
 
 
 class MissingExtension(RuntimeError):
@@ -23,7 +24,7 @@ def lib_path():
 def load(require_device=True):
     """Return the bound library. Raises MissingExtension when the .so cannot be loaded/built, and
     RuntimeError when `require_device` and no CUDA device is usable."""
-    global _LIB
+    global _LIB, _DEVICE_OK
     if _LIB is None:
         path = lib_path()
         if not os.path.exists(path):
@@ -40,11 +41,12 @@ def load(require_device=True):
             raise MissingExtension(f"cannot load {path}: {e}") from e
         if _LIB.hdpo_abi_version() != 1:
             raise MissingExtension(f"{path}: ABI version {_LIB.hdpo_abi_version()} != 1 (stale build?)")
-    if require_device:
+    if require_device and not _DEVICE_OK:
         sm, major, minor = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         name = ctypes.create_string_buffer(128)
         rc = _LIB.hdpo_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor), name, 128)
         if rc != 0:
             raise RuntimeError("HDPO engine needs a CUDA device (sm_100a build, no CPU fallback): "
                                + _LIB.hdpo_last_error().decode())
+        _DEVICE_OK = True
     return _LIB

@@ -127,7 +127,7 @@ size_t workspace_bytes(const HdpoRolloutDesc* d) {
 
 static int sm_count() {
 #ifdef HDPO_EMU
-  return 2;
+  return 1;
 #else
   static int cached = 0;
   if (!cached) {
@@ -141,6 +141,15 @@ static int sm_count() {
 }
 
 constexpr int kFwdNS = 2;
+
+// With few scenario tiles (training batches of a few thousand scenarios) one warp per CTA spreads the tiles over all
+// SMs and shortens the latency-bound per-tile time; big batches use 4 warps per CTA to share the staged weights.
+static int pick_warps_per_cta(int n_tiles) {
+  const int sms = sm_count();
+  if (n_tiles <= 4 * sms) return 1;
+  if (n_tiles <= 8 * sms) return 2;
+  return kWarpsPerCta;
+}
 
 int forward(const HdpoRolloutDesc* d, const float* params, const float* demands, const HdpoStatics* st,
             const HdpoState* init, float* cost_b, float* report_b, float* reward_tb, double* totals,
@@ -159,22 +168,22 @@ int forward(const HdpoRolloutDesc* d, const float* params, const float* demands,
   HdpoState fin = {nullptr, nullptr, nullptr};
   if (final_state) fin = *final_state;
   const int rows = 32 * kFwdNS;
-  const size_t smem = (static_cast<size_t>((c.s_total + 3) & ~3) + static_cast<size_t>(kWarpsPerCta) * rows * (c.XS + HS)) *
-                      sizeof(float);
   const int n_tiles = ceil_div(c.B, rows);
-  const int ctas_needed = ceil_div(n_tiles, kWarpsPerCta);
+  const int wpc = pick_warps_per_cta(n_tiles);
+  const size_t smem_max = (static_cast<size_t>((c.s_total + 3) & ~3) + static_cast<size_t>(kWarpsPerCta) * rows * (c.XS + HS)) *
+                          sizeof(float);
+  const size_t smem = (static_cast<size_t>((c.s_total + 3) & ~3) + static_cast<size_t>(wpc) * rows * (c.XS + HS)) * sizeof(float);
+  const int ctas_needed = ceil_div(n_tiles, wpc);
   const int max_ctas = sm_count() * 3;
   const int grid = ctas_needed < max_ctas ? ctas_needed : max_ctas;
   if (c.arch == HDPO_ARCH_VANILLA_ONE_STORE) {
     auto k = small_fwd_kernel<HDPO_ARCH_VANILLA_ONE_STORE, kFwdNS>;
-    HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    HDPO_LAUNCH(k, grid, kWarpsPerCta * 32, smem, stream, c, params, demands, *st, *init, cost_b, report_b, reward_tb,
-                tape, fin);
+    HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)));
+    HDPO_LAUNCH(k, grid, wpc * 32, smem, stream, c, params, demands, *st, *init, cost_b, report_b, reward_tb, tape, fin);
   } else {
     auto k = small_fwd_kernel<HDPO_ARCH_VANILLA_SERIAL, kFwdNS>;
-    HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    HDPO_LAUNCH(k, grid, kWarpsPerCta * 32, smem, stream, c, params, demands, *st, *init, cost_b, report_b, reward_tb,
-                tape, fin);
+    HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)));
+    HDPO_LAUNCH(k, grid, wpc * 32, smem, stream, c, params, demands, *st, *init, cost_b, report_b, reward_tb, tape, fin);
   }
   HDPO_LAUNCH_OK();
   if (totals) {
@@ -200,18 +209,19 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
   float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + tape_bytes);
   const int p_stride = (c.P + 3) & ~3;
   const int n_tiles = ceil_div(c.B, 32);
-  const int ctas_needed = ceil_div(n_tiles, kWarpsPerCta);
-  int max_ctas = sm_count() * 2;
-  if (max_ctas * kWarpsPerCta > kMaxPartialRows) max_ctas = kMaxPartialRows / kWarpsPerCta;
+  const int wpc = pick_warps_per_cta(n_tiles);
+  const int ctas_needed = ceil_div(n_tiles, wpc);
+  int max_ctas = sm_count() * 2 * (kWarpsPerCta / wpc);
+  if (max_ctas * wpc > kMaxPartialRows) max_ctas = kMaxPartialRows / wpc;
   const int grid = ctas_needed < max_ctas ? ctas_needed : max_ctas;
   int rc;
 #define HDPO_BWD_CASE(KQ0)                                                                                          \
   case KQ0:                                                                                                         \
     rc = (c.arch == HDPO_ARCH_VANILLA_ONE_STORE)                                                                    \
              ? launch_bwd_nhh<HDPO_ARCH_VANILLA_ONE_STORE, KQ0>(c, params, demands, st, tape, g_total, g_report,     \
-                                                                partials, p_stride, grid, stream)                   \
+                                                                partials, p_stride, grid, wpc, stream)              \
              : launch_bwd_nhh<HDPO_ARCH_VANILLA_SERIAL, KQ0>(c, params, demands, st, tape, g_total, g_report,        \
-                                                             partials, p_stride, grid, stream);                     \
+                                                             partials, p_stride, grid, wpc, stream);                \
     break;
   switch (c.IN4 / 4) {
     HDPO_BWD_CASE(1)
@@ -224,7 +234,7 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
 #undef HDPO_BWD_CASE
   if (rc) return rc;
   auto kr = reduce_partials_kernel;
-  HDPO_LAUNCH(kr, ceil_div(c.P, 256), 256, 0, stream, static_cast<const float*>(partials), grid * kWarpsPerCta,
+  HDPO_LAUNCH(kr, ceil_div(c.P, 256), 256, 0, stream, static_cast<const float*>(partials), grid * wpc,
               p_stride, c.P, grad_params);
   HDPO_LAUNCH_OK();
   return HDPO_OK;

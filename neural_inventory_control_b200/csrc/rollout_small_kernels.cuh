@@ -373,7 +373,8 @@ small_fwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
   float* Hw = Xw + rows * c.XS;
   const int tile_scen = 32 * NS;
   const int n_tiles = ceil_div(c.B, tile_scen);
-  const int gwarp = blockIdx.x * kWarpsPerCta + warp, nwarps = gridDim.x * kWarpsPerCta;
+  const int wpc = blockDim.x >> 5;  // warps per CTA: 4 for big batches, 2 / 1 when there are few tiles (latency)
+  const int gwarp = blockIdx.x * wpc + warp, nwarps = gridDim.x * wpc;
 
   for (int tile = gwarp; tile < n_tiles; tile += nwarps) {
     int b[NS];
@@ -593,7 +594,8 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
   for (int o = 0; o < kMaxOut; ++o) ao[o] = 0.f;
 
   const int n_tiles = ceil_div(c.B, 32);
-  const int gwarp = blockIdx.x * kWarpsPerCta + warp, nwarps = gridDim.x * kWarpsPerCta;
+  const int wpc = blockDim.x >> 5;  // warps per CTA: 4 for big batches, 2 / 1 when there are few tiles (latency)
+  const int gwarp = blockIdx.x * wpc + warp, nwarps = gridDim.x * wpc;
   for (int tile = gwarp; tile < n_tiles; tile += nwarps) {
     const int bb = tile * 32 + lane;
     const bool valid = bb < c.B;
@@ -779,17 +781,19 @@ static __global__ void __launch_bounds__(256) reduce_partials_kernel(const float
 // launch of one adjoint instantiation (defined per <ARCH, KQ0> in the rollout_small_bwd_*.cu units)
 template <int ARCH, int KQ0>
 int launch_bwd_nhh(const Cfg& c, const float* params, const float* demands, const HdpoStatics* st, const float* tape,
-                   float g_total, float g_report, float* partials, int p_stride, int grid, void* stream);
+                   float g_total, float g_report, float* partials, int p_stride, int grid, int wpc, void* stream);
 
 template <int ARCH, int KQ0, int NHH>
 int launch_bwd(const Cfg& c, const float* params, const float* demands, const HdpoStatics* st, const float* tape,
-               float g_total, float g_report, float* partials, int p_stride, int grid, void* stream) {
+               float g_total, float g_report, float* partials, int p_stride, int grid, int wpc, void* stream) {
   const int per_warp = 32 * (2 * c.XS + (NHH + 1) * HS + kMaxOut);
-  const size_t smem = (static_cast<size_t>((c.s_total + 3) & ~3) + static_cast<size_t>(kWarpsPerCta) * per_warp) * sizeof(float);
+  const size_t smem = (static_cast<size_t>((c.s_total + 3) & ~3) + static_cast<size_t>(wpc) * per_warp) * sizeof(float);
   auto k = small_bwd_kernel<ARCH, KQ0, NHH>;
   HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  HDPO_LAUNCH(k, grid, kWarpsPerCta * 32, smem, stream, c, params, demands, *st, tape, g_total, g_report, partials,
-              p_stride);
+  HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>((static_cast<size_t>((c.s_total + 3) & ~3) +
+                                                      static_cast<size_t>(kWarpsPerCta) * per_warp) * sizeof(float))));
+  HDPO_LAUNCH(k, grid, wpc * 32, smem, stream, c, params, demands, *st, tape, g_total, g_report, partials, p_stride);
   HDPO_LAUNCH_OK();
   return HDPO_OK;
 }
@@ -798,12 +802,12 @@ int launch_bwd(const Cfg& c, const float* params, const float* demands, const Hd
   template <>                                                                                                      \
   int launch_bwd_nhh<ARCH, KQ0>(const Cfg& c, const float* params, const float* demands, const HdpoStatics* st,    \
                                 const float* tape, float g_total, float g_report, float* partials, int p_stride,   \
-                                int grid, void* stream) {                                                          \
+                                int grid, int wpc, void* stream) {                                                 \
     switch (c.NHH) {                                                                                               \
-      case 0: return launch_bwd<ARCH, KQ0, 0>(c, params, demands, st, tape, g_total, g_report, partials, p_stride, grid, stream); \
-      case 1: return launch_bwd<ARCH, KQ0, 1>(c, params, demands, st, tape, g_total, g_report, partials, p_stride, grid, stream); \
-      case 2: return launch_bwd<ARCH, KQ0, 2>(c, params, demands, st, tape, g_total, g_report, partials, p_stride, grid, stream); \
-      case 3: return launch_bwd<ARCH, KQ0, 3>(c, params, demands, st, tape, g_total, g_report, partials, p_stride, grid, stream); \
+      case 0: return launch_bwd<ARCH, KQ0, 0>(c, params, demands, st, tape, g_total, g_report, partials, p_stride, grid, wpc, stream); \
+      case 1: return launch_bwd<ARCH, KQ0, 1>(c, params, demands, st, tape, g_total, g_report, partials, p_stride, grid, wpc, stream); \
+      case 2: return launch_bwd<ARCH, KQ0, 2>(c, params, demands, st, tape, g_total, g_report, partials, p_stride, grid, wpc, stream); \
+      case 3: return launch_bwd<ARCH, KQ0, 3>(c, params, demands, st, tape, g_total, g_report, partials, p_stride, grid, wpc, stream); \
     }                                                                                                              \
     set_error("unsupported hidden depth %d", c.NHH);                                                               \
     return HDPO_E_INVALID;                                                                                         \

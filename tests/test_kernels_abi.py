@@ -157,6 +157,37 @@ def test_rollout_ragged_batches_against_oracle(be_name, name, n, T, ignore):
         assert np.all(leg_tail["grad_flat"] == 0)
 
 
+@pytest.mark.parametrize("be_name,n", [pytest.param("emu", 300, id="emu-300"),
+                                       pytest.param("cuda", 300, id="cuda-300", marks=pytest.mark.gpu),
+                                       pytest.param("cuda", 100000, id="cuda-100000", marks=pytest.mark.gpu)])
+@pytest.mark.parametrize("name", ["one_store_backlogged", "serial_system"])
+def test_rollout_many_tiles_all_launch_shapes(be_name, n, name):
+    """Batches spanning many warp tiles (1, 2 and 4 warps per CTA, persistent tile loops, ragged last tile):
+    per-scenario costs of replicated scenarios must repeat exactly and the gradient must equal the oracle's."""
+    be = backend(be_name)
+    meta, g = G.load("rollout", name)
+    base = 50
+    reps = -(-n // base)
+    data = {k: np.concatenate([v[:base]] * reps, 0)[:n] for k, v in g["data"].items()}
+    T, ignore = 6, 2
+    out = D.rollout(be, meta, g["param"], data, T=T, ignore=ignore)
+    first = out["cost_b"][:base]
+    for r in range(1, n // base):
+        assert np.array_equal(out["cost_b"][r * base:(r + 1) * base], first)
+    pb = G.problem_from_meta(meta)
+    pol = G.policy_from_golden(meta, g["param"], np.float64)
+    small = {k: v[:base].astype(np.float64) for k, v in g["data"].items()}
+    fwd, grads = O.rollout_grad(pol, pb, small, T, grad_scale=1.0)
+    np.testing.assert_allclose(first, fwd["reward_tb"].sum(0), rtol=1e-5)
+    # gradient of the replicated batch = (n / base) x the base gradient (up to the ragged tail), scaled by 1/(n T S)
+    flat = O.flatten_grads(pol, grads)
+    if n % base == 0:
+        want = np.concatenate([flat[k].ravel() for k in sorted(flat)]) * (n // base) / (n * T * pb.n_stores)
+        got = np.concatenate([out["grad"][k].ravel() for k in sorted(flat)])
+        assert G.rel_l2(got, want) < 1e-5
+    assert abs(out["totals"][0] - out["cost_b"].astype(np.float64).sum()) <= 1e-9 * abs(out["totals"][0])
+
+
 @pytest.mark.parametrize("be_name", BACKENDS)
 def test_discrete_allocation_forward(be_name):
     be = backend(be_name)
