@@ -257,8 +257,8 @@ def main():
     roofline = {
         "bound": "tensor",
         "kernel": ("small_bwd_kernel (reverse-time adjoint, SIMT fp32 parity mode)" if small else
-                   f"adjoint sweep ({precision}): gemm_tc_kernel dgrad tiles (tcgen05) + sgemm_kernel wgrad (SIMT) + "
-                   "warehouse_head_bwd" if precision != "fp32" else
+                   f"adjoint sweep ({precision}): gemm_tc_kernel dgrad + weight-gradient tiles (tcgen05/TMEM/TMA) + "
+                   "warehouse_head_bwd + bias column sums" if precision != "fp32" else
                    "adjoint sweep: sgemm_kernel dgrad+wgrad tiles (SIMT fp32 parity mode) + warehouse_head_bwd"),
         "precision": precision,
         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": None,

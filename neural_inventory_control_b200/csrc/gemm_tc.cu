@@ -81,8 +81,7 @@ __device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// programmatic dependent launch: wait for the producing grid's memory / allow the dependent grid's prologue to start
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// programmatic dependent launch (pdl_wait() is in hdpo_platform.cuh): allow the dependent grid's prologue to start
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ float tf32_hi(float x) {
   uint32_t u;

@@ -33,6 +33,31 @@ void count_launch();  // capi.cu
   } while (0)
 #endif
 
+// Programmatic dependent launch (PDL): a kernel launched with HDPO_LAUNCH_PDL may be scheduled while its predecessor
+// in the stream is still draining; it MUST call pdl_wait() before touching memory the predecessor wrote. This hides
+// the launch latency of the long chains of short dependent kernels in the wide rollout (5 launches per period).
+#ifndef HDPO_EMU
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#define HDPO_LAUNCH_PDL(kfn, grid, block, smem, stream, ...)                                  \
+  do {                                                                                        \
+    cudaLaunchConfig_t hdpo_cfg_{};                                                           \
+    hdpo_cfg_.gridDim = dim3(grid);                                                           \
+    hdpo_cfg_.blockDim = dim3(block);                                                         \
+    hdpo_cfg_.dynamicSmemBytes = (smem);                                                      \
+    hdpo_cfg_.stream = reinterpret_cast<cudaStream_t>(stream);                                \
+    cudaLaunchAttribute hdpo_attr_[1];                                                        \
+    hdpo_attr_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                    \
+    hdpo_attr_[0].val.programmaticStreamSerializationAllowed = 1;                             \
+    hdpo_cfg_.attrs = hdpo_attr_;                                                             \
+    hdpo_cfg_.numAttrs = 1;                                                                   \
+    cudaLaunchKernelEx(&hdpo_cfg_, kfn, __VA_ARGS__);                                         \
+    ::hdpo::count_launch();                                                                   \
+  } while (0)
+#else
+inline void pdl_wait() {}
+#define HDPO_LAUNCH_PDL(kfn, grid, block, smem, stream, ...) HDPO_LAUNCH(kfn, grid, block, smem, stream, __VA_ARGS__)
+#endif
+
 constexpr int kWarp = 32;
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

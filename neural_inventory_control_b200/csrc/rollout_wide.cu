@@ -161,6 +161,7 @@ struct GemmArgs {
 
 template <int BM, bool A_T, bool B_T, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(GemmArgs g) {
+  pdl_wait();
   constexpr int TM = BM / 16;  // rows per thread (8 or 4)
   __shared__ __align__(16) float As[2][BK][BM];
   __shared__ __align__(16) float Bs[2][BK][BN];
@@ -320,10 +321,10 @@ static int sgemm(const GemmArgs& g, int splits, void* stream) {
   const bool big = (g.M % 128 == 0) && (static_cast<long long>(g.M / 128) * (g.N / BN) * splits >= 148);
   if (big) {
     auto k = sgemm_kernel<128, A_T, B_T, EPI>;
-    HDPO_LAUNCH(k, dim3(g.N / BN, g.M / 128, splits), GEMM_THREADS, 0, stream, g);
+    HDPO_LAUNCH_PDL(k, dim3(g.N / BN, g.M / 128, splits), GEMM_THREADS, 0, stream, g);
   } else {
     auto k = sgemm_kernel<64, A_T, B_T, EPI>;
-    HDPO_LAUNCH(k, dim3(g.N / BN, g.M / 64, splits), GEMM_THREADS, 0, stream, g);
+    HDPO_LAUNCH_PDL(k, dim3(g.N / BN, g.M / 64, splits), GEMM_THREADS, 0, stream, g);
   }
   HDPO_LAUNCH_OK();
   return HDPO_OK;
@@ -349,6 +350,7 @@ __global__ void __launch_bounds__(256) pack_layer_kernel(const float* __restrict
                                                          int Np, int Kp, float* __restrict__ Wp, float* __restrict__ bp,
                                                          float* __restrict__ W_lo, float* __restrict__ WT,
                                                          float* __restrict__ WT_lo) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Np * Kp) {
     const int n = i / Kp, k = i % Kp;
@@ -369,6 +371,7 @@ __global__ void __launch_bounds__(256) pack_layer_kernel(const float* __restrict
 // row-wise split of a [rows][ld] fp32 array into (hi, lo)
 __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, float* __restrict__ hi,
                                                          float* __restrict__ lo, size_t n) {
+  pdl_wait();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = x[i], h = tf32_round(v);
@@ -380,6 +383,7 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) init_state_kernel(const float* __restrict__ store, const float* __restrict__ wh,
                                                          int B, int Bp, int nS, int nW, int ldx, float* __restrict__ X,
                                                          float* __restrict__ cost_b, float* __restrict__ report_b) {
+  pdl_wait();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < static_cast<size_t>(Bp) * ldx) {
     const int b = static_cast<int>(i / ldx), k = static_cast<int>(i % ldx);
@@ -397,6 +401,7 @@ __global__ void __launch_bounds__(256) init_state_kernel(const float* __restrict
 }
 
 __global__ void __launch_bounds__(256) zero_kernel(float* __restrict__ p, size_t n) {
+  pdl_wait();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0.f;
 }
@@ -404,6 +409,7 @@ __global__ void __launch_bounds__(256) zero_kernel(float* __restrict__ p, size_t
 // final state rows -> reference layouts
 __global__ void __launch_bounds__(256) export_state_kernel(const float* __restrict__ X, int B, int nS, int nW, int ldx,
                                                            float* __restrict__ store, float* __restrict__ wh) {
+  pdl_wait();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<size_t>(B) * (nS + nW)) return;
   const int b = static_cast<int>(i / (nS + nW)), k = static_cast<int>(i % (nS + nW));
@@ -476,6 +482,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32)
 warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ Xn,
                           float* __restrict__ cost_b, float* __restrict__ report_b, float* __restrict__ reward_t,
                           float* __restrict__ Xn_hi, float* __restrict__ Xn_lo) {
+  pdl_wait();
   HDPO_DYN_SMEM(float, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * HEAD_WARPS + warp;
@@ -574,6 +581,7 @@ warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
 __global__ void __launch_bounds__(HEAD_WARPS * 32)
 warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ gX,
                           float* __restrict__ gY, float rb, float* __restrict__ gY_lo) {
+  pdl_wait();
   HDPO_DYN_SMEM(float, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * HEAD_WARPS + warp;
@@ -682,6 +690,7 @@ warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
 __global__ void __launch_bounds__(256) colsum_stage1_kernel(const float* __restrict__ G, const float* __restrict__ G2,
                                                             size_t rows, int ld, int n_chunks,
                                                             float* __restrict__ part) {
+  pdl_wait();
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int chunk = blockIdx.y;
   if (col >= ld) return;
@@ -702,6 +711,7 @@ __global__ void __launch_bounds__(256) unpack_grad_kernel(const float* __restric
                                                           int transposed, int N, int K, const float* __restrict__ bpart,
                                                           int n_chunks, int ldb, int gw, int gb,
                                                           float* __restrict__ grad) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N * K) {
     const int n = i / K, k = i % K;
@@ -719,6 +729,7 @@ __global__ void __launch_bounds__(256) unpack_grad_kernel(const float* __restric
 
 __global__ void __launch_bounds__(1024) totals_kernel(const float* __restrict__ cost_b, const float* __restrict__ report_b,
                                                       int B, double* __restrict__ totals) {
+  pdl_wait();
   __shared__ double s0[1024];
   __shared__ double s1[1024];
   double a = 0.0, r = 0.0;
@@ -802,7 +813,7 @@ int forward(const HdpoRolloutDesc* d, const float* params, const float* demands,
   for (int l = 0; l < p.n; ++l) {
     const int cnt = p.wp[l + 1] * p.wp[l];
     auto k = pack_layer_kernel;
-    HDPO_LAUNCH(k, ceil_div(cnt, 256), 256, 0, stream, params, p.gw[l], p.gb[l], p.w[l + 1], p.w[l], p.wp[l + 1],
+    HDPO_LAUNCH_PDL(k, ceil_div(cnt, 256), 256, 0, stream, params, p.gw[l], p.gb[l], p.w[l + 1], p.w[l], p.wp[l + 1],
                 p.wp[l], wsf(ws, p.o_W[l]), wsf(ws, p.o_b[l]), p.tc ? wsf(ws, p.o_W_lo[l]) : static_cast<float*>(nullptr),
                 p.tc ? wsf(ws, p.o_WT[l]) : static_cast<float*>(nullptr),
                 p.tc ? wsf(ws, p.o_WT_lo[l]) : static_cast<float*>(nullptr));
@@ -811,12 +822,12 @@ int forward(const HdpoRolloutDesc* d, const float* params, const float* demands,
   {
     auto k = init_state_kernel;
     const size_t cnt = static_cast<size_t>(p.Bp) * p.wp[0];
-    HDPO_LAUNCH(k, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream, init->store, init->warehouse, p.B, p.Bp,
+    HDPO_LAUNCH_PDL(k, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream, init->store, init->warehouse, p.B, p.Bp,
                 nS, nW, p.wp[0], wsf(ws, p.o_X), cost_b, report_b);
     HDPO_LAUNCH_OK();
     if (p.tc) {
       auto ks = split_rows_kernel;
-      HDPO_LAUNCH(ks, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream,
+      HDPO_LAUNCH_PDL(ks, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream,
                   static_cast<const float*>(wsf(ws, p.o_X)), wsf(ws, p.o_X_hi), wsf(ws, p.o_X_lo), cnt);
       HDPO_LAUNCH_OK();
     }
@@ -895,7 +906,7 @@ int forward(const HdpoRolloutDesc* d, const float* params, const float* demands,
       xn_lo = wsf(ws, p.o_X_lo) + slot * p.x_stride;
     }
     auto k = warehouse_head_fwd_kernel;
-    HDPO_LAUNCH(k, ceil_div(p.Bp, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, in, Xn, cost_b, report_b,
+    HDPO_LAUNCH_PDL(k, ceil_div(p.Bp, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, in, Xn, cost_b, report_b,
                 reward_tb ? reward_tb + static_cast<size_t>(t) * p.B : static_cast<float*>(nullptr), xn_hi, xn_lo);
     HDPO_LAUNCH_OK();
   }
@@ -903,14 +914,14 @@ int forward(const HdpoRolloutDesc* d, const float* params, const float* demands,
     const size_t xf = p.save ? static_cast<size_t>(p.T) : static_cast<size_t>(p.T & 1);
     auto k = export_state_kernel;
     const size_t cnt = static_cast<size_t>(p.B) * (nS + nW);
-    HDPO_LAUNCH(k, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream,
+    HDPO_LAUNCH_PDL(k, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream,
                 static_cast<const float*>(wsf(ws, p.o_X) + xf * p.x_stride), p.B, nS, nW, p.wp[0], final_state->store,
                 final_state->warehouse);
     HDPO_LAUNCH_OK();
   }
   if (totals) {
     auto k = totals_kernel;
-    HDPO_LAUNCH(k, 1, 1024, 0, stream, static_cast<const float*>(cost_b), static_cast<const float*>(report_b), p.B,
+    HDPO_LAUNCH_PDL(k, 1, 1024, 0, stream, static_cast<const float*>(cost_b), static_cast<const float*>(report_b), p.B,
                 totals);
     HDPO_LAUNCH_OK();
   }
@@ -930,7 +941,7 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
   float* gX = wsf(ws, p.o_gx);
   {
     auto k = zero_kernel;
-    HDPO_LAUNCH(k, static_cast<unsigned>(ceil_div64(p.x_stride, 256)), 256, 0, stream, gX, p.x_stride);
+    HDPO_LAUNCH_PDL(k, static_cast<unsigned>(ceil_div64(p.x_stride, 256)), 256, 0, stream, gX, p.x_stride);
     HDPO_LAUNCH_OK();
   }
 #ifndef HDPO_EMU
@@ -955,7 +966,7 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
     HeadArgs a = head_args(d, p, demands, st, t);
     const float rb = g_total + (t >= d->ignore_periods ? g_report : 0.f);
     auto k = warehouse_head_bwd_kernel;
-    HDPO_LAUNCH(k, ceil_div(p.Bp, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, Y, gX, gY, rb, gY_lo);
+    HDPO_LAUNCH_PDL(k, ceil_div(p.Bp, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, Y, gX, gY, rb, gY_lo);
     HDPO_LAUNCH_OK();
     // dgrad chain: gz_{l-1} = (gz_l W_l) * act'(h_{l-1});  finally gX += gz_0 W_0
     for (int l = last; l >= 0; --l) {
@@ -1070,11 +1081,11 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
     }
     const int n_chunks = 128;
     auto k1 = colsum_stage1_kernel;
-    HDPO_LAUNCH(k1, dim3(ceil_div(p.wp[l + 1], 256), n_chunks), 256, 0, stream, gz_hi, gz_lo, rows, p.wp[l + 1], n_chunks,
+    HDPO_LAUNCH_PDL(k1, dim3(ceil_div(p.wp[l + 1], 256), n_chunks), 256, 0, stream, gz_hi, gz_lo, rows, p.wp[l + 1], n_chunks,
                 wsf(ws, p.o_bpart));
     HDPO_LAUNCH_OK();
     auto k2 = unpack_grad_kernel;
-    HDPO_LAUNCH(k2, ceil_div(p.w[l + 1] * p.w[l], 256), 256, 0, stream, static_cast<const float*>(wsf(ws, p.o_part)),
+    HDPO_LAUNCH_PDL(k2, ceil_div(p.w[l + 1] * p.w[l], 256), 256, 0, stream, static_cast<const float*>(wsf(ws, p.o_part)),
                 used_splits, c_slice, ldp, transposed, p.w[l + 1], p.w[l],
                 static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1], p.gw[l], p.gb[l], grad_params);
     HDPO_LAUNCH_OK();

@@ -312,3 +312,53 @@ def test_wide_rollout_512_wide_tc_vs_simt_and_padding_rows():
         errs[prec] = G.rel_l2(got, want)
     print("512-wide gradient rel-L2 error vs float64:", errs)
     assert errs["tf32x3"] <= max(1e-5, 3 * errs["fp32"]), errs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,precision", [("one_store_lost", "fp32"), ("serial_system", "fp32"),
+                                            ("many_warehouses_2x10", "tf32x3")])
+def test_rollout_train_host_entry_point(name, precision):
+    """hdpo_rollout_train_host (HOST buffers in, totals + gradient out; what bench.py's `e2e` times) returns the
+    same numbers as the device-pointer forward + adjoint pair with dLoss/dtotal = 1/(B*T*S)."""
+    import ctypes as C
+    import torch
+    be = backend("cuda")
+    meta, g = G.load("rollout", name)
+    ref = D.rollout(be, meta, g["param"], g["data"], precision=precision)
+    pp = meta["problem_params"]
+    host = {k: np.ascontiguousarray(v, np.float32) for k, v in g["data"].items()}
+    flat, shapes, names = D.flat_params(g["param"])
+    widths = D.spec.mlp_widths(shapes)
+    B, S, L = host["initial_inventories"].shape
+    W, E = pp["n_warehouses"], pp["n_extra_echelons"]
+    Lw = host["initial_warehouse_inventories"].shape[2] if W else 0
+    Le = host["initial_echelon_inventories"].shape[2] if E else 0
+    pb = D.spec.problem(B, S, W, E, L, Lw, Le, pp["lost_demand"], pp["maximize_profit"],
+                        host.get("warehouse_edge_costs") is not None)
+    adj = pp.get("warehouse_store_adjacency")
+    h_adj = None if adj is None else np.ascontiguousarray(np.asarray(adj), np.int32)
+    desc = D.spec.rollout_desc(meta["nn_name"], pb, meta["T"], host["demands"].shape[2],
+                               (widths, meta["inner_layer_activations"]["master"], None),
+                               ignore_periods=meta["ignore_periods"], precision=precision,
+                               warehouse_upper_bound=meta["warehouse_upper_bound"])
+    hp = lambda k: host[k].ctypes.data if k in host else None  # noqa: E731
+    st = K.Statics(hp("holding_costs"), hp("underage_costs"), hp("lead_times"), hp("warehouse_lead_times"),
+                   hp("warehouse_holding_costs"), hp("warehouse_edge_costs"), hp("echelon_lead_times"),
+                   hp("echelon_holding_costs"), hp("mean"), hp("std"))
+    init = K.State(hp("initial_inventories"), hp("initial_warehouse_inventories"), hp("initial_echelon_inventories"))
+    ws_bytes = be.lib.hdpo_rollout_host_workspace_bytes(C.byref(desc))
+    assert ws_bytes > 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    totals = np.zeros(2, np.float64)
+    grad = np.full(flat.size, np.nan, np.float32)
+    rc = be.lib.hdpo_rollout_train_host(C.byref(desc), flat.ctypes.data, host["demands"].ctypes.data, C.byref(st),
+                                        C.byref(init), None if h_adj is None else h_adj.ctypes.data,
+                                        totals.ctypes.data, grad.ctypes.data, ws.data_ptr(), ws_bytes, None)
+    K.check(be.lib, rc, "hdpo_rollout_train_host")
+    np.testing.assert_allclose(totals, ref["totals"], rtol=1e-6)
+    assert G.rel_l2(grad, ref["grad_flat"]) < 1e-6
+    # too-small workspace is refused, not overrun
+    rc = be.lib.hdpo_rollout_train_host(C.byref(desc), flat.ctypes.data, host["demands"].ctypes.data, C.byref(st),
+                                        C.byref(init), None if h_adj is None else h_adj.ctypes.data,
+                                        totals.ctypes.data, grad.ctypes.data, ws.data_ptr(), 1024, None)
+    assert rc == -4
