@@ -63,13 +63,25 @@ def build(force=False, verbose=False, extra_flags=()):
     os.makedirs(build_dir, exist_ok=True)
     nvcc = _nvcc()
     procs = []
+    hdr = hashlib.sha256(" ".join([*NVCC_FLAGS, *extra_flags]).encode())
+    for root in (CSRC, os.path.join(os.path.dirname(PKG), "include")):
+        for name in sorted(os.listdir(root)):
+            if name.endswith((".cuh", ".h")):
+                with open(os.path.join(root, name), "rb") as f:
+                    hdr.update(name.encode() + f.read())
+    stamps = []
     for src in sources():
         obj = os.path.join(build_dir, os.path.basename(src) + ".o")
+        with open(src, "rb") as f:
+            key = hashlib.sha256(hdr.hexdigest().encode() + f.read()).hexdigest()
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.exists(obj + ".key") and open(obj + ".key").read() == key:
+            continue  # object up to date (same source, headers and flags)
+        stamps.append((obj + ".key", key))
         cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-I", CSRC, "-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
     failed = False
     for src, p in procs:
         out, _ = p.communicate()
@@ -80,6 +92,9 @@ def build(force=False, verbose=False, extra_flags=()):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc failed (see above)")
+    for path, key in stamps:
+        with open(path, "w") as f:
+            f.write(key)
     cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     subprocess.check_call(cmd)
     with open(STAMP, "w") as f:

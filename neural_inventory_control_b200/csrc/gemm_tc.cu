@@ -234,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                              (static_cast<uint32_t>(128 >> 4) << 24) | (MN ? ((1u << 15) | (1u << 16)) : 0u);
-      const int nch = n_kb < kHiChunks ? n_kb : kHiChunks;
+      const int nch = n_kb < g.hi_chunks ? n_kb : g.hi_chunks;
       uint32_t started = 0;  // bit i: accumulator i already holds data
       for (int kb = 0; kb < n_kb; ++kb) {
         const int s = kb % P::kStages;
@@ -274,7 +274,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const size_t rbase = static_cast<size_t>(row) * g.ldc + (MN ? static_cast<size_t>(blockIdx.z) * g.c_slice : 0);
-    const int nch = n_kb < kHiChunks ? n_kb : kHiChunks;
+    const int nch = n_kb < g.hi_chunks ? n_kb : g.hi_chunks;
     const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
     for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
@@ -333,6 +333,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           v[4 * j4 + 1] += c.y;
           v[4 * j4 + 2] += c.z;
           v[4 * j4 + 3] += c.w;
+        }
+      }
+      if (EPI == EPI_DGRAD_HIDDEN) {
+        if (g.colsum_part) {
+          // bias-gradient partials: column sums over this warp's 32 rows by a reduce-scatter butterfly (16 shuffles
+          // for 16 columns); lane pairs end up with column 8*b4 + 4*b3 + 2*b2 + b1 of the chunk (b_i = lane bits)
+          float w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = v[j];
+#pragma unroll
+          for (int h = 8, o = 16; h >= 1; h >>= 1, o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int j = 0; j < h; ++j) {
+              const float send = up ? w[j] : w[j + h];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, o);
+              w[j] = (up ? w[j + h] : w[j]) + recv;
+            }
+          }
+          w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
+          if ((lane & 1) == 0) {
+            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            const size_t rblk = static_cast<size_t>(g.a_row0 + m0 + q * 32) >> 5;
+            g.colsum_part[rblk * g.ldc + n + col] = w[0];
+          }
         }
       }
       if (EPI == EPI_FWD_HIDDEN || EPI == EPI_DGRAD_HIDDEN) {
@@ -406,9 +431,21 @@ int make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t
   return HDPO_OK;
 }
 
+static int env_hi_chunks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HDPO_TC_HI_CHUNKS");
+    v = e ? atoi(e) : kHiChunks;
+    if (v < 1 || v > kHiChunks) v = kHiChunks;
+  }
+  return v;
+}
+
 template <int BN, int EPI, bool MN = false>
 static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                  const GemmTcArgs& g, void* stream) {
+                  const GemmTcArgs& g_in, void* stream) {
+  GemmTcArgs g = g_in;
+  if (g.hi_chunks <= 0) g.hi_chunks = env_hi_chunks();
   auto k = gemm_tc_kernel<BN, EPI, MN>;
   static bool configured = false;
   if (!configured) {

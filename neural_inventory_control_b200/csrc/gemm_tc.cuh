@@ -28,6 +28,7 @@ struct GemmTcArgs {
   int k_per_split;      // weight-gradient form only: contraction rows handled by one blockIdx.z slice
   size_t c_slice;       // weight-gradient form only: floats between the partial outputs of consecutive slices
   int n_pass;           // 3 = 3xTF32, 1 = single-pass TF32
+  int hi_chunks;        // accumulators the hi*hi term is spread over (0 = default, see gemm_tc.cu)
   int a_row0, b_row0;   // row origin of this GEMM inside the A / B tensor maps (e.g. t * Bp for tapes)
   int ldc;              // leading dimension (floats) of every output / aux array
   int act;              // HDPO_ACT_* of the epilogue
@@ -37,6 +38,8 @@ struct GemmTcArgs {
   const float* bias;    // EPI_FWD_*
   const float* aux_hi;  // EPI_DGRAD_HIDDEN: saved layer output h = aux_hi + aux_lo
   const float* aux_lo;
+  float* colsum_part;   // EPI_DGRAD_HIDDEN, optional: [rows / 32][ldc] column sums of each 32-row block of the output
+                        // (bias-gradient partials; the row index includes a_row0, i.e. it follows the gz tape)
 };
 
 // one 2-D fp32 tensor map over a row-major [rows][ld] array, box = [box_rows][32 floats]; 128B swizzle for K-major

@@ -38,13 +38,13 @@ void count_launch();  // capi.cu
 // the launch latency of the long chains of short dependent kernels in the wide rollout (5 launches per period).
 #ifndef HDPO_EMU
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-#define HDPO_LAUNCH_PDL(kfn, grid, block, smem, stream, ...)                                  \
+#define HDPO_LAUNCH_PDL(kfn, grid, block, smem, stream_, ...)                                 \
   do {                                                                                        \
     cudaLaunchConfig_t hdpo_cfg_{};                                                           \
     hdpo_cfg_.gridDim = dim3(grid);                                                           \
     hdpo_cfg_.blockDim = dim3(block);                                                         \
     hdpo_cfg_.dynamicSmemBytes = (smem);                                                      \
-    hdpo_cfg_.stream = reinterpret_cast<cudaStream_t>(stream);                                \
+    hdpo_cfg_.stream = reinterpret_cast<cudaStream_t>(stream_);                               \
     cudaLaunchAttribute hdpo_attr_[1];                                                        \
     hdpo_attr_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                    \
     hdpo_attr_[0].val.programmaticStreamSerializationAllowed = 1;                             \

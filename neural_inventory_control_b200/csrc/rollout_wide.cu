@@ -19,6 +19,11 @@
 #include "rollout_wide.cuh"
 #include "gemm_tc.cuh"
 
+#include <cstdlib>
+#ifndef HDPO_EMU
+#include <mutex>
+#endif
+
 namespace hdpo {
 namespace wide {
 
@@ -58,6 +63,7 @@ struct Plan {
   size_t o_W[HDPO_MAX_LAYERS], o_b[HDPO_MAX_LAYERS];       // packed weights / biases
   size_t o_X, o_act[HDPO_MAX_LAYERS], o_gz[HDPO_MAX_LAYERS];  // tapes
   size_t o_gx, o_part, o_bpart, total;                      // state adjoint, split-K partials
+  size_t o_csum[HDPO_MAX_LAYERS];  // tensor-core mode: [T*Bp/32][wp] column sums of 32-row blocks of gz_l (hidden l)
   // tensor-core mode extras: lo halves, transposed weights (dgrad B operand), split state tape
   size_t o_W_lo[HDPO_MAX_LAYERS], o_WT[HDPO_MAX_LAYERS], o_WT_lo[HDPO_MAX_LAYERS];
   size_t o_X_hi, o_X_lo, o_act_lo[HDPO_MAX_LAYERS], o_gz_lo[HDPO_MAX_LAYERS];
@@ -65,11 +71,11 @@ struct Plan {
   int max_wk;
 };
 
-static Plan make_plan(const HdpoRolloutDesc* d) {
+static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
   Plan p;
   const HdpoMlp& m = d->master;
   p.n = m.n_layers;
-  p.B = d->pb.B;
+  p.B = Bc;
   p.Bp = pad_to(p.B > 0 ? p.B : 1, kRowPad);
   p.T = d->T;
   p.save = d->save_for_backward;
@@ -119,6 +125,8 @@ static Plan make_plan(const HdpoRolloutDesc* d) {
     p.o_gz_lo[l] = (p.save && p.tc) ? take(tslots * p.act_stride[l]) : 0;
   }
   p.o_gx = p.save ? take(p.x_stride) : 0;
+  for (int l = 0; l < p.n; ++l)
+    p.o_csum[l] = (p.save && p.tc && l + 1 < p.n) ? take(tslots * p.act_stride[l] / 32) : 0;
   {
     // short K slices keep the tensor core's truncating accumulation fp32-grade (see gemm_tc.cu)
     const size_t rows = static_cast<size_t>(p.T) * p.Bp;
@@ -133,7 +141,6 @@ static Plan make_plan(const HdpoRolloutDesc* d) {
   return p;
 }
 
-size_t workspace_bytes(const HdpoRolloutDesc* d) { return make_plan(d).total; }
 
 // ------------------------------------------------------------------------------------------------------------
 // fp32 SIMT tile GEMM:  C[M,N] = epi( sum_k A(m,k) * B(k,n) ),  all dims multiples of the tile, ld* multiples of 4
@@ -438,6 +445,7 @@ __device__ __forceinline__ float warp_max(float v) {
 struct HeadArgs {
   int B, Bp, S, W, L, Lw, T_stride, tt;  // tt = t + period_shift (demand column); Bp = rows incl. tile padding
   int ldx, ldy, demand_layout;
+  int demand_bstride;  // HDPO_DEMAND_TSB: scenarios in the WHOLE batch (this launch may cover a chunk of them)
   int lost, profit, has_edge, transshipment, discrete, in_report;
   float wub;
   const int32_t* adjacency;  // [W][S] or null
@@ -448,7 +456,7 @@ struct HeadArgs {
 constexpr int HEAD_WARPS = 4;
 
 __device__ __forceinline__ float demand_of(const HeadArgs& a, int b, int s) {
-  if (a.demand_layout == HDPO_DEMAND_TSB) return __ldg(a.demands + (static_cast<size_t>(a.tt) * a.S + s) * a.B + b);
+  if (a.demand_layout == HDPO_DEMAND_TSB) return __ldg(a.demands + (static_cast<size_t>(a.tt) * a.S + s) * a.demand_bstride + b);
   return __ldg(a.demands + (static_cast<size_t>(b) * a.S + s) * a.T_stride + a.tt);
 }
 
@@ -535,12 +543,17 @@ warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
       }
     }
   }
-  // ---- warehouses: lane w
+  // ---- warehouses: lane w (the draw-down of every warehouse is reduced by the whole warp first)
+  float drawn = 0.f;
+  for (int w = 0; w < a.W; ++w) {
+    float part = 0.f;
+    for (int s = lane; s < a.S; s += 32) part += share[s * a.W + w];
+    part = warp_sum(part);
+    if (lane == w) drawn = part;
+  }
   if (lane < a.W) {
     const int w = lane;
     const int bw = b * a.W + w;
-    float drawn = 0.f;
-    for (int s = 0; s < a.S; ++s) drawn += share[s * a.W + w];
     const float* xw = x + nS + w * a.Lw;
     float* xo = xn + nS + w * a.Lw;
     const float raw = xw[0] - drawn;
@@ -604,12 +617,18 @@ warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
   const int nS = a.S * a.L;
   softmax_shares(a, y, share, lane);
   // ---- warehouses first (lane w): g_raw_w feeds the store-allocation adjoints
+  float drawn = 0.f;
+  for (int w = 0; w < a.W; ++w) {
+    const float W0w = x[nS + w * a.Lw];
+    float part = 0.f;
+    for (int s = lane; s < a.S; s += 32) part += share[s * a.W + w] * W0w;
+    part = warp_sum(part);
+    if (lane == w) drawn = part;
+  }
   if (lane < a.W) {
     const int w = lane;
     const int bw = b * a.W + w;
     const float W0 = x[nS + w * a.Lw];
-    float drawn = 0.f;
-    for (int s = 0; s < a.S; ++s) drawn += share[s * a.W + w] * W0;
     const float raw = W0 - drawn;
     float* gw = g + nS + w * a.Lw;
     const float sg = sigmoid_f(y[SW + w]);
@@ -686,23 +705,47 @@ warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
   }
 }
 
-// column sums of a [rows][ld] matrix (bias gradients), two deterministic stages
+// column sums of a [rows][ld] matrix (bias gradients), two deterministic stages. Stage 1: CTA (x, chunk) sums 64
+// columns (16 float4 groups) over the rows of its chunk with 16 row lanes, then a fixed-order shared-memory reduction.
 __global__ void __launch_bounds__(256) colsum_stage1_kernel(const float* __restrict__ G, const float* __restrict__ G2,
                                                             size_t rows, int ld, int n_chunks,
                                                             float* __restrict__ part) {
   pdl_wait();
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float4 red[16][16];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int col = blockIdx.x * 64 + tx * 4;
   const int chunk = blockIdx.y;
-  if (col >= ld) return;
   const size_t per = (rows + n_chunks - 1) / n_chunks;
   const size_t r0 = chunk * per, r1 = (r0 + per < rows) ? r0 + per : rows;
-  float s = 0.f;
-  if (G2) {
-    for (size_t r = r0; r < r1; ++r) s += G[r * ld + col] + G2[r * ld + col];
-  } else {
-    for (size_t r = r0; r < r1; ++r) s += G[r * ld + col];
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < ld) {
+    for (size_t r = r0 + ty; r < r1; r += 16) {
+      float4 v = *reinterpret_cast<const float4*>(G + r * ld + col);
+      if (G2) {
+        const float4 w = *reinterpret_cast<const float4*>(G2 + r * ld + col);
+        v.x += w.x;
+        v.y += w.y;
+        v.z += w.z;
+        v.w += w.w;
+      }
+      s.x += v.x;
+      s.y += v.y;
+      s.z += v.z;
+      s.w += v.w;
+    }
   }
-  part[static_cast<size_t>(chunk) * ld + col] = s;
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && col < ld) {
+    for (int i = 1; i < 16; ++i) {
+      const float4 v = red[i][tx];
+      s.x += v.x;
+      s.y += v.y;
+      s.z += v.z;
+      s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(part + static_cast<size_t>(chunk) * ld + col) = s;
+  }
 }
 
 // grad[gw + n*K + k] = sum_z part[z][n][k] ; grad[gb + n] = sum_chunks bpart[chunk][n]
@@ -756,33 +799,99 @@ __global__ void __launch_bounds__(1024) totals_kernel(const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------------------
-static HeadArgs head_args(const HdpoRolloutDesc* d, const Plan& p, const float* demands, const HdpoStatics* st, int t) {
-  HeadArgs a;
-  a.B = p.B;
-  a.Bp = p.Bp;
-  a.S = d->pb.S;
-  a.W = d->pb.W;
-  a.L = d->pb.L;
-  a.Lw = d->pb.Lw;
-  a.T_stride = d->t_stride;
-  a.tt = t + d->period_shift;
-  a.ldx = p.wp[0];
-  a.ldy = p.wp[p.n];
-  a.demand_layout = d->demand_layout;
-  a.lost = d->pb.lost_demand;
-  a.profit = d->pb.maximize_profit;
-  a.has_edge = d->pb.has_edge_cost;
-  a.transshipment = d->transshipment;
-  a.discrete = d->discrete_allocation;
-  a.in_report = t >= d->ignore_periods;
-  a.wub = d->warehouse_upper_bound;
-  a.adjacency = d->pb.W > 1 ? d->adjacency : nullptr;
-  a.demands = demands;
-  a.st = *st;
-  return a;
+// The batch is cut into independent scenario CHUNKS that run on concurrent streams. Every kernel of the period chain
+// is short (15-45 us) and ends with a drained tail (partial second wave, un-overlapped epilogue, warp-per-scenario
+// heads), and consecutive kernels of one chain are strictly dependent; two or more independent chains keep every SM
+// fed. Chunks share nothing but the (read-only) parameters; the parameter gradient is their fixed-order sum.
+constexpr int kMaxChunks = 4;
+constexpr int kChunkMinRows = 2048;
+
+struct Chunking {
+  int n, P;
+  int b0[kMaxChunks], rows[kMaxChunks];
+  size_t ws_off[kMaxChunks];  // byte offset of each chunk's private workspace
+  size_t grad_off;            // (n - 1) * P floats: gradients of chunks 1.. before the fixed-order sum
+  size_t total;
+};
+
+static int requested_chunks(int B) {
+#ifdef HDPO_EMU
+  (void)B;
+  return 1;  // the host-thread emulator has no streams
+#else
+  static int env = -2;
+  if (env == -2) {
+    const char* e = getenv("HDPO_WIDE_CHUNKS");
+    env = e ? atoi(e) : -1;
+  }
+  int n = env > 0 ? env : (B / kChunkMinRows > 1 ? B / kChunkMinRows : 1);
+  if (n > kMaxChunks) n = kMaxChunks;
+  while (n > 1 && B / n < kRowPad) --n;
+  return n;
+#endif
 }
 
+static Chunking make_chunking(const HdpoRolloutDesc* d) {
+  Chunking c;
+  const int B = d->pb.B;
+  const int want = requested_chunks(B);
+  const int per = pad_to((B + want - 1) / want, kRowPad);
+  c.n = 0;
+  size_t o = 0;
+  for (int i = 0; i < want; ++i) {
+    const int b0 = i * per;
+    const int rows = (B - b0 < per) ? B - b0 : per;
+    if (rows <= 0 && i > 0) break;
+    c.b0[i] = b0;
+    c.rows[i] = rows > 0 ? rows : 0;
+    c.ws_off[i] = o;
+    const Plan p = make_plan(d, c.rows[i]);
+    o += a256(p.total);
+    c.P = p.P;
+    c.n = i + 1;
+  }
+  c.grad_off = o;
+  o += a256(static_cast<size_t>(c.n > 1 ? c.n - 1 : 0) * c.P * sizeof(float));
+  c.total = o + 256;
+  return c;
+}
+
+size_t workspace_bytes(const HdpoRolloutDesc* d) { return make_chunking(d).total; }
+
+#ifndef HDPO_EMU
+// side streams of the current device (created once); serialised by a mutex so that two host threads forking at the
+// same time cannot interleave their event records
+struct SideStreams {
+  cudaStream_t s[kMaxChunks - 1];
+  cudaEvent_t fork, join[kMaxChunks - 1];
+  bool ready;
+};
+static std::mutex g_side_mutex;
+static SideStreams g_side[64];
+
+static int get_side_streams(SideStreams** out) {
+  int dev = 0;
+  HDPO_CUDA_OK(cudaGetDevice(&dev));
+  HDPO_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  SideStreams& ss = g_side[dev];
+  if (!ss.ready) {
+    for (int i = 0; i < kMaxChunks - 1; ++i) {
+      HDPO_CUDA_OK(cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking));
+      HDPO_CUDA_OK(cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming));
+    }
+    HDPO_CUDA_OK(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+    ss.ready = true;
+  }
+  *out = &ss;
+  return HDPO_OK;
+}
+#endif
+
 static float* wsf(void* ws, size_t off) { return reinterpret_cast<float*>(static_cast<char*>(ws) + off); }
+template <typename T>
+static T* shifted(T* p, size_t n) {
+  return p ? p + n : nullptr;
+}
 
 #ifndef HDPO_EMU
 // tensor maps of one (hi, lo) operand pair
@@ -796,16 +905,76 @@ static int make_pair(MapPair* m, const float* hi, const float* lo, uint64_t rows
 }
 #endif
 
-int forward(const HdpoRolloutDesc* d, const float* params, const float* demands, const HdpoStatics* st,
-            const HdpoState* init, float* cost_b, float* report_b, float* reward_tb, double* totals,
-            HdpoState* final_state, void* ws, size_t ws_bytes, void* stream) {
-  const Plan p = make_plan(d);
-  HDPO_REQUIRE(ws != nullptr, "the wide rollout needs its workspace (hdpo_rollout_workspace_bytes)");
-  if (ws_bytes < p.total) {
-    set_error("workspace too small: %zu < %zu", ws_bytes, p.total);
-    return HDPO_E_WORKSPACE;
-  }
-  HDPO_REQUIRE(d->pb.W == 1 || d->adjacency != nullptr, "warehouse_store_adjacency required for n_warehouses > 1");
+// one chunk of scenarios [b0, b0 + p.B): every pointer below is already shifted to the chunk's first scenario
+struct ChunkCtx {
+  Plan p;
+  void* ws;
+  void* stream;
+  const float* demands;
+  HdpoStatics st;
+  HdpoState init, fin;
+  float *cost_b, *report_b, *reward_tb;  // reward_tb rows are B_total apart
+  float* grad;
+#ifndef HDPO_EMU
+  MapPair mA[HDPO_MAX_LAYERS], mB[HDPO_MAX_LAYERS];
+#endif
+};
+
+static void bind_chunk(ChunkCtx* c, const HdpoRolloutDesc* d, const Chunking& ck, int i, const float* demands,
+                       const HdpoStatics* st, void* ws, void* stream) {
+  const HdpoProblem& pb = d->pb;
+  const size_t b0 = static_cast<size_t>(ck.b0[i]), S = pb.S, W = pb.W;
+  c->p = make_plan(d, ck.rows[i]);
+  c->ws = static_cast<char*>(ws) + ck.ws_off[i];
+  c->stream = stream;
+  c->demands = d->demand_layout == HDPO_DEMAND_TSB ? demands + b0 : demands + b0 * S * d->t_stride;
+  c->st = *st;
+  c->st.holding_costs = shifted(st->holding_costs, b0 * S);
+  c->st.underage_costs = shifted(st->underage_costs, b0 * S);
+  c->st.lead_times = shifted(st->lead_times, b0 * S * W);
+  c->st.warehouse_lead_times = shifted(st->warehouse_lead_times, b0 * W);
+  c->st.warehouse_holding_costs = shifted(st->warehouse_holding_costs, b0 * W);
+  c->st.warehouse_edge_costs = shifted(st->warehouse_edge_costs, b0 * W);
+  c->st.mean = shifted(st->mean, b0 * S);
+  c->st.std = shifted(st->std, b0 * S);
+  c->init = HdpoState{nullptr, nullptr, nullptr};
+  c->fin = HdpoState{nullptr, nullptr, nullptr};
+  c->cost_b = c->report_b = c->reward_tb = c->grad = nullptr;
+}
+
+static HeadArgs head_args(const HdpoRolloutDesc* d, const ChunkCtx& c, int t) {
+  const Plan& p = c.p;
+  HeadArgs a;
+  a.B = p.B;
+  a.Bp = p.Bp;
+  a.S = d->pb.S;
+  a.W = d->pb.W;
+  a.L = d->pb.L;
+  a.Lw = d->pb.Lw;
+  a.T_stride = d->t_stride;
+  a.tt = t + d->period_shift;
+  a.ldx = p.wp[0];
+  a.ldy = p.wp[p.n];
+  a.demand_layout = d->demand_layout;
+  a.demand_bstride = d->pb.B;
+  a.lost = d->pb.lost_demand;
+  a.profit = d->pb.maximize_profit;
+  a.has_edge = d->pb.has_edge_cost;
+  a.transshipment = d->transshipment;
+  a.discrete = d->discrete_allocation;
+  a.in_report = t >= d->ignore_periods;
+  a.wub = d->warehouse_upper_bound;
+  a.adjacency = d->pb.W > 1 ? d->adjacency : nullptr;
+  a.demands = c.demands;
+  a.st = c.st;
+  return a;
+}
+
+// ---- forward: prologue (pack weights, initial state), one period, epilogue (final state) of one chunk ----
+static int fwd_begin(ChunkCtx& c, const HdpoRolloutDesc* d, const float* params) {
+  const Plan& p = c.p;
+  void* ws = c.ws;
+  void* stream = c.stream;
   const HdpoProblem& pb = d->pb;
   const int nS = pb.S * pb.L, nW = pb.W * pb.Lw;
   const size_t tslots = p.save ? static_cast<size_t>(p.T) : 1;
@@ -814,212 +983,318 @@ int forward(const HdpoRolloutDesc* d, const float* params, const float* demands,
     const int cnt = p.wp[l + 1] * p.wp[l];
     auto k = pack_layer_kernel;
     HDPO_LAUNCH_PDL(k, ceil_div(cnt, 256), 256, 0, stream, params, p.gw[l], p.gb[l], p.w[l + 1], p.w[l], p.wp[l + 1],
-                p.wp[l], wsf(ws, p.o_W[l]), wsf(ws, p.o_b[l]), p.tc ? wsf(ws, p.o_W_lo[l]) : static_cast<float*>(nullptr),
-                p.tc ? wsf(ws, p.o_WT[l]) : static_cast<float*>(nullptr),
-                p.tc ? wsf(ws, p.o_WT_lo[l]) : static_cast<float*>(nullptr));
+                    p.wp[l], wsf(ws, p.o_W[l]), wsf(ws, p.o_b[l]),
+                    p.tc ? wsf(ws, p.o_W_lo[l]) : static_cast<float*>(nullptr),
+                    p.tc ? wsf(ws, p.o_WT[l]) : static_cast<float*>(nullptr),
+                    p.tc ? wsf(ws, p.o_WT_lo[l]) : static_cast<float*>(nullptr));
     HDPO_LAUNCH_OK();
   }
   {
     auto k = init_state_kernel;
     const size_t cnt = static_cast<size_t>(p.Bp) * p.wp[0];
-    HDPO_LAUNCH_PDL(k, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream, init->store, init->warehouse, p.B, p.Bp,
-                nS, nW, p.wp[0], wsf(ws, p.o_X), cost_b, report_b);
+    HDPO_LAUNCH_PDL(k, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream,
+                    static_cast<const float*>(c.init.store), static_cast<const float*>(c.init.warehouse), p.B, p.Bp, nS,
+                    nW, p.wp[0], wsf(ws, p.o_X), c.cost_b, c.report_b);
     HDPO_LAUNCH_OK();
     if (p.tc) {
       auto ks = split_rows_kernel;
       HDPO_LAUNCH_PDL(ks, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream,
-                  static_cast<const float*>(wsf(ws, p.o_X)), wsf(ws, p.o_X_hi), wsf(ws, p.o_X_lo), cnt);
+                      static_cast<const float*>(wsf(ws, p.o_X)), wsf(ws, p.o_X_hi), wsf(ws, p.o_X_lo), cnt);
       HDPO_LAUNCH_OK();
     }
   }
 #ifndef HDPO_EMU
-  MapPair mA[HDPO_MAX_LAYERS], mB[HDPO_MAX_LAYERS];
   if (p.tc) {
     for (int l = 0; l < p.n; ++l) {
       const float* a_hi = (l == 0) ? wsf(ws, p.o_X_hi) : wsf(ws, p.o_act[l - 1]);
       const float* a_lo = (l == 0) ? wsf(ws, p.o_X_lo) : wsf(ws, p.o_act_lo[l - 1]);
-      int rc = make_pair(&mA[l], a_hi, a_lo, tslots * p.Bp, p.wp[l], tc::kBoxRowsA);
+      int rc = make_pair(&c.mA[l], a_hi, a_lo, tslots * p.Bp, p.wp[l], tc::kBoxRowsA);
       if (rc) return rc;
-      rc = make_pair(&mB[l], wsf(ws, p.o_W[l]), wsf(ws, p.o_W_lo[l]), p.wp[l + 1], p.wp[l], tc::pick_bn(p.wp[l + 1]));
+      rc = make_pair(&c.mB[l], wsf(ws, p.o_W[l]), wsf(ws, p.o_W_lo[l]), p.wp[l + 1], p.wp[l], tc::pick_bn(p.wp[l + 1]));
       if (rc) return rc;
     }
   }
 #endif
-  const size_t head_smem = static_cast<size_t>(HEAD_WARPS) * (pb.S * pb.W + 32) * sizeof(float);
-  for (int t = 0; t < p.T; ++t) {
-    const size_t xs = p.save ? static_cast<size_t>(t) : static_cast<size_t>(t & 1);
-    const size_t xn = p.save ? static_cast<size_t>(t + 1) : static_cast<size_t>((t + 1) & 1);
-    const size_t as = p.save ? static_cast<size_t>(t) : 0;
-    const float* X = wsf(ws, p.o_X) + xs * p.x_stride;
-    float* Xn = wsf(ws, p.o_X) + xn * p.x_stride;
-    const float* in = X;
-    for (int l = 0; l < p.n; ++l) {
-      float* out = wsf(ws, p.o_act[l]) + as * p.act_stride[l];
-      const int act = (l + 1 < p.n) ? d->master.hidden_act : d->master.out_act;
-      int rc;
-      if (!p.tc) {
-        GemmArgs g{};
-        g.A = in;
-        g.B = wsf(ws, p.o_W[l]);
-        g.C = out;
-        g.M = p.Bp;
-        g.N = p.wp[l + 1];
-        g.K = p.wp[l];
-        g.lda = p.wp[l];
-        g.ldb = p.wp[l];
-        g.ldc = p.wp[l + 1];
-        g.bias = wsf(ws, p.o_b[l]);
-        g.act = act;
-        rc = sgemm<false, true, EPI_BIAS_ACT>(g, 1, stream);
-      } else {
+  return HDPO_OK;
+}
+
+static int fwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t) {
+  const Plan& p = c.p;
+  void* ws = c.ws;
+  void* stream = c.stream;
+  const HdpoProblem& pb = d->pb;
+  const size_t xs = p.save ? static_cast<size_t>(t) : static_cast<size_t>(t & 1);
+  const size_t xn = p.save ? static_cast<size_t>(t + 1) : static_cast<size_t>((t + 1) & 1);
+  const size_t as = p.save ? static_cast<size_t>(t) : 0;
+  const float* X = wsf(ws, p.o_X) + xs * p.x_stride;
+  float* Xn = wsf(ws, p.o_X) + xn * p.x_stride;
+  const float* in = X;
+  for (int l = 0; l < p.n; ++l) {
+    float* out = wsf(ws, p.o_act[l]) + as * p.act_stride[l];
+    const int act = (l + 1 < p.n) ? d->master.hidden_act : d->master.out_act;
+    int rc;
+    if (!p.tc) {
+      GemmArgs g{};
+      g.A = in;
+      g.B = wsf(ws, p.o_W[l]);
+      g.C = out;
+      g.M = p.Bp;
+      g.N = p.wp[l + 1];
+      g.K = p.wp[l];
+      g.lda = p.wp[l];
+      g.ldb = p.wp[l];
+      g.ldc = p.wp[l + 1];
+      g.bias = wsf(ws, p.o_b[l]);
+      g.act = act;
+      rc = sgemm<false, true, EPI_BIAS_ACT>(g, 1, stream);
+    } else {
 #ifndef HDPO_EMU
-        tc::GemmTcArgs g{};
-        g.M = p.Bp;
-        g.N = p.wp[l + 1];
-        g.K = p.wp[l];
-        g.n_pass = p.n_pass;
-        g.a_row0 = static_cast<int>(as * p.Bp);
-        g.b_row0 = 0;
-        g.ldc = p.wp[l + 1];
-        g.act = act;
-        g.bias = wsf(ws, p.o_b[l]);
-        const bool hidden = l + 1 < p.n;
-        g.c_full = out;
-        g.c_hi = out;
-        g.c_lo = hidden ? wsf(ws, p.o_act_lo[l]) + as * p.act_stride[l] : nullptr;
-        rc = tc::gemm(mA[l].hi, mA[l].lo, mB[l].hi, mB[l].lo, g, hidden ? tc::EPI_FWD_HIDDEN : tc::EPI_FWD_OUT,
-                      tc::pick_bn(p.wp[l + 1]), stream);
+      tc::GemmTcArgs g{};
+      g.M = p.Bp;
+      g.N = p.wp[l + 1];
+      g.K = p.wp[l];
+      g.n_pass = p.n_pass;
+      g.a_row0 = static_cast<int>(as * p.Bp);
+      g.b_row0 = 0;
+      g.ldc = p.wp[l + 1];
+      g.act = act;
+      g.bias = wsf(ws, p.o_b[l]);
+      const bool hidden = l + 1 < p.n;
+      g.c_full = out;
+      g.c_hi = out;
+      g.c_lo = hidden ? wsf(ws, p.o_act_lo[l]) + as * p.act_stride[l] : nullptr;
+      rc = tc::gemm(c.mA[l].hi, c.mA[l].lo, c.mB[l].hi, c.mB[l].lo, g, hidden ? tc::EPI_FWD_HIDDEN : tc::EPI_FWD_OUT,
+                    tc::pick_bn(p.wp[l + 1]), stream);
 #else
-        rc = HDPO_E_INVALID;
+      rc = HDPO_E_INVALID;
 #endif
-      }
-      if (rc) return rc;
-      in = out;
     }
-    HeadArgs a = head_args(d, p, demands, st, t);
-    // tensor-core mode: the state written for period t+1 is also split into the (hi, lo) tape slot t+1
-    float* xn_hi = nullptr;
-    float* xn_lo = nullptr;
-    if (p.tc && (t + 1 < p.T)) {
-      const size_t slot = p.save ? static_cast<size_t>(t + 1) : 0;
-      xn_hi = wsf(ws, p.o_X_hi) + slot * p.x_stride;
-      xn_lo = wsf(ws, p.o_X_lo) + slot * p.x_stride;
-    }
-    auto k = warehouse_head_fwd_kernel;
-    HDPO_LAUNCH_PDL(k, ceil_div(p.Bp, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, in, Xn, cost_b, report_b,
-                reward_tb ? reward_tb + static_cast<size_t>(t) * p.B : static_cast<float*>(nullptr), xn_hi, xn_lo);
-    HDPO_LAUNCH_OK();
+    if (rc) return rc;
+    in = out;
   }
-  if (final_state && (final_state->store || final_state->warehouse)) {
+  HeadArgs a = head_args(d, c, t);
+  // tensor-core mode: the state written for period t+1 is also split into the (hi, lo) tape slot t+1
+  float* xn_hi = nullptr;
+  float* xn_lo = nullptr;
+  if (p.tc && (t + 1 < p.T)) {
+    const size_t slot = p.save ? static_cast<size_t>(t + 1) : 0;
+    xn_hi = wsf(ws, p.o_X_hi) + slot * p.x_stride;
+    xn_lo = wsf(ws, p.o_X_lo) + slot * p.x_stride;
+  }
+  const size_t head_smem = static_cast<size_t>(HEAD_WARPS) * (pb.S * pb.W + 32) * sizeof(float);
+  auto k = warehouse_head_fwd_kernel;
+  HDPO_LAUNCH_PDL(k, ceil_div(p.Bp, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, in, Xn, c.cost_b, c.report_b,
+                  c.reward_tb ? c.reward_tb + static_cast<size_t>(t) * d->pb.B : static_cast<float*>(nullptr), xn_hi,
+                  xn_lo);
+  HDPO_LAUNCH_OK();
+  return HDPO_OK;
+}
+
+static int fwd_end(ChunkCtx& c, const HdpoRolloutDesc* d) {
+  const Plan& p = c.p;
+  const HdpoProblem& pb = d->pb;
+  const int nS = pb.S * pb.L, nW = pb.W * pb.Lw;
+  if (c.fin.store || c.fin.warehouse) {
     const size_t xf = p.save ? static_cast<size_t>(p.T) : static_cast<size_t>(p.T & 1);
     auto k = export_state_kernel;
     const size_t cnt = static_cast<size_t>(p.B) * (nS + nW);
-    HDPO_LAUNCH_PDL(k, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, stream,
-                static_cast<const float*>(wsf(ws, p.o_X) + xf * p.x_stride), p.B, nS, nW, p.wp[0], final_state->store,
-                final_state->warehouse);
-    HDPO_LAUNCH_OK();
-  }
-  if (totals) {
-    auto k = totals_kernel;
-    HDPO_LAUNCH_PDL(k, 1, 1024, 0, stream, static_cast<const float*>(cost_b), static_cast<const float*>(report_b), p.B,
-                totals);
+    HDPO_LAUNCH_PDL(k, static_cast<unsigned>(ceil_div64(cnt, 256)), 256, 0, c.stream,
+                    static_cast<const float*>(wsf(c.ws, p.o_X) + xf * p.x_stride), p.B, nS, nW, p.wp[0], c.fin.store,
+                    c.fin.warehouse);
     HDPO_LAUNCH_OK();
   }
   return HDPO_OK;
 }
 
-int backward(const HdpoRolloutDesc* d, const float* params, const float* demands, const HdpoStatics* st, float g_total,
-             float g_report, float* grad_params, void* ws, size_t ws_bytes, void* stream) {
-  (void)params;
-  const Plan p = make_plan(d);
-  HDPO_REQUIRE(ws != nullptr && p.save, "backward needs the workspace of a forward run with save_for_backward = 1");
-  if (ws_bytes < p.total) {
-    set_error("workspace too small: %zu < %zu", ws_bytes, p.total);
+// fork / join of the chunk streams around a region of `stream` (no-ops for a single chunk)
+struct StreamFork {
+#ifndef HDPO_EMU
+  SideStreams* ss = nullptr;
+  std::unique_lock<std::mutex> lock;
+#endif
+  int n = 1;
+  void* main = nullptr;
+  int begin(int n_chunks, void* stream) {
+    n = n_chunks;
+    main = stream;
+#ifndef HDPO_EMU
+    if (n > 1) {
+      lock = std::unique_lock<std::mutex>(g_side_mutex);
+      int rc = get_side_streams(&ss);
+      if (rc) return rc;
+      HDPO_CUDA_OK(cudaEventRecord(ss->fork, static_cast<cudaStream_t>(main)));
+      for (int i = 1; i < n; ++i) HDPO_CUDA_OK(cudaStreamWaitEvent(ss->s[i - 1], ss->fork, 0));
+    }
+#endif
+    return HDPO_OK;
+  }
+  void* stream_of(int i) const {
+#ifndef HDPO_EMU
+    if (i > 0) return ss->s[i - 1];
+#endif
+    (void)i;
+    return main;
+  }
+  int end() {
+#ifndef HDPO_EMU
+    if (n > 1) {
+      for (int i = 1; i < n; ++i) {
+        HDPO_CUDA_OK(cudaEventRecord(ss->join[i - 1], ss->s[i - 1]));
+        HDPO_CUDA_OK(cudaStreamWaitEvent(static_cast<cudaStream_t>(main), ss->join[i - 1], 0));
+      }
+    }
+#endif
+    return HDPO_OK;
+  }
+};
+
+int forward(const HdpoRolloutDesc* d, const float* params, const float* demands, const HdpoStatics* st,
+            const HdpoState* init, float* cost_b, float* report_b, float* reward_tb, double* totals,
+            HdpoState* final_state, void* ws, size_t ws_bytes, void* stream) {
+  const Chunking ck = make_chunking(d);
+  HDPO_REQUIRE(ws != nullptr, "the wide rollout needs its workspace (hdpo_rollout_workspace_bytes)");
+  if (ws_bytes < ck.total) {
+    set_error("workspace too small: %zu < %zu", ws_bytes, ck.total);
     return HDPO_E_WORKSPACE;
   }
+  HDPO_REQUIRE(d->pb.W == 1 || d->adjacency != nullptr, "warehouse_store_adjacency required for n_warehouses > 1");
   const HdpoProblem& pb = d->pb;
+  StreamFork fork;
+  int rc = fork.begin(ck.n, stream);
+  if (rc) return rc;
+  ChunkCtx ctx[kMaxChunks];
+  for (int i = 0; i < ck.n; ++i) {
+    ChunkCtx& c = ctx[i];
+    const size_t b0 = static_cast<size_t>(ck.b0[i]);
+    bind_chunk(&c, d, ck, i, demands, st, ws, fork.stream_of(i));
+    c.init.store = init->store + b0 * pb.S * pb.L;
+    c.init.warehouse = init->warehouse + b0 * pb.W * pb.Lw;
+    if (final_state) {
+      c.fin.store = shifted(final_state->store, b0 * pb.S * pb.L);
+      c.fin.warehouse = shifted(final_state->warehouse, b0 * pb.W * pb.Lw);
+    }
+    c.cost_b = cost_b + b0;
+    c.report_b = shifted(report_b, b0);
+    c.reward_tb = shifted(reward_tb, b0);
+    if ((rc = fwd_begin(c, d, params))) return rc;
+  }
+  // period-major issue order: the chunks advance together, so their kernels interleave on the device
+  for (int t = 0; t < d->T; ++t)
+    for (int i = 0; i < ck.n; ++i)
+      if ((rc = fwd_period(ctx[i], d, t))) return rc;
+  for (int i = 0; i < ck.n; ++i)
+    if ((rc = fwd_end(ctx[i], d))) return rc;
+  if ((rc = fork.end())) return rc;
+  if (totals) {
+    auto k = totals_kernel;
+    HDPO_LAUNCH_PDL(k, 1, 1024, 0, stream, static_cast<const float*>(cost_b), static_cast<const float*>(report_b), pb.B,
+                    totals);
+    HDPO_LAUNCH_OK();
+  }
+  return HDPO_OK;
+}
+
+// ---- adjoint ----
+static int bwd_begin(ChunkCtx& c) {
+  const Plan& p = c.p;
+  void* ws = c.ws;
   float* gX = wsf(ws, p.o_gx);
   {
     auto k = zero_kernel;
-    HDPO_LAUNCH_PDL(k, static_cast<unsigned>(ceil_div64(p.x_stride, 256)), 256, 0, stream, gX, p.x_stride);
+    HDPO_LAUNCH_PDL(k, static_cast<unsigned>(ceil_div64(p.x_stride, 256)), 256, 0, c.stream, gX, p.x_stride);
     HDPO_LAUNCH_OK();
   }
 #ifndef HDPO_EMU
-  MapPair mA[HDPO_MAX_LAYERS], mB[HDPO_MAX_LAYERS];
   if (p.tc) {
     for (int l = 0; l < p.n; ++l) {  // dgrad of layer l: A = gz_l [rows][wp[l+1]], B = W_l^T [wp[l]][wp[l+1]]
-      int rc = make_pair(&mA[l], wsf(ws, p.o_gz[l]), wsf(ws, p.o_gz_lo[l]), static_cast<uint64_t>(p.T) * p.Bp,
+      int rc = make_pair(&c.mA[l], wsf(ws, p.o_gz[l]), wsf(ws, p.o_gz_lo[l]), static_cast<uint64_t>(p.T) * p.Bp,
                          p.wp[l + 1], tc::kBoxRowsA);
       if (rc) return rc;
-      rc = make_pair(&mB[l], wsf(ws, p.o_WT[l]), wsf(ws, p.o_WT_lo[l]), p.wp[l], p.wp[l + 1], tc::pick_bn(p.wp[l]));
+      rc = make_pair(&c.mB[l], wsf(ws, p.o_WT[l]), wsf(ws, p.o_WT_lo[l]), p.wp[l], p.wp[l + 1], tc::pick_bn(p.wp[l]));
       if (rc) return rc;
     }
   }
 #endif
-  const size_t head_smem = static_cast<size_t>(HEAD_WARPS) * (2 * pb.S * pb.W + 64) * sizeof(float);
+  return HDPO_OK;
+}
+
+static int bwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t, float rb) {
+  const Plan& p = c.p;
+  void* ws = c.ws;
+  void* stream = c.stream;
+  const HdpoProblem& pb = d->pb;
+  float* gX = wsf(ws, p.o_gx);
   const int last = p.n - 1;
-  for (int t = p.T - 1; t >= 0; --t) {
-    const float* X = wsf(ws, p.o_X) + static_cast<size_t>(t) * p.x_stride;
-    const float* Y = wsf(ws, p.o_act[last]) + static_cast<size_t>(t) * p.act_stride[last];
-    float* gY = wsf(ws, p.o_gz[last]) + static_cast<size_t>(t) * p.act_stride[last];
-    float* gY_lo = p.tc ? wsf(ws, p.o_gz_lo[last]) + static_cast<size_t>(t) * p.act_stride[last] : nullptr;
-    HeadArgs a = head_args(d, p, demands, st, t);
-    const float rb = g_total + (t >= d->ignore_periods ? g_report : 0.f);
-    auto k = warehouse_head_bwd_kernel;
-    HDPO_LAUNCH_PDL(k, ceil_div(p.Bp, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, Y, gX, gY, rb, gY_lo);
-    HDPO_LAUNCH_OK();
-    // dgrad chain: gz_{l-1} = (gz_l W_l) * act'(h_{l-1});  finally gX += gz_0 W_0
-    for (int l = last; l >= 0; --l) {
-      int rc;
-      if (!p.tc) {
-        GemmArgs g{};
-        g.A = wsf(ws, p.o_gz[l]) + static_cast<size_t>(t) * p.act_stride[l];
-        g.B = wsf(ws, p.o_W[l]);
-        g.M = p.Bp;
-        g.N = p.wp[l];
-        g.K = p.wp[l + 1];
-        g.lda = p.wp[l + 1];
-        g.ldb = p.wp[l];
-        g.ldc = p.wp[l];
-        g.act = d->master.hidden_act;
-        if (l > 0) {
-          g.C = wsf(ws, p.o_gz[l - 1]) + static_cast<size_t>(t) * p.act_stride[l - 1];
-          g.aux = wsf(ws, p.o_act[l - 1]) + static_cast<size_t>(t) * p.act_stride[l - 1];
-          rc = sgemm<false, false, EPI_MUL_ACTGRAD>(g, 1, stream);
-        } else {
-          g.C = gX;
-          rc = sgemm<false, false, EPI_ACCUM>(g, 1, stream);
-        }
+  const size_t head_smem = static_cast<size_t>(HEAD_WARPS) * (2 * pb.S * pb.W + 64) * sizeof(float);
+  const float* X = wsf(ws, p.o_X) + static_cast<size_t>(t) * p.x_stride;
+  const float* Y = wsf(ws, p.o_act[last]) + static_cast<size_t>(t) * p.act_stride[last];
+  float* gY = wsf(ws, p.o_gz[last]) + static_cast<size_t>(t) * p.act_stride[last];
+  float* gY_lo = p.tc ? wsf(ws, p.o_gz_lo[last]) + static_cast<size_t>(t) * p.act_stride[last] : nullptr;
+  HeadArgs a = head_args(d, c, t);
+  auto k = warehouse_head_bwd_kernel;
+  HDPO_LAUNCH_PDL(k, ceil_div(p.Bp, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, Y, gX, gY, rb, gY_lo);
+  HDPO_LAUNCH_OK();
+  // dgrad chain: gz_{l-1} = (gz_l W_l) * act'(h_{l-1});  finally gX += gz_0 W_0
+  for (int l = last; l >= 0; --l) {
+    int rc;
+    if (!p.tc) {
+      GemmArgs g{};
+      g.A = wsf(ws, p.o_gz[l]) + static_cast<size_t>(t) * p.act_stride[l];
+      g.B = wsf(ws, p.o_W[l]);
+      g.M = p.Bp;
+      g.N = p.wp[l];
+      g.K = p.wp[l + 1];
+      g.lda = p.wp[l + 1];
+      g.ldb = p.wp[l];
+      g.ldc = p.wp[l];
+      g.act = d->master.hidden_act;
+      if (l > 0) {
+        g.C = wsf(ws, p.o_gz[l - 1]) + static_cast<size_t>(t) * p.act_stride[l - 1];
+        g.aux = wsf(ws, p.o_act[l - 1]) + static_cast<size_t>(t) * p.act_stride[l - 1];
+        rc = sgemm<false, false, EPI_MUL_ACTGRAD>(g, 1, stream);
       } else {
-#ifndef HDPO_EMU
-        tc::GemmTcArgs g{};
-        g.M = p.Bp;
-        g.N = p.wp[l];
-        g.K = p.wp[l + 1];
-        g.n_pass = p.n_pass;
-        g.a_row0 = t * p.Bp;
-        g.b_row0 = 0;
-        g.ldc = p.wp[l];
-        g.act = d->master.hidden_act;
-        if (l > 0) {
-          const size_t off = static_cast<size_t>(t) * p.act_stride[l - 1];
-          g.c_hi = wsf(ws, p.o_gz[l - 1]) + off;
-          g.c_lo = wsf(ws, p.o_gz_lo[l - 1]) + off;
-          g.aux_hi = wsf(ws, p.o_act[l - 1]) + off;
-          g.aux_lo = wsf(ws, p.o_act_lo[l - 1]) + off;
-          rc = tc::gemm(mA[l].hi, mA[l].lo, mB[l].hi, mB[l].lo, g, tc::EPI_DGRAD_HIDDEN, tc::pick_bn(p.wp[l]), stream);
-        } else {
-          g.c_full = gX;
-          rc = tc::gemm(mA[l].hi, mA[l].lo, mB[l].hi, mB[l].lo, g, tc::EPI_DGRAD_ACCUM, tc::pick_bn(p.wp[l]), stream);
-        }
-#else
-        rc = HDPO_E_INVALID;
-#endif
+        g.C = gX;
+        rc = sgemm<false, false, EPI_ACCUM>(g, 1, stream);
       }
-      if (rc) return rc;
+    } else {
+#ifndef HDPO_EMU
+      tc::GemmTcArgs g{};
+      g.M = p.Bp;
+      g.N = p.wp[l];
+      g.K = p.wp[l + 1];
+      g.n_pass = p.n_pass;
+      g.a_row0 = t * p.Bp;
+      g.b_row0 = 0;
+      g.ldc = p.wp[l];
+      g.act = d->master.hidden_act;
+      if (l > 0) {
+        const size_t off = static_cast<size_t>(t) * p.act_stride[l - 1];
+        g.c_hi = wsf(ws, p.o_gz[l - 1]) + off;
+        g.c_lo = wsf(ws, p.o_gz_lo[l - 1]) + off;
+        g.aux_hi = wsf(ws, p.o_act[l - 1]) + off;
+        g.aux_lo = wsf(ws, p.o_act_lo[l - 1]) + off;
+        g.colsum_part = wsf(ws, p.o_csum[l - 1]);
+        rc = tc::gemm(c.mA[l].hi, c.mA[l].lo, c.mB[l].hi, c.mB[l].lo, g, tc::EPI_DGRAD_HIDDEN, tc::pick_bn(p.wp[l]),
+                      stream);
+      } else {
+        g.c_full = gX;
+        rc = tc::gemm(c.mA[l].hi, c.mA[l].lo, c.mB[l].hi, c.mB[l].lo, g, tc::EPI_DGRAD_ACCUM, tc::pick_bn(p.wp[l]),
+                      stream);
+      }
+#else
+      rc = HDPO_E_INVALID;
+#endif
     }
+    if (rc) return rc;
   }
-  // weight gradients: dW_l[n][k] = sum over all (t, b) rows of gz_l[row][n] * in_l[row][k], split-K over the rows
+  return HDPO_OK;
+}
+
+// weight gradients: dW_l[n][k] = sum over all (t, b) rows of gz_l[row][n] * in_l[row][k], split-K over the rows
+static int bwd_end(ChunkCtx& c) {
+  const Plan& p = c.p;
+  void* ws = c.ws;
+  void* stream = c.stream;
   const size_t rows = static_cast<size_t>(p.T) * p.Bp;
   int splits = kSplitK;
   while (splits > 1 && (rows / splits) % BK != 0) splits >>= 1;
@@ -1081,13 +1356,66 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
     }
     const int n_chunks = 128;
     auto k1 = colsum_stage1_kernel;
-    HDPO_LAUNCH_PDL(k1, dim3(ceil_div(p.wp[l + 1], 256), n_chunks), 256, 0, stream, gz_hi, gz_lo, rows, p.wp[l + 1], n_chunks,
-                wsf(ws, p.o_bpart));
+    if (p.tc && l + 1 < p.n) {  // the dgrad epilogue already reduced every 32-row block (full fp32 values)
+      HDPO_LAUNCH_PDL(k1, dim3(ceil_div(p.wp[l + 1], 64), n_chunks), 256, 0, stream,
+                      static_cast<const float*>(wsf(ws, p.o_csum[l])), static_cast<const float*>(nullptr), rows / 32,
+                      p.wp[l + 1], n_chunks, wsf(ws, p.o_bpart));
+    } else {
+      HDPO_LAUNCH_PDL(k1, dim3(ceil_div(p.wp[l + 1], 64), n_chunks), 256, 0, stream, gz_hi, gz_lo, rows, p.wp[l + 1],
+                      n_chunks, wsf(ws, p.o_bpart));
+    }
     HDPO_LAUNCH_OK();
     auto k2 = unpack_grad_kernel;
     HDPO_LAUNCH_PDL(k2, ceil_div(p.w[l + 1] * p.w[l], 256), 256, 0, stream, static_cast<const float*>(wsf(ws, p.o_part)),
-                used_splits, c_slice, ldp, transposed, p.w[l + 1], p.w[l],
-                static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1], p.gw[l], p.gb[l], grad_params);
+                    used_splits, c_slice, ldp, transposed, p.w[l + 1], p.w[l],
+                    static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1], p.gw[l], p.gb[l], c.grad);
+    HDPO_LAUNCH_OK();
+  }
+  return HDPO_OK;
+}
+
+// grad[i] += extra[0][i] + extra[1][i] + ...  (fixed order: the chunked gradient is deterministic)
+__global__ void __launch_bounds__(256) sum_chunk_grads_kernel(float* __restrict__ grad, const float* __restrict__ extra,
+                                                              int n_extra, int P) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  float s = grad[i];
+  for (int c = 0; c < n_extra; ++c) s += extra[static_cast<size_t>(c) * P + i];
+  grad[i] = s;
+}
+
+int backward(const HdpoRolloutDesc* d, const float* params, const float* demands, const HdpoStatics* st, float g_total,
+             float g_report, float* grad_params, void* ws, size_t ws_bytes, void* stream) {
+  (void)params;
+  const Chunking ck = make_chunking(d);
+  HDPO_REQUIRE(ws != nullptr && d->save_for_backward,
+               "backward needs the workspace of a forward run with save_for_backward = 1");
+  if (ws_bytes < ck.total) {
+    set_error("workspace too small: %zu < %zu", ws_bytes, ck.total);
+    return HDPO_E_WORKSPACE;
+  }
+  StreamFork fork;
+  int rc = fork.begin(ck.n, stream);
+  if (rc) return rc;
+  ChunkCtx ctx[kMaxChunks];
+  float* extra = reinterpret_cast<float*>(static_cast<char*>(ws) + ck.grad_off);
+  for (int i = 0; i < ck.n; ++i) {
+    bind_chunk(&ctx[i], d, ck, i, demands, st, ws, fork.stream_of(i));
+    ctx[i].grad = i == 0 ? grad_params : extra + static_cast<size_t>(i - 1) * ck.P;
+    if ((rc = bwd_begin(ctx[i]))) return rc;
+  }
+  for (int t = d->T - 1; t >= 0; --t) {
+    const float rb = g_total + (t >= d->ignore_periods ? g_report : 0.f);
+    for (int i = 0; i < ck.n; ++i)
+      if ((rc = bwd_period(ctx[i], d, t, rb))) return rc;
+  }
+  for (int i = 0; i < ck.n; ++i)
+    if ((rc = bwd_end(ctx[i]))) return rc;
+  if ((rc = fork.end())) return rc;
+  if (ck.n > 1) {
+    auto k = sum_chunk_grads_kernel;
+    HDPO_LAUNCH_PDL(k, ceil_div(ck.P, 256), 256, 0, stream, grad_params, static_cast<const float*>(extra), ck.n - 1, ck.P);
     HDPO_LAUNCH_OK();
   }
   return HDPO_OK;

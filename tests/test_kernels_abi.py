@@ -362,3 +362,37 @@ def test_rollout_train_host_entry_point(name, precision):
                                         C.byref(init), None if h_adj is None else h_adj.ctypes.data,
                                         totals.ctypes.data, grad.ctypes.data, ws.data_ptr(), 1024, None)
     assert rc == -4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("name,n,T,ignore", [("many_warehouses_2x10", 4096 + 300, 5, 2), ("one_warehouse_s5", 4096, 4, 0)])
+def test_wide_rollout_concurrent_chunks_against_oracle(precision, name, n, T, ignore):
+    """Batches of >= 4096 scenarios are cut into chunks that run on concurrent streams (rollout_wide.cu "host
+    orchestration"); the ragged case leaves the second chunk with a partial row tile. Costs, per-period rewards,
+    final state and the fixed-order-summed gradient must match the float64 oracle exactly as for one chunk."""
+    be = backend("cuda")
+    meta, g = G.load("rollout", name)
+    reps = -(-n // next(iter(g["data"].values())).shape[0])
+    rng = np.random.RandomState(n)
+    data = {k: np.concatenate([v] * reps, 0)[:n].copy() for k, v in g["data"].items()}
+    # de-duplicate the tiled scenarios: scale demands and initial inventories per scenario
+    scale_b = rng.uniform(0.6, 1.4, n).astype(np.float32)
+    data["demands"] *= scale_b[:, None, None]
+    data["initial_inventories"] *= scale_b[:, None, None]
+    pb = G.problem_from_meta(meta)
+    pol = G.policy_from_golden(meta, g["param"], np.float64)
+    fwd, grads = O.rollout_grad(pol, pb, G.cast(data, np.float64), T)
+    flat = O.flatten_grads(pol, grads)
+    want = np.concatenate([flat[k].ravel() for k in sorted(flat)])
+    scale = np.abs(fwd["reward_tb"]).max()
+    for layout in (K.DEMAND_BST, K.DEMAND_TSB):
+        out = D.rollout(be, meta, g["param"], data, T=T, ignore=ignore, precision=precision, demand_layout=layout)
+        assert np.abs(out["reward_tb"] - fwd["reward_tb"]).max() <= 1e-5 * scale, layout
+        np.testing.assert_allclose(out["cost_b"], fwd["reward_tb"].sum(0), rtol=1e-5)
+        np.testing.assert_allclose(out["report_b"], fwd["reward_tb"][ignore:].sum(0), rtol=1e-5, atol=1e-5 * scale)
+        assert abs(out["totals"][0] / fwd["reward_tb"].sum() - 1) < 1e-6
+        mine = np.concatenate([out["grad"][k].ravel() for k in sorted(flat)])
+        assert G.rel_l2(mine, want) <= 2e-5, (layout, G.rel_l2(mine, want))
+        for k in ("store", "wh"):
+            np.testing.assert_allclose(out["final"][k], fwd["final"][k], rtol=1e-4, atol=1e-4)
