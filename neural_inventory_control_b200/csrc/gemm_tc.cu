@@ -40,6 +40,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// shared -> global tile store (bulk async group); the source must stay valid until tma_store_wait_all()
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA store engine)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -154,8 +165,11 @@ struct SmemPlan {
 #endif
 template <int BN, int EPI, bool MN>
 __global__ void __launch_bounds__(kThreads, HDPO_TC_MIN_CTAS(BN))
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-               const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, GemmTcArgs g) {
+gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
+  const CUtensorMap& tm_a_hi = tm.a_hi;
+  const CUtensorMap& tm_a_lo = tm.a_lo;
+  const CUtensorMap& tm_b_hi = tm.b_hi;
+  const CUtensorMap& tm_b_lo = tm.b_lo;
   using P = SmemPlan<BN>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -163,7 +177,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P::kStages * P::kStageBytes);
   uint64_t* empty_bar = full_bar + P::kStages;
   uint64_t* accum_bar = empty_bar + P::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* epi_bar = accum_bar + 1;  // one per epilogue warp: its TMA loads of the tile the epilogue combines with
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + kEpiWarps);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * 128, n0 = blockIdx.x * BN;
@@ -183,6 +198,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(accum_bar, 1);
+    for (int w = 0; w < kEpiWarps; ++w) mbar_init(&epi_bar[w], 1);
+    prefetch_tmap(&tm.c0);
+    if (EPI == EPI_FWD_HIDDEN || EPI == EPI_DGRAD_HIDDEN) prefetch_tmap(&tm.c1);
+    if (EPI == EPI_DGRAD_HIDDEN || EPI == EPI_DGRAD_ACCUM) prefetch_tmap(&tm.x0);
+    if (EPI == EPI_DGRAD_HIDDEN) prefetch_tmap(&tm.x1);
     fence_barrier_init();
   }
   // TMEM: kAccums accumulators of BN fp32 columns each (see "accumulator splitting" at the MMA loop)
@@ -268,16 +288,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
   } else {
     // ===== epilogue: warp q = warp % 4 owns TMEM lanes [32q, 32q+32) = tile rows =====
+    // Tiles move between shared and global memory by TMA only: a lane owns one output ROW, so direct global
+    // accesses would touch 32 different rows per instruction (measured: the un-coalesced epilogue cost as much as
+    // the mainloop). Each warp stages its 32 x (BN/2) sub-tile in 32-row x 32-float boxes (128-byte swizzle, bank
+    // conflict free for one 16-byte chunk per lane) inside the operand ring, which is idle once accum_bar fired.
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;       // which half of the tile's columns this warp drains
-    const int row = m0 + q * 32 + lane;
+    const int we = warp - 2;                // epilogue warp index 0..7
+    const int half = we >> 2;               // which half of the tile's columns this warp drains
+    constexpr int kBoxes = BN / 64;         // 32-column boxes per warp and array
+    constexpr int kBoxBytes = 32 * 128;
+    const int cbase = half * (BN / 2);
+    const int grow = (MN ? static_cast<int>(blockIdx.z) * g.M : g.c_row0) + m0 + q * 32;  // first output row of this warp
+    unsigned char* stg = smem + we * (2 * kBoxes * kBoxBytes);  // [array 0 | array 1][box][32 rows x 128 B]
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const size_t rbase = static_cast<size_t>(row) * g.ldc + (MN ? static_cast<size_t>(blockIdx.z) * g.c_slice : 0);
+    if (EPI == EPI_DGRAD_HIDDEN || EPI == EPI_DGRAD_ACCUM) {
+      // the tile this epilogue combines with (saved layer output hi/lo, or the running state adjoint)
+      constexpr int kArr = EPI == EPI_DGRAD_HIDDEN ? 2 : 1;
+      if (lane == 0) {
+        mbar_expect_tx(&epi_bar[we], kArr * kBoxes * kBoxBytes);
+        const int xrow = g.x_row0 + m0 + q * 32;
+#pragma unroll
+        for (int b = 0; b < kBoxes; ++b) {
+          tma_load_2d(stg + b * kBoxBytes, &tm.x0, &epi_bar[we], n0 + cbase + 32 * b, xrow);
+          if (kArr == 2) tma_load_2d(stg + (kBoxes + b) * kBoxBytes, &tm.x1, &epi_bar[we], n0 + cbase + 32 * b, xrow);
+        }
+      }
+      mbar_wait(&epi_bar[we], 0);
+    }
     const int nch = n_kb < g.hi_chunks ? n_kb : g.hi_chunks;
     const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
+    for (int cc = 0; cc < BN / 2; cc += 16) {
+      const int c0 = cbase + cc;
       uint32_t r0[16], r1[16], r2[16], r3[16];
       float v[16];
       // issue every accumulator's load for this column chunk, then wait once
@@ -295,6 +338,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         v[j] = a;
       }
       const int n = n0 + c0;
+      // staging addresses of this lane's four 16-byte chunks (array 0; array 1 is kBoxes boxes further)
+      unsigned char* box = stg + (cc >> 5) * kBoxBytes + lane * 128;
+      const int ch0 = (cc & 31) >> 2;
+      auto chunk_ptr = [&](int arr, int j4) {
+        return reinterpret_cast<float4*>(box + arr * (kBoxes * kBoxBytes) + (((ch0 + j4) ^ (lane & 7)) << 4));
+      };
       if (EPI == EPI_FWD_HIDDEN || EPI == EPI_FWD_OUT) {
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
@@ -313,8 +362,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         float h[16];
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 a = *reinterpret_cast<const float4*>(g.aux_hi + rbase + n + 4 * j4);
-          const float4 b = *reinterpret_cast<const float4*>(g.aux_lo + rbase + n + 4 * j4);
+          const float4 a = *chunk_ptr(0, j4);
+          const float4 b = *chunk_ptr(1, j4);
           h[4 * j4 + 0] = a.x + b.x;
           h[4 * j4 + 1] = a.y + b.y;
           h[4 * j4 + 2] = a.z + b.z;
@@ -328,7 +377,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       } else if (EPI == EPI_DGRAD_ACCUM) {
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 c = *reinterpret_cast<const float4*>(g.c_full + rbase + n + 4 * j4);
+          const float4 c = *chunk_ptr(0, j4);
           v[4 * j4 + 0] += c.x;
           v[4 * j4 + 1] += c.y;
           v[4 * j4 + 2] += c.z;
@@ -355,7 +404,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
           if ((lane & 1) == 0) {
             const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            const size_t rblk = static_cast<size_t>(g.a_row0 + m0 + q * 32) >> 5;
+            const size_t rblk = static_cast<size_t>(grow) >> 5;
             g.colsum_part[rblk * g.ldc + n + col] = w[0];
           }
         }
@@ -373,15 +422,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           lo.y = tf32_hi(v[4 * j4 + 1] - hi.y);
           lo.z = tf32_hi(v[4 * j4 + 2] - hi.z);
           lo.w = tf32_hi(v[4 * j4 + 3] - hi.w);
-          *reinterpret_cast<float4*>(g.c_hi + rbase + n + 4 * j4) = hi;
-          *reinterpret_cast<float4*>(g.c_lo + rbase + n + 4 * j4) = lo;
+          *chunk_ptr(0, j4) = hi;
+          *chunk_ptr(1, j4) = lo;
         }
       } else {
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4)
-          *reinterpret_cast<float4*>(g.c_full + rbase + n + 4 * j4) =
-              make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          *chunk_ptr(0, j4) = make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
       }
+    }
+    // staged sub-tile -> global: one TMA store per 32 x 32 box
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int b = 0; b < kBoxes; ++b) {
+        tma_store_2d(&tm.c0, stg + b * kBoxBytes, n0 + cbase + 32 * b, grow);
+        if (EPI == EPI_FWD_HIDDEN || EPI == EPI_DGRAD_HIDDEN)
+          tma_store_2d(&tm.c1, stg + (kBoxes + b) * kBoxBytes, n0 + cbase + 32 * b, grow);
+      }
+      tma_store_commit();
+      tma_store_wait_all();  // shared memory (and TMEM) are released right after the final barrier
     }
   }
   tc_fence_before();
@@ -431,21 +492,10 @@ int make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t
   return HDPO_OK;
 }
 
-static int env_hi_chunks() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("HDPO_TC_HI_CHUNKS");
-    v = e ? atoi(e) : kHiChunks;
-    if (v < 1 || v > kHiChunks) v = kHiChunks;
-  }
-  return v;
-}
-
 template <int BN, int EPI, bool MN = false>
-static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                  const GemmTcArgs& g_in, void* stream) {
+static int launch(const GemmTcMaps& tm, const GemmTcArgs& g_in, void* stream) {
   GemmTcArgs g = g_in;
-  if (g.hi_chunks <= 0) g.hi_chunks = env_hi_chunks();
+  if (g.hi_chunks <= 0 || g.hi_chunks > kHiChunks) g.hi_chunks = kHiChunks;
   auto k = gemm_tc_kernel<BN, EPI, MN>;
   static bool configured = false;
   if (!configured) {
@@ -463,45 +513,42 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtens
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  HDPO_CUDA_OK(cudaLaunchKernelEx(&cfg, k, a_hi, a_lo, b_hi, b_lo, g));
+  HDPO_CUDA_OK(cudaLaunchKernelEx(&cfg, k, tm, g));
   count_launch();
   HDPO_LAUNCH_OK();
   return HDPO_OK;
 }
 
 template <int BN>
-static int launch_epi(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                      const GemmTcArgs& g, int epi, void* stream) {
+static int launch_epi(const GemmTcMaps& tm, const GemmTcArgs& g, int epi, void* stream) {
   switch (epi) {
-    case EPI_FWD_HIDDEN: return launch<BN, EPI_FWD_HIDDEN>(a_hi, a_lo, b_hi, b_lo, g, stream);
-    case EPI_FWD_OUT: return launch<BN, EPI_FWD_OUT>(a_hi, a_lo, b_hi, b_lo, g, stream);
-    case EPI_DGRAD_HIDDEN: return launch<BN, EPI_DGRAD_HIDDEN>(a_hi, a_lo, b_hi, b_lo, g, stream);
-    case EPI_DGRAD_ACCUM: return launch<BN, EPI_DGRAD_ACCUM>(a_hi, a_lo, b_hi, b_lo, g, stream);
-    case EPI_STORE: return launch<BN, EPI_STORE>(a_hi, a_lo, b_hi, b_lo, g, stream);
+    case EPI_FWD_HIDDEN: return launch<BN, EPI_FWD_HIDDEN>(tm, g, stream);
+    case EPI_FWD_OUT: return launch<BN, EPI_FWD_OUT>(tm, g, stream);
+    case EPI_DGRAD_HIDDEN: return launch<BN, EPI_DGRAD_HIDDEN>(tm, g, stream);
+    case EPI_DGRAD_ACCUM: return launch<BN, EPI_DGRAD_ACCUM>(tm, g, stream);
+    case EPI_STORE: return launch<BN, EPI_STORE>(tm, g, stream);
   }
   set_error("bad epilogue %d", epi);
   return HDPO_E_INVALID;
 }
 
-int gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-         const GemmTcArgs& g, int epi, int bn, void* stream) {
+int gemm(const GemmTcMaps& tm, const GemmTcArgs& g, int epi, int bn, void* stream) {
   HDPO_REQUIRE(g.M % 128 == 0 && g.N % bn == 0 && g.K % kBK == 0 && g.K > 0, "tcgen05 GEMM shape %dx%dx%d not tileable",
                g.M, g.N, g.K);
   HDPO_REQUIRE(g.n_pass == 1 || g.n_pass == 3, "n_pass must be 1 or 3");
-  if (bn == 128) return launch_epi<128>(a_hi, a_lo, b_hi, b_lo, g, epi, stream);
-  if (bn == 64) return launch_epi<64>(a_hi, a_lo, b_hi, b_lo, g, epi, stream);
+  if (bn == 128) return launch_epi<128>(tm, g, epi, stream);
+  if (bn == 64) return launch_epi<64>(tm, g, epi, stream);
   set_error("unsupported BN %d", bn);
   return HDPO_E_INVALID;
 }
 
-int gemm_wgrad(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-               const GemmTcArgs& g, int bn, void* stream) {
+int gemm_wgrad(const GemmTcMaps& tm, const GemmTcArgs& g, int bn, void* stream) {
   HDPO_REQUIRE(g.M % 128 == 0 && g.N % bn == 0 && g.k_per_split % kBK == 0 && g.k_per_split > 0 &&
                    g.K % g.k_per_split == 0,
                "tcgen05 weight-gradient GEMM shape %dx%dx%d (k_per_split %d) not tileable", g.M, g.N, g.K, g.k_per_split);
   HDPO_REQUIRE(g.n_pass == 1 || g.n_pass == 3, "n_pass must be 1 or 3");
-  if (bn == 128) return launch<128, EPI_STORE, true>(a_hi, a_lo, b_hi, b_lo, g, stream);
-  if (bn == 64) return launch<64, EPI_STORE, true>(a_hi, a_lo, b_hi, b_lo, g, stream);
+  if (bn == 128) return launch<128, EPI_STORE, true>(tm, g, stream);
+  if (bn == 64) return launch<64, EPI_STORE, true>(tm, g, stream);
   set_error("unsupported BN %d", bn);
   return HDPO_E_INVALID;
 }
@@ -539,20 +586,21 @@ extern "C" int hdpo_debug_gemm_tc(const float* A, const float* B, float* C, int3
   count_launch();
   HDPO_LAUNCH_OK();
   const int bn = tc::pick_bn(N);
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  tc::GemmTcMaps tm{};
   int rc;
-  if ((rc = tc::make_tensor_map(&ma_hi, a_hi, M, K, K, 128))) return rc;
-  if ((rc = tc::make_tensor_map(&ma_lo, a_lo, M, K, K, 128))) return rc;
-  if ((rc = tc::make_tensor_map(&mb_hi, b_hi, N, K, K, bn))) return rc;
-  if ((rc = tc::make_tensor_map(&mb_lo, b_lo, N, K, K, bn))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.a_hi, a_hi, M, K, K, 128))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.a_lo, a_lo, M, K, K, 128))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.b_hi, b_hi, N, K, K, bn))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.b_lo, b_lo, N, K, K, bn))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.c0, C, M, N, N, tc::kBoxRowsC))) return rc;
+  tm.c1 = tm.x0 = tm.x1 = tm.c0;
   tc::GemmTcArgs g{};
   g.M = M;
   g.N = N;
   g.K = K;
   g.n_pass = n_pass;
   g.ldc = N;
-  g.c_full = C;
-  return tc::gemm(ma_hi, ma_lo, mb_hi, mb_lo, g, tc::EPI_STORE, bn, stream);
+  return tc::gemm(tm, g, tc::EPI_STORE, bn, stream);
 }
 
 // sum of the K-slice partials: C[i] = sum_z part[z*slice + i] (double accumulation)
@@ -586,12 +634,14 @@ extern "C" int hdpo_debug_gemm_tc_wgrad(const float* A, const float* B, float* C
   count_launch();
   HDPO_LAUNCH_OK();
   const int bn = tc::pick_bn(N);
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  tc::GemmTcMaps tm{};
   int rc;
-  if ((rc = tc::make_tensor_map(&ma_hi, a_hi, K, M, M, 32, true))) return rc;
-  if ((rc = tc::make_tensor_map(&ma_lo, a_lo, K, M, M, 32, true))) return rc;
-  if ((rc = tc::make_tensor_map(&mb_hi, b_hi, K, N, N, 32, true))) return rc;
-  if ((rc = tc::make_tensor_map(&mb_lo, b_lo, K, N, N, 32, true))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.a_hi, a_hi, K, M, M, 32, true))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.a_lo, a_lo, K, M, M, 32, true))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.b_hi, b_hi, K, N, N, 32, true))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.b_lo, b_lo, K, N, N, 32, true))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.c0, part, static_cast<uint64_t>(K / k_per_split) * M, N, N, tc::kBoxRowsC))) return rc;
+  tm.c1 = tm.x0 = tm.x1 = tm.c0;
   tc::GemmTcArgs g{};
   g.M = M;
   g.N = N;
@@ -600,8 +650,7 @@ extern "C" int hdpo_debug_gemm_tc_wgrad(const float* A, const float* B, float* C
   g.c_slice = static_cast<size_t>(M) * N;
   g.n_pass = n_pass;
   g.ldc = N;
-  g.c_full = part;
-  if ((rc = tc::gemm_wgrad(ma_hi, ma_lo, mb_hi, mb_lo, g, bn, stream))) return rc;
+  if ((rc = tc::gemm_wgrad(tm, g, bn, stream))) return rc;
   const size_t slice = static_cast<size_t>(M) * N;
   sum_partials_kernel<<<static_cast<unsigned>((slice + 255) / 256), 256, 0, st>>>(part, K / k_per_split, slice, C);
   count_launch();

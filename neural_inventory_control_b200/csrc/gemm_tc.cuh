@@ -30,16 +30,21 @@ struct GemmTcArgs {
   int n_pass;           // 3 = 3xTF32, 1 = single-pass TF32
   int hi_chunks;        // accumulators the hi*hi term is spread over (0 = default, see gemm_tc.cu)
   int a_row0, b_row0;   // row origin of this GEMM inside the A / B tensor maps (e.g. t * Bp for tapes)
-  int ldc;              // leading dimension (floats) of every output / aux array
+  int c_row0, x_row0;   // row origin of the output tile inside maps c0/c1, of the combined tile inside x0/x1
+  int ldc;              // leading dimension (floats) of the output (used by colsum_part only)
   int act;              // HDPO_ACT_* of the epilogue
-  float* c_full;        // EPI_FWD_OUT / EPI_DGRAD_ACCUM / EPI_STORE
-  float* c_hi;          // EPI_FWD_HIDDEN / EPI_DGRAD_HIDDEN
-  float* c_lo;
   const float* bias;    // EPI_FWD_*
-  const float* aux_hi;  // EPI_DGRAD_HIDDEN: saved layer output h = aux_hi + aux_lo
-  const float* aux_lo;
   float* colsum_part;   // EPI_DGRAD_HIDDEN, optional: [rows / 32][ldc] column sums of each 32-row block of the output
                         // (bias-gradient partials; the row index includes a_row0, i.e. it follows the gz tape)
+};
+
+// Tensor maps of one GEMM launch. Operands: box = [128 | BN rows][32 floats] (K-major) or [32 k][32 mn] (MN-major).
+// Outputs and the tiles an epilogue combines with: box = [kBoxRowsC rows][32 floats], 128-byte swizzle.
+//   c0: output (hi half for EPI_FWD_HIDDEN / EPI_DGRAD_HIDDEN, full fp32 otherwise)   c1: lo half
+//   x0 / x1: EPI_DGRAD_HIDDEN saved layer output h = x0 + x1 (act' is evaluated from it); EPI_DGRAD_ACCUM: x0 = the
+//            array the product is added to (normally the same array as c0)
+struct GemmTcMaps {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo, c0, c1, x0, x1;
 };
 
 // one 2-D fp32 tensor map over a row-major [rows][ld] array, box = [box_rows][32 floats]; 128B swizzle for K-major
@@ -49,13 +54,13 @@ int make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t
 
 // weight-gradient form: D[M,N] (per K slice) = sum_k A[k][m] * B[k][n] with A = [K][M], B = [K][N] row-major arrays
 // (tensor maps with box_rows = 32); partial slice z is written at c_full + z * c_slice.
-int gemm_wgrad(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-               const GemmTcArgs& g, int bn, void* stream);
+// (the partial slices form one [n_slices * M][N] array behind map c0)
+int gemm_wgrad(const GemmTcMaps& tm, const GemmTcArgs& g, int bn, void* stream);
 
-int gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-         const GemmTcArgs& g, int epi, int bn, void* stream);
+int gemm(const GemmTcMaps& tm, const GemmTcArgs& g, int epi, int bn, void* stream);
 
 constexpr int kBoxRowsA = 128;
+constexpr int kBoxRowsC = 32;
 #ifdef HDPO_TC_BN64_EXPERIMENT
 inline int pick_bn(int) { return 64; }
 #else

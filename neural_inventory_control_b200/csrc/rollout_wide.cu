@@ -916,7 +916,10 @@ struct ChunkCtx {
   float *cost_b, *report_b, *reward_tb;  // reward_tb rows are B_total apart
   float* grad;
 #ifndef HDPO_EMU
-  MapPair mA[HDPO_MAX_LAYERS], mB[HDPO_MAX_LAYERS];
+  MapPair mA[HDPO_MAX_LAYERS], mB[HDPO_MAX_LAYERS];  // GEMM operands (forward: layer input / W; adjoint: gz / W^T)
+  MapPair mAct[HDPO_MAX_LAYERS];                     // layer-output tapes as 32-row output boxes (lo unused for the last)
+  MapPair mGz[HDPO_MAX_LAYERS];                      // pre-activation adjoint tapes as output boxes
+  CUtensorMap mGx;                                   // state adjoint [Bp][wp0]
 #endif
 };
 
@@ -970,6 +973,27 @@ static HeadArgs head_args(const HdpoRolloutDesc* d, const ChunkCtx& c, int t) {
   return a;
 }
 
+#ifndef HDPO_EMU
+// output-side tensor maps (32-row boxes) of the activation tapes, and for the adjoint of the gz tapes and gX
+static int make_tape_maps(ChunkCtx& c) {
+  const Plan& p = c.p;
+  void* ws = c.ws;
+  const uint64_t tslots = p.save ? static_cast<uint64_t>(p.T) : 1;
+  for (int l = 0; l < p.n; ++l) {
+    const bool hidden = l + 1 < p.n;
+    int rc = make_pair(&c.mAct[l], wsf(ws, p.o_act[l]), hidden ? wsf(ws, p.o_act_lo[l]) : wsf(ws, p.o_act[l]),
+                       tslots * p.Bp, p.wp[l + 1], tc::kBoxRowsC);
+    if (rc) return rc;
+    if (p.save) {
+      rc = make_pair(&c.mGz[l], wsf(ws, p.o_gz[l]), wsf(ws, p.o_gz_lo[l]), tslots * p.Bp, p.wp[l + 1], tc::kBoxRowsC);
+      if (rc) return rc;
+    }
+  }
+  if (p.save) return tc::make_tensor_map(&c.mGx, wsf(ws, p.o_gx), p.Bp, p.wp[0], p.wp[0], tc::kBoxRowsC);
+  return HDPO_OK;
+}
+#endif
+
 // ---- forward: prologue (pack weights, initial state), one period, epilogue (final state) of one chunk ----
 static int fwd_begin(ChunkCtx& c, const HdpoRolloutDesc* d, const float* params) {
   const Plan& p = c.p;
@@ -1005,6 +1029,7 @@ static int fwd_begin(ChunkCtx& c, const HdpoRolloutDesc* d, const float* params)
   }
 #ifndef HDPO_EMU
   if (p.tc) {
+    int rc_maps = 0;
     for (int l = 0; l < p.n; ++l) {
       const float* a_hi = (l == 0) ? wsf(ws, p.o_X_hi) : wsf(ws, p.o_act[l - 1]);
       const float* a_lo = (l == 0) ? wsf(ws, p.o_X_lo) : wsf(ws, p.o_act_lo[l - 1]);
@@ -1013,6 +1038,7 @@ static int fwd_begin(ChunkCtx& c, const HdpoRolloutDesc* d, const float* params)
       rc = make_pair(&c.mB[l], wsf(ws, p.o_W[l]), wsf(ws, p.o_W_lo[l]), p.wp[l + 1], p.wp[l], tc::pick_bn(p.wp[l + 1]));
       if (rc) return rc;
     }
+    if ((rc_maps = make_tape_maps(c))) return rc_maps;
   }
 #endif
   return HDPO_OK;
@@ -1056,15 +1082,14 @@ static int fwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t) {
       g.n_pass = p.n_pass;
       g.a_row0 = static_cast<int>(as * p.Bp);
       g.b_row0 = 0;
+      g.c_row0 = g.a_row0;
       g.ldc = p.wp[l + 1];
       g.act = act;
       g.bias = wsf(ws, p.o_b[l]);
       const bool hidden = l + 1 < p.n;
-      g.c_full = out;
-      g.c_hi = out;
-      g.c_lo = hidden ? wsf(ws, p.o_act_lo[l]) + as * p.act_stride[l] : nullptr;
-      rc = tc::gemm(c.mA[l].hi, c.mA[l].lo, c.mB[l].hi, c.mB[l].lo, g, hidden ? tc::EPI_FWD_HIDDEN : tc::EPI_FWD_OUT,
-                    tc::pick_bn(p.wp[l + 1]), stream);
+      tc::GemmTcMaps tm{c.mA[l].hi, c.mA[l].lo, c.mB[l].hi, c.mB[l].lo, c.mAct[l].hi, c.mAct[l].lo, c.mAct[l].hi,
+                        c.mAct[l].lo};
+      rc = tc::gemm(tm, g, hidden ? tc::EPI_FWD_HIDDEN : tc::EPI_FWD_OUT, tc::pick_bn(p.wp[l + 1]), stream);
 #else
       rc = HDPO_E_INVALID;
 #endif
@@ -1213,6 +1238,8 @@ static int bwd_begin(ChunkCtx& c) {
       rc = make_pair(&c.mB[l], wsf(ws, p.o_WT[l]), wsf(ws, p.o_WT_lo[l]), p.wp[l], p.wp[l + 1], tc::pick_bn(p.wp[l]));
       if (rc) return rc;
     }
+    int rc = make_tape_maps(c);
+    if (rc) return rc;
   }
 #endif
   return HDPO_OK;
@@ -1268,18 +1295,15 @@ static int bwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t, float rb) {
       g.ldc = p.wp[l];
       g.act = d->master.hidden_act;
       if (l > 0) {
-        const size_t off = static_cast<size_t>(t) * p.act_stride[l - 1];
-        g.c_hi = wsf(ws, p.o_gz[l - 1]) + off;
-        g.c_lo = wsf(ws, p.o_gz_lo[l - 1]) + off;
-        g.aux_hi = wsf(ws, p.o_act[l - 1]) + off;
-        g.aux_lo = wsf(ws, p.o_act_lo[l - 1]) + off;
+        g.c_row0 = g.x_row0 = t * p.Bp;
         g.colsum_part = wsf(ws, p.o_csum[l - 1]);
-        rc = tc::gemm(c.mA[l].hi, c.mA[l].lo, c.mB[l].hi, c.mB[l].lo, g, tc::EPI_DGRAD_HIDDEN, tc::pick_bn(p.wp[l]),
-                      stream);
+        tc::GemmTcMaps tm{c.mA[l].hi,      c.mA[l].lo,      c.mB[l].hi,       c.mB[l].lo,
+                          c.mGz[l - 1].hi, c.mGz[l - 1].lo, c.mAct[l - 1].hi, c.mAct[l - 1].lo};
+        rc = tc::gemm(tm, g, tc::EPI_DGRAD_HIDDEN, tc::pick_bn(p.wp[l]), stream);
       } else {
-        g.c_full = gX;
-        rc = tc::gemm(c.mA[l].hi, c.mA[l].lo, c.mB[l].hi, c.mB[l].lo, g, tc::EPI_DGRAD_ACCUM, tc::pick_bn(p.wp[l]),
-                      stream);
+        g.c_row0 = g.x_row0 = 0;
+        tc::GemmTcMaps tm{c.mA[l].hi, c.mA[l].lo, c.mB[l].hi, c.mB[l].lo, c.mGx, c.mGx, c.mGx, c.mGx};
+        rc = tc::gemm(tm, g, tc::EPI_DGRAD_ACCUM, tc::pick_bn(p.wp[l]), stream);
       }
 #else
       rc = HDPO_E_INVALID;
@@ -1326,9 +1350,13 @@ static int bwd_end(ChunkCtx& c) {
       g.c_slice = c_slice;
       g.n_pass = p.n_pass;
       g.ldc = g.N;
-      g.c_full = wsf(ws, p.o_part);
-      rc = transposed ? tc::gemm_wgrad(mi.hi, mi.lo, mg.hi, mg.lo, g, tc::pick_bn(g.N), stream)
-                      : tc::gemm_wgrad(mg.hi, mg.lo, mi.hi, mi.lo, g, tc::pick_bn(g.N), stream);
+      CUtensorMap mpart;  // the partial slices as one [n_slices * M][N] array
+      rc = tc::make_tensor_map(&mpart, wsf(ws, p.o_part), static_cast<uint64_t>(p.wg_splits) * g.M, g.N, g.N,
+                               tc::kBoxRowsC);
+      if (rc) return rc;
+      tc::GemmTcMaps tm = transposed ? tc::GemmTcMaps{mi.hi, mi.lo, mg.hi, mg.lo, mpart, mpart, mpart, mpart}
+                                     : tc::GemmTcMaps{mg.hi, mg.lo, mi.hi, mi.lo, mpart, mpart, mpart, mpart};
+      rc = tc::gemm_wgrad(tm, g, tc::pick_bn(g.N), stream);
       if (rc) return rc;
       used_splits = p.wg_splits;
       ldp = g.N;
