@@ -18,7 +18,19 @@ void set_error(const char* fmt, ...) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static unsigned long long* g_trace_buf = nullptr;
+static unsigned int g_trace_cap = 0;
+TraceRef trace_ref(unsigned int tag) { return TraceRef{g_trace_buf, g_trace_cap, tag}; }
+
 }  // namespace hdpo
+
+// Debug hook: register (or clear with NULL) a device buffer of 4 + 4 * capacity uint64 that instrumented kernels
+// append one {start ns, end ns, smid | tag << 16, block} record per CTA to; buf[0] (zeroed by the caller) counts.
+extern "C" int hdpo_debug_set_trace(unsigned long long* buf, int64_t capacity) {
+  hdpo::g_trace_buf = buf;
+  hdpo::g_trace_cap = buf ? static_cast<unsigned int>(capacity) : 0u;
+  return HDPO_OK;
+}
 
 extern "C" const char* hdpo_last_error(void) { return hdpo::g_err; }
 extern "C" int hdpo_abi_version(void) { return HDPO_ABI_VERSION; }

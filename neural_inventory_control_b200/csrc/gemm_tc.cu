@@ -40,7 +40,7 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// shared -> global tile store (bulk async group); the source must stay valid until tma_store_wait_all()
+// shared -> global tile store (bulk async group); the source must stay valid until tma_store_wait_read()
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(map)),
@@ -48,7 +48,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// waits until the staged tiles have been READ (shared memory reusable / releasable); the global writes themselves
+// complete before the grid does, which is what the next kernel in the stream (griddepcontrol.wait) relies on
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // generic-proxy shared-memory writes -> visible to the async proxy (TMA store engine)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -182,6 +184,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * 128, n0 = blockIdx.x * BN;
+  long long* dbg = g.dbg_clock ? g.dbg_clock + 8 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  const unsigned long long trace_t0 = (g.trace.buf && threadIdx.x == 0) ? trace_now() : 0ull;
   const int n_kb = (MN ? g.k_per_split : g.K) / kBK;
   const int k_begin = MN ? static_cast<int>(blockIdx.z) * g.k_per_split : 0;
   const bool three = g.n_pass == 3;
@@ -214,6 +219,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
   // everything above overlapped the tail of the previous kernel in the stream (PDL); from here on we read its output
   pdl_wait();
   pdl_launch_dependents();
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -263,6 +269,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
         const uint32_t d_hi = tmem_d + static_cast<uint32_t>(chunk * BN);
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (dbg && kb == 0) dbg[2] = clock64();
         const uint32_t st = smem_u32(smem + s * P::kStageBytes);
         constexpr uint32_t kLbo = kBK * 128;
         const uint64_t a_hi = MN ? make_mnmajor_desc(st, kLbo) : make_kmajor_desc(st);
@@ -284,6 +291,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
         }
         umma_commit(&empty_bar[s]);  // frees the ring slot once these MMAs have read it
       }
+      if (dbg) dbg[3] = clock64();
       umma_commit(accum_bar);        // accumulator complete
     }
   } else {
@@ -302,6 +310,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
     unsigned char* stg = smem + we * (2 * kBoxes * kBoxBytes);  // [array 0 | array 1][box][32 rows x 128 B]
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    if (dbg && warp == 2 && lane == 0) dbg[4] = clock64();
     if (EPI == EPI_DGRAD_HIDDEN || EPI == EPI_DGRAD_ACCUM) {
       // the tile this epilogue combines with (saved layer output hi/lo, or the running state adjoint)
       constexpr int kArr = EPI == EPI_DGRAD_HIDDEN ? 2 : 1;
@@ -432,6 +441,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
       }
     }
     // staged sub-tile -> global: one TMA store per 32 x 32 box
+    if (dbg && warp == 2 && lane == 0) dbg[5] = clock64();
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
@@ -442,12 +452,15 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
           tma_store_2d(&tm.c1, stg + (kBoxes + b) * kBoxBytes, n0 + cbase + 32 * b, grow);
       }
       tma_store_commit();
-      tma_store_wait_all();  // shared memory (and TMEM) are released right after the final barrier
+      tma_store_wait_read();  // shared memory (and TMEM) are released right after the final barrier
+      if (dbg && warp == 2) dbg[6] = clock64();
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_d, kAccums * BN);
+  if (dbg && threadIdx.x == 0) dbg[7] = clock64();
+  if (threadIdx.x == 0) trace_emit(g.trace, trace_t0, blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -496,6 +509,7 @@ template <int BN, int EPI, bool MN = false>
 static int launch(const GemmTcMaps& tm, const GemmTcArgs& g_in, void* stream) {
   GemmTcArgs g = g_in;
   if (g.hi_chunks <= 0 || g.hi_chunks > kHiChunks) g.hi_chunks = kHiChunks;
+  g.trace = trace_ref((g_in.trace.tag << 8) | (static_cast<unsigned>(EPI) << 4) | (MN ? 8u : 0u) | (BN == 128 ? 1u : 0u));
   auto k = gemm_tc_kernel<BN, EPI, MN>;
   static bool configured = false;
   if (!configured) {
@@ -600,6 +614,34 @@ extern "C" int hdpo_debug_gemm_tc(const float* A, const float* B, float* C, int3
   g.K = K;
   g.n_pass = n_pass;
   g.ldc = N;
+  return tc::gemm(tm, g, tc::EPI_STORE, bn, stream);
+}
+
+// Same as hdpo_debug_gemm_tc with per-CTA clock64 stamps: dbg_clock[8 * n_ctas] (device), see gemm_tc_kernel.
+extern "C" int hdpo_debug_gemm_tc_timeline(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
+                                           int32_t n_pass, float* scratch, long long* dbg_clock, void* stream) {
+  HDPO_REQUIRE(A && B && C && scratch && dbg_clock, "null argument");
+  HDPO_REQUIRE(M % 128 == 0 && N % 64 == 0 && K % 32 == 0 && M > 0 && N > 0 && K > 0, "shape not tileable");
+  float* a_hi = scratch;
+  float* a_lo = a_hi + static_cast<size_t>(M) * K;
+  float* b_hi = a_lo + static_cast<size_t>(M) * K;
+  float* b_lo = b_hi + static_cast<size_t>(N) * K;
+  const int bn = tc::pick_bn(N);
+  tc::GemmTcMaps tm{};
+  int rc;
+  if ((rc = tc::make_tensor_map(&tm.a_hi, a_hi, M, K, K, 128))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.a_lo, a_lo, M, K, K, 128))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.b_hi, b_hi, N, K, K, bn))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.b_lo, b_lo, N, K, K, bn))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.c0, C, M, N, N, tc::kBoxRowsC))) return rc;
+  tm.c1 = tm.x0 = tm.x1 = tm.c0;
+  tc::GemmTcArgs g{};
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.n_pass = n_pass;
+  g.ldc = N;
+  g.dbg_clock = dbg_clock;
   return tc::gemm(tm, g, tc::EPI_STORE, bn, stream);
 }
 

@@ -34,6 +34,8 @@ struct GemmTcArgs {
   int ldc;              // leading dimension (floats) of the output (used by colsum_part only)
   int act;              // HDPO_ACT_* of the epilogue
   const float* bias;    // EPI_FWD_*
+  TraceRef trace;       // optional per-CTA trace records (hdpo_debug_set_trace); tag set by the caller
+  long long* dbg_clock; // optional: 8 clock64 stamps per CTA (tools/gemm_timeline.py)
   float* colsum_part;   // EPI_DGRAD_HIDDEN, optional: [rows / 32][ldc] column sums of each 32-row block of the output
                         // (bias-gradient partials; the row index includes a_row0, i.e. it follows the gz tape)
 };

@@ -58,6 +58,39 @@ inline void pdl_wait() {}
 #define HDPO_LAUNCH_PDL(kfn, grid, block, smem, stream, ...) HDPO_LAUNCH(kfn, grid, block, smem, stream, __VA_ARGS__)
 #endif
 
+// Optional device-side trace (tools/trace_step.py): one record per CTA {start ns, end ns, smid | tag << 16, block id}
+// appended to a caller-provided buffer (buf[0] = record counter, records from buf[4]). Null buffer = disabled.
+struct TraceRef {
+  unsigned long long* buf;
+  unsigned int cap, tag;
+};
+TraceRef trace_ref(unsigned int tag);  // capi.cu: the buffer registered with hdpo_debug_set_trace, or {nullptr}
+#ifndef HDPO_EMU
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_emit(const TraceRef& tr, unsigned long long t0, unsigned int block_linear,
+                                           unsigned int aux = 0) {
+  if (!tr.buf) return;
+  const unsigned long long t1 = trace_now();
+  unsigned int smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  const unsigned int idx = atomicAdd(reinterpret_cast<unsigned int*>(tr.buf), 1u);
+  if (idx < tr.cap) {
+    unsigned long long* rec = tr.buf + 4 + 4ull * idx;
+    rec[0] = t0;
+    rec[1] = t1;
+    rec[2] = static_cast<unsigned long long>(smid) | (static_cast<unsigned long long>(tr.tag) << 16);
+    rec[3] = static_cast<unsigned long long>(block_linear) | (static_cast<unsigned long long>(aux) << 32);
+  }
+}
+#else
+inline unsigned long long trace_now() { return 0; }
+inline void trace_emit(const TraceRef&, unsigned long long, unsigned int, unsigned int = 0) {}
+#endif
+
 constexpr int kWarp = 32;
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -31,6 +31,16 @@ constexpr int kRowPad = 128;   // scenarios padded to the GEMM M tile
 constexpr int kColPad = 64;    // layer widths padded to the GEMM N tile
 constexpr int kMaxStoresPerWarp = 256;
 constexpr int kSplitK = 16;
+constexpr size_t kHeadSmemMax = 200 * 1024;  // dynamic shared memory the head kernels may ask for
+constexpr int HEAD_WARPS = 4;              // scenarios (warps) per CTA of the head kernels
+
+// floats of shared memory one warp of a head kernel needs (see HeadSmem)
+__host__ __device__ inline int head_smem_floats(int S, int W, int ldx, int ldy, bool bwd) {
+  const int SW = S * W;
+  const int n = (bwd ? 2 * SW + 64 : SW + 32) + 2 * ldx + (bwd ? 2 : 1) * ldy + SW + 3 * S + 16;
+  return (n + 3) & ~3;  // every warp's region starts 16-byte aligned
+}
+
 
 static inline int pad_to(int x, int q) { return (x + q - 1) / q * q; }
 static inline size_t a256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
@@ -47,6 +57,9 @@ bool supported(const HdpoRolloutDesc* d) {
   if (m.widths[0] != pb.S * pb.L + pb.W * pb.Lw) return false;
   if (m.widths[m.n_layers] != pb.S * pb.W + pb.W) return false;
   if (m.out_act != HDPO_ACT_NONE) return false;
+  const int ldx = pad_to(m.widths[0], kColPad), ldy = pad_to(m.widths[m.n_layers], kColPad);
+  if (static_cast<size_t>(HEAD_WARPS) * head_smem_floats(pb.S, pb.W, ldx, ldy, true) * sizeof(float) > kHeadSmemMax)
+    return false;
   return true;
 }
 
@@ -451,9 +464,9 @@ struct HeadArgs {
   const int32_t* adjacency;  // [W][S] or null
   const float* demands;
   HdpoStatics st;
+  TraceRef trace;
 };
 
-constexpr int HEAD_WARPS = 4;
 
 __device__ __forceinline__ float demand_of(const HeadArgs& a, int b, int s) {
   if (a.demand_layout == HDPO_DEMAND_TSB) return __ldg(a.demands + (static_cast<size_t>(a.tt) * a.S + s) * a.demand_bstride + b);
@@ -486,31 +499,101 @@ __device__ __forceinline__ void softmax_shares(const HeadArgs& a, const float* _
   __syncwarp();
 }
 
+// Per-warp shared-memory rows. Everything a scenario needs is fetched with ONE round of independent, coalesced loads
+// (state row, policy output row, lead times, cost coefficients, demands), the period is computed in shared memory,
+// and the result rows go back with coalesced float4 stores: the kernels sit on the dependent chain of every period,
+// so their latency (not their throughput) is what matters.
+struct HeadSmem {
+  float *share, *xs, *xo, *y, *lt, *h, *p, *d;
+};
+__device__ __forceinline__ HeadSmem head_smem_rows(float* base, const HeadArgs& a, bool bwd) {
+  const int SW = a.S * a.W;
+  HeadSmem r;
+  // rows that are accessed as float4 first (the dynamic shared memory base is 16-byte aligned, ldx / ldy % 4 == 0)
+  r.xs = base;
+  r.xo = r.xs + a.ldx;
+  r.y = r.xo + a.ldx;
+  float* q = r.y + (bwd ? 2 : 1) * a.ldy;  // bwd: y row followed by the gy row
+  r.share = q;
+  q += bwd ? 2 * SW + 64 : SW + 32;
+  r.lt = q;
+  q += SW;
+  r.h = q;
+  q += a.S;
+  r.p = q;
+  q += a.S;
+  r.d = q;
+  return r;
+}
+// stage the rows of scenario b (all loads are independent of each other)
+__device__ __forceinline__ void head_stage(const HeadArgs& a, const HeadSmem& r, const float* __restrict__ x,
+                                           const float* __restrict__ y, int b, int lane) {
+  for (int k = lane * 4; k < a.ldx; k += 128)
+    *reinterpret_cast<float4*>(r.xs + k) = *reinterpret_cast<const float4*>(x + k);
+  for (int k = lane * 4; k < a.ldy; k += 128)
+    *reinterpret_cast<float4*>(r.y + k) = *reinterpret_cast<const float4*>(y + k);
+  const int SW = a.S * a.W;
+  const float* lt = a.st.lead_times + static_cast<size_t>(b) * SW;
+  for (int k = lane; k < SW; k += 32) r.lt[k] = __ldg(lt + k);
+  const float* hc = a.st.holding_costs + static_cast<size_t>(b) * a.S;
+  const float* pc = a.st.underage_costs + static_cast<size_t>(b) * a.S;
+  for (int s = lane; s < a.S; s += 32) {
+    r.h[s] = __ldg(hc + s);
+    r.p[s] = __ldg(pc + s);
+    r.d[s] = demand_of(a, b, s);
+  }
+}
+
 __global__ void __launch_bounds__(HEAD_WARPS * 32)
 warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ Xn,
                           float* __restrict__ cost_b, float* __restrict__ report_b, float* __restrict__ reward_t,
                           float* __restrict__ Xn_hi, float* __restrict__ Xn_lo) {
   pdl_wait();
   HDPO_DYN_SMEM(float, smem);
+  struct TraceScope {  // one record per CTA, emitted when the first thread leaves the kernel body
+    const TraceRef& tr;
+    unsigned long long t0;
+    unsigned int staged_ns;  // time until the staged rows were readable (bits 32.. of the block field)
+    __device__ ~TraceScope() {
+      if (threadIdx.x == 0) trace_emit(tr, t0, blockIdx.x, staged_ns);
+    }
+  } trace_scope{a.trace, (a.trace.buf && threadIdx.x == 0) ? trace_now() : 0ull, 0u};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * HEAD_WARPS + warp;
   if (b >= a.Bp) return;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (b >= a.B) {  // tile-padding rows stay exactly zero so that they never contribute to a weight gradient
-    for (int k = lane; k < a.ldx; k += 32) {
-      Xn[static_cast<size_t>(b) * a.ldx + k] = 0.f;
+    for (int k = lane * 4; k < a.ldx; k += 128) {
+      *reinterpret_cast<float4*>(Xn + static_cast<size_t>(b) * a.ldx + k) = zero4;
       if (Xn_hi) {
-        Xn_hi[static_cast<size_t>(b) * a.ldx + k] = 0.f;
-        Xn_lo[static_cast<size_t>(b) * a.ldx + k] = 0.f;
+        *reinterpret_cast<float4*>(Xn_hi + static_cast<size_t>(b) * a.ldx + k) = zero4;
+        *reinterpret_cast<float4*>(Xn_lo + static_cast<size_t>(b) * a.ldx + k) = zero4;
       }
     }
     return;
   }
   const int SW = a.S * a.W;
-  float* share = smem + warp * (SW + 32);  // alloc[s*W+w]; tail: per-warehouse scratch
-  const float* x = X + static_cast<size_t>(b) * a.ldx;
-  const float* y = Y + static_cast<size_t>(b) * a.ldy;
-  float* xn = Xn + static_cast<size_t>(b) * a.ldx;
   const int nS = a.S * a.L;
+  const HeadSmem r = head_smem_rows(smem + warp * head_smem_floats(a.S, a.W, a.ldx, a.ldy, false), a, false);
+  float* share = r.share;  // alloc[s*W+w]
+  head_stage(a, r, X + static_cast<size_t>(b) * a.ldx, Y + static_cast<size_t>(b) * a.ldy, b, lane);
+  // statics of the warehouses (lane w)
+  float wh_hold = 0.f, wh_edge = 0.f, wh_lead = 0.f;
+  if (lane < a.W) {
+    const int bw = b * a.W + lane;
+    wh_hold = __ldg(a.st.warehouse_holding_costs + bw);
+    wh_lead = __ldg(a.st.warehouse_lead_times + bw);
+    if (a.has_edge) wh_edge = __ldg(a.st.warehouse_edge_costs + bw);
+  }
+  __syncwarp();
+  if (a.trace.buf && threadIdx.x == 0) {
+    volatile float probe = r.xs[0] + r.d[0] + r.h[0];  // force the staged loads to have landed
+    (void)probe;
+    trace_scope.staged_ns = static_cast<unsigned int>(trace_now() - trace_scope.t0);
+  }
+  const float* x = r.xs;
+  const float* y = r.y;
+  float* xn = r.xo;
   softmax_shares(a, y, share, lane);
   // allocations = share * warehouse on-hand (optionally rounded half-to-even)
   for (int i = lane; i < SW; i += 32) {
@@ -525,11 +608,10 @@ warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
   for (int s = lane; s < a.S; s += 32) {
     const float* xs = x + s * a.L;
     float* xo = xn + s * a.L;
-    const int bs = b * a.S + s;
     const float on_hand = xs[0];
-    const float d = demand_of(a, b, s);
+    const float d = r.d[s];
     const float raw = on_hand - d;
-    const float h = a.st.holding_costs[bs], p = a.st.underage_costs[bs];
+    const float h = r.h[s], p = r.p[s];
     cost += a.profit ? (-p * fminf(on_hand, d) + h * relu0(raw)) : (p * relu0(-raw) + h * relu0(raw));
     const float post = a.lost ? relu0(raw) : raw;
     xo[0] = post + xs[1];
@@ -538,7 +620,7 @@ warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
     for (int w = 0; w < a.W; ++w) {
       const float al = share[s * a.W + w];
       if (al != 0.f) {
-        const int slot = static_cast<int>(a.st.lead_times[static_cast<size_t>(bs) * a.W + w]) - 1;
+        const int slot = static_cast<int>(r.lt[s * a.W + w]) - 1;
         if (slot >= 0 && slot < a.L) xo[slot] += al;
       }
     }
@@ -553,33 +635,41 @@ warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
   }
   if (lane < a.W) {
     const int w = lane;
-    const int bw = b * a.W + w;
     const float* xw = x + nS + w * a.Lw;
     float* xo = xn + nS + w * a.Lw;
     const float raw = xw[0] - drawn;
     float aw = sigmoid_f(y[SW + w]) * a.wub;
     if (a.discrete) aw = rintf(aw);
-    float cw = a.st.warehouse_holding_costs[bw] * relu0(raw);
-    if (a.has_edge) cw += a.st.warehouse_edge_costs[bw] * aw;
+    float cw = wh_hold * relu0(raw);
+    if (a.has_edge) cw += wh_edge * aw;
     cost += cw;
     xo[0] = raw + xw[1];
     for (int k = 1; k < a.Lw - 1; ++k) xo[k] = xw[k + 1];
     xo[a.Lw - 1] = 0.f;
     if (aw != 0.f) {
-      const int slot = static_cast<int>(a.st.warehouse_lead_times[bw]) - 1;
+      const int slot = static_cast<int>(wh_lead) - 1;
       if (slot >= 0 && slot < a.Lw) xo[slot] += aw;
     }
   }
   // padding columns of the next state row stay zero
   for (int k = nS + a.W * a.Lw + lane; k < a.ldx; k += 32) xn[k] = 0.f;
-  if (Xn_hi) {  // tensor-core mode: the next period's layer-0 GEMM reads the state as a (hi, lo) pair
-    __syncwarp();
-    float* xh = Xn_hi + static_cast<size_t>(b) * a.ldx;
-    float* xl = Xn_lo + static_cast<size_t>(b) * a.ldx;
-    for (int k = lane; k < a.ldx; k += 32) {
-      const float v = xn[k], h = tf32_round(v);
-      xh[k] = h;
-      xl[k] = tf32_round(v - h);
+  __syncwarp();
+  // next state row (and, tensor-core mode, its (hi, lo) split for the next period's layer-0 GEMM): coalesced stores
+  for (int k = lane * 4; k < a.ldx; k += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xn + k);
+    *reinterpret_cast<float4*>(Xn + static_cast<size_t>(b) * a.ldx + k) = v;
+    if (Xn_hi) {
+      float4 hi, lo;
+      hi.x = tf32_round(v.x);
+      hi.y = tf32_round(v.y);
+      hi.z = tf32_round(v.z);
+      hi.w = tf32_round(v.w);
+      lo.x = tf32_round(v.x - hi.x);
+      lo.y = tf32_round(v.y - hi.y);
+      lo.z = tf32_round(v.z - hi.z);
+      lo.w = tf32_round(v.w - hi.w);
+      *reinterpret_cast<float4*>(Xn_hi + static_cast<size_t>(b) * a.ldx + k) = hi;
+      *reinterpret_cast<float4*>(Xn_lo + static_cast<size_t>(b) * a.ldx + k) = lo;
     }
   }
   cost = warp_sum(cost);
@@ -596,24 +686,45 @@ warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
                           float* __restrict__ gY, float rb, float* __restrict__ gY_lo) {
   pdl_wait();
   HDPO_DYN_SMEM(float, smem);
+  struct TraceScope {
+    const TraceRef& tr;
+    unsigned long long t0;
+    __device__ ~TraceScope() {
+      if (threadIdx.x == 0) trace_emit(tr, t0, blockIdx.x);
+    }
+  } trace_scope{a.trace, (a.trace.buf && threadIdx.x == 0) ? trace_now() : 0ull};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * HEAD_WARPS + warp;
   if (b >= a.Bp) return;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (b >= a.B) {
-    for (int k = lane; k < a.ldy; k += 32) {
-      gY[static_cast<size_t>(b) * a.ldy + k] = 0.f;
-      if (gY_lo) gY_lo[static_cast<size_t>(b) * a.ldy + k] = 0.f;
+    for (int k = lane * 4; k < a.ldy; k += 128) {
+      *reinterpret_cast<float4*>(gY + static_cast<size_t>(b) * a.ldy + k) = zero4;
+      if (gY_lo) *reinterpret_cast<float4*>(gY_lo + static_cast<size_t>(b) * a.ldy + k) = zero4;
     }
     return;
   }
   const int SW = a.S * a.W;
-  float* share = smem + warp * (2 * SW + 64);  // p[s*W+w]
-  float* galloc = share + SW;                  // adjoint of the allocations
-  float* wscr = galloc + SW;                   // [0..W): g_raw_w, [W..2W): on-hand W0, [2W..3W): sum_s g_p*p
-  const float* x = X + static_cast<size_t>(b) * a.ldx;
-  const float* y = Y + static_cast<size_t>(b) * a.ldy;
-  float* g = gX + static_cast<size_t>(b) * a.ldx;
-  float* gy = gY + static_cast<size_t>(b) * a.ldy;
+  const HeadSmem r = head_smem_rows(smem + warp * head_smem_floats(a.S, a.W, a.ldx, a.ldy, true), a, true);
+  float* share = r.share;      // p[s*W+w]
+  float* galloc = share + SW;  // adjoint of the allocations
+  float* wscr = galloc + SW;   // [0..W): g_raw_w, [W..2W): on-hand W0
+  float* g = r.xo;             // adjoint row: staged, updated in place, written back
+  float* gy = r.y + a.ldy;
+  head_stage(a, r, X + static_cast<size_t>(b) * a.ldx, Y + static_cast<size_t>(b) * a.ldy, b, lane);
+  float* gx_row = gX + static_cast<size_t>(b) * a.ldx;
+  for (int k = lane * 4; k < a.ldx; k += 128)
+    *reinterpret_cast<float4*>(g + k) = *reinterpret_cast<const float4*>(gx_row + k);
+  float wh_hold = 0.f, wh_edge = 0.f, wh_lead = 0.f;
+  if (lane < a.W) {
+    const int bw = b * a.W + lane;
+    wh_hold = __ldg(a.st.warehouse_holding_costs + bw);
+    wh_lead = __ldg(a.st.warehouse_lead_times + bw);
+    if (a.has_edge) wh_edge = __ldg(a.st.warehouse_edge_costs + bw);
+  }
+  __syncwarp();
+  const float* x = r.xs;
+  const float* y = r.y;
   const int nS = a.S * a.L;
   softmax_shares(a, y, share, lane);
   // ---- warehouses first (lane w): g_raw_w feeds the store-allocation adjoints
@@ -627,7 +738,6 @@ warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
   }
   if (lane < a.W) {
     const int w = lane;
-    const int bw = b * a.W + w;
     const float W0 = x[nS + w * a.Lw];
     const float raw = W0 - drawn;
     float* gw = g + nS + w * a.Lw;
@@ -635,12 +745,12 @@ warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
     const float aw = sg * a.wub;
     float gaw = 0.f;
     if (aw != 0.f) {
-      const int slot = static_cast<int>(a.st.warehouse_lead_times[bw]) - 1;
+      const int slot = static_cast<int>(wh_lead) - 1;
       if (slot >= 0 && slot < a.Lw) gaw = gw[slot];
     }
-    if (a.has_edge) gaw += rb * a.st.warehouse_edge_costs[bw];
+    if (a.has_edge) gaw += rb * wh_edge;
     const float gn0 = gw[0];
-    const float g_raw = rb * a.st.warehouse_holding_costs[bw] * ge0(raw) + gn0;
+    const float g_raw = rb * wh_hold * ge0(raw) + gn0;
     for (int k = a.Lw - 1; k >= 2; --k) gw[k] = gw[k - 1];
     gw[1] = gn0;
     gw[0] = g_raw;
@@ -653,16 +763,15 @@ warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
   for (int s = lane; s < a.S; s += 32) {
     const float* xs = x + s * a.L;
     float* gs = g + s * a.L;
-    const int bs = b * a.S + s;
     const float on_hand = xs[0];
-    const float d = demand_of(a, b, s);
+    const float d = r.d[s];
     const float raw = on_hand - d;
-    const float h = a.st.holding_costs[bs], p = a.st.underage_costs[bs];
+    const float h = r.h[s], p = r.p[s];
     for (int w = 0; w < a.W; ++w) {
       const float al = share[s * a.W + w] * wscr[a.W + w];
       float ga = 0.f;
       if (al != 0.f) {
-        const int slot = static_cast<int>(a.st.lead_times[static_cast<size_t>(bs) * a.W + w]) - 1;
+        const int slot = static_cast<int>(r.lt[s * a.W + w]) - 1;
         if (slot >= 0 && slot < a.L) ga = gs[slot];
       }
       galloc[s * a.W + w] = ga - wscr[w];
@@ -694,13 +803,26 @@ warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
     }
   }
   for (int k = SW + a.W + lane; k < a.ldy; k += 32) gy[k] = 0.f;
-  if (gY_lo) {  // tensor-core mode: gY (in place) becomes the hi half, gY_lo the remainder
-    __syncwarp();
-    float* gl = gY_lo + static_cast<size_t>(b) * a.ldy;
-    for (int k = lane; k < a.ldy; k += 32) {
-      const float v = gy[k], h = tf32_round(v);
-      gy[k] = h;
-      gl[k] = tf32_round(v - h);
+  __syncwarp();
+  // write back: adjoint row of X_t (direct part) and gY (tensor-core mode: hi half in place, remainder in gY_lo)
+  for (int k = lane * 4; k < a.ldx; k += 128)
+    *reinterpret_cast<float4*>(gx_row + k) = *reinterpret_cast<const float4*>(g + k);
+  for (int k = lane * 4; k < a.ldy; k += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(gy + k);
+    if (gY_lo) {
+      float4 hi, lo;
+      hi.x = tf32_round(v.x);
+      hi.y = tf32_round(v.y);
+      hi.z = tf32_round(v.z);
+      hi.w = tf32_round(v.w);
+      lo.x = tf32_round(v.x - hi.x);
+      lo.y = tf32_round(v.y - hi.y);
+      lo.z = tf32_round(v.z - hi.z);
+      lo.w = tf32_round(v.w - hi.w);
+      *reinterpret_cast<float4*>(gY + static_cast<size_t>(b) * a.ldy + k) = hi;
+      *reinterpret_cast<float4*>(gY_lo + static_cast<size_t>(b) * a.ldy + k) = lo;
+    } else {
+      *reinterpret_cast<float4*>(gY + static_cast<size_t>(b) * a.ldy + k) = v;
     }
   }
 }
@@ -910,6 +1032,7 @@ struct ChunkCtx {
   Plan p;
   void* ws;
   void* stream;
+  int index;  // chunk number (trace tags)
   const float* demands;
   HdpoStatics st;
   HdpoState init, fin;
@@ -928,6 +1051,7 @@ static void bind_chunk(ChunkCtx* c, const HdpoRolloutDesc* d, const Chunking& ck
   const HdpoProblem& pb = d->pb;
   const size_t b0 = static_cast<size_t>(ck.b0[i]), S = pb.S, W = pb.W;
   c->p = make_plan(d, ck.rows[i]);
+  c->index = i;
   c->ws = static_cast<char*>(ws) + ck.ws_off[i];
   c->stream = stream;
   c->demands = d->demand_layout == HDPO_DEMAND_TSB ? demands + b0 : demands + b0 * S * d->t_stride;
@@ -970,6 +1094,7 @@ static HeadArgs head_args(const HdpoRolloutDesc* d, const ChunkCtx& c, int t) {
   a.adjacency = d->pb.W > 1 ? d->adjacency : nullptr;
   a.demands = c.demands;
   a.st = c.st;
+  a.trace = trace_ref(0xF00u | static_cast<unsigned>(c.index));  // tag: head kernel of chunk index
   return a;
 }
 
@@ -1083,6 +1208,7 @@ static int fwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t) {
       g.a_row0 = static_cast<int>(as * p.Bp);
       g.b_row0 = 0;
       g.c_row0 = g.a_row0;
+      g.trace.tag = static_cast<unsigned>(c.index);
       g.ldc = p.wp[l + 1];
       g.act = act;
       g.bias = wsf(ws, p.o_b[l]);
@@ -1106,8 +1232,11 @@ static int fwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t) {
     xn_hi = wsf(ws, p.o_X_hi) + slot * p.x_stride;
     xn_lo = wsf(ws, p.o_X_lo) + slot * p.x_stride;
   }
-  const size_t head_smem = static_cast<size_t>(HEAD_WARPS) * (pb.S * pb.W + 32) * sizeof(float);
+  const size_t head_smem = static_cast<size_t>(HEAD_WARPS) * head_smem_floats(pb.S, pb.W, p.wp[0], p.wp[p.n], false) * sizeof(float);
   auto k = warehouse_head_fwd_kernel;
+#ifndef HDPO_EMU
+  if (head_smem > 48 * 1024) HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHeadSmemMax)));
+#endif
   HDPO_LAUNCH_PDL(k, ceil_div(p.Bp, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, in, Xn, c.cost_b, c.report_b,
                   c.reward_tb ? c.reward_tb + static_cast<size_t>(t) * d->pb.B : static_cast<float*>(nullptr), xn_hi,
                   xn_lo);
@@ -1252,13 +1381,16 @@ static int bwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t, float rb) {
   const HdpoProblem& pb = d->pb;
   float* gX = wsf(ws, p.o_gx);
   const int last = p.n - 1;
-  const size_t head_smem = static_cast<size_t>(HEAD_WARPS) * (2 * pb.S * pb.W + 64) * sizeof(float);
+  const size_t head_smem = static_cast<size_t>(HEAD_WARPS) * head_smem_floats(pb.S, pb.W, p.wp[0], p.wp[p.n], true) * sizeof(float);
   const float* X = wsf(ws, p.o_X) + static_cast<size_t>(t) * p.x_stride;
   const float* Y = wsf(ws, p.o_act[last]) + static_cast<size_t>(t) * p.act_stride[last];
   float* gY = wsf(ws, p.o_gz[last]) + static_cast<size_t>(t) * p.act_stride[last];
   float* gY_lo = p.tc ? wsf(ws, p.o_gz_lo[last]) + static_cast<size_t>(t) * p.act_stride[last] : nullptr;
   HeadArgs a = head_args(d, c, t);
   auto k = warehouse_head_bwd_kernel;
+#ifndef HDPO_EMU
+  if (head_smem > 48 * 1024) HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHeadSmemMax)));
+#endif
   HDPO_LAUNCH_PDL(k, ceil_div(p.Bp, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, Y, gX, gY, rb, gY_lo);
   HDPO_LAUNCH_OK();
   // dgrad chain: gz_{l-1} = (gz_l W_l) * act'(h_{l-1});  finally gX += gz_0 W_0
@@ -1292,6 +1424,7 @@ static int bwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t, float rb) {
       g.n_pass = p.n_pass;
       g.a_row0 = t * p.Bp;
       g.b_row0 = 0;
+      g.trace.tag = static_cast<unsigned>(c.index);
       g.ldc = p.wp[l];
       g.act = d->master.hidden_act;
       if (l > 0) {
@@ -1349,6 +1482,7 @@ static int bwd_end(ChunkCtx& c) {
       g.k_per_split = p.wg_kps;
       g.c_slice = c_slice;
       g.n_pass = p.n_pass;
+      g.trace.tag = static_cast<unsigned>(c.index);
       g.ldc = g.N;
       CUtensorMap mpart;  // the partial slices as one [n_slices * M][N] array
       rc = tc::make_tensor_map(&mpart, wsf(ws, p.o_part), static_cast<uint64_t>(p.wg_splits) * g.M, g.N, g.N,
