@@ -1,6 +1,8 @@
 // gemm_tc.cu - tcgen05 / TMEM / TMA tile GEMM (see gemm_tc.cuh). Inline PTX only; no CUTLASS dependency.
 #include "gemm_tc.cuh"
 
+#include <cstdlib>
+
 #ifndef HDPO_EMU
 
 namespace hdpo {
@@ -31,6 +33,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// one lane of a CONVERGED warp; keeping the surrounding control flow warp-uniform lets the compiler hold descriptors
+// and coordinates in uniform registers (a loop under `if (lane == 0)` costs ~10 extra instructions per UTCHMMA / UTMALDG)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -53,6 +68,62 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // generic-proxy shared-memory writes -> visible to the async proxy (TMA store engine)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// --- CTA-pair (cta_group::2) variants ---
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (an address in this CTA's shared memory) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+// TMA load of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes are counted on the mbarrier
+// at shared::cluster address `bar_cluster` (the leader CTA's full barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[128 rows in each CTA's smem] * B[N/2 rows in each CTA's smem]; issued by the leader only
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrive on the mbarrier at this offset in BOTH CTAs of the pair once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+// pull a tile into L2 only (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -143,50 +214,57 @@ constexpr int kBK = 32;  // floats per K block = one 128-byte swizzle row
 constexpr int kAccums = 4;
 constexpr int kHiChunks = kAccums - 1;
 
-template <int BN>
+// CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x BN tile; each CTA stages its own 128 A rows
+// and HALF of the B rows, so the shared-memory traffic (TMA fills + MMA operand reads, the measured mainloop bound of
+// the single-CTA form) and the L2 traffic per flop drop by a quarter.
+// EARLY_AUX (CTA-pair dgrad epilogue): one stage less, and 64 KB after the ring receive half of the saved-activation
+// tile before the mainloop starts (the other half is fetched into the idle ring once the accumulators are ready).
+template <int BN, int CG = 1, bool EARLY_AUX = false>
 struct SmemPlan {
-#ifdef HDPO_TC_BN64_EXPERIMENT
-  static constexpr int kStages = (BN == 128) ? 3 : 2;   // 2 x 48 KB: two CTAs per SM overlap mainloop and epilogue
-#else
-  static constexpr int kStages = (BN == 128) ? 3 : 4;
-#endif
+  static constexpr int kStages = (BN == 128 && CG == 1) ? 3 : (EARLY_AUX ? 3 : 4);
+  static constexpr int kAuxBytes = EARLY_AUX ? kEpiWarps * 2 * 32 * 128 : 0;
   static constexpr int kABytes = 128 * kBK * 4;
-  static constexpr int kBBytes = BN * kBK * 4;
+  static constexpr int kBBytes = (BN / CG) * kBK * 4;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kTotal = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int kRing = kStages * kStageBytes;
+  static constexpr int kTotal = kRing + kAuxBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 4 /*bias tile*/;
 };
 
 // MN = false: D[M,N] = A[M,K] B[N,K]^T, operands K-major (rows = m / n, contiguous k).
 // MN = true : D[M,N] = sum_k A[k][m] B[k][n], operands MN-major (rows = k, contiguous m / n): the weight-gradient
 //             form dW = gz^T h straight from the [row][feature] tapes; blockIdx.z selects a K range of k_per_split rows
 //             and writes its own partial slice (short ranges keep the truncating accumulation fp32-grade).
-#ifdef HDPO_TC_BN64_EXPERIMENT
-#define HDPO_TC_MIN_CTAS(BN) ((BN) == 64 ? 2 : 1)
-#else
-#define HDPO_TC_MIN_CTAS(BN) 1
-#endif
-template <int BN, int EPI, bool MN>
-__global__ void __launch_bounds__(kThreads, HDPO_TC_MIN_CTAS(BN))
+template <int BN, int EPI, bool MN, int CG = 1>
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
+  static_assert(CG == 1 || !MN, "the CTA-pair form is K-major only");
   const CUtensorMap& tm_a_hi = tm.a_hi;
   const CUtensorMap& tm_a_lo = tm.a_lo;
   const CUtensorMap& tm_b_hi = tm.b_hi;
   const CUtensorMap& tm_b_lo = tm.b_lo;
-  using P = SmemPlan<BN>;
+  // Measured on B200 (cfg 4, in the pipeline): with the early half-tile the dgrad epilogue shrinks 4.25 -> 3.6 us but
+  // the 3-stage ring lengthens the mainloop 6.6 -> 7.7 us, a net loss; the path is kept for A/B runs only.
+  constexpr bool kEarlyAux = false && CG == 2 && EPI == EPI_DGRAD_HIDDEN;
+  using P = SmemPlan<BN, CG, kEarlyAux>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   unsigned char* smem = smem_raw + ((1024 - (raw_addr & 1023)) & 1023);  // SW128 needs 1024-byte aligned tiles
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P::kStages * P::kStageBytes);
+  unsigned char* aux_early = smem + P::kRing;  // [epilogue warp][hi | lo][32 rows x 128 B], kEarlyAux only
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P::kRing + P::kAuxBytes);
   uint64_t* empty_bar = full_bar + P::kStages;
   uint64_t* accum_bar = empty_bar + P::kStages;
   uint64_t* epi_bar = accum_bar + 1;  // one per epilogue warp: its TMA loads of the tile the epilogue combines with
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + kEpiWarps);
+  uint64_t* aux_bar = epi_bar + kEpiWarps;  // one per epilogue warp: the early half of the combined tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + kEpiWarps);
+  float* bias_s = reinterpret_cast<float*>(smem + P::kRing + P::kAuxBytes + 256);  // [BN], forward epilogues
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * BN;
+  // CG = 1: grid (N tiles, M tiles, K slices); CG = 2: grid (2 = CTA of the pair, 256-row tiles, N tiles)
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int m0 = CG == 2 ? blockIdx.y * 256 + static_cast<int>(rank) * 128 : blockIdx.y * 128;
+  const int n0 = CG == 2 ? blockIdx.z * BN : blockIdx.x * BN;
   long long* dbg = g.dbg_clock ? g.dbg_clock + 8 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
-  const unsigned long long trace_t0 = (g.trace.buf && threadIdx.x == 0) ? trace_now() : 0ull;
   const int n_kb = (MN ? g.k_per_split : g.K) / kBK;
   const int k_begin = MN ? static_cast<int>(blockIdx.z) * g.k_per_split : 0;
   const bool three = g.n_pass == 3;
@@ -203,33 +281,86 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(accum_bar, 1);
-    for (int w = 0; w < kEpiWarps; ++w) mbar_init(&epi_bar[w], 1);
+    for (int w = 0; w < kEpiWarps; ++w) {
+      mbar_init(&epi_bar[w], 1);
+      mbar_init(&aux_bar[w], 1);
+    }
     prefetch_tmap(&tm.c0);
     if (EPI == EPI_FWD_HIDDEN || EPI == EPI_DGRAD_HIDDEN) prefetch_tmap(&tm.c1);
     if (EPI == EPI_DGRAD_HIDDEN || EPI == EPI_DGRAD_ACCUM) prefetch_tmap(&tm.x0);
     if (EPI == EPI_DGRAD_HIDDEN) prefetch_tmap(&tm.x1);
     fence_barrier_init();
   }
+  // Inputs that were produced at least two kernels back are touched BEFORE the dependency wait (and before the set-up barrier
+  // below, which also publishes the bias tile to the other epilogue warps), so that their latency
+  // (several microseconds when the memory system is busy) overlaps the predecessor: the bias tile goes to shared
+  // memory, the saved-activation tile of the dgrad epilogue is pulled into L2.
+  if (warp >= 2) {
+    const int we0 = warp - 2, q0 = warp & 3, half0 = we0 >> 2;
+    if (EPI == EPI_FWD_HIDDEN || EPI == EPI_FWD_OUT) {
+      const int t = threadIdx.x - 64;
+      if (t < BN) bias_s[t] = g.bias[n0 + t];
+    }
+    if (EPI == EPI_DGRAD_HIDDEN && lane == 0) {
+      const int xrow = g.x_row0 + m0 + q0 * 32;
+#pragma unroll
+      for (int b = kEarlyAux ? 1 : 0; b < BN / 64; ++b) {
+        tma_prefetch_l2_2d(&tm.x0, n0 + half0 * (BN / 2) + 32 * b, xrow);
+        tma_prefetch_l2_2d(&tm.x1, n0 + half0 * (BN / 2) + 32 * b, xrow);
+      }
+    }
+  }
+  if (CG == 2) cluster_sync_all();  // the peer's barriers exist before anything can arrive on them
   // TMEM: kAccums accumulators of BN fp32 columns each (see "accumulator splitting" at the MMA loop)
-  if (warp == 1) tmem_alloc(tmem_slot, kAccums * BN);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_pair(tmem_slot, kAccums * BN);
+    else tmem_alloc(tmem_slot, kAccums * BN);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  if (kEarlyAux && warp >= 2 && lane == 0) {
+    // first 32-column box (hi and lo) of this warp's saved-activation sub-tile: a forward tape, independent of the
+    // predecessor kernel, so the load is in flight during the dependency wait and the whole mainloop
+    const int we0 = warp - 2, q0 = warp & 3, half0 = we0 >> 2;
+    unsigned char* dst = aux_early + we0 * (2 * 32 * 128);
+    mbar_expect_tx(&aux_bar[we0], 2 * 32 * 128);
+    tma_load_2d(dst, &tm.x0, &aux_bar[we0], n0 + half0 * (BN / 2), g.x_row0 + m0 + q0 * 32);
+    tma_load_2d(dst + 32 * 128, &tm.x1, &aux_bar[we0], n0 + half0 * (BN / 2), g.x_row0 + m0 + q0 * 32);
+  }
   // everything above overlapped the tail of the previous kernel in the stream (PDL); from here on we read its output
   pdl_wait();
   pdl_launch_dependents();
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+  // trace records start once the predecessor's data is visible (a PDL-launched CTA may have idled above for long)
+  const unsigned long long trace_t0 = (g.trace.buf && threadIdx.x == 0) ? trace_now() : 0ull;
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      const uint32_t tx = three ? P::kStageBytes : (P::kABytes + P::kBBytes);
+    // CTA pair: the whole warp runs the loop and one elected lane issues (warp-uniform control flow keeps the
+    // descriptors in uniform registers; measured: the pair's mainloop drops from ~1000 to ~780 cycles per K block,
+    // the MMA floor). Single CTA: lane 0 alone runs the loop (measured faster there: 19.1k vs 20.7k cycles per tile).
+    if (CG == 2 || lane == 0) {
+      const uint32_t tx = (three ? P::kStageBytes : (P::kABytes + P::kBBytes)) * CG;
       for (int kb = 0; kb < n_kb; ++kb) {
         const int s = kb % P::kStages;
         const uint32_t ph = (kb / P::kStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         unsigned char* st = smem + s * P::kStageBytes;
+        if (CG == 1 || elect_one()) {
+        if (CG == 2) {
+          // both CTAs fill their own stage; all bytes are counted on the LEADER's full barrier (the MMA issuer's)
+          if (rank == 0) mbar_expect_tx(&full_bar[s], tx);
+          const uint32_t bar = mapa_u32(&full_bar[s], 0);
+          const int brow = g.b_row0 + n0 + static_cast<int>(rank) * (BN / 2);
+          tma_load_2d_pair(st, &tm_a_hi, bar, kb * kBK, g.a_row0 + m0);
+          tma_load_2d_pair(st + 2 * P::kABytes, &tm_b_hi, bar, kb * kBK, brow);
+          if (three) {
+            tma_load_2d_pair(st + P::kABytes, &tm_a_lo, bar, kb * kBK, g.a_row0 + m0);
+            tma_load_2d_pair(st + 2 * P::kABytes + P::kBBytes, &tm_b_lo, bar, kb * kBK, brow);
+          }
+        } else {
         mbar_expect_tx(&full_bar[s], tx);
         if (!MN) {
           tma_load_2d(st, &tm_a_hi, &full_bar[s], kb * kBK, g.a_row0 + m0);
@@ -252,23 +383,28 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
                           g.b_row0 + krow);
           }
         }
+        }
+        }
+        if (CG == 2) __syncwarp();  // lanes running ahead would spin on the next barrier and steal issue slots
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (CTA pair: the leader's warp runs the loop, one elected lane issues for both CTAs) =====
+    if (rank == 0 && (CG == 2 || lane == 0)) {
       // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
-                             (static_cast<uint32_t>(128 >> 4) << 24) | (MN ? ((1u << 15) | (1u << 16)) : 0u);
+                             (static_cast<uint32_t>((128 * CG) >> 4) << 24) | (MN ? ((1u << 15) | (1u << 16)) : 0u);
       const int nch = n_kb < g.hi_chunks ? n_kb : g.hi_chunks;
-      uint32_t started = 0;  // bit i: accumulator i already holds data
       for (int kb = 0; kb < n_kb; ++kb) {
         const int s = kb % P::kStages;
         const uint32_t ph = (kb / P::kStages) & 1;
         const int chunk = 1 + (kb * nch) / n_kb;
+        // the first MMA into an accumulator overwrites it (warp-uniform: derived from kb, not from per-lane state)
+        const bool chunk_first = kb == 0 || chunk != 1 + ((kb - 1) * nch) / n_kb;
         const uint32_t d_hi = tmem_d + static_cast<uint32_t>(chunk * BN);
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (CG == 1 || elect_one()) {
         if (dbg && kb == 0) dbg[2] = clock64();
         const uint32_t st = smem_u32(smem + s * P::kStageBytes);
         constexpr uint32_t kLbo = kBK * 128;
@@ -281,18 +417,33 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
         for (int k = 0; k < kBK / 8; ++k) {
           // K-major: 32 bytes per K=8 step inside the swizzle row; MN-major: one 1024-byte atom (8 k rows) per step
           const uint64_t adv = static_cast<uint64_t>((MN ? k * 1024 : k * 8 * 4) >> 4);
-          umma_tf32(d_hi, a_hi + adv, b_hi + adv, idesc, (started >> chunk) & 1u);
-          started |= 1u << chunk;
+          const uint32_t acc_hi = (chunk_first && k == 0) ? 0u : 1u;
+          const uint32_t acc_x = (kb == 0 && k == 0) ? 0u : 1u;
+          if (CG == 2) {
+            umma_tf32_pair(d_hi, a_hi + adv, b_hi + adv, idesc, acc_hi);
+            if (three) {
+              umma_tf32_pair(tmem_d, a_lo + adv, b_hi + adv, idesc, acc_x);
+              umma_tf32_pair(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+            }
+            continue;
+          }
+          umma_tf32(d_hi, a_hi + adv, b_hi + adv, idesc, acc_hi);
           if (three) {
-            umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, started & 1u);
+            umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, acc_x);
             umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
-            started |= 1u;
           }
         }
-        umma_commit(&empty_bar[s]);  // frees the ring slot once these MMAs have read it
+        // frees the ring slot (in both CTAs of a pair) once these MMAs have read it
+        if (CG == 2) umma_commit_pair(&empty_bar[s]);
+        else umma_commit(&empty_bar[s]);
+        }
+        if (CG == 2) __syncwarp();
       }
-      if (dbg) dbg[3] = clock64();
-      umma_commit(accum_bar);        // accumulator complete
+      if (CG == 1 || elect_one()) {
+        if (dbg) dbg[3] = clock64();
+        if (CG == 2) umma_commit_pair(accum_bar);  // accumulators complete (each CTA drains its own 128 rows)
+        else umma_commit(accum_bar);
+      }
     }
   } else {
     // ===== epilogue: warp q = warp % 4 owns TMEM lanes [32q, 32q+32) = tile rows =====
@@ -311,19 +462,22 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     if (dbg && warp == 2 && lane == 0) dbg[4] = clock64();
+    if (g.trace.buf && warp == 2 && lane == 0) tmem_slot[1] = static_cast<uint32_t>(trace_now());  // accumulators ready
     if (EPI == EPI_DGRAD_HIDDEN || EPI == EPI_DGRAD_ACCUM) {
       // the tile this epilogue combines with (saved layer output hi/lo, or the running state adjoint)
       constexpr int kArr = EPI == EPI_DGRAD_HIDDEN ? 2 : 1;
+      constexpr int kFirstBox = kEarlyAux ? 1 : 0;  // box 0 arrived in aux_early long ago
       if (lane == 0) {
-        mbar_expect_tx(&epi_bar[we], kArr * kBoxes * kBoxBytes);
+        mbar_expect_tx(&epi_bar[we], kArr * (kBoxes - kFirstBox) * kBoxBytes);
         const int xrow = g.x_row0 + m0 + q * 32;
 #pragma unroll
-        for (int b = 0; b < kBoxes; ++b) {
+        for (int b = kFirstBox; b < kBoxes; ++b) {
           tma_load_2d(stg + b * kBoxBytes, &tm.x0, &epi_bar[we], n0 + cbase + 32 * b, xrow);
           if (kArr == 2) tma_load_2d(stg + (kBoxes + b) * kBoxBytes, &tm.x1, &epi_bar[we], n0 + cbase + 32 * b, xrow);
         }
       }
-      mbar_wait(&epi_bar[we], 0);
+      if (kEarlyAux) mbar_wait(&aux_bar[we], 0);  // box 0 is processed first; box 1 is awaited when it is reached
+      else mbar_wait(&epi_bar[we], 0);
     }
     const int nch = n_kb < g.hi_chunks ? n_kb : g.hi_chunks;
     const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
@@ -347,32 +501,44 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
         v[j] = a;
       }
       const int n = n0 + c0;
+      if (kEarlyAux && cc == 32) mbar_wait(&epi_bar[we], 0);  // second box of the combined tile has landed by now
       // staging addresses of this lane's four 16-byte chunks (array 0; array 1 is kBoxes boxes further)
       unsigned char* box = stg + (cc >> 5) * kBoxBytes + lane * 128;
       const int ch0 = (cc & 31) >> 2;
       auto chunk_ptr = [&](int arr, int j4) {
         return reinterpret_cast<float4*>(box + arr * (kBoxes * kBoxBytes) + (((ch0 + j4) ^ (lane & 7)) << 4));
       };
+      // where the combined tile's chunks are read from: the early box lives in its own region
+      auto aux_ptr = [&](int arr, int j4) {
+        if (kEarlyAux && cc < 32)
+          return reinterpret_cast<const float4*>(aux_early + we * (2 * kBoxBytes) + arr * kBoxBytes + lane * 128 +
+                                                 (((ch0 + j4) ^ (lane & 7)) << 4));
+        return reinterpret_cast<const float4*>(chunk_ptr(arr, j4));
+      };
       if (EPI == EPI_FWD_HIDDEN || EPI == EPI_FWD_OUT) {
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(g.bias + n + 4 * j4);
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j4);
           v[4 * j4 + 0] += b4.x;
           v[4 * j4 + 1] += b4.y;
           v[4 * j4 + 2] += b4.z;
           v[4 * j4 + 3] += b4.w;
         }
-        dispatch_act(g.act, [&](auto tag) {
-          constexpr int ACT = decltype(tag)::value;
+        if (g.act == HDPO_ACT_ELU) {
+          elu_inplace(v);  // branch-free, element chains overlap
+        } else {
+          dispatch_act(g.act, [&](auto tag) {
+            constexpr int ACT = decltype(tag)::value;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = act_fwd_t<ACT>(v[j]);
-        });
+            for (int j = 0; j < 16; ++j) v[j] = act_fwd_t<ACT>(v[j]);
+          });
+        }
       } else if (EPI == EPI_DGRAD_HIDDEN) {
         float h[16];
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 a = *chunk_ptr(0, j4);
-          const float4 b = *chunk_ptr(1, j4);
+          const float4 a = *aux_ptr(0, j4);
+          const float4 b = *aux_ptr(1, j4);
           h[4 * j4 + 0] = a.x + b.x;
           h[4 * j4 + 1] = a.y + b.y;
           h[4 * j4 + 2] = a.z + b.z;
@@ -442,6 +608,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
     }
     // staged sub-tile -> global: one TMA store per 32 x 32 box
     if (dbg && warp == 2 && lane == 0) dbg[5] = clock64();
+    if (g.trace.buf && warp == 2 && lane == 0) tmem_slot[2] = static_cast<uint32_t>(trace_now());  // tile staged
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
@@ -454,13 +621,23 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
       tma_store_commit();
       tma_store_wait_read();  // shared memory (and TMEM) are released right after the final barrier
       if (dbg && warp == 2) dbg[6] = clock64();
+      if (g.trace.buf && warp == 2) tmem_slot[3] = static_cast<uint32_t>(trace_now());  // staged tile read by TMA
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_d, kAccums * BN);
+  if (CG == 2) cluster_sync_all();  // neither CTA may release shared memory / TMEM the pair's MMAs and commits still use
+  if (warp == 1) {
+    if (CG == 2) tmem_dealloc_pair(tmem_d, kAccums * BN);
+    else tmem_dealloc(tmem_d, kAccums * BN);
+  }
   if (dbg && threadIdx.x == 0) dbg[7] = clock64();
-  if (threadIdx.x == 0) trace_emit(g.trace, trace_t0, blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+  if (threadIdx.x == 0 && g.trace.buf)
+    trace_emit(g.trace, trace_t0, blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z),
+               // aux: ns/32 from start to "accumulators ready" | "tile staged" | "stores read" (10 bits each)
+               (((tmem_slot[1] - static_cast<uint32_t>(trace_t0)) >> 5) & 1023u) |
+                   ((((tmem_slot[2] - static_cast<uint32_t>(trace_t0)) >> 5) & 1023u) << 10) |
+                   ((((tmem_slot[3] - static_cast<uint32_t>(trace_t0)) >> 5) & 1023u) << 20));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -480,6 +657,15 @@ static EncodeTiledFn encode_fn() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+
+int pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HDPO_TC_PAIR");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v;
 }
 
 int make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
@@ -505,28 +691,32 @@ int make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t
   return HDPO_OK;
 }
 
-template <int BN, int EPI, bool MN = false>
+template <int BN, int EPI, bool MN = false, int CG = 1>
 static int launch(const GemmTcMaps& tm, const GemmTcArgs& g_in, void* stream) {
   GemmTcArgs g = g_in;
   if (g.hi_chunks <= 0 || g.hi_chunks > kHiChunks) g.hi_chunks = kHiChunks;
   g.trace = trace_ref((g_in.trace.tag << 8) | (static_cast<unsigned>(EPI) << 4) | (MN ? 8u : 0u) | (BN == 128 ? 1u : 0u));
-  auto k = gemm_tc_kernel<BN, EPI, MN>;
+  auto k = gemm_tc_kernel<BN, EPI, MN, CG>;
   static bool configured = false;
   if (!configured) {
-    HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlan<BN>::kTotal));
+    HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlan<BN, CG, false>::kTotal));
     configured = true;
   }
   const unsigned nz = MN ? static_cast<unsigned>(g.K / g.k_per_split) : 1u;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(g.N / BN, g.M / 128, nz);
+  cfg.gridDim = CG == 2 ? dim3(2, g.M / 256, g.N / BN) : dim3(g.N / BN, g.M / 128, nz);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = SmemPlan<BN>::kTotal;
+  cfg.dynamicSmemBytes = SmemPlan<BN, CG, false>::kTotal;
   cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: prologue overlaps the previous kernel's tail
   attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;                 // CTA pair
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = CG == 2 ? 2 : 1;
   HDPO_CUDA_OK(cudaLaunchKernelEx(&cfg, k, tm, g));
   count_launch();
   HDPO_LAUNCH_OK();
@@ -547,9 +737,20 @@ static int launch_epi(const GemmTcMaps& tm, const GemmTcArgs& g, int epi, void* 
 }
 
 int gemm(const GemmTcMaps& tm, const GemmTcArgs& g, int epi, int bn, void* stream) {
-  HDPO_REQUIRE(g.M % 128 == 0 && g.N % bn == 0 && g.K % kBK == 0 && g.K > 0, "tcgen05 GEMM shape %dx%dx%d not tileable",
-               g.M, g.N, g.K);
+  const int bn_cols = bn == kBnPair ? 128 : bn;
+  HDPO_REQUIRE(g.M % 128 == 0 && g.N % bn_cols == 0 && g.K % kBK == 0 && g.K > 0,
+               "tcgen05 GEMM shape %dx%dx%d not tileable", g.M, g.N, g.K);
   HDPO_REQUIRE(g.n_pass == 1 || g.n_pass == 3, "n_pass must be 1 or 3");
+  if (bn == kBnPair) {  // CTA-pair form: 256 x 128 tiles (the B map must have BN / 2 = 64-row boxes)
+    HDPO_REQUIRE(g.M % 256 == 0 && g.N % 128 == 0, "CTA-pair GEMM shape %dx%d not tileable", g.M, g.N);
+    switch (epi) {
+      case EPI_FWD_HIDDEN: return launch<128, EPI_FWD_HIDDEN, false, 2>(tm, g, stream);
+      case EPI_DGRAD_HIDDEN: return launch<128, EPI_DGRAD_HIDDEN, false, 2>(tm, g, stream);
+      case EPI_STORE: return launch<128, EPI_STORE, false, 2>(tm, g, stream);
+    }
+    set_error("the CTA-pair GEMM has no epilogue %d", epi);
+    return HDPO_E_INVALID;
+  }
   if (bn == 128) return launch_epi<128>(tm, g, epi, stream);
   if (bn == 64) return launch_epi<64>(tm, g, epi, stream);
   set_error("unsupported BN %d", bn);
@@ -599,13 +800,13 @@ extern "C" int hdpo_debug_gemm_tc(const float* A, const float* B, float* C, int3
   count_launch();
   count_launch();
   HDPO_LAUNCH_OK();
-  const int bn = tc::pick_bn(N);
+  const int bn = tc::pick_bn_pair(M, N);
   tc::GemmTcMaps tm{};
   int rc;
   if ((rc = tc::make_tensor_map(&tm.a_hi, a_hi, M, K, K, 128))) return rc;
   if ((rc = tc::make_tensor_map(&tm.a_lo, a_lo, M, K, K, 128))) return rc;
-  if ((rc = tc::make_tensor_map(&tm.b_hi, b_hi, N, K, K, bn))) return rc;
-  if ((rc = tc::make_tensor_map(&tm.b_lo, b_lo, N, K, K, bn))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.b_hi, b_hi, N, K, K, tc::b_box_rows(bn)))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.b_lo, b_lo, N, K, K, tc::b_box_rows(bn)))) return rc;
   if ((rc = tc::make_tensor_map(&tm.c0, C, M, N, N, tc::kBoxRowsC))) return rc;
   tm.c1 = tm.x0 = tm.x1 = tm.c0;
   tc::GemmTcArgs g{};
@@ -618,21 +819,23 @@ extern "C" int hdpo_debug_gemm_tc(const float* A, const float* B, float* C, int3
 }
 
 // Same as hdpo_debug_gemm_tc with per-CTA clock64 stamps: dbg_clock[8 * n_ctas] (device), see gemm_tc_kernel.
+// epi = 4 (plain store) or 0 (bias + ELU + (hi, lo) split; C_lo and bias must then be given)
 extern "C" int hdpo_debug_gemm_tc_timeline(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
-                                           int32_t n_pass, float* scratch, long long* dbg_clock, void* stream) {
+                                           int32_t n_pass, float* scratch, long long* dbg_clock, void* stream,
+                                           int32_t epi, float* C_lo, const float* bias) {
   HDPO_REQUIRE(A && B && C && scratch && dbg_clock, "null argument");
   HDPO_REQUIRE(M % 128 == 0 && N % 64 == 0 && K % 32 == 0 && M > 0 && N > 0 && K > 0, "shape not tileable");
   float* a_hi = scratch;
   float* a_lo = a_hi + static_cast<size_t>(M) * K;
   float* b_hi = a_lo + static_cast<size_t>(M) * K;
   float* b_lo = b_hi + static_cast<size_t>(N) * K;
-  const int bn = tc::pick_bn(N);
+  const int bn = tc::pick_bn_pair(M, N);
   tc::GemmTcMaps tm{};
   int rc;
   if ((rc = tc::make_tensor_map(&tm.a_hi, a_hi, M, K, K, 128))) return rc;
   if ((rc = tc::make_tensor_map(&tm.a_lo, a_lo, M, K, K, 128))) return rc;
-  if ((rc = tc::make_tensor_map(&tm.b_hi, b_hi, N, K, K, bn))) return rc;
-  if ((rc = tc::make_tensor_map(&tm.b_lo, b_lo, N, K, K, bn))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.b_hi, b_hi, N, K, K, tc::b_box_rows(bn)))) return rc;
+  if ((rc = tc::make_tensor_map(&tm.b_lo, b_lo, N, K, K, tc::b_box_rows(bn)))) return rc;
   if ((rc = tc::make_tensor_map(&tm.c0, C, M, N, N, tc::kBoxRowsC))) return rc;
   tm.c1 = tm.x0 = tm.x1 = tm.c0;
   tc::GemmTcArgs g{};
@@ -642,6 +845,13 @@ extern "C" int hdpo_debug_gemm_tc_timeline(const float* A, const float* B, float
   g.n_pass = n_pass;
   g.ldc = N;
   g.dbg_clock = dbg_clock;
+  if (epi == tc::EPI_FWD_HIDDEN) {
+    HDPO_REQUIRE(C_lo && bias, "null argument");
+    if ((rc = tc::make_tensor_map(&tm.c1, C_lo, M, N, N, tc::kBoxRowsC))) return rc;
+    g.bias = bias;
+    g.act = HDPO_ACT_ELU;
+    return tc::gemm(tm, g, tc::EPI_FWD_HIDDEN, bn, stream);
+  }
   return tc::gemm(tm, g, tc::EPI_STORE, bn, stream);
 }
 

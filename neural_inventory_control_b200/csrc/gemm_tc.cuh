@@ -63,11 +63,13 @@ int gemm(const GemmTcMaps& tm, const GemmTcArgs& g, int epi, int bn, void* strea
 
 constexpr int kBoxRowsA = 128;
 constexpr int kBoxRowsC = 32;
-#ifdef HDPO_TC_BN64_EXPERIMENT
-inline int pick_bn(int) { return 64; }
-#else
 inline int pick_bn(int N) { return (N % 128 == 0) ? 128 : 64; }
-#endif
+// `bn` selector of gemm(): 64 / 128 = single-CTA tiles 128 x bn; kBnPair = CTA-pair (cta_group::2) tiles 256 x 128.
+constexpr int kBnPair = 1128;
+inline int b_box_rows(int bn) { return bn == kBnPair ? 64 : bn; }  // rows of the B operand's TMA box
+// the pair form needs 256-row and 128-column tiles; HDPO_TC_PAIR=0 disables it (A/B comparison on the GPU box)
+int pair_enabled();
+inline int pick_bn_pair(int M, int N) { return (pair_enabled() && M % 256 == 0 && N % 128 == 0) ? kBnPair : pick_bn(N); }
 
 }  // namespace tc
 }  // namespace hdpo

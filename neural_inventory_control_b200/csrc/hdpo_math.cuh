@@ -30,6 +30,44 @@ __device__ __forceinline__ float expm1_nonpos(float x) {
 #endif
 }
 
+// Branch-free ELU over a small register array (same arithmetic as elu_f). In a tile epilogue every lane holds 16
+// unrelated values: the per-element `x > 0 ? ... : ...` of elu_f compiles to one divergent region per element with a
+// serial 7-FMA Horner chain inside (measured: 5.8 us per 128 x 128 tile, as long as the tile's whole mainloop);
+// evaluating both branches for all elements lets the chains of different elements overlap.
+template <int N>
+__device__ __forceinline__ void elu_inplace(float (&v)[N]) {
+  float xm[N], p[N], e[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) xm[j] = fminf(v[j], 0.f);
+#pragma unroll
+  for (int j = 0; j < N; ++j) p[j] = fmaf(xm[j], 1.f / 5040.f, 1.f / 720.f);
+#pragma unroll
+  for (int j = 0; j < N; ++j) p[j] = fmaf(xm[j], p[j], 1.f / 120.f);
+#pragma unroll
+  for (int j = 0; j < N; ++j) p[j] = fmaf(xm[j], p[j], 1.f / 24.f);
+#pragma unroll
+  for (int j = 0; j < N; ++j) p[j] = fmaf(xm[j], p[j], 1.f / 6.f);
+#pragma unroll
+  for (int j = 0; j < N; ++j) p[j] = fmaf(xm[j], p[j], 0.5f);
+#pragma unroll
+  for (int j = 0; j < N; ++j) p[j] = fmaf(xm[j], p[j], 1.f);
+#pragma unroll
+  for (int j = 0; j < N; ++j) p[j] = xm[j] * p[j];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+#ifdef HDPO_EMU
+    e[j] = expf(xm[j]) - 1.f;
+#else
+    e[j] = __expf(xm[j]) - 1.f;
+#endif
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const float r = xm[j] > -0.35f ? p[j] : e[j];
+    v[j] = v[j] > 0.f ? v[j] : r;
+  }
+}
+
 // nn.ELU(alpha=1): x > 0 ? x : expm1(x)
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1_nonpos(x); }
 // derivative expressed with the OUTPUT y: 1 for x > 0, exp(x) = y + 1 for x <= 0 (y == 0 at x == 0 -> 1)

@@ -525,13 +525,15 @@ __device__ __forceinline__ HeadSmem head_smem_rows(float* base, const HeadArgs& 
   r.d = q;
   return r;
 }
-// stage the rows of scenario b (all loads are independent of each other)
+// stage the rows of scenario b (all loads are independent of each other). `x` (and `y` when given) must not be
+// produced by the kernel's immediate predecessor when this is called before griddepcontrol.wait.
 __device__ __forceinline__ void head_stage(const HeadArgs& a, const HeadSmem& r, const float* __restrict__ x,
                                            const float* __restrict__ y, int b, int lane) {
   for (int k = lane * 4; k < a.ldx; k += 128)
     *reinterpret_cast<float4*>(r.xs + k) = *reinterpret_cast<const float4*>(x + k);
-  for (int k = lane * 4; k < a.ldy; k += 128)
-    *reinterpret_cast<float4*>(r.y + k) = *reinterpret_cast<const float4*>(y + k);
+  if (y)
+    for (int k = lane * 4; k < a.ldy; k += 128)
+      *reinterpret_cast<float4*>(r.y + k) = *reinterpret_cast<const float4*>(y + k);
   const int SW = a.S * a.W;
   const float* lt = a.st.lead_times + static_cast<size_t>(b) * SW;
   for (int k = lane; k < SW; k += 32) r.lt[k] = __ldg(lt + k);
@@ -548,7 +550,9 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32)
 warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ Xn,
                           float* __restrict__ cost_b, float* __restrict__ report_b, float* __restrict__ reward_t,
                           float* __restrict__ Xn_hi, float* __restrict__ Xn_lo) {
-  pdl_wait();
+  // Launched with PDL: everything up to pdl_wait() overlaps the predecessor (the output-layer GEMM that writes Y).
+  // X_t, the cost coefficients, lead times and demands were produced at least two kernels back, so their (cold,
+  // HBM-latency) loads are issued first and only the Y row waits for the predecessor.
   HDPO_DYN_SMEM(float, smem);
   struct TraceScope {  // one record per CTA, emitted when the first thread leaves the kernel body
     const TraceRef& tr;
@@ -563,6 +567,7 @@ warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
   if (b >= a.Bp) return;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (b >= a.B) {  // tile-padding rows stay exactly zero so that they never contribute to a weight gradient
+    pdl_wait();
     for (int k = lane * 4; k < a.ldx; k += 128) {
       *reinterpret_cast<float4*>(Xn + static_cast<size_t>(b) * a.ldx + k) = zero4;
       if (Xn_hi) {
@@ -576,7 +581,7 @@ warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
   const int nS = a.S * a.L;
   const HeadSmem r = head_smem_rows(smem + warp * head_smem_floats(a.S, a.W, a.ldx, a.ldy, false), a, false);
   float* share = r.share;  // alloc[s*W+w]
-  head_stage(a, r, X + static_cast<size_t>(b) * a.ldx, Y + static_cast<size_t>(b) * a.ldy, b, lane);
+  head_stage(a, r, X + static_cast<size_t>(b) * a.ldx, nullptr, b, lane);
   // statics of the warehouses (lane w)
   float wh_hold = 0.f, wh_edge = 0.f, wh_lead = 0.f;
   if (lane < a.W) {
@@ -584,6 +589,13 @@ warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
     wh_hold = __ldg(a.st.warehouse_holding_costs + bw);
     wh_lead = __ldg(a.st.warehouse_lead_times + bw);
     if (a.has_edge) wh_edge = __ldg(a.st.warehouse_edge_costs + bw);
+  }
+  pdl_wait();
+  trace_scope.t0 = (a.trace.buf && threadIdx.x == 0) ? trace_now() : 0ull;  // records start after the dependency wait
+  {
+    const float* yrow = Y + static_cast<size_t>(b) * a.ldy;
+    for (int k = lane * 4; k < a.ldy; k += 128)
+      *reinterpret_cast<float4*>(r.y + k) = *reinterpret_cast<const float4*>(yrow + k);
   }
   __syncwarp();
   if (a.trace.buf && threadIdx.x == 0) {
@@ -684,7 +696,8 @@ warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
 __global__ void __launch_bounds__(HEAD_WARPS * 32)
 warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ gX,
                           float* __restrict__ gY, float rb, float* __restrict__ gY_lo) {
-  pdl_wait();
+  // PDL: X_t, Y_t (forward tapes) and the statics do not depend on the predecessor (the dgrad GEMM that finishes
+  // gX of period t+1); they are staged before pdl_wait(), only the gX row is read after it.
   HDPO_DYN_SMEM(float, smem);
   struct TraceScope {
     const TraceRef& tr;
@@ -698,6 +711,7 @@ warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
   if (b >= a.Bp) return;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (b >= a.B) {
+    pdl_wait();
     for (int k = lane * 4; k < a.ldy; k += 128) {
       *reinterpret_cast<float4*>(gY + static_cast<size_t>(b) * a.ldy + k) = zero4;
       if (gY_lo) *reinterpret_cast<float4*>(gY_lo + static_cast<size_t>(b) * a.ldy + k) = zero4;
@@ -712,9 +726,6 @@ warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
   float* g = r.xo;             // adjoint row: staged, updated in place, written back
   float* gy = r.y + a.ldy;
   head_stage(a, r, X + static_cast<size_t>(b) * a.ldx, Y + static_cast<size_t>(b) * a.ldy, b, lane);
-  float* gx_row = gX + static_cast<size_t>(b) * a.ldx;
-  for (int k = lane * 4; k < a.ldx; k += 128)
-    *reinterpret_cast<float4*>(g + k) = *reinterpret_cast<const float4*>(gx_row + k);
   float wh_hold = 0.f, wh_edge = 0.f, wh_lead = 0.f;
   if (lane < a.W) {
     const int bw = b * a.W + lane;
@@ -722,6 +733,11 @@ warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
     wh_lead = __ldg(a.st.warehouse_lead_times + bw);
     if (a.has_edge) wh_edge = __ldg(a.st.warehouse_edge_costs + bw);
   }
+  pdl_wait();
+  trace_scope.t0 = (a.trace.buf && threadIdx.x == 0) ? trace_now() : 0ull;
+  float* gx_row = gX + static_cast<size_t>(b) * a.ldx;
+  for (int k = lane * 4; k < a.ldx; k += 128)
+    *reinterpret_cast<float4*>(g + k) = *reinterpret_cast<const float4*>(gx_row + k);
   __syncwarp();
   const float* x = r.xs;
   const float* y = r.y;
@@ -1099,6 +1115,13 @@ static HeadArgs head_args(const HdpoRolloutDesc* d, const ChunkCtx& c, int t) {
 }
 
 #ifndef HDPO_EMU
+// tile form of the forward GEMM of layer l / of the dgrad GEMM that consumes gz_l: hidden-layer epilogues exist in the
+// CTA-pair form (256 x 128 tiles), the output layer and the accumulation into gX use single-CTA tiles
+static int fwd_bn(const Plan& p, int l) {
+  return l + 1 < p.n ? tc::pick_bn_pair(p.Bp, p.wp[l + 1]) : tc::pick_bn(p.wp[l + 1]);
+}
+static int dgrad_bn(const Plan& p, int l) { return l > 0 ? tc::pick_bn_pair(p.Bp, p.wp[l]) : tc::pick_bn(p.wp[l]); }
+
 // output-side tensor maps (32-row boxes) of the activation tapes, and for the adjoint of the gz tapes and gX
 static int make_tape_maps(ChunkCtx& c) {
   const Plan& p = c.p;
@@ -1160,7 +1183,8 @@ static int fwd_begin(ChunkCtx& c, const HdpoRolloutDesc* d, const float* params)
       const float* a_lo = (l == 0) ? wsf(ws, p.o_X_lo) : wsf(ws, p.o_act_lo[l - 1]);
       int rc = make_pair(&c.mA[l], a_hi, a_lo, tslots * p.Bp, p.wp[l], tc::kBoxRowsA);
       if (rc) return rc;
-      rc = make_pair(&c.mB[l], wsf(ws, p.o_W[l]), wsf(ws, p.o_W_lo[l]), p.wp[l + 1], p.wp[l], tc::pick_bn(p.wp[l + 1]));
+      rc = make_pair(&c.mB[l], wsf(ws, p.o_W[l]), wsf(ws, p.o_W_lo[l]), p.wp[l + 1], p.wp[l],
+                     tc::b_box_rows(fwd_bn(p, l)));
       if (rc) return rc;
     }
     if ((rc_maps = make_tape_maps(c))) return rc_maps;
@@ -1215,7 +1239,7 @@ static int fwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t) {
       const bool hidden = l + 1 < p.n;
       tc::GemmTcMaps tm{c.mA[l].hi, c.mA[l].lo, c.mB[l].hi, c.mB[l].lo, c.mAct[l].hi, c.mAct[l].lo, c.mAct[l].hi,
                         c.mAct[l].lo};
-      rc = tc::gemm(tm, g, hidden ? tc::EPI_FWD_HIDDEN : tc::EPI_FWD_OUT, tc::pick_bn(p.wp[l + 1]), stream);
+      rc = tc::gemm(tm, g, hidden ? tc::EPI_FWD_HIDDEN : tc::EPI_FWD_OUT, fwd_bn(p, l), stream);
 #else
       rc = HDPO_E_INVALID;
 #endif
@@ -1364,7 +1388,8 @@ static int bwd_begin(ChunkCtx& c) {
       int rc = make_pair(&c.mA[l], wsf(ws, p.o_gz[l]), wsf(ws, p.o_gz_lo[l]), static_cast<uint64_t>(p.T) * p.Bp,
                          p.wp[l + 1], tc::kBoxRowsA);
       if (rc) return rc;
-      rc = make_pair(&c.mB[l], wsf(ws, p.o_WT[l]), wsf(ws, p.o_WT_lo[l]), p.wp[l], p.wp[l + 1], tc::pick_bn(p.wp[l]));
+      rc = make_pair(&c.mB[l], wsf(ws, p.o_WT[l]), wsf(ws, p.o_WT_lo[l]), p.wp[l], p.wp[l + 1],
+                     tc::b_box_rows(dgrad_bn(p, l)));
       if (rc) return rc;
     }
     int rc = make_tape_maps(c);
@@ -1432,11 +1457,11 @@ static int bwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t, float rb) {
         g.colsum_part = wsf(ws, p.o_csum[l - 1]);
         tc::GemmTcMaps tm{c.mA[l].hi,      c.mA[l].lo,      c.mB[l].hi,       c.mB[l].lo,
                           c.mGz[l - 1].hi, c.mGz[l - 1].lo, c.mAct[l - 1].hi, c.mAct[l - 1].lo};
-        rc = tc::gemm(tm, g, tc::EPI_DGRAD_HIDDEN, tc::pick_bn(p.wp[l]), stream);
+        rc = tc::gemm(tm, g, tc::EPI_DGRAD_HIDDEN, dgrad_bn(p, l), stream);
       } else {
         g.c_row0 = g.x_row0 = 0;
         tc::GemmTcMaps tm{c.mA[l].hi, c.mA[l].lo, c.mB[l].hi, c.mB[l].lo, c.mGx, c.mGx, c.mGx, c.mGx};
-        rc = tc::gemm(tm, g, tc::EPI_DGRAD_ACCUM, tc::pick_bn(p.wp[l]), stream);
+        rc = tc::gemm(tm, g, tc::EPI_DGRAD_ACCUM, dgrad_bn(p, l), stream);
       }
 #else
       rc = HDPO_E_INVALID;

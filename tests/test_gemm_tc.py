@@ -10,8 +10,9 @@ from neural_inventory_control_b200 import _capi as K
 pytestmark = pytest.mark.gpu
 
 
+# M % 256 == 0 and N % 128 == 0 select the CTA-pair (cta_group::2) form, everything else the single-CTA tiles
 @pytest.mark.parametrize("M,N,Kd", [(128, 64, 32), (128, 128, 64), (256, 192, 96), (384, 512, 512), (1024, 64, 512),
-                                    (2048, 512, 192)])
+                                    (2048, 512, 192), (256, 128, 32), (512, 256, 512), (2048, 512, 512)])
 def test_gemm_tc_matches_float64(M, N, Kd):
     be = D.CudaBackend()
     rng = np.random.RandomState(M + N + Kd)

@@ -58,7 +58,12 @@ for phase in ("forward", "backward"):
     for k in sorted(set(kinds)):
         m = kinds == k
         d = (t1 - t0)[m]
-        print(f"   {k:13s} CTAs {m.sum():7d}  mean {d.mean() / 1e3:7.2f} us  SM-time {d.sum() / 1e6:8.2f} ms  = {d.sum() / span / 148 * 100:5.1f}% of 148 SMs x span")
+        extra = ""
+        if k != "head":
+            aux = (rec[:, 3] >> 32)[m]
+            ph = [((aux >> sh) & 1023).astype(np.float64).mean() * 32 / 1e3 for sh in (0, 10, 20)]
+            extra = f"  | accumulators ready {ph[0]:5.2f}, tile staged {ph[1]:5.2f}, stores read {ph[2]:5.2f} us after start"
+        print(f"   {k:13s} CTAs {m.sum():7d}  mean {d.mean() / 1e3:7.2f} us  SM-time {d.sum() / 1e6:8.2f} ms  = {d.sum() / span / 148 * 100:5.1f}% of 148 SMs x span{extra}")
     hm = kinds == "head"
     if phase == "forward" and hm.any():
         staged = (rec[:, 3] >> 32)[hm].astype(np.float64)
