@@ -95,19 +95,29 @@ def cpu_port_setup(workload, B, T, seed=0):
     from neural_inventory_control_b200 import workloads as WL
     pspec, pp, data, widths = WL.WORKLOADS[workload]("cpu", B=B, T=T)
     g = torch.Generator().manual_seed(seed)
-    flat = WL.init_flat_params(widths, g, "cpu")
-    layers, o = [], 0
-    for i in range(len(widths) - 1):
-        n = widths[i + 1] * widths[i]
-        w = flat[o:o + n].view(widths[i + 1], widths[i]).clone().requires_grad_(True)
-        o += n
-        b = flat[o:o + widths[i + 1]].clone().requires_grad_(True)
-        o += widths[i + 1]
-        layers.append((w, b))
-    pol = {"arch": pspec.arch, "layers": layers, "hidden_act": pspec.master[1], "out_act": pspec.master[2],
+    flat = WL.init_params(widths, g, "cpu")
+    nets, o = {}, 0
+    for name, ws in WL.net_list(widths):
+        layers = []
+        for i in range(len(ws) - 1):
+            n = ws[i + 1] * ws[i]
+            w = flat[o:o + n].view(ws[i + 1], ws[i]).clone().requires_grad_(True)
+            o += n
+            b = flat[o:o + ws[i + 1]].clone().requires_grad_(True)
+            o += ws[i + 1]
+            layers.append((w, b))
+        nets[name] = layers
+    first = nets["master"] if "master" in nets else nets["context"]
+    pol = {"arch": pspec.arch, "layers": [wb for layers in nets.values() for wb in layers],
+           "hidden_act": pspec.master[1], "out_act": pspec.master[2],
            "wub": torch.tensor([pspec.warehouse_upper_bound]),
            "adjacency": None if pspec.adjacency is None else torch.tensor(pspec.adjacency),
            "transshipment": pspec.transshipment}
+    if pspec.arch == "symmetry_aware":
+        pol["nets"] = {"context": (first, pspec.master[1], pspec.master[2]),
+                       "store": (nets["store"], pspec.store_net[1], pspec.store_net[2]),
+                       "warehouse": (nets["warehouse"], pspec.warehouse_net[1], pspec.warehouse_net[2])}
+        pol["prop_eps"] = pspec.prop_eps
     pb = dict(pp, period_shift=0)
     return pol, pb, data
 
@@ -129,7 +139,8 @@ def time_cpu_port(workload, B, T, steps, warmup):
 
 def cpu_sample_size(workload):
     return {"one_store_backlogged_lead20": 16384, "one_store_lost": 16384, "serial_system": 8192,
-            "one_warehouse_lost_demand": 512, "many_warehouses_lost_demand": 512}.get(workload, 1024)
+            "one_warehouse_lost_demand": 512, "many_warehouses_lost_demand": 512,
+            "one_warehouse_lost_demand_symmetry_aware": 512}.get(workload, 1024)
 
 
 def run_reference(args):
@@ -192,7 +203,7 @@ def main():
     pspec, pp, data, widths = WL.WORKLOADS[args.workload](dev, seed=57 + rank, **kw)
     B, S, T = data["demands"].shape[0], pp["n_stores"], args.periods
     gen = torch.Generator(device=dev).manual_seed(0)  # identical weights on every rank
-    flat = WL.init_flat_params(widths, gen, dev)
+    flat = WL.init_params(widths, gen, dev)
     small = pspec.arch in ("vanilla_one_store", "vanilla_serial")
     precision = args.precision or ("fp32" if small else "tf32x3")
     eng = EN.FusedRollout(pspec, pp, data, T, ignore_periods=30, precision=precision)
@@ -248,15 +259,19 @@ def main():
     fwd_ms = time_region(lambda: eng.forward(flat, data), n_k)
     bwd_ms = time_region(lambda: eng.backward(g_total, 0.0, out=grad), n_k)
     peaks = load_peaks()
-    macs = sum(widths[i] * widths[i + 1] for i in range(len(widths) - 1))
+    macs = WL.forward_macs(widths, S)
     detached = pspec.arch == "vanilla_serial"
-    flops_step = WL.flops_per_scenario_period(widths, first_layer_dgrad=not detached)
+    flops_step = WL.flops_per_scenario_period(widths, first_layer_dgrad=not detached, n_stores=S)
+    sym = pspec.arch == "symmetry_aware"
     flops_bwd = flops_step - 2 * macs  # dgrad + wgrad; the adjoint kernel's recompute is not counted
     tf32_peak = peaks["bf16_tflops"] / 2.0
     achieved = flops_bwd * B * T / (bwd_ms * 1e-3) / 1e12
     roofline = {
         "bound": "tensor",
         "kernel": ("small_bwd_kernel (reverse-time adjoint, SIMT fp32 parity mode)" if small else
+                   f"adjoint sweep ({precision}): sym_head_bwd_kernel (store / warehouse nets recomputed + adjoint, SIMT "
+                   "fp32) + gemm_tc_kernel dgrad / weight-gradient tiles of the context trunk (tcgen05/TMEM/TMA)" if sym
+                   and precision != "fp32" else
                    f"adjoint sweep ({precision}): gemm_tc_kernel dgrad + weight-gradient tiles (tcgen05/TMEM/TMA) + "
                    "warehouse_head_bwd + bias column sums" if precision != "fp32" else
                    "adjoint sweep: sgemm_kernel dgrad+wgrad tiles (SIMT fp32 parity mode) + warehouse_head_bwd"),
@@ -333,7 +348,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload, "scenarios_per_gpu": B, "periods": T, "stores": S,
                        "policy_widths": widths, "l2": "inputs larger than L2 (demand + state tape per step)"
-                       if B * T * 4 * (1 + widths[0]) > 126e6 else "working set below L2 size; no flush",
+                       if B * T * 4 * (1 + WL.net_list(widths)[0][1][0]) > 126e6 else "working set below L2 size; no flush",
                        "parallelism": f"dp{world} (scenario shards, gradient all-reduce)" if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -17,6 +17,7 @@
 // This file holds the fp32 SIMT tile GEMM (parity mode). The tcgen05 3xTF32 GEMM replaces `sgemm` call sites
 // one-for-one (same operand layouts) - see gemm_tc.cuh.
 #include "rollout_wide.cuh"
+#include "rollout_sym.cuh"
 #include "gemm_tc.cuh"
 
 #include <cstdlib>
@@ -46,10 +47,11 @@ static inline int pad_to(int x, int q) { return (x + q - 1) / q * q; }
 static inline size_t a256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 bool supported(const HdpoRolloutDesc* d) {
-  if (d->arch != HDPO_ARCH_VANILLA_WAREHOUSE) return false;
 #ifdef HDPO_EMU
   if (d->precision != HDPO_PREC_FP32) return false;  // tensor cores cannot be emulated
 #endif
+  if (d->arch == HDPO_ARCH_SYMMETRY_AWARE) return sym::supported(d);
+  if (d->arch != HDPO_ARCH_VANILLA_WAREHOUSE) return false;
   const HdpoProblem& pb = d->pb;
   if (pb.W < 1 || pb.E != 0 || pb.W > 8) return false;
   if (pb.S * pb.W > 1024 || pb.S > kMaxStoresPerWarp) return false;
@@ -68,6 +70,10 @@ bool supported(const HdpoRolloutDesc* d) {
 // ------------------------------------------------------------------------------------------------------------
 struct Plan {
   int n, B, Bp, T, save;
+  int sym;                      // SymmetryAware: layers 0..n-2 = context net, layer n-1 = 64-column projection
+  int act[HDPO_MAX_LAYERS];     // activation after layer l
+  size_t o_so, so_stride;       // sym: store-output tape [T][Bp][ldo]
+  size_t o_slab;                // sym: per-warp gradient slabs of the local nets
   int tc, n_pass;  // tensor-core mode: every GEMM operand is kept as a (tf32 hi, remainder lo) pair
   int wg_kps, wg_splits;  // tensor-core weight gradient: contraction rows per partial slice, number of slices
   int w[HDPO_MAX_LAYERS + 1], wp[HDPO_MAX_LAYERS + 1];
@@ -87,7 +93,8 @@ struct Plan {
 static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
   Plan p;
   const HdpoMlp& m = d->master;
-  p.n = m.n_layers;
+  p.sym = d->arch == HDPO_ARCH_SYMMETRY_AWARE;
+  p.n = m.n_layers + (p.sym ? 1 : 0);
   p.B = Bc;
   p.Bp = pad_to(p.B > 0 ? p.B : 1, kRowPad);
   p.T = d->T;
@@ -96,16 +103,25 @@ static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
   p.n_pass = d->precision == HDPO_PREC_TF32 ? 1 : 3;
   int off = 0;
   for (int i = 0; i <= p.n; ++i) {
-    p.w[i] = m.widths[i];
-    p.wp[i] = pad_to(m.widths[i], kColPad);
+    p.w[i] = (p.sym && i == p.n) ? 64 : m.widths[i];
+    p.wp[i] = pad_to(p.w[i], kColPad);
   }
   for (int l = 0; l < p.n; ++l) {
+    if (p.sym)
+      p.act[l] = l + 2 < p.n ? m.hidden_act : (l + 2 == p.n ? m.out_act : HDPO_ACT_NONE);
+    else
+      p.act[l] = l + 1 < p.n ? m.hidden_act : m.out_act;
     p.gw[l] = off;
     off += p.w[l + 1] * p.w[l];
     p.gb[l] = off;
     off += p.w[l + 1];
   }
-  p.P = off;
+  p.P = off;  // sym: overwritten below with the parameter count of all three nets (the projection has no own block)
+  sym::Cfg sc{};
+  if (p.sym) {
+    sym::build_cfg(d, p.B, p.Bp, p.wp[0], p.wp[p.n], &sc);
+    p.P = sc.P;
+  }
   const size_t f = sizeof(float);
   size_t o = 0;
   auto take = [&](size_t n_floats) {
@@ -150,6 +166,9 @@ static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
   int max_wp = 0;
   for (int i = 0; i <= p.n; ++i) max_wp = p.wp[i] > max_wp ? p.wp[i] : max_wp;
   p.o_bpart = p.save ? take(static_cast<size_t>(128) * max_wp) : 0;
+  p.so_stride = p.sym ? static_cast<size_t>(p.Bp) * sc.ldo : 0;
+  p.o_so = (p.sym && p.save) ? take(tslots * p.so_stride) : 0;
+  p.o_slab = (p.sym && p.save) ? take(static_cast<size_t>(sym::bwd_warps(sc)) * sc.q_total) : 0;
   p.total = o + 256;
   return p;
 }
@@ -888,22 +907,24 @@ __global__ void __launch_bounds__(256) colsum_stage1_kernel(const float* __restr
 
 // grad[gw + n*K + k] = sum_z part[z][n][k] ; grad[gb + n] = sum_chunks bpart[chunk][n]
 // `transposed`: the partial slices hold dW^T ([Kp rows][Np cols], leading dimension ldp = Np) instead of dW ([..][Kp])
+// Rows n0 .. n0+N-1 of the computed gradient go to grad[gw + n*dst_ld + k] (dst_ld = K for a plain layer; the
+// SymmetryAware projection scatters its two row blocks into the context columns of the store / warehouse nets).
 __global__ void __launch_bounds__(256) unpack_grad_kernel(const float* __restrict__ part, int splits, size_t slice, int ldp,
                                                           int transposed, int N, int K, const float* __restrict__ bpart,
                                                           int n_chunks, int ldb, int gw, int gb,
-                                                          float* __restrict__ grad) {
+                                                          float* __restrict__ grad, int n0, int dst_ld) {
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N * K) {
     const int n = i / K, k = i % K;
-    const size_t at = transposed ? static_cast<size_t>(k) * ldp + n : static_cast<size_t>(n) * ldp + k;
+    const size_t at = transposed ? static_cast<size_t>(k) * ldp + (n0 + n) : static_cast<size_t>(n0 + n) * ldp + k;
     double s = 0.0;  // hundreds of partial slices: accumulate in double so the reduction adds no fp32 error
     for (int z = 0; z < splits; ++z) s += static_cast<double>(part[z * slice + at]);
-    grad[gw + i] = static_cast<float>(s);
+    grad[gw + n * dst_ld + k] = static_cast<float>(s);
   }
   if (i < N) {
     float s = 0.f;
-    for (int c = 0; c < n_chunks; ++c) s += bpart[static_cast<size_t>(c) * ldb + i];
+    for (int c = 0; c < n_chunks; ++c) s += bpart[static_cast<size_t>(c) * ldb + n0 + i];
     grad[gb + i] = s;
   }
 }
@@ -1054,6 +1075,8 @@ struct ChunkCtx {
   HdpoState init, fin;
   float *cost_b, *report_b, *reward_tb;  // reward_tb rows are B_total apart
   float* grad;
+  const float* params;  // flat parameter vector (the SymmetryAware heads stage the local nets from it)
+  sym::Cfg sc;          // SymmetryAware head configuration (p.sym only)
 #ifndef HDPO_EMU
   MapPair mA[HDPO_MAX_LAYERS], mB[HDPO_MAX_LAYERS];  // GEMM operands (forward: layer input / W; adjoint: gz / W^T)
   MapPair mAct[HDPO_MAX_LAYERS];                     // layer-output tapes as 32-row output boxes (lo unused for the last)
@@ -1083,6 +1106,17 @@ static void bind_chunk(ChunkCtx* c, const HdpoRolloutDesc* d, const Chunking& ck
   c->init = HdpoState{nullptr, nullptr, nullptr};
   c->fin = HdpoState{nullptr, nullptr, nullptr};
   c->cost_b = c->report_b = c->reward_tb = c->grad = nullptr;
+  c->params = nullptr;
+  if (c->p.sym) sym::build_cfg(d, c->p.B, c->p.Bp, c->p.wp[0], c->p.wp[c->p.n], &c->sc);
+}
+
+static sym::PeriodArgs sym_period_args(const HdpoRolloutDesc* d, const ChunkCtx& c, int t) {
+  sym::PeriodArgs a;
+  a.tt = t + d->period_shift;
+  a.in_report = t >= d->ignore_periods;
+  a.demands = c.demands;
+  a.st = c.st;
+  return a;
 }
 
 static HeadArgs head_args(const HdpoRolloutDesc* d, const ChunkCtx& c, int t) {
@@ -1151,8 +1185,17 @@ static int fwd_begin(ChunkCtx& c, const HdpoRolloutDesc* d, const float* params)
   const int nS = pb.S * pb.L, nW = pb.W * pb.Lw;
   const size_t tslots = p.save ? static_cast<size_t>(p.T) : 1;
   // pack weights (tensor-core mode: hi/lo halves and their transposes)
+  c.params = params;
   for (int l = 0; l < p.n; ++l) {
     const int cnt = p.wp[l + 1] * p.wp[l];
+    if (p.sym && l + 1 == p.n) {
+      int rc = sym::pack_projection(c.sc, params, p.wp[l], wsf(ws, p.o_W[l]), wsf(ws, p.o_b[l]),
+                                    p.tc ? wsf(ws, p.o_W_lo[l]) : static_cast<float*>(nullptr),
+                                    p.tc ? wsf(ws, p.o_WT[l]) : static_cast<float*>(nullptr),
+                                    p.tc ? wsf(ws, p.o_WT_lo[l]) : static_cast<float*>(nullptr), stream);
+      if (rc) return rc;
+      continue;
+    }
     auto k = pack_layer_kernel;
     HDPO_LAUNCH_PDL(k, ceil_div(cnt, 256), 256, 0, stream, params, p.gw[l], p.gb[l], p.w[l + 1], p.w[l], p.wp[l + 1],
                     p.wp[l], wsf(ws, p.o_W[l]), wsf(ws, p.o_b[l]),
@@ -1206,7 +1249,7 @@ static int fwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t) {
   const float* in = X;
   for (int l = 0; l < p.n; ++l) {
     float* out = wsf(ws, p.o_act[l]) + as * p.act_stride[l];
-    const int act = (l + 1 < p.n) ? d->master.hidden_act : d->master.out_act;
+    const int act = p.act[l];
     int rc;
     if (!p.tc) {
       GemmArgs g{};
@@ -1247,7 +1290,6 @@ static int fwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t) {
     if (rc) return rc;
     in = out;
   }
-  HeadArgs a = head_args(d, c, t);
   // tensor-core mode: the state written for period t+1 is also split into the (hi, lo) tape slot t+1
   float* xn_hi = nullptr;
   float* xn_lo = nullptr;
@@ -1256,6 +1298,15 @@ static int fwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t) {
     xn_hi = wsf(ws, p.o_X_hi) + slot * p.x_stride;
     xn_lo = wsf(ws, p.o_X_lo) + slot * p.x_stride;
   }
+  if (p.sym) {
+    const sym::PeriodArgs sa = sym_period_args(d, c, t);
+    return sym::head_fwd(c.sc, sa, c.params, X, in, Xn, xn_hi, xn_lo,
+                         p.save ? wsf(ws, p.o_so) + static_cast<size_t>(t) * p.so_stride : static_cast<float*>(nullptr),
+                         c.cost_b, c.report_b,
+                         c.reward_tb ? c.reward_tb + static_cast<size_t>(t) * d->pb.B : static_cast<float*>(nullptr),
+                         stream);
+  }
+  HeadArgs a = head_args(d, c, t);
   const size_t head_smem = static_cast<size_t>(HEAD_WARPS) * head_smem_floats(pb.S, pb.W, p.wp[0], p.wp[p.n], false) * sizeof(float);
   auto k = warehouse_head_fwd_kernel;
 #ifndef HDPO_EMU
@@ -1411,13 +1462,20 @@ static int bwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t, float rb) {
   const float* Y = wsf(ws, p.o_act[last]) + static_cast<size_t>(t) * p.act_stride[last];
   float* gY = wsf(ws, p.o_gz[last]) + static_cast<size_t>(t) * p.act_stride[last];
   float* gY_lo = p.tc ? wsf(ws, p.o_gz_lo[last]) + static_cast<size_t>(t) * p.act_stride[last] : nullptr;
-  HeadArgs a = head_args(d, c, t);
-  auto k = warehouse_head_bwd_kernel;
+  if (p.sym) {
+    const sym::PeriodArgs sa = sym_period_args(d, c, t);
+    int rc = sym::head_bwd(c.sc, sa, c.params, X, Y, wsf(ws, p.o_so) + static_cast<size_t>(t) * p.so_stride, gX, gY,
+                           gY_lo, rb, wsf(ws, p.o_slab), t == p.T - 1, stream);
+    if (rc) return rc;
+  } else {
+    HeadArgs a = head_args(d, c, t);
+    auto k = warehouse_head_bwd_kernel;
 #ifndef HDPO_EMU
-  if (head_smem > 48 * 1024) HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHeadSmemMax)));
+    if (head_smem > 48 * 1024) HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHeadSmemMax)));
 #endif
-  HDPO_LAUNCH_PDL(k, ceil_div(p.Bp, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, Y, gX, gY, rb, gY_lo);
-  HDPO_LAUNCH_OK();
+    HDPO_LAUNCH_PDL(k, ceil_div(p.Bp, HEAD_WARPS), HEAD_WARPS * 32, head_smem, stream, a, X, Y, gX, gY, rb, gY_lo);
+    HDPO_LAUNCH_OK();
+  }
   // dgrad chain: gz_{l-1} = (gz_l W_l) * act'(h_{l-1});  finally gX += gz_0 W_0
   for (int l = last; l >= 0; --l) {
     int rc;
@@ -1431,7 +1489,7 @@ static int bwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t, float rb) {
       g.lda = p.wp[l + 1];
       g.ldb = p.wp[l];
       g.ldc = p.wp[l];
-      g.act = d->master.hidden_act;
+      g.act = l > 0 ? p.act[l - 1] : HDPO_ACT_NONE;
       if (l > 0) {
         g.C = wsf(ws, p.o_gz[l - 1]) + static_cast<size_t>(t) * p.act_stride[l - 1];
         g.aux = wsf(ws, p.o_act[l - 1]) + static_cast<size_t>(t) * p.act_stride[l - 1];
@@ -1451,7 +1509,7 @@ static int bwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t, float rb) {
       g.b_row0 = 0;
       g.trace.tag = static_cast<unsigned>(c.index);
       g.ldc = p.wp[l];
-      g.act = d->master.hidden_act;
+      g.act = l > 0 ? p.act[l - 1] : HDPO_ACT_NONE;
       if (l > 0) {
         g.c_row0 = g.x_row0 = t * p.Bp;
         g.colsum_part = wsf(ws, p.o_csum[l - 1]);
@@ -1553,11 +1611,29 @@ static int bwd_end(ChunkCtx& c) {
     }
     HDPO_LAUNCH_OK();
     auto k2 = unpack_grad_kernel;
+    if (p.sym && l + 1 == p.n) {
+      // projection layer: rows 0.. -> context columns of the store net's first layer (+ its bias), rows 32.. -> the
+      // warehouse net's
+      const sym::Cfg& sc = c.sc;
+      HDPO_LAUNCH_PDL(k2, ceil_div(sc.s_w[0] * sc.C, 256), 256, 0, stream,
+                      static_cast<const float*>(wsf(ws, p.o_part)), used_splits, c_slice, ldp, transposed, sc.s_w[0], sc.C,
+                      static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1], sc.g_s_w0 + sc.s_in,
+                      sc.g_s_b0, c.grad, 0, sc.s_ld0);
+      HDPO_LAUNCH_OK();
+      HDPO_LAUNCH_PDL(k2, ceil_div(sc.w_w[0] * sc.C, 256), 256, 0, stream,
+                      static_cast<const float*>(wsf(ws, p.o_part)), used_splits, c_slice, ldp, transposed, sc.w_w[0], sc.C,
+                      static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1], sc.g_w_w0 + sc.Lw,
+                      sc.g_w_b0, c.grad, 32, sc.w_ld0);
+      HDPO_LAUNCH_OK();
+      continue;
+    }
     HDPO_LAUNCH_PDL(k2, ceil_div(p.w[l + 1] * p.w[l], 256), 256, 0, stream, static_cast<const float*>(wsf(ws, p.o_part)),
                     used_splits, c_slice, ldp, transposed, p.w[l + 1], p.w[l],
-                    static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1], p.gw[l], p.gb[l], c.grad);
+                    static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1], p.gw[l], p.gb[l], c.grad, 0,
+                    p.w[l]);
     HDPO_LAUNCH_OK();
   }
+  if (p.sym) return sym::reduce_slabs(c.sc, wsf(ws, p.o_slab), c.grad, stream);
   return HDPO_OK;
 }
 
@@ -1574,7 +1650,6 @@ __global__ void __launch_bounds__(256) sum_chunk_grads_kernel(float* __restrict_
 
 int backward(const HdpoRolloutDesc* d, const float* params, const float* demands, const HdpoStatics* st, float g_total,
              float g_report, float* grad_params, void* ws, size_t ws_bytes, void* stream) {
-  (void)params;
   const Chunking ck = make_chunking(d);
   HDPO_REQUIRE(ws != nullptr && d->save_for_backward,
                "backward needs the workspace of a forward run with save_for_backward = 1");
@@ -1590,6 +1665,7 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
   for (int i = 0; i < ck.n; ++i) {
     bind_chunk(&ctx[i], d, ck, i, demands, st, ws, fork.stream_of(i));
     ctx[i].grad = i == 0 ? grad_params : extra + static_cast<size_t>(i - 1) * ck.P;
+    ctx[i].params = params;
     if ((rc = bwd_begin(ctx[i]))) return rc;
   }
   for (int t = d->T - 1; t >= 0; --t) {

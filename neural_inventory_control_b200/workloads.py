@@ -83,9 +83,33 @@ def serial_system(device, B=1 << 20, T=50, seed=57):
     return PolicySpec("vanilla_serial", (widths, "elu", None), warehouse_upper_bound=20.0), pp, data, widths
 
 
-def flops_per_scenario_period(widths, first_layer_dgrad=True):
+def net_list(widths):
+    """[(name, widths)] of a workload's nets in state_dict order (a plain list = the single 'master' net)."""
+    if isinstance(widths, dict):
+        return [(m, widths[m]) for m in ("context", "store", "warehouse")]
+    return [("master", widths)]
+
+
+def init_params(widths, gen, device):
+    """Flat parameter vector of every net of the workload, state_dict order."""
+    return torch.cat([init_flat_params(w, gen, device) for _, w in net_list(widths)]).contiguous()
+
+
+def forward_macs(widths, n_stores=1):
+    """MLP multiply-accumulates per scenario-period of the forward pass. SymmetryAware uses the FACTORED count of
+    SURVEY.md 8d: the context half of the first store / warehouse layer is computed once per scenario."""
+    dense = lambda w: sum(w[i] * w[i + 1] for i in range(len(w) - 1))  # noqa: E731
+    if not isinstance(widths, dict):
+        return dense(widths)
+    ctx, st, wh = widths["context"], widths["store"], widths["warehouse"]
+    C = ctx[-1]
+    local = lambda w: (w[0] - C) * w[1] + dense(w[1:])  # noqa: E731
+    return dense(ctx) + C * (st[1] + wh[1]) + n_stores * local(st) + local(wh)
+
+
+def flops_per_scenario_period(widths, first_layer_dgrad=True, n_stores=1):
     """Algorithmic FLOPs: 2*3*MACs_fwd (forward + dgrad + wgrad); recompute is not counted."""
-    macs = sum(widths[i] * widths[i + 1] for i in range(len(widths) - 1))
+    macs = forward_macs(widths, n_stores)
     f = 2 * 3 * macs
     if not first_layer_dgrad:
         f -= 2 * widths[0] * widths[1]
@@ -149,3 +173,19 @@ def many_warehouses_lost_demand(device, B=1024, T=50, seed=57):
     lead = (torch.randint(1, 7, (S, W), generator=g) * adj.t()).float().to(device)
     return _many_stores(device, B, T, S, W, seed, adjacency=adj.tolist(), lead=lead, wh_holding=(0.3, 0.4, 0.2),
                         wh_edge=(0.5, 1.5, 0.7))
+
+
+@register("one_warehouse_lost_demand_symmetry_aware")
+def one_warehouse_lost_demand_symmetry_aware(device, B=8192, T=50, seed=57):
+    """cfg 4 as BASELINE.json names it: one_warehouse_lost_demand.yml at 50 stores + the weight-duplicated
+    SymmetryAware policy with this repo's symmetry_aware.yml widths (context 153->256->256 sigmoid, store
+    (3+4+256)->32->32->1 softplus applied to every store, warehouse (3+256)->16->16->1 sigmoid)."""
+    pspec, pp, data, w = _many_stores(device, B, T, 50, 1, seed)
+    C = 256
+    L = data["initial_inventories"].shape[2]
+    widths = {"context": [w[0], 256, C], "store": [L + 4 + C, 32, 32, 1], "warehouse": [3 + C, 16, 16, 1]}
+    sym = PolicySpec("symmetry_aware", (widths["context"], "elu", "sigmoid"),
+                     warehouse_upper_bound=pspec.warehouse_upper_bound,
+                     store_net=(widths["store"], "elu", "softplus"), warehouse_net=(widths["warehouse"], "elu", "sigmoid"),
+                     prop_eps=1e-15)
+    return sym, pp, data, widths

@@ -103,6 +103,16 @@ def policy(pol, pb, state, data):
             cols.append(col)
         stores = torch.stack(cols, 2)
         return {"stores": stores, "warehouses": (torch.sigmoid(y[:, S * W:]) * pol["wub"]).unsqueeze(2)}
+    if arch == "symmetry_aware":  # SURVEY.md 2.3 (recovered forward), neural_networks.py:111-138,168-187
+        wh = state["wh"]
+        S, W = store.shape[1], wh.shape[1]
+        nets = pol["nets"]
+        feats = torch.stack([data["mean"], data["std"], data["underage_costs"], data["lead_times"][:, :, 0]], 2)
+        ctx = mlp(torch.cat([store.flatten(1), wh.flatten(1)], 1), *nets["context"])
+        wo = mlp(torch.cat([wh, ctx.unsqueeze(1).expand(B, W, -1)], 2), *nets["warehouse"])[:, :, 0]
+        so = mlp(torch.cat([store, feats, ctx.unsqueeze(1).expand(B, S, -1)], 2), *nets["store"])[:, :, 0]
+        scale = torch.clip(wh[:, :, 0].sum(1) / (so.sum(1) + pol.get("prop_eps", 1e-15)), max=1)
+        return {"stores": (so * scale[:, None]).unsqueeze(2), "warehouses": (wo * pol["wub"].unsqueeze(1)).unsqueeze(2)}
     raise KeyError(arch)
 
 

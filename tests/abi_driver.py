@@ -130,8 +130,14 @@ def rollout(be, meta, params, data, T=None, ignore=None, demand_layout=K.DEMAND_
     bt = Batch(be, pp, data)
     T = meta["T"] if T is None else T
     ignore = meta["ignore_periods"] if ignore is None else ignore
-    flat, shapes, names = flat_params(params)
-    widths = spec.mlp_widths(shapes)
+    modules = ["context", "store", "warehouse"] if meta["nn_name"] == "symmetry_aware" else ["master"]
+    flats, names, nets = [], [], {}
+    for m in modules:
+        f_m, shapes, names_m = flat_params(params, m)
+        flats.append(f_m)
+        names += names_m
+        nets[m] = (spec.mlp_widths(shapes), meta["inner_layer_activations"][m], meta["output_layer_activation"][m])
+    flat = np.concatenate(flats)
     dem = np.asarray(data["demands"], np.float32)
     t_stride = dem.shape[2]
     if demand_layout == K.DEMAND_TSB:
@@ -139,9 +145,9 @@ def rollout(be, meta, params, data, T=None, ignore=None, demand_layout=K.DEMAND_
     dem_h = be.put(dem)
     adj = pp.get("warehouse_store_adjacency")
     adj_h = None if adj is None else be.put(np.asarray(adj), np.int32)
-    desc = spec.rollout_desc(meta["nn_name"], bt.pb, T, t_stride,
-                             (widths, meta["inner_layer_activations"]["master"],
-                              meta["output_layer_activation"]["master"]),
+    desc = spec.rollout_desc(meta["nn_name"], bt.pb, T, t_stride, nets[modules[0]],
+                             store_net=nets.get("store"), warehouse_net=nets.get("warehouse"),
+                             prop_eps=meta.get("prop_eps", 1e-15),
                              period_shift=meta.get("period_shift", 0), ignore_periods=ignore,
                              demand_layout=demand_layout, discrete_allocation=discrete,
                              transshipment=meta.get("transshipment", False), save_for_backward=backward,

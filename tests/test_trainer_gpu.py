@@ -170,10 +170,12 @@ def test_training_loop_reduces_loss_and_eval_modes_run():
     assert np.isfinite(loss) and np.isfinite(report) and report > 0
 
 
-def test_symmetry_aware_generic_path_matches_oracle():
-    """The re-created SymmetryAware policy (absent from the reference snapshot's sources) through the
-    GENERIC path (torch policy + K3 step kernels + torch autograd) against the float64 oracle restatement of the same
-    recovered forward: costs and all three nets' gradients."""
+@pytest.mark.parametrize("fused", [False, True], ids=["generic", "fused"])
+def test_symmetry_aware_trainer_paths_match_oracle(fused):
+    """The re-created SymmetryAware policy (absent from the reference snapshot's sources) through
+    Trainer.simulate_batch on both paths - GENERIC (torch policy + K3 step kernels + torch autograd) and FUSED (trunk
+    GEMMs + rollout_sym.cu heads, one autograd node) - against the float64 oracle restatement of the same recovered
+    forward: costs and all three nets' gradients."""
     from neural_inventory_control_b200.environment import Simulator
     from neural_inventory_control_b200.loss_functions import PolicyLoss
     from neural_inventory_control_b200.neural_networks import NeuralNetworkCreator
@@ -192,10 +194,10 @@ def test_symmetry_aware_generic_path_matches_oracle():
     data = {k: torch.tensor(v[:16], device=dev) for k, v in g["data"].items()}
     obs_params = _obs_params(meta)
     tr, sim = Trainer(device=dev), Simulator(device=dev)
-    tr.use_fused = False
+    tr.use_fused = fused
     T = 10
     total, report = tr.simulate_batch(PolicyLoss(), sim, model, T, pp, data, obs_params, 3)
-    assert tr.last_path == "generic"
+    assert tr.last_path == ("fused" if fused else "generic")
     B = 16
     (total / (B * T * pp["n_stores"])).backward()
     sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
