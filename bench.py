@@ -89,6 +89,57 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def load_traffic(workload):
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed ncu --set full
+    captures (profiles/r1_traffic.json names the capture each number comes from); None when there is none."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(workload)
+    return None
+
+
+def time_dominant_gemm(lib, torch, dev, stream, M, N, K, n_pass, reps=64):
+    """The dominant kernel of the wide rollout timed ALONE: gemm_tc_kernel (tcgen05 / TMEM / TMA, CTA-pair tiles) in
+    its forward hidden-layer form (bias + ELU epilogue, (hi, lo) outputs) at the shape one scenario chunk launches.
+    CUDA events on the launching stream; operands rotate through 16 buffer sets (> L2) so that no launch finds its
+    inputs in L2 from the launch before."""
+    lib.hdpo_debug_gemm_tc_timeline.argtypes = ([C.c_void_p] * 3 + [C.c_int32] * 4 +
+                                                [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p])
+    lib.hdpo_debug_gemm_tc_timeline.restype = C.c_int
+    nbuf = 16
+    g = torch.Generator(device=dev).manual_seed(1)
+    A = torch.randn(M, K, generator=g, device=dev)
+    Bm = torch.randn(N, K, generator=g, device=dev) / K ** 0.5
+    bias = torch.zeros(N, device=dev)
+    sets = []
+    for _ in range(nbuf):
+        scratch = torch.empty(2 * (M * K + N * K), device=dev)
+        Cm, Clo = torch.empty(M, N, device=dev), torch.empty(M, N, device=dev)
+        rc = lib.hdpo_debug_gemm_tc(A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(), M, N, K, n_pass, scratch.data_ptr(), stream)
+        assert rc == 0, lib.hdpo_last_error()
+        sets.append((scratch, Cm, Clo))
+    dbg = torch.zeros(8 * 4096, dtype=torch.int64, device=dev)
+
+    def run(i):
+        scratch, Cm, Clo = sets[i % nbuf]
+        rc = lib.hdpo_debug_gemm_tc_timeline(A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(), M, N, K, n_pass,
+                                             scratch.data_ptr(), dbg.data_ptr(), stream, 0, Clo.data_ptr(),
+                                             bias.data_ptr())
+        assert rc == 0, lib.hdpo_last_error()
+
+    for i in range(nbuf):
+        run(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(reps):
+        run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3  # seconds per launch
+
+
 def cpu_port_setup(workload, B, T, seed=0):
     """The same synthetic workload on the host, as inputs of the PyTorch-eager port (oracle/torch_port.py)."""
     import torch
@@ -266,8 +317,8 @@ def main():
     flops_bwd = flops_step - 2 * macs  # dgrad + wgrad; the adjoint kernel's recompute is not counted
     tf32_peak = peaks["bf16_tflops"] / 2.0
     achieved = flops_bwd * B * T / (bwd_ms * 1e-3) / 1e12
-    roofline = {
-        "bound": "tensor",
+    traffic = load_traffic(args.workload)
+    group = {
         "kernel": ("small_bwd_kernel (reverse-time adjoint, SIMT fp32 parity mode)" if small else
                    f"adjoint sweep ({precision}): sym_head_bwd_kernel (store / warehouse nets recomputed + adjoint, SIMT "
                    "fp32) + gemm_tc_kernel dgrad / weight-gradient tiles of the context trunk (tcgen05/TMEM/TMA)" if sym
@@ -275,13 +326,38 @@ def main():
                    f"adjoint sweep ({precision}): gemm_tc_kernel dgrad + weight-gradient tiles (tcgen05/TMEM/TMA) + "
                    "warehouse_head_bwd + bias column sums" if precision != "fp32" else
                    "adjoint sweep: sgemm_kernel dgrad+wgrad tiles (SIMT fp32 parity mode) + warehouse_head_bwd"),
-        "precision": precision,
-        "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": None,
+        "achieved": achieved, "frac": achieved / tf32_peak, "kernel_ms": bwd_ms, "fwd_kernel_ms": fwd_ms,
+        "flops_per_launch": flops_bwd * B * T,
+    }
+    roofline = {
+        "bound": "tensor", "kernel": group["kernel"], "precision": precision,
+        "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+        "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+        "traffic_source": traffic["source"] if traffic else None,
         "peak_source": f"{peaks['source']}: tf32 taken as bf16_tflops/2 (burst, kernel timed alone)",
-        "kernel_ms": bwd_ms, "fwd_kernel_ms": fwd_ms,
+        "kernel_ms": bwd_ms, "fwd_kernel_ms": fwd_ms, "flops_per_launch": flops_bwd * B * T,
         "step_frac": flops_step * B * T / (ms_per_step * 1e-3) / 1e12 / (peaks["bf16_tflops_sustained"] / 2.0),
         "hbm_frac": 8.0 * S * B * T / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
     }
+    if pspec.arch == "vanilla_warehouse" and precision != "fp32":
+        # dominant single kernel (56 % of the step in the ncu launch list): the hidden-layer tile GEMM, timed alone at
+        # the shape one scenario chunk launches; the whole adjoint group stays reported beside it
+        n_chunks = int(os.environ.get("HDPO_WIDE_CHUNKS", "0")) or max(1, min(4, B // 2048))
+        per_chunk = -(-B // n_chunks)
+        Mc = -(-per_chunk // 128) * 128  # rows of one chunk, padded to the 128-row tile
+        hidden = widths[1]
+        n_pass = 3 if precision == "tf32x3" else 1
+        sec = time_dominant_gemm(lib, torch, dev, EN.current_stream_ptr(dev), Mc, hidden, hidden, n_pass)
+        fl = 2.0 * Mc * hidden * hidden
+        roofline.update({
+            "kernel": f"gemm_tc_kernel<128, FWD_HIDDEN, CTA pair> (tcgen05 kind::tf32 {precision}, TMEM accumulators, "
+                      f"TMA operands): [{Mc} x {hidden}] x [{hidden} x {hidden}] + bias + ELU + (hi, lo) split",
+            "achieved": fl / sec / 1e12, "frac": fl / sec / 1e12 / tf32_peak, "flops_per_launch": fl,
+            "launch_us": sec * 1e6, "launches_per_step": 2 * (len(widths) - 3) * n_chunks * T,
+            "note": "algorithmic FLOPs: the 3 tensor passes of the fp32-grade split count once (ceiling 1/3)"
+                    if n_pass == 3 else "single tensor pass",
+            "adjoint_group": group,
+        })
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D of the batch + D2H of loss and gradient
     e2e = None

@@ -15,6 +15,8 @@
 // fixed order once per batch, so the gradient is deterministic.
 #include "rollout_sym.cuh"
 
+#include <cstdlib>
+
 #include "rollout_small_kernels.cuh"
 
 namespace hdpo {
@@ -179,8 +181,18 @@ __host__ __device__ inline int wacc_floats(const Cfg& c) {
   const int lws = c.Lw | 1;
   return H * lws + c.w_nhh * (H * WS + H) + H + 4;
 }
+// stores per lane of one forward store-net pass (tuning knob: HDPO_SYM_FWD_NS)
+static int fwd_ns(const Cfg& c) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("HDPO_SYM_FWD_NS");
+    env = e ? atoi(e) : 0;
+  }
+  if (env == 1 || env == 2) return env;
+  return c.S > 32 ? 2 : 1;
+}
 int fwd_smem_floats_per_warp(const Cfg& c) {
-  const int ns = c.S > 32 ? 2 : 1;
+  const int ns = fwd_ns(c);
   const int n = 2 * c.ldx + c.ldy + 7 * c.SP + ns * 32 * (c.s_xs + HS) + (kMaxHH + 1) * H + 32;
   return pad_to(n, 4);
 }
@@ -192,6 +204,14 @@ int bwd_smem_floats_per_warp(const Cfg& c) {
 
 static int warps_per_cta(const Cfg& c, int per_warp_floats, int rows) {
   int w = kMaxWarps;
+  {
+    static int env = -1;
+    if (env < 0) {
+      const char* e = getenv("HDPO_SYM_WPC");
+      env = e ? atoi(e) : 0;
+    }
+    if (env >= 1 && env <= kMaxWarps) w = env;
+  }
   while (w > 1 && (static_cast<size_t>(pad_to(c.m_total, 4)) + static_cast<size_t>(w) * per_warp_floats) * sizeof(float) > kSmemMax) --w;
   while (w > 1 && rows < w * 8) w >>= 1;  // few scenarios: more, smaller CTAs
   return w;
@@ -324,23 +344,67 @@ __device__ __forceinline__ float out_dot(const float* __restrict__ wo, const flo
   return (s0 + s1) + (s2 + s3);
 }
 
+// apply the hidden activation in place to NS rows of H floats. A short rolled loop on purpose: the heads run once
+// per scenario through a long instruction stream, so unrolled activation code (32 elements x NS rows x call sites)
+// overflowed the 32 KB instruction cache (ncu: no_instruction was the top stall); the extra LDS/STS pair per float4
+// is noise next to the 256 LDS.128 of a layer.
+template <int NS>
+__device__ __forceinline__ void act_rows_inplace(int act, float* const (&row)[NS]) {
+  dispatch_act(act, [&](auto tag) {
+    constexpr int ACT = decltype(tag)::value;
+#pragma unroll 1
+    for (int n4 = 0; n4 < H / 4; ++n4) {
+      float v[4 * NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const float4 t = reinterpret_cast<float4*>(row[j])[n4];
+        v[4 * j + 0] = t.x;
+        v[4 * j + 1] = t.y;
+        v[4 * j + 2] = t.z;
+        v[4 * j + 3] = t.w;
+      }
+      if (ACT == HDPO_ACT_ELU) {
+        elu_inplace(v);  // branch-free: the per-element `x > 0 ? :` form costs a divergent region per element
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4 * NS; ++i) v[i] = act_fwd_t<ACT>(v[i]);
+      }
+#pragma unroll
+      for (int j = 0; j < NS; ++j)
+        reinterpret_cast<float4*>(row[j])[n4] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  });
+}
+
 // store net for NS rows of this lane. hid[j] + l * layer_stride receives the activations of hidden layer l
-// (layer_stride = 0: in place, forward). Returns the pre-activation outputs.
+// (layer_stride = 0: in place, forward). Returns the pre-activation outputs. ONE call site of the layer code inside a
+// rolled loop over the layers (instruction-cache footprint, see act_rows_inplace).
 template <int NS>
 __device__ __forceinline__ void store_net_fwd(const Cfg& c, const float* __restrict__ Ws, const float* __restrict__ prj,
                                               const float* const (&loc)[NS], float* const (&hid)[NS], int layer_stride,
                                               float (&y)[NS]) {
-  float2 acc[NS][H / 2];
-  small::layer_fwd<NS>(Ws + c.m_s_wt0, prj, c.s_in4 / 4, loc, acc);
-#pragma unroll
-  for (int j = 0; j < NS; ++j) small::act_store_row(c.s_hact, acc[j], hid[j]);
-  for (int l = 0; l < c.s_nhh; ++l) {
+#pragma unroll 1
+  for (int l = 0; l <= c.s_nhh; ++l) {
+    const float* Wt = Ws + (l == 0 ? c.m_s_wt0 : c.m_s_wth[l - 1]);
+    const float* bias = l == 0 ? prj : Ws + c.m_s_bh[l - 1];
+    const int K4 = l == 0 ? c.s_in4 / 4 : H / 4;
     const float* in[NS];
+    float* out[NS];
 #pragma unroll
-    for (int j = 0; j < NS; ++j) in[j] = hid[j] + l * layer_stride;
-    small::layer_fwd<NS>(Ws + c.m_s_wth[l], Ws + c.m_s_bh[l], H / 4, in, acc);
+    for (int j = 0; j < NS; ++j) {
+      in[j] = l == 0 ? loc[j] : hid[j] + (l - 1) * layer_stride;
+      out[j] = hid[j] + l * layer_stride;
+    }
+    float2 acc[NS][H / 2];
+    small::layer_fwd<NS>(Wt, bias, K4, in, acc);
 #pragma unroll
-    for (int j = 0; j < NS; ++j) small::act_store_row(c.s_hact, acc[j], hid[j] + (l + 1) * layer_stride);
+    for (int j = 0; j < NS; ++j) {
+#pragma unroll
+      for (int n4 = 0; n4 < H / 4; ++n4)
+        reinterpret_cast<float4*>(out[j])[n4] =
+            make_float4(acc[j][2 * n4].x, acc[j][2 * n4].y, acc[j][2 * n4 + 1].x, acc[j][2 * n4 + 1].y);
+    }
+    act_rows_inplace<NS>(c.s_hact, out);
   }
 #pragma unroll
   for (int j = 0; j < NS; ++j) y[j] = Ws[c.m_s_bo] + out_dot(Ws + c.m_s_wo, hid[j] + c.s_nhh * layer_stride);
@@ -960,14 +1024,15 @@ static int set_smem(K k, size_t bytes) {
 int head_fwd(const Cfg& c, const PeriodArgs& a, const float* params, const float* X, const float* PRJ, float* Xn,
              float* Xn_hi, float* Xn_lo, float* so_tape, float* cost_b, float* report_b, float* reward_t, void* stream) {
   const int per_warp = fwd_smem_floats_per_warp(c);
-  const int wpc = warps_per_cta(c, per_warp, c.Bp);
+  int wpc = warps_per_cta(c, per_warp, c.Bp);
+  if (wpc > 4 && !getenv("HDPO_SYM_WPC")) wpc = 4;  // measured: 2 resident CTAs of 4 warps beat 1 of 8 (finer tail)
   const size_t smem = smem_bytes(c, wpc, per_warp);
   int grid = ceil_div(ceil_div(c.Bp, 2), wpc);
   const int cap = max_resident_ctas(smem);
   if (grid > cap) grid = cap;
   HDPO_REQUIRE(smem <= kSmemMax, "symmetry-aware head: %zu bytes of shared memory needed", smem);
   int rc;
-  if (c.S > 32) {
+  if (fwd_ns(c) == 2) {
     auto k = sym_head_fwd_kernel<2>;
     if ((rc = set_smem(k, smem))) return rc;
     HDPO_LAUNCH_PDL(k, grid, wpc * 32, smem, stream, c, a, params, X, PRJ, Xn, Xn_hi, Xn_lo, so_tape, cost_b, report_b,
