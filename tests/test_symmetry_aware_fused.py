@@ -116,6 +116,34 @@ def test_symmetry_aware_fused_time_major_and_forward_only(be_name, precision):
     np.testing.assert_allclose(dsc["cost_b"], fwd["reward_tb"].sum(0), rtol=1e-5)
 
 
+@pytest.mark.parametrize("be_name,precision", MODES)
+@pytest.mark.parametrize("variant", ["backlogged_edge_cost", "maximize_profit", "relu_tanh"])
+def test_symmetry_aware_fused_problem_variants(be_name, precision, variant):
+    """Simulator switches the shipped one_warehouse setting does not use: backlogged demand (no clip of the post-demand
+    inventory), warehouse edge costs (environment.py:254), the profit objective with its min() tie convention
+    (environment.py:190-194), other activations."""
+    be = backend(be_name)
+    act = "relu" if variant == "relu_tanh" else "elu"
+    meta, params, data = sym_case("one_warehouse_s5", {"context": [24], "store": [16, 16], "warehouse": [8, 8]}, 12,
+                                  seed=21, hidden_act=act)
+    data = dict(D.slice_batch(data, 13))
+    meta["problem_params"] = dict(meta["problem_params"])
+    if variant == "backlogged_edge_cost":
+        meta["problem_params"]["lost_demand"] = False
+        data["warehouse_edge_costs"] = np.full_like(data["warehouse_holding_costs"], 0.7)
+    elif variant == "maximize_profit":
+        meta["problem_params"]["maximize_profit"] = True
+        data["demands"] = np.round(data["demands"])           # integer demands and inventories: exact ties in min()
+        data["initial_inventories"] = np.round(data["initial_inventories"])
+    else:
+        meta["inner_layer_activations"]["warehouse"] = "tanh"
+    T, ignore = 6, 2
+    out = D.rollout(be, meta, params, data, T=T, ignore=ignore, precision=precision)
+    pol = oracle_policy(meta, params)
+    fwd, grads = O.rollout_grad(pol, G.problem_from_meta(meta), G.cast(data, np.float64), T)
+    check(out, fwd, grads, pol, ignore)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 def test_symmetry_aware_fused_default_widths_many_scenarios(precision):
