@@ -1154,10 +1154,25 @@ static HeadArgs head_args(const HdpoRolloutDesc* d, const ChunkCtx& c, int t) {
 #ifndef HDPO_EMU
 // tile form of the forward GEMM of layer l / of the dgrad GEMM that consumes gz_l: hidden-layer epilogues exist in the
 // CTA-pair form (256 x 128 tiles), the output layer and the accumulation into gX use single-CTA tiles
-static int fwd_bn(const Plan& p, int l) {
-  return l + 1 < p.n ? tc::pick_bn_pair(p.Bp, p.wp[l + 1]) : tc::pick_bn(p.wp[l + 1]);
+// HDPO_TC_BN = 64 | 128 forces single-CTA tiles of that width everywhere (A/B comparison on the GPU box)
+static int forced_bn() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HDPO_TC_BN");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
 }
-static int dgrad_bn(const Plan& p, int l) { return l > 0 ? tc::pick_bn_pair(p.Bp, p.wp[l]) : tc::pick_bn(p.wp[l]); }
+static int tile_bn(int rows, int cols, bool pair_ok) {
+  const int f = forced_bn();
+  if (f == 64 || (f == 128 && cols % 128 == 0)) return f;
+  // few tiles (e.g. 1024 scenarios per GPU): 128 x 64 tiles double the CTAs of a launch that cannot fill the machine
+  // anyway (measured on many_warehouses 3 x 50, 1024 scenarios: 7.77 -> 7.32 ms per step; 2048-row chunks lose 25 %)
+  if (f == 0 && pair_ok && (rows / 128) * (cols / 128) <= 32 && cols % 128 == 0) return 64;
+  return pair_ok ? tc::pick_bn_pair(rows, cols) : tc::pick_bn(cols);
+}
+static int fwd_bn(const Plan& p, int l) { return tile_bn(p.Bp, p.wp[l + 1], l + 1 < p.n); }
+static int dgrad_bn(const Plan& p, int l) { return tile_bn(p.Bp, p.wp[l], l > 0); }
 
 // output-side tensor maps (32-row boxes) of the activation tapes, and for the adjoint of the gz tapes and gX
 static int make_tape_maps(ChunkCtx& c) {
