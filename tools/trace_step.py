@@ -11,7 +11,7 @@ dev = torch.device("cuda", 0)
 name = sys.argv[1] if len(sys.argv) > 1 else "one_warehouse_lost_demand"
 pspec, pp, data, widths = WL.WORKLOADS[name](dev, seed=57, T=50)
 B, S, T = data["demands"].shape[0], pp["n_stores"], 50
-flat = WL.init_flat_params(widths, torch.Generator(device=dev).manual_seed(0), dev)
+flat = WL.init_params(widths, torch.Generator(device=dev).manual_seed(0), dev)
 eng = EN.FusedRollout(pspec, pp, data, T, ignore_periods=30, precision="tf32x3")
 grad = torch.zeros_like(flat)
 g = 1.0 / (B * T * S)
