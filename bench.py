@@ -227,6 +227,8 @@ def main():
                     help="policy-MLP matmul mode (default: tf32x3 = parity-grade tcgen05 where available, else fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-others", action="store_true",
+                    help="skip the short device-timed runs of the other BASELINE configs reported under 'other_workloads'")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -409,6 +411,33 @@ def main():
                "api": "hdpo_rollout_train_host (C ABI, pinned host buffers)"}
         del ws
 
+    # ---- the other BASELINE.json configs, device-timed the same way on a short run (context for the headline line)
+    others = None
+    if world == 1 and not args.no_others and args.workload == DEFAULT_WORKLOAD and not args.batch:
+        del eng
+        torch.cuda.empty_cache()
+        others = {}
+        for name in ("one_warehouse_lost_demand_symmetry_aware", "one_store_backlogged_lead20", "serial_system",
+                     "one_store_lost", "many_warehouses_lost_demand"):
+            ps2, pp2, data2, widths2 = WL.WORKLOADS[name](dev, seed=57, T=T)
+            B2, S2 = data2["demands"].shape[0], pp2["n_stores"]
+            flat2 = WL.init_params(widths2, torch.Generator(device=dev).manual_seed(0), dev)
+            prec2 = "fp32" if ps2.arch in ("vanilla_one_store", "vanilla_serial") else "tf32x3"
+            eng2 = EN.FusedRollout(ps2, pp2, data2, T, ignore_periods=30, precision=prec2)
+            grad2 = torch.zeros_like(flat2)
+
+            def step2():
+                eng2.forward(flat2, data2)
+                eng2.backward(1.0 / (B2 * T * S2), 0.0, out=grad2)
+
+            for _ in range(3):
+                step2()
+            ms2 = time_region(step2, 10)
+            others[name] = {"value": B2 * T / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "scenarios": B2,
+                            "precision": prec2, "steps": 10, "warmup": 3}
+            del eng2, data2, flat2, grad2
+            torch.cuda.empty_cache()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         Bc = cpu_sample_size(args.workload)
@@ -429,7 +458,7 @@ def main():
                        if B * T * 4 * (1 + WL.net_list(widths)[0][1][0]) > 126e6 else "working set below L2 size; no flush",
                        "parallelism": f"dp{world} (scenario shards, gradient all-reduce)" if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "other_workloads": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
