@@ -17,6 +17,7 @@
 
 #include <cstdlib>
 
+#include "mma32.cuh"
 #include "rollout_small_kernels.cuh"
 
 namespace hdpo {
@@ -139,6 +140,31 @@ int build_cfg(const HdpoRolloutDesc* d, int B, int Bp, int ldx, int ldy, Cfg* c)
   }
   c->m_w_wo = take(H);
   c->m_w_bo = take(4);
+  c->m_total_simt = s;  // weight block of a kernel that does not use the mma forms
+#ifdef HDPO_EMU
+  c->tc = 0;
+#else
+  c->tc = d->precision != HDPO_PREC_FP32;
+#endif
+  // Where the mma.sync forms pay (measured, 8192 scenarios x 50 stores): adjoint head 18.3 -> 16.9 ms per step; the
+  // forward head is FASTER in the FFMA2 form (6.8 vs 7.1 - 8.0 ms: at 8 warps per SM the HMMA latency is not hidden and
+  // two stores per lane amortise the weight loads), so it stays SIMT. HDPO_SYM_TC_FWD / HDPO_SYM_TC_RECOMPUTE override.
+  {
+    const char* e = getenv("HDPO_SYM_TC_FWD");
+    c->tc_fwd = c->tc && e && atoi(e) != 0;
+    e = getenv("HDPO_SYM_TC_RECOMPUTE");
+    c->tc_recompute = c->tc && (!e || atoi(e) != 0);
+  }
+  if (c->tc) {
+    c->m_s_w0n_hi = take(H * c->s_xs);
+    c->m_s_w0n_lo = take(H * c->s_xs);
+    for (int l = 0; l < c->s_nhh; ++l) {
+      c->m_s_whn_hi[l] = take(H * HS);
+      c->m_s_whn_lo[l] = take(H * HS);
+      c->m_s_whk_hi[l] = take(H * HS);
+      c->m_s_whk_lo[l] = take(H * HS);
+    }
+  }
   c->m_total = s;
   // gradient slab + parameter blocks
   int q = 0, nb = 0;
@@ -202,7 +228,13 @@ int bwd_smem_floats_per_warp(const Cfg& c) {
   return pad_to(n, 4);
 }
 
-static int warps_per_cta(const Cfg& c, int per_warp_floats, int rows) {
+// floats of the shared weight block a head kernel stages: the mma copies only where that kernel uses them
+__host__ __device__ inline int weight_floats(const Cfg& c, bool bwd) {
+  const bool mma = bwd ? c.tc != 0 : c.tc_fwd != 0;
+  return ((mma ? c.m_total : c.m_total_simt) + 3) & ~3;
+}
+
+static int warps_per_cta(const Cfg& c, int per_warp_floats, int rows, bool bwd) {
   int w = kMaxWarps;
   {
     static int env = -1;
@@ -212,7 +244,7 @@ static int warps_per_cta(const Cfg& c, int per_warp_floats, int rows) {
     }
     if (env >= 1 && env <= kMaxWarps) w = env;
   }
-  while (w > 1 && (static_cast<size_t>(pad_to(c.m_total, 4)) + static_cast<size_t>(w) * per_warp_floats) * sizeof(float) > kSmemMax) --w;
+  while (w > 1 && (static_cast<size_t>(weight_floats(c, bwd)) + static_cast<size_t>(w) * per_warp_floats) * sizeof(float) > kSmemMax) --w;
   while (w > 1 && rows < w * 8) w >>= 1;  // few scenarios: more, smaller CTAs
   return w;
 }
@@ -232,8 +264,8 @@ static int sm_count() {
 #endif
 }
 
-static size_t smem_bytes(const Cfg& c, int wpc, int per_warp_floats) {
-  return (static_cast<size_t>(pad_to(c.m_total, 4)) + static_cast<size_t>(wpc) * per_warp_floats) * sizeof(float);
+static size_t smem_bytes(const Cfg& c, int wpc, int per_warp_floats, bool bwd) {
+  return (static_cast<size_t>(weight_floats(c, bwd)) + static_cast<size_t>(wpc) * per_warp_floats) * sizeof(float);
 }
 // persistent grid: at most the CTAs that are resident at once (shared memory decides how many fit on an SM)
 static int max_resident_ctas(size_t smem) {
@@ -246,10 +278,10 @@ static int max_resident_ctas(size_t smem) {
 // launch shape of the adjoint head: fixed by (B, shapes) so that warp w owns the same scenarios in every period
 static void bwd_shape(const Cfg& c, int* grid, int* wpc) {
   const int per_warp = bwd_smem_floats_per_warp(c);
-  *wpc = warps_per_cta(c, per_warp, c.Bp);
+  *wpc = warps_per_cta(c, per_warp, c.Bp, true);
   const int warps = ceil_div(c.Bp, 4);  // >= 4 scenarios per warp amortise the slab update
   *grid = ceil_div(warps, *wpc);
-  const int cap = max_resident_ctas(smem_bytes(c, *wpc, per_warp));
+  const int cap = max_resident_ctas(smem_bytes(c, *wpc, per_warp, true));
   if (*grid > cap) *grid = cap;
 }
 int bwd_warps(const Cfg& c) {
@@ -284,9 +316,11 @@ __device__ __forceinline__ float demand_of(const Cfg& c, const PeriodArgs& a, in
 }
 
 // flat parameter vector -> shared weight block (zero padded). Store net: Wt[k][n] stride H; warehouse net: stride WS.
-static __device__ void stage_weights(const Cfg& c, const float* __restrict__ params, float* __restrict__ Ws) {
+static __device__ void stage_weights(const Cfg& c, const float* __restrict__ params, float* __restrict__ Ws, bool bwd) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < c.m_total; i += nt) Ws[i] = 0.f;
+  const int n_floats = weight_floats(c, bwd);
+  const bool mma = n_floats > ((c.m_total_simt + 3) & ~3);
+  for (int i = tid; i < n_floats; i += nt) Ws[i] = 0.f;
   __syncthreads();
   for (int i = tid; i < c.s_w[0] * c.s_in; i += nt) {
     const int n = i / c.s_in, k = i % c.s_in;
@@ -302,6 +336,29 @@ static __device__ void stage_weights(const Cfg& c, const float* __restrict__ par
   }
   for (int i = tid; i < c.s_w[c.s_nhh]; i += nt) Ws[c.m_s_wo + i] = params[c.g_s_wo + i];
   if (tid == 0) Ws[c.m_s_bo] = params[c.g_s_bo];
+#ifndef HDPO_EMU
+  if (mma) {  // (hi, lo) copies for the tensor-core fragments; padding stays zero
+    for (int i = tid; i < c.s_w[0] * c.s_in; i += nt) {
+      const int n = i / c.s_in, k = i % c.s_in;
+      unsigned hi, lo;
+      mma32::split(params[c.g_s_w0 + n * c.s_ld0 + k], hi, lo);
+      Ws[c.m_s_w0n_hi + n * c.s_xs + k] = __uint_as_float(hi);
+      Ws[c.m_s_w0n_lo + n * c.s_xs + k] = __uint_as_float(lo);
+    }
+    for (int l = 0; l < c.s_nhh; ++l) {
+      const int n_out = c.s_w[l + 1], n_in = c.s_w[l];
+      for (int i = tid; i < n_out * n_in; i += nt) {
+        const int n = i / n_in, k = i % n_in;
+        unsigned hi, lo;
+        mma32::split(params[c.g_s_wh[l] + i], hi, lo);
+        Ws[c.m_s_whn_hi[l] + n * HS + k] = __uint_as_float(hi);
+        Ws[c.m_s_whn_lo[l] + n * HS + k] = __uint_as_float(lo);
+        Ws[c.m_s_whk_hi[l] + k * HS + n] = __uint_as_float(hi);
+        Ws[c.m_s_whk_lo[l] + k * HS + n] = __uint_as_float(lo);
+      }
+    }
+  }
+#endif
   for (int i = tid; i < c.w_w[0] * c.Lw; i += nt) {
     const int n = i / c.Lw, k = i % c.Lw;
     Ws[c.m_w_wt0 + k * WS + n] = params[c.g_w_w0 + n * c.w_ld0 + k];
@@ -382,7 +439,7 @@ __device__ __forceinline__ void act_rows_inplace(int act, float* const (&row)[NS
 template <int NS>
 __device__ __forceinline__ void store_net_fwd(const Cfg& c, const float* __restrict__ Ws, const float* __restrict__ prj,
                                               const float* const (&loc)[NS], float* const (&hid)[NS], int layer_stride,
-                                              float (&y)[NS]) {
+                                              float (&y)[NS], bool use_mma) {
 #pragma unroll 1
   for (int l = 0; l <= c.s_nhh; ++l) {
     const float* Wt = Ws + (l == 0 ? c.m_s_wt0 : c.m_s_wth[l - 1]);
@@ -395,14 +452,27 @@ __device__ __forceinline__ void store_net_fwd(const Cfg& c, const float* __restr
       in[j] = l == 0 ? loc[j] : hid[j] + (l - 1) * layer_stride;
       out[j] = hid[j] + l * layer_stride;
     }
-    float2 acc[NS][H / 2];
-    small::layer_fwd<NS>(Wt, bias, K4, in, acc);
+#ifndef HDPO_EMU
+    if (use_mma) {
+      // tensor-core form: the 32 NS rows of the warp as one M = 32 NS product (rows of block j follow block j - 1)
+      const int lane = threadIdx.x & 31;
+      const int in_stride = l == 0 ? c.s_xs : HS;
+      __syncwarp();  // the input rows were written lane-by-lane
+      mma32::layer<2 * NS>(Ws + (l == 0 ? c.m_s_w0n_hi : c.m_s_whn_hi[l - 1]), Ws + (l == 0 ? c.m_s_w0n_lo : c.m_s_whn_lo[l - 1]),
+                           in_stride, bias, in[0] - lane * in_stride, in_stride, l == 0 ? c.s_in4 / 8 : H / 8,
+                           out[0] - lane * HS, HS, lane);
+    } else
+#endif
+    {
+      float2 acc[NS][H / 2];
+      small::layer_fwd<NS>(Wt, bias, K4, in, acc);
 #pragma unroll
-    for (int j = 0; j < NS; ++j) {
+      for (int j = 0; j < NS; ++j) {
 #pragma unroll
-      for (int n4 = 0; n4 < H / 4; ++n4)
-        reinterpret_cast<float4*>(out[j])[n4] =
-            make_float4(acc[j][2 * n4].x, acc[j][2 * n4].y, acc[j][2 * n4 + 1].x, acc[j][2 * n4 + 1].y);
+        for (int n4 = 0; n4 < H / 4; ++n4)
+          reinterpret_cast<float4*>(out[j])[n4] =
+              make_float4(acc[j][2 * n4].x, acc[j][2 * n4].y, acc[j][2 * n4 + 1].x, acc[j][2 * n4 + 1].y);
+      }
     }
     act_rows_inplace<NS>(c.s_hact, out);
   }
@@ -504,12 +574,12 @@ sym_head_fwd_kernel(Cfg c, PeriodArgs a, const float* __restrict__ params, const
                     float* __restrict__ report_b, float* __restrict__ reward_t, int per_warp) {
   HDPO_DYN_SMEM(float, smem);
   float* Ws = smem;
-  stage_weights(c, params, Ws);  // parameters do not depend on the predecessor kernel
+  stage_weights(c, params, Ws, false);  // parameters do not depend on the predecessor kernel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpc = blockDim.x >> 5;
   const int gwarp = blockIdx.x * wpc + warp, nwarps = gridDim.x * wpc;
   Rows r;
-  float* q = carve_rows(c, smem + ((c.m_total + 3) & ~3) + static_cast<size_t>(warp) * per_warp, r, false);
+  float* q = carve_rows(c, smem + weight_floats(c, false) + static_cast<size_t>(warp) * per_warp, r, false);
   float* loc = q;
   q += NS * 32 * c.s_xs;
   float* hid = q;
@@ -549,7 +619,7 @@ sym_head_fwd_kernel(Cfg c, PeriodArgs a, const float* __restrict__ params, const
         hidr[j] = hid + (j * 32 + lane) * HS;
       }
       float y[NS];
-      store_net_fwd<NS>(c, Ws, r.prj, locr, hidr, 0, y);
+      store_net_fwd<NS>(c, Ws, r.prj, locr, hidr, 0, y, c.tc_fwd != 0);
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
         const int s = s0 + j * 32 + lane;
@@ -629,7 +699,9 @@ sym_head_fwd_kernel(Cfg c, PeriodArgs a, const float* __restrict__ params, const
 // ------------------------------------------------------------------------------------------------------------
 // adjoint head
 // ------------------------------------------------------------------------------------------------------------
-template <int KQ0, int NHH>
+// TC: the store net's GEMM-shaped steps (recompute, hidden-layer dgrad, weight gradients) on mma.sync (mma32.cuh); the
+// gradient accumulators are then mma C fragments instead of the SIMT 4 x KQ tiles.
+template <int KQ0, int NHH, bool TC>
 __global__ void __launch_bounds__(kMaxWarps * 32)
 sym_head_bwd_kernel(Cfg c, PeriodArgs a, const float* __restrict__ params, const float* __restrict__ X,
                     const float* __restrict__ PRJ, const float* __restrict__ so_tape, float* __restrict__ gX,
@@ -637,12 +709,12 @@ sym_head_bwd_kernel(Cfg c, PeriodArgs a, const float* __restrict__ params, const
                     int per_warp) {
   HDPO_DYN_SMEM(float, smem);
   float* Ws = smem;
-  stage_weights(c, params, Ws);
+  stage_weights(c, params, Ws, true);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpc = blockDim.x >> 5;
   const int gwarp = blockIdx.x * wpc + warp, nwarps = gridDim.x * wpc;
   Rows r;
-  float* q = carve_rows(c, smem + ((c.m_total + 3) & ~3) + static_cast<size_t>(warp) * per_warp, r, true);
+  float* q = carve_rows(c, smem + weight_floats(c, true) + static_cast<size_t>(warp) * per_warp, r, true);
   float* g = r.xo;               // adjoint row: staged, updated in place, written back
   float* gprj = r.prj + c.ldy;   // adjoint of the projection row
   float* ga = q;                 // adjoint of the allocations, then of the store outputs
@@ -668,12 +740,31 @@ sym_head_bwd_kernel(Cfg c, PeriodArgs a, const float* __restrict__ params, const
   for (int i = lane; i < wacc_floats(c); i += 32) wacc[i] = 0.f;
 
   // register-resident gradient tiles of the store net
-  small::WgradAcc<KQ0> a0;
-  small::WgradAcc<8> ah[NHH > 0 ? NHH : 1];
+  small::WgradAcc<TC ? 1 : KQ0> a0;
+  small::WgradAcc<TC ? 1 : 8> ah[NHH > 0 ? NHH : 1];
   float ao = 0.f, bo = 0.f;  // lane = k for ao
   a0.clear();
 #pragma unroll
   for (int l = 0; l < (NHH > 0 ? NHH : 1); ++l) ah[l].clear();
+  // tensor-core mode: mma C fragments (element i of [mt][nt]: n = 16 mt + (lane >> 2) + 8 (i >> 1),
+  // k = 8 nt + 2 (lane & 3) + (i & 1)) and the bias sums with lane = n
+  constexpr int NT0 = KQ0 / 2;  // 8-column blocks of the local first-layer inputs (s_in4 = 4 KQ0)
+  float a0f[2][TC ? NT0 : 1][4], ahf[NHH > 0 ? NHH : 1][2][TC ? 4 : 1][4], bhf[NHH > 0 ? NHH : 1];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int nt = 0; nt < (TC ? NT0 : 1); ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a0f[mt][nt][i] = 0.f;
+#pragma unroll
+    for (int l = 0; l < (NHH > 0 ? NHH : 1); ++l) {
+      bhf[l] = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < (TC ? 4 : 1); ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ahf[l][mt][nt][i] = 0.f;
+    }
+  }
 
   pdl_wait();
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -819,7 +910,7 @@ sym_head_bwd_kernel(Cfg c, PeriodArgs a, const float* __restrict__ params, const
       {
         const float* xin[1] = {xrow};
         float* hr[1] = {hrow};
-        store_net_fwd<1>(c, Ws, r.prj, xin, hr, HL, y);
+        store_net_fwd<1>(c, Ws, r.prj, xin, hr, HL, y, c.tc_recompute != 0);
       }
       const float gy = valid ? ga[s] * act_grad(c.s_oact, y[0], act_fwd(c.s_oact, y[0])) : 0.f;
       Gy[lane] = gy;
@@ -854,6 +945,27 @@ sym_head_bwd_kernel(Cfg c, PeriodArgs a, const float* __restrict__ params, const
 #pragma unroll
       for (int l = NHH - 1; l >= 0; --l) {
         __syncwarp();
+        if constexpr (TC) {
+#ifndef HDPO_EMU
+          const float* Gz = Hb + (l + 1) * HL;
+          mma32::wgrad<4>(Gz, HS, Hb + l * HL, HS, lane, ahf[l]);
+          float bs = 0.f;
+          for (int cidx = 0; cidx < 32; ++cidx) bs += Gz[cidx * HS + lane];
+          bhf[l] += bs;
+          dispatch_act(c.s_hact, [&](auto tag) {
+            constexpr int ACT = decltype(tag)::value;
+            mma32::dgrad_inplace(Ws + c.m_s_whk_hi[l], Ws + c.m_s_whk_lo[l], HS, Gz, HS, Hb + l * HL, HS, lane,
+                                 [](float y) { return act_grad_out_t<ACT>(y); });
+          });
+          float* hq = hrow + l * HL;  // this lane's row of the new pre-activation adjoints
+#pragma unroll
+          for (int k4 = 0; k4 < H / 4; ++k4) {
+            const float4 v = reinterpret_cast<const float4*>(hq)[k4];
+            gz[2 * k4 + 0] = make_float2(v.x, v.y);
+            gz[2 * k4 + 1] = make_float2(v.z, v.w);
+          }
+#endif
+        } else {
         small::wgrad_tile<8>(Hb + (l + 1) * HL, HS, Hb + l * HL, HS, lane, ah[l]);
         __syncwarp();
         float* hp = hrow + l * HL;
@@ -877,10 +989,17 @@ sym_head_bwd_kernel(Cfg c, PeriodArgs a, const float* __restrict__ params, const
           gz[2 * k4 + 0] = make_float2(v.x, v.y);
           gz[2 * k4 + 1] = make_float2(v.z, v.w);
         }
+        }  // SIMT form
       }
       // layer 0: local weight gradient, projection adjoint (column sums over the rows), pipeline adjoint
       __syncwarp();
-      small::wgrad_tile<KQ0>(Hb, HS, loc, c.s_xs, lane, a0);
+      if constexpr (TC) {
+#ifndef HDPO_EMU
+        mma32::wgrad<NT0>(Hb, HS, loc, c.s_xs, lane, a0f);
+#endif
+      } else {
+        small::wgrad_tile<KQ0>(Hb, HS, loc, c.s_xs, lane, a0);
+      }
       for (int cidx = 0; cidx < 32; ++cidx) gprj_s += Hb[cidx * HS + lane];
       if (valid) {
         float* gs = g + s * c.L;
@@ -907,20 +1026,37 @@ sym_head_bwd_kernel(Cfg c, PeriodArgs a, const float* __restrict__ params, const
   float* out = slabs + static_cast<size_t>(gwarp) * c.q_total;
   auto put = [&](int at, float v) { out[at] = first ? v : out[at] + v; };
   const int ni = lane >> 2, ki = lane & 3;
+  if constexpr (TC) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int n = 4 * ni + i;
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int qq = 0; qq < KQ0; ++qq) put(c.q_s_w0 + n * c.s_in4 + ki * KQ0 + qq, a0.at(i, qq));
-  }
+      for (int i = 0; i < 4; ++i) {
+        const int n = 16 * mt + ni + 8 * (i >> 1), k = 2 * ki + (i & 1);
 #pragma unroll
-  for (int l = 0; l < NHH; ++l) {
+        for (int nt = 0; nt < (TC ? NT0 : 1); ++nt) put(c.q_s_w0 + n * c.s_in4 + 8 * nt + k, a0f[mt][nt][i]);
+#pragma unroll
+        for (int l = 0; l < NHH; ++l)
+#pragma unroll
+          for (int nt = 0; nt < (TC ? 4 : 1); ++nt) put(c.q_s_wh[l] + n * H + 8 * nt + k, ahf[l][mt][nt][i]);
+      }
+#pragma unroll
+    for (int l = 0; l < NHH; ++l) put(c.q_s_bh[l] + lane, bhf[l]);
+  } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int n = 4 * ni + i;
 #pragma unroll
-      for (int qq = 0; qq < 8; ++qq) put(c.q_s_wh[l] + n * H + ki * 8 + qq, ah[l].at(i, qq));
-      if (ki == 0) put(c.q_s_bh[l] + n, ah[l].bias[i]);
+      for (int qq = 0; qq < (TC ? 1 : KQ0); ++qq) put(c.q_s_w0 + n * c.s_in4 + ki * KQ0 + qq, a0.at(i, qq));
+    }
+#pragma unroll
+    for (int l = 0; l < NHH; ++l) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = 4 * ni + i;
+#pragma unroll
+        for (int qq = 0; qq < (TC ? 1 : 8); ++qq) put(c.q_s_wh[l] + n * H + ki * 8 + qq, ah[l].at(i, qq));
+        if (ki == 0) put(c.q_s_bh[l] + n, ah[l].bias[i]);
+      }
     }
   }
   put(c.q_s_wo + lane, ao);
@@ -1024,9 +1160,9 @@ static int set_smem(K k, size_t bytes) {
 int head_fwd(const Cfg& c, const PeriodArgs& a, const float* params, const float* X, const float* PRJ, float* Xn,
              float* Xn_hi, float* Xn_lo, float* so_tape, float* cost_b, float* report_b, float* reward_t, void* stream) {
   const int per_warp = fwd_smem_floats_per_warp(c);
-  int wpc = warps_per_cta(c, per_warp, c.Bp);
+  int wpc = warps_per_cta(c, per_warp, c.Bp, false);
   if (wpc > 4 && !getenv("HDPO_SYM_WPC")) wpc = 4;  // measured: 2 resident CTAs of 4 warps beat 1 of 8 (finer tail)
-  const size_t smem = smem_bytes(c, wpc, per_warp);
+  const size_t smem = smem_bytes(c, wpc, per_warp, false);
   int grid = ceil_div(ceil_div(c.Bp, 2), wpc);
   const int cap = max_resident_ctas(smem);
   if (grid > cap) grid = cap;
@@ -1047,22 +1183,32 @@ int head_fwd(const Cfg& c, const PeriodArgs& a, const float* params, const float
   return HDPO_OK;
 }
 
-template <int KQ0, int NHH>
-static int launch_bwd(const Cfg& c, const PeriodArgs& a, const float* params, const float* X, const float* PRJ,
+template <int KQ0, int NHH, bool TC>
+static int launch_bwd_tc(const Cfg& c, const PeriodArgs& a, const float* params, const float* X, const float* PRJ,
                       const float* so_tape, float* gX, float* gPRJ, float* gPRJ_lo, float rb, float* slabs, int first,
                       void* stream) {
   int grid, wpc;
   bwd_shape(c, &grid, &wpc);
   const int per_warp = bwd_smem_floats_per_warp(c);
-  const size_t smem = smem_bytes(c, wpc, per_warp);
+  const size_t smem = smem_bytes(c, wpc, per_warp, true);
   HDPO_REQUIRE(smem <= kSmemMax, "symmetry-aware adjoint head: %zu bytes of shared memory needed", smem);
-  auto k = sym_head_bwd_kernel<KQ0, NHH>;
+  auto k = sym_head_bwd_kernel<KQ0, NHH, TC>;
   int rc = set_smem(k, smem);
   if (rc) return rc;
   HDPO_LAUNCH_PDL(k, grid, wpc * 32, smem, stream, c, a, params, X, PRJ, so_tape, gX, gPRJ, gPRJ_lo, rb, slabs, first,
                   per_warp);
   HDPO_LAUNCH_OK();
   return HDPO_OK;
+}
+
+template <int KQ0, int NHH>
+static int launch_bwd(const Cfg& c, const PeriodArgs& a, const float* params, const float* X, const float* PRJ,
+                      const float* so_tape, float* gX, float* gPRJ, float* gPRJ_lo, float rb, float* slabs, int first,
+                      void* stream) {
+#ifndef HDPO_EMU
+  if (c.tc) return launch_bwd_tc<KQ0, NHH, true>(c, a, params, X, PRJ, so_tape, gX, gPRJ, gPRJ_lo, rb, slabs, first, stream);
+#endif
+  return launch_bwd_tc<KQ0, NHH, false>(c, a, params, X, PRJ, so_tape, gX, gPRJ, gPRJ_lo, rb, slabs, first, stream);
 }
 
 template <int KQ0>

@@ -36,7 +36,11 @@ struct Cfg {
   int P;              // parameters of all three nets
   // shared-memory weight block (floats)
   int m_s_wt0, m_s_wth[kMaxHH], m_s_bh[kMaxHH], m_s_wo, m_s_bo;
-  int m_w_wt0, m_w_wth[kMaxHH], m_w_bh[kMaxHH], m_w_wo, m_w_bo, m_total;
+  int m_w_wt0, m_w_wth[kMaxHH], m_w_bh[kMaxHH], m_w_wo, m_w_bo, m_total, m_total_simt;
+  // tensor-core mode (tc): pre-split (hi, lo) weight copies W[n][k] for the mma.sync fragments (mma32.cuh): first
+  // store layer (local columns, row stride s_xs), hidden layers as W[n][k] and transposed W^T[k][n] (row stride 36)
+  int tc, tc_fwd, tc_recompute;  // adjoint dgrad / wgrad; forward head; recompute inside the adjoint head
+  int m_s_w0n_hi, m_s_w0n_lo, m_s_whn_hi[kMaxHH], m_s_whn_lo[kMaxHH], m_s_whk_hi[kMaxHH], m_s_whk_lo[kMaxHH];
   // per-warp gradient slab (floats) and its blocks
   int q_s_w0, q_s_wh[kMaxHH], q_s_bh[kMaxHH], q_s_wo, q_s_bo;
   int q_w_w0, q_w_wh[kMaxHH], q_w_bh[kMaxHH], q_w_wo, q_w_bo, q_total;
