@@ -260,7 +260,9 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(0)  # identical weights on every rank
     flat = WL.init_params(widths, gen, dev)
     small = pspec.arch in ("vanilla_one_store", "vanilla_serial")
-    precision = args.precision or ("fp32" if small else "tf32x3")
+    # tf32x3 everywhere: tcgen05 GEMMs in the wide path, warp-level mma.sync in the adjoint of the small nets and of the
+    # SymmetryAware heads - all with the fp32-grade 3xTF32 split (parity-tested at the same 1e-5 bar as fp32)
+    precision = args.precision or "tf32x3"
     eng = EN.FusedRollout(pspec, pp, data, T, ignore_periods=30, precision=precision)
     grad = torch.zeros_like(flat)
     lib = eng.lib
@@ -323,7 +325,9 @@ def main():
     achieved = flops_bwd * B * T / (bwd_ms * 1e-3) / 1e12
     traffic = load_traffic(args.workload)
     group = {
-        "kernel": ("small_bwd_kernel (reverse-time adjoint, SIMT fp32 parity mode)" if small else
+        "kernel": (("small_bwd_kernel (reverse-time adjoint; HxH layers on mma.sync 3xTF32, first / output layer and simulator in "
+                    "fp32 FFMA)" if precision != "fp32" else "small_bwd_kernel (reverse-time adjoint, SIMT fp32 parity mode)")
+                   if small else
                    f"adjoint sweep ({precision}): sym_head_bwd_kernel (store / warehouse nets recomputed + adjoint, SIMT "
                    "fp32) + gemm_tc_kernel dgrad / weight-gradient tiles of the context trunk (tcgen05/TMEM/TMA)" if sym
                    and precision != "fp32" else
@@ -422,7 +426,7 @@ def main():
             ps2, pp2, data2, widths2 = WL.WORKLOADS[name](dev, seed=57, T=T)
             B2, S2 = data2["demands"].shape[0], pp2["n_stores"]
             flat2 = WL.init_params(widths2, torch.Generator(device=dev).manual_seed(0), dev)
-            prec2 = "fp32" if ps2.arch in ("vanilla_one_store", "vanilla_serial") else "tf32x3"
+            prec2 = "tf32x3"
             eng2 = EN.FusedRollout(ps2, pp2, data2, T, ignore_periods=30, precision=prec2)
             grad2 = torch.zeros_like(flat2)
 

@@ -195,6 +195,103 @@ __device__ __forceinline__ void wgrad(const float* __restrict__ G, int gs, const
       for (int i = 0; i < 4; ++i) acc[mt][nt][i] += c[mt][nt][i];
 }
 
+// ---- variants with ONE fp32 weight copy W[n][k] (row stride ws), split into (hi, lo) on the fly: 3 ALU operations
+// per B element instead of a second and third copy in shared memory (the small-net adjoint keeps two CTAs per SM).
+// TRANSPOSED = false: c[r][n] += sum_k A[r][k] W[n][k]   (layer);  true: c[r][k] += sum_n A[r][n] W[n][k]   (dgrad)
+template <int MT, bool TRANSPOSED>
+__device__ __forceinline__ void product_f32(const float* __restrict__ W, int ws, const float* __restrict__ in_rows,
+                                            int in_stride, int KT, int lane, float (&c)[MT][4][4]) {
+  const int g = lane >> 2, t = lane & 3;
+  for (int kt = 0; kt < KT; ++kt) {
+    unsigned ahi[MT][4], alo[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const float* r0 = in_rows + (16 * mt + g) * in_stride + 8 * kt + t;
+      split(r0[0], ahi[mt][0], alo[mt][0]);
+      split(r0[8 * in_stride], ahi[mt][1], alo[mt][1]);
+      split(r0[4], ahi[mt][2], alo[mt][2]);
+      split(r0[8 * in_stride + 4], ahi[mt][3], alo[mt][3]);
+    }
+    unsigned bh[4][2], bl[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      // B fragment element (contraction index 8 kt + t (+4), output index 8 nt + g)
+      const float* w = TRANSPOSED ? W + (8 * kt + t) * ws + 8 * nt + g : W + (8 * nt + g) * ws + 8 * kt + t;
+      split(w[0], bh[nt][0], bl[nt][0]);
+      split(w[TRANSPOSED ? 4 * ws : 4], bh[nt][1], bl[nt][1]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma_tf32(c[mt][nt], alo[mt], bh[nt][0], bh[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma_tf32(c[mt][nt], ahi[mt], bl[nt][0], bl[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma_tf32(c[mt][nt], ahi[mt], bh[nt][0], bh[nt][1]);
+  }
+}
+
+template <int MT>
+__device__ __forceinline__ void layer_f32(const float* __restrict__ W, int ws, const float* __restrict__ bias,
+                                          const float* __restrict__ in_rows, int in_stride, int KT,
+                                          float* __restrict__ out_rows, int out_stride, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  float c[MT][4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const float2 bv = *reinterpret_cast<const float2*>(bias + 8 * nt + 2 * t);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      c[mt][nt][0] = bv.x;
+      c[mt][nt][1] = bv.y;
+      c[mt][nt][2] = bv.x;
+      c[mt][nt][3] = bv.y;
+    }
+  }
+  product_f32<MT, false>(W, ws, in_rows, in_stride, KT, lane, c);
+  __syncwarp();
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float* o = out_rows + (16 * mt + g) * out_stride + 8 * nt + 2 * t;
+      *reinterpret_cast<float2*>(o) = make_float2(c[mt][nt][0], c[mt][nt][1]);
+      *reinterpret_cast<float2*>(o + 8 * out_stride) = make_float2(c[mt][nt][2], c[mt][nt][3]);
+    }
+  __syncwarp();
+}
+
+template <class DACT>
+__device__ __forceinline__ void dgrad_inplace_f32(const float* __restrict__ W, int ws, const float* __restrict__ gz_rows,
+                                                  int gz_stride, float* __restrict__ h_rows, int h_stride, int lane,
+                                                  DACT dact) {
+  const int g = lane >> 2, t = lane & 3;
+  float c[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[mt][nt][i] = 0.f;
+  product_f32<2, true>(W, ws, gz_rows, gz_stride, 4, lane, c);
+  __syncwarp();
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float* o = h_rows + (16 * mt + g) * h_stride + 8 * nt + 2 * t;
+      const float2 h0 = *reinterpret_cast<const float2*>(o);
+      const float2 h1 = *reinterpret_cast<const float2*>(o + 8 * h_stride);
+      *reinterpret_cast<float2*>(o) = make_float2(c[mt][nt][0] * dact(h0.x), c[mt][nt][1] * dact(h0.y));
+      *reinterpret_cast<float2*>(o + 8 * h_stride) = make_float2(c[mt][nt][2] * dact(h1.x), c[mt][nt][3] * dact(h1.y));
+    }
+  __syncwarp();
+}
+
 }  // namespace mma32
 }  // namespace hdpo
 #endif  // HDPO_EMU

@@ -106,6 +106,17 @@ int build_cfg(const HdpoRolloutDesc* d, int, Cfg* c) {
   c->s_bo = s;
   s += kMaxOut;
   c->s_total = s;
+#ifdef HDPO_EMU
+  c->tc = 0;
+#else
+  c->tc = d->precision != HDPO_PREC_FP32 && c->NHH > 0;
+#endif
+  s = (s + 3) & ~3;
+  for (int i = 0; i < c->NHH; ++i) {
+    c->s_wn[i] = s;
+    if (c->tc) s += H * HS;
+  }
+  c->s_total_bwd = c->tc ? s : c->s_total;
   c->tape_stride = c->IN4;
   return HDPO_OK;
 }

@@ -4,6 +4,7 @@
 // over several translation units so that nvcc builds them in parallel).
 #pragma once
 
+#include "mma32.cuh"
 #include "rollout_small.cuh"
 
 namespace hdpo {
@@ -41,9 +42,11 @@ __device__ __forceinline__ void load_statics(const Cfg& c, const HdpoStatics& st
 }
 
 // stage the parameter vector into the shared weight block: Wt[k][n] (transposed, zero padded), biases, Wo[o][k]
-static __device__ void stage_weights(const Cfg& c, const float* __restrict__ params, float* __restrict__ Ws) {
+static __device__ void stage_weights(const Cfg& c, const float* __restrict__ params, float* __restrict__ Ws,
+                                     bool bwd = false) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < c.s_total; i += nt) Ws[i] = 0.f;
+  const int n_floats = bwd ? c.s_total_bwd : c.s_total;
+  for (int i = tid; i < n_floats; i += nt) Ws[i] = 0.f;
   __syncthreads();
   {  // layer 0: W0 [w1][IN]
     const int n_out = c.w[1], n_in = c.IN;
@@ -58,6 +61,7 @@ static __device__ void stage_weights(const Cfg& c, const float* __restrict__ par
     for (int i = tid; i < n_out * n_in; i += nt) {
       int n = i / n_in, k = i % n_in;
       Ws[c.s_wth[l] + k * H + n] = params[c.gw[l + 1] + i];
+      if (bwd && c.tc) Ws[c.s_wn[l] + n * HS + k] = params[c.gw[l + 1] + i];  // W[n][k] for the mma fragments
     }
     for (int i = tid; i < n_out; i += nt) Ws[c.s_bh[l] + i] = params[c.gb[l + 1] + i];
   }
@@ -174,6 +178,48 @@ __device__ __forceinline__ void mlp_fwd(const Cfg& c, const float* __restrict__ 
 #pragma unroll
   for (int j = 0; j < NS; ++j) out_layer_fwd(c, Ws, hrow[j] + c.NHH * h_layer_stride, y[j]);
 }
+
+// hidden activation applied in place to this lane's row (rolled loop: instruction-cache footprint)
+__device__ __forceinline__ void act_row_inplace(int act, float* __restrict__ row) {
+  dispatch_act(act, [&](auto tag) {
+    constexpr int ACT = decltype(tag)::value;
+#pragma unroll 1
+    for (int n4 = 0; n4 < H / 4; ++n4) {
+      const float4 t = reinterpret_cast<float4*>(row)[n4];
+      float v[4] = {t.x, t.y, t.z, t.w};
+      if (ACT == HDPO_ACT_ELU) {
+        elu_inplace(v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = act_fwd_t<ACT>(v[i]);
+      }
+      reinterpret_cast<float4*>(row)[n4] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  });
+}
+
+#ifndef HDPO_EMU
+// Recompute of the adjoint kernel in tensor-core mode: first layer (K = padded inputs, not a multiple of 8 in general)
+// and output layer in the FFMA form, the HxH layers as warp-level mma.sync products over the warp's 32 rows
+// (mma32.cuh). Hb = base of the [NHH + 1][32][HS] activation rows of the warp.
+__device__ __forceinline__ void mlp_fwd_tc(const Cfg& c, const float* __restrict__ Ws, const float* __restrict__ xrow,
+                                           float* __restrict__ Hb, int layer_stride, int lane, float (&y)[kMaxOut]) {
+  float* hrow = Hb + lane * HS;
+  {
+    float2 acc[1][H / 2];
+    const float* xin[1] = {xrow};
+    layer_fwd<1>(Ws + c.s_wt0, Ws + c.s_b0, c.IN4 / 4, xin, acc);
+    act_store_row(c.hidden_act, acc[0], hrow);
+  }
+  for (int l = 0; l < c.NHH; ++l) {
+    __syncwarp();
+    mma32::layer_f32<2>(Ws + c.s_wn[l], HS, Ws + c.s_bh[l], Hb + l * layer_stride, HS, H / 8, Hb + (l + 1) * layer_stride,
+                        HS, lane);
+    act_row_inplace(c.hidden_act, hrow + (l + 1) * layer_stride);
+  }
+  out_layer_fwd(c, Ws, hrow + c.NHH * layer_stride, y);
+}
+#endif
 
 // ---- policy head (neural_networks.py:211-214 / 335-349): y -> allocations a[], plus what the adjoint needs
 struct Head {
@@ -563,18 +609,18 @@ __device__ __forceinline__ float dgrad_dot(const float* __restrict__ Wt_row, con
   return (s01.x + s01.y) + (s23.x + s23.y);
 }
 
-template <int ARCH, int KQ0, int NHH>
+template <int ARCH, int KQ0, int NHH, bool TC>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restrict__ demands, HdpoStatics st,
                  const float* __restrict__ tape, float g_total, float g_report, float* __restrict__ partials,
                  int p_stride) {
   HDPO_DYN_SMEM(float, smem);
   float* Ws = smem;
-  stage_weights(c, params, Ws);
+  stage_weights(c, params, Ws, true);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NHB = NHH + 1;  // hidden rows kept per scenario
   const int per_warp = 32 * (2 * c.XS + NHB * HS + kMaxOut);
-  float* Xw = smem + ((c.s_total + 3) & ~3) + warp * per_warp;  // state rows x_t
+  float* Xw = smem + ((c.s_total_bwd + 3) & ~3) + warp * per_warp;  // state rows x_t
   float* Gx = Xw + 32 * c.XS;                                   // state adjoint rows
   float* Hb = Gx + 32 * c.XS;                                   // [NHB][32][HS] activations -> overwritten by gz
   float* Gy = Hb + NHB * 32 * HS;                               // [32][kMaxOut] output adjoints
@@ -585,11 +631,24 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
 
   // register-resident parameter-gradient tiles
   WgradAcc<KQ0> a0;
-  WgradAcc<8> ah[NHH > 0 ? NHH : 1];
+  WgradAcc<TC ? 1 : 8> ah[NHH > 0 ? NHH : 1];
   float ao[kMaxOut], bo = 0.f;  // lane = k for ao; lane = o for bo
   a0.clear();
 #pragma unroll
   for (int l = 0; l < (NHH > 0 ? NHH : 1); ++l) ah[l].clear();
+  // tensor-core mode: the HxH weight gradients are mma C fragments (element i of [mt][nt]: n = 16 mt + (lane >> 2) +
+  // 8 (i >> 1), k = 8 nt + 2 (lane & 3) + (i & 1)), their bias sums live with lane = n
+  float ahf[NHH > 0 ? NHH : 1][2][TC ? 4 : 1][4], bhf[NHH > 0 ? NHH : 1];
+#pragma unroll
+  for (int l = 0; l < (NHH > 0 ? NHH : 1); ++l) {
+    bhf[l] = 0.f;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < (TC ? 4 : 1); ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ahf[l][mt][nt][i] = 0.f;
+  }
 #pragma unroll
   for (int o = 0; o < kMaxOut; ++o) ao[o] = 0.f;
 
@@ -613,7 +672,11 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
       const float rb = valid ? (g_total + (t >= c.ignore ? g_report : 0.f)) : 0.f;
       // B. recompute the activations (rows hb[0..NHH]) and the outputs
       float y[1][kMaxOut];
-      {
+      if constexpr (TC) {
+#ifndef HDPO_EMU
+        mlp_fwd_tc(c, Ws, xrow, Hb, HL, lane, y[0]);
+#endif
+      } else {
         const float* xin[1] = {xrow};
         float* hr[1] = {hrow};
         mlp_fwd<1>(c, Ws, xin, hr, HL, y);
@@ -682,6 +745,27 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
 #pragma unroll
       for (int l = NHH - 1; l >= 0; --l) {
         __syncwarp();
+        if constexpr (TC) {
+#ifndef HDPO_EMU
+          const float* Gz = Hb + (l + 1) * HL;
+          mma32::wgrad<4>(Gz, HS, Hb + l * HL, HS, lane, ahf[l]);
+          float bs = 0.f;
+          for (int cidx = 0; cidx < 32; ++cidx) bs += Gz[cidx * HS + lane];
+          bhf[l] += bs;
+          dispatch_act(c.hidden_act, [&](auto tag) {
+            constexpr int ACT = decltype(tag)::value;
+            mma32::dgrad_inplace_f32(Ws + c.s_wn[l], HS, Gz, HS, Hb + l * HL, HS, lane,
+                                     [](float yv) { return act_grad_out_t<ACT>(yv); });
+          });
+          float* hq = hrow + l * HL;
+#pragma unroll
+          for (int k4 = 0; k4 < H / 4; ++k4) {
+            const float4 v = reinterpret_cast<const float4*>(hq)[k4];
+            gz[2 * k4 + 0] = make_float2(v.x, v.y);
+            gz[2 * k4 + 1] = make_float2(v.z, v.w);
+          }
+#endif
+        } else {
         wgrad_tile<8>(Hb + (l + 1) * HL, HS, Hb + l * HL, HS, lane, ah[l]);
         __syncwarp();
         float* hp = hrow + l * HL;
@@ -706,6 +790,7 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
           gz[2 * k4 + 0] = make_float2(v.x, v.y);
           gz[2 * k4 + 1] = make_float2(v.z, v.w);
         }
+        }  // FFMA form
       }
       // F. layer 0: dW0 += gz0^T x ; state adjoint += W0^T gz0 unless the input was detached
       __syncwarp();
@@ -738,16 +823,29 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
 #pragma unroll
   for (int l = 0; l < NHH; ++l) {
     const int n_out = c.w[l + 2], n_in = c.w[l + 1];
+    if constexpr (TC) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int n = 4 * ni + i;
-      if (n < n_out) {
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int k = ki * 8 + q;
-          if (k < n_in) out[c.gw[l + 1] + n * n_in + k] = ah[l].at(i, q);
+        for (int nt = 0; nt < (TC ? 4 : 1); ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = 16 * mt + ni + 8 * (i >> 1), k = 8 * nt + 2 * ki + (i & 1);
+            if (n < n_out && k < n_in) out[c.gw[l + 1] + n * n_in + k] = ahf[l][mt][nt][i];
+          }
+      if (lane < n_out) out[c.gb[l + 1] + lane] = bhf[l];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = 4 * ni + i;
+        if (n < n_out) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int k = ki * 8 + q;
+            if (k < n_in) out[c.gw[l + 1] + n * n_in + k] = ah[l].at(i, q);
+          }
+          if (ki == 0) out[c.gb[l + 1] + n] = ah[l].bias[i];
         }
-        if (ki == 0) out[c.gb[l + 1] + n] = ah[l].bias[i];
       }
     }
   }
@@ -783,19 +881,29 @@ template <int ARCH, int KQ0>
 int launch_bwd_nhh(const Cfg& c, const float* params, const float* demands, const HdpoStatics* st, const float* tape,
                    float g_total, float g_report, float* partials, int p_stride, int grid, int wpc, void* stream);
 
-template <int ARCH, int KQ0, int NHH>
-int launch_bwd(const Cfg& c, const float* params, const float* demands, const HdpoStatics* st, const float* tape,
-               float g_total, float g_report, float* partials, int p_stride, int grid, int wpc, void* stream) {
+template <int ARCH, int KQ0, int NHH, bool TC>
+int launch_bwd_tc(const Cfg& c, const float* params, const float* demands, const HdpoStatics* st, const float* tape,
+                  float g_total, float g_report, float* partials, int p_stride, int grid, int wpc, void* stream) {
   const int per_warp = 32 * (2 * c.XS + (NHH + 1) * HS + kMaxOut);
-  const size_t smem = (static_cast<size_t>((c.s_total + 3) & ~3) + static_cast<size_t>(wpc) * per_warp) * sizeof(float);
-  auto k = small_bwd_kernel<ARCH, KQ0, NHH>;
-  HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const size_t wfl = static_cast<size_t>((c.s_total_bwd + 3) & ~3);
+  const size_t smem = (wfl + static_cast<size_t>(wpc) * per_warp) * sizeof(float);
+  auto k = small_bwd_kernel<ARCH, KQ0, NHH, TC>;
   HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>((static_cast<size_t>((c.s_total + 3) & ~3) +
-                                                      static_cast<size_t>(kWarpsPerCta) * per_warp) * sizeof(float))));
+                                    static_cast<int>((wfl + static_cast<size_t>(kWarpsPerCta) * per_warp) * sizeof(float))));
   HDPO_LAUNCH(k, grid, wpc * 32, smem, stream, c, params, demands, *st, tape, g_total, g_report, partials, p_stride);
   HDPO_LAUNCH_OK();
   return HDPO_OK;
+}
+template <int ARCH, int KQ0, int NHH>
+int launch_bwd(const Cfg& c, const float* params, const float* demands, const HdpoStatics* st, const float* tape,
+               float g_total, float g_report, float* partials, int p_stride, int grid, int wpc, void* stream) {
+#ifndef HDPO_EMU
+  if (NHH > 0 && c.tc)
+    return launch_bwd_tc<ARCH, KQ0, NHH, (NHH > 0)>(c, params, demands, st, tape, g_total, g_report, partials, p_stride,
+                                                    grid, wpc, stream);
+#endif
+  return launch_bwd_tc<ARCH, KQ0, NHH, false>(c, params, demands, st, tape, g_total, g_report, partials, p_stride, grid,
+                                              wpc, stream);
 }
 
 #define HDPO_SMALL_BWD_INSTANCE(ARCH, KQ0)                                                                         \

@@ -25,6 +25,9 @@ CASES = [
     ("one_store_lost", 8192, "fp32", 48, 1e-5),
     ("one_store_backlogged_lead20", 1 << 20, "fp32", 48, 1e-5),
     ("serial_system", 1 << 20, "fp32", 48, 1e-5),
+    # the same small nets with the adjoint's HxH layers on warp-level tensor cores (mma.sync 3xTF32)
+    ("one_store_backlogged_lead20", 1 << 20, "tf32x3", 48, 1e-5),
+    ("serial_system", 1 << 20, "tf32x3", 48, 1e-5),
     # 50 periods of the 50-store warehouse settings are chaotic (the reference's own fp32 run is 1e-3..1e-2 from its
     # float64 run): the oracle bar at T = 50 is relaxed accordingly, the exact properties are not
     ("one_warehouse_lost_demand", 8192, "tf32x3", 6, 2e-2),
@@ -68,7 +71,7 @@ def _oracle_policy(pspec, widths, flat):
     return O.Policy(pspec.arch, nets, pspec.warehouse_upper_bound, adj, pspec.transshipment, prop_eps=pspec.prop_eps)
 
 
-@pytest.mark.parametrize("workload,B,precision,n_oracle,tol", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("workload,B,precision,n_oracle,tol", CASES, ids=[f"{c[0]}-{c[2]}" for c in CASES])
 def test_full_size_rollout_properties(workload, B, precision, n_oracle, tol):
     from neural_inventory_control_b200 import workloads as WL
     dev = torch.device("cuda", 0)

@@ -92,12 +92,17 @@ def test_allocation_shift_bit_exact(be_name):
     assert np.array_equal(be.get(h), g["ref"]["allocation_shift"])  # the reference's own table
 
 
-@pytest.mark.parametrize("be_name", BACKENDS)
+SMALL_MODES = [pytest.param("emu", "fp32", id="emu"), pytest.param("cuda", "fp32", id="cuda", marks=pytest.mark.gpu),
+               # adjoint with the HxH layers on warp-level tensor cores (mma.sync 3xTF32, mma32.cuh)
+               pytest.param("cuda", "tf32x3", id="cuda-tf32x3", marks=pytest.mark.gpu)]
+
+
+@pytest.mark.parametrize("be_name,precision", SMALL_MODES)
 @pytest.mark.parametrize("name", SMALL)
-def test_rollout_costs_and_gradients_match_reference(be_name, name):
+def test_rollout_costs_and_gradients_match_reference(be_name, precision, name):
     be = backend(be_name)
     meta, g = G.load("rollout", name)
-    out = D.rollout(be, meta, g["param"], g["data"])
+    out = D.rollout(be, meta, g["param"], g["data"], precision=precision)
     check_rollout_against_golden(out, meta, g, meta["T"], meta["ignore_periods"])
     ref, ref64 = g["ref"], g["ref64"]
     keys = sorted(out["grad"])

@@ -15,7 +15,7 @@ pspec, pp, data, widths = WL.WORKLOADS[name](dev, seed=57, T=50, **({"B": int(sy
 B, S, T = data["demands"].shape[0], pp["n_stores"], 50
 flat = WL.init_params(widths, torch.Generator(device=dev).manual_seed(0), dev)
 small = pspec.arch in ("vanilla_one_store", "vanilla_serial")
-precision = sys.argv[2] if len(sys.argv) > 2 else ("fp32" if small else "tf32x3")
+precision = sys.argv[2] if len(sys.argv) > 2 else "tf32x3"
 eng = EN.FusedRollout(pspec, pp, data, T, ignore_periods=30, precision=precision)
 grad = torch.zeros_like(flat)
 g = 1.0 / (B * T * S)
