@@ -198,9 +198,9 @@ __device__ __forceinline__ void wgrad(const float* __restrict__ G, int gs, const
 // ---- variants with ONE fp32 weight copy W[n][k] (row stride ws), split into (hi, lo) on the fly: 3 ALU operations
 // per B element instead of a second and third copy in shared memory (the small-net adjoint keeps two CTAs per SM).
 // TRANSPOSED = false: c[r][n] += sum_k A[r][k] W[n][k]   (layer);  true: c[r][k] += sum_n A[r][n] W[n][k]   (dgrad)
-template <int MT, bool TRANSPOSED>
+template <int MT, bool TRANSPOSED, int NT = 4>
 __device__ __forceinline__ void product_f32(const float* __restrict__ W, int ws, const float* __restrict__ in_rows,
-                                            int in_stride, int KT, int lane, float (&c)[MT][4][4]) {
+                                            int in_stride, int KT, int lane, float (&c)[MT][NT][4]) {
   const int g = lane >> 2, t = lane & 3;
   for (int kt = 0; kt < KT; ++kt) {
     unsigned ahi[MT][4], alo[MT][4];
@@ -212,24 +212,24 @@ __device__ __forceinline__ void product_f32(const float* __restrict__ W, int ws,
       split(r0[4], ahi[mt][2], alo[mt][2]);
       split(r0[8 * in_stride + 4], ahi[mt][3], alo[mt][3]);
     }
-    unsigned bh[4][2], bl[4][2];
+    unsigned bh[NT][2], bl[NT][2];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       // B fragment element (contraction index 8 kt + t (+4), output index 8 nt + g)
       const float* w = TRANSPOSED ? W + (8 * kt + t) * ws + 8 * nt + g : W + (8 * nt + g) * ws + 8 * kt + t;
       split(w[0], bh[nt][0], bl[nt][0]);
       split(w[TRANSPOSED ? 4 * ws : 4], bh[nt][1], bl[nt][1]);
     }
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) mma_tf32(c[mt][nt], alo[mt], bh[nt][0], bh[nt][1]);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) mma_tf32(c[mt][nt], ahi[mt], bl[nt][0], bl[nt][1]);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) mma_tf32(c[mt][nt], ahi[mt], bh[nt][0], bh[nt][1]);
   }
@@ -288,6 +288,36 @@ __device__ __forceinline__ void dgrad_inplace_f32(const float* __restrict__ W, i
       const float2 h1 = *reinterpret_cast<const float2*>(o + 8 * h_stride);
       *reinterpret_cast<float2*>(o) = make_float2(c[mt][nt][0] * dact(h0.x), c[mt][nt][1] * dact(h0.y));
       *reinterpret_cast<float2*>(o + 8 * h_stride) = make_float2(c[mt][nt][2] * dact(h1.x), c[mt][nt][3] * dact(h1.y));
+    }
+  __syncwarp();
+}
+
+// rows[r][k] += sum_n gz[r][n] W[n][k] for k < 8 NT (first-layer dgrad into the state-adjoint rows; no activation)
+template <int NT>
+__device__ __forceinline__ void dgrad_accum_f32(const float* __restrict__ W, int ws, const float* __restrict__ gz_rows,
+                                                int gz_stride, float* __restrict__ rows, int row_stride, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  float c[2][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[mt][nt][i] = 0.f;
+  product_f32<2, true, NT>(W, ws, gz_rows, gz_stride, 4, lane, c);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float* o = rows + (16 * mt + g) * row_stride + 8 * nt + 2 * t;
+      float2 v0 = *reinterpret_cast<const float2*>(o);
+      float2 v1 = *reinterpret_cast<const float2*>(o + 8 * row_stride);
+      v0.x += c[mt][nt][0];
+      v0.y += c[mt][nt][1];
+      v1.x += c[mt][nt][2];
+      v1.y += c[mt][nt][3];
+      *reinterpret_cast<float2*>(o) = v0;
+      *reinterpret_cast<float2*>(o + 8 * row_stride) = v1;
     }
   __syncwarp();
 }

@@ -116,6 +116,13 @@ int build_cfg(const HdpoRolloutDesc* d, int, Cfg* c) {
     c->s_wn[i] = s;
     if (c->tc) s += H * HS;
   }
+  c->K0 = (c->IN4 + 7) & ~7;
+  c->XSb = c->XS;
+  c->s_w0n = s;
+  if (c->tc) {
+    c->XSb = c->K0 + 4;  // adjoint rows hold the zero-padded K0 inputs of the mma first layer; stride stays 4 * odd
+    s += H * c->XSb;
+  }
   c->s_total_bwd = c->tc ? s : c->s_total;
   c->tape_stride = c->IN4;
   return HDPO_OK;

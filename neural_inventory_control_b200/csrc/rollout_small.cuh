@@ -34,6 +34,8 @@ struct Cfg {
   // tensor-core adjoint (precision != fp32): fp32 copies W[n][k] (row stride HS) of the HxH layers for the mma.sync
   // fragments, staged by the adjoint kernel only (after the s_total block the forward kernel uses)
   int tc, s_wn[kMaxHH], s_total_bwd;
+  int K0, XSb, s_w0n;  // tc: first-layer contraction length padded to 8, row stride of the ADJOINT kernel's state rows
+                       // (K0 + 4; = XS otherwise), fp32 copy W0[n][k] with row stride XSb
 };
 
 bool supported(const HdpoRolloutDesc* d);

@@ -53,6 +53,7 @@ static __device__ void stage_weights(const Cfg& c, const float* __restrict__ par
     for (int i = tid; i < n_out * n_in; i += nt) {
       int n = i / n_in, k = i % n_in;
       Ws[c.s_wt0 + k * H + n] = params[c.gw[0] + i];
+      if (bwd && c.tc) Ws[c.s_w0n + n * c.XSb + k] = params[c.gw[0] + i];  // W0[n][k] for the mma fragments
     }
     for (int i = tid; i < n_out; i += nt) Ws[c.s_b0 + i] = params[c.gb[0] + i];
   }
@@ -199,18 +200,15 @@ __device__ __forceinline__ void act_row_inplace(int act, float* __restrict__ row
 }
 
 #ifndef HDPO_EMU
-// Recompute of the adjoint kernel in tensor-core mode: first layer (K = padded inputs, not a multiple of 8 in general)
-// and output layer in the FFMA form, the HxH layers as warp-level mma.sync products over the warp's 32 rows
-// (mma32.cuh). Hb = base of the [NHH + 1][32][HS] activation rows of the warp.
-__device__ __forceinline__ void mlp_fwd_tc(const Cfg& c, const float* __restrict__ Ws, const float* __restrict__ xrow,
+// Recompute of the adjoint kernel in tensor-core mode: first layer (inputs zero-padded to K0 = a multiple of 8 in the
+// state rows) and HxH layers as warp-level mma.sync products over the warp's 32 rows (mma32.cuh), output layer in the
+// FFMA form. Xw / Hb = bases of the warp's state rows [32][XS] and activation rows [NHH + 1][32][HS].
+__device__ __forceinline__ void mlp_fwd_tc(const Cfg& c, const float* __restrict__ Ws, const float* __restrict__ Xw,
                                            float* __restrict__ Hb, int layer_stride, int lane, float (&y)[kMaxOut]) {
   float* hrow = Hb + lane * HS;
-  {
-    float2 acc[1][H / 2];
-    const float* xin[1] = {xrow};
-    layer_fwd<1>(Ws + c.s_wt0, Ws + c.s_b0, c.IN4 / 4, xin, acc);
-    act_store_row(c.hidden_act, acc[0], hrow);
-  }
+  __syncwarp();  // the state rows were written lane by lane
+  mma32::layer_f32<2>(Ws + c.s_w0n, c.XSb, Ws + c.s_b0, Xw, c.XSb, c.K0 / 8, Hb, HS, lane);
+  act_row_inplace(c.hidden_act, hrow);
   for (int l = 0; l < c.NHH; ++l) {
     __syncwarp();
     mma32::layer_f32<2>(Ws + c.s_wn[l], HS, Ws + c.s_bh[l], Hb + l * layer_stride, HS, H / 8, Hb + (l + 1) * layer_stride,
@@ -619,19 +617,27 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
   stage_weights(c, params, Ws, true);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NHB = NHH + 1;  // hidden rows kept per scenario
-  const int per_warp = 32 * (2 * c.XS + NHB * HS + kMaxOut);
+  const int per_warp = 32 * (2 * c.XSb + NHB * HS + kMaxOut);
   float* Xw = smem + ((c.s_total_bwd + 3) & ~3) + warp * per_warp;  // state rows x_t
-  float* Gx = Xw + 32 * c.XS;                                   // state adjoint rows
-  float* Hb = Gx + 32 * c.XS;                                   // [NHB][32][HS] activations -> overwritten by gz
+  float* Gx = Xw + 32 * c.XSb;                                   // state adjoint rows
+  float* Hb = Gx + 32 * c.XSb;                                   // [NHB][32][HS] activations -> overwritten by gz
   float* Gy = Hb + NHB * 32 * HS;                               // [32][kMaxOut] output adjoints
-  float* xrow = Xw + lane * c.XS;
-  float* grow = Gx + lane * c.XS;
+  float* xrow = Xw + lane * c.XSb;
+  float* grow = Gx + lane * c.XSb;
   float* hrow = Hb + lane * HS;
   constexpr int HL = 32 * HS;  // layer stride inside Hb
 
   // register-resident parameter-gradient tiles
-  WgradAcc<KQ0> a0;
+  WgradAcc<TC ? 1 : KQ0> a0;
   WgradAcc<TC ? 1 : 8> ah[NHH > 0 ? NHH : 1];
+  constexpr int NT0 = (KQ0 + 1) / 2;  // 8-column blocks of the zero-padded first-layer inputs (K0 = 8 NT0)
+  float a0f[2][TC ? NT0 : 1][4], b0f = 0.f;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < (TC ? NT0 : 1); ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a0f[mt][nt][i] = 0.f;
   float ao[kMaxOut], bo = 0.f;  // lane = k for ao; lane = o for bo
   a0.clear();
 #pragma unroll
@@ -655,13 +661,14 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
   const int n_tiles = ceil_div(c.B, 32);
   const int wpc = blockDim.x >> 5;  // warps per CTA: 4 for big batches, 2 / 1 when there are few tiles (latency)
   const int gwarp = blockIdx.x * wpc + warp, nwarps = gridDim.x * wpc;
+  for (int k = c.IN4; k < c.XSb; ++k) xrow[k] = 0.f;  // padding columns (read by the mma first layer) stay zero
   for (int tile = gwarp; tile < n_tiles; tile += nwarps) {
     const int bb = tile * 32 + lane;
     const bool valid = bb < c.B;
     const int b = valid ? bb : c.B - 1;
     Statics s;
     load_statics<ARCH>(c, st, b, s);
-    for (int k = 0; k < c.XS; ++k) grow[k] = 0.f;
+    for (int k = 0; k < c.XSb; ++k) grow[k] = 0.f;
     for (int t = c.T - 1; t >= 0; --t) {
       // A. state x_t from the tape, demand
       {
@@ -674,7 +681,7 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
       float y[1][kMaxOut];
       if constexpr (TC) {
 #ifndef HDPO_EMU
-        mlp_fwd_tc(c, Ws, xrow, Hb, HL, lane, y[0]);
+        mlp_fwd_tc(c, Ws, Xw, Hb, HL, lane, y[0]);
 #endif
       } else {
         const float* xin[1] = {xrow};
@@ -794,11 +801,21 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
       }
       // F. layer 0: dW0 += gz0^T x ; state adjoint += W0^T gz0 unless the input was detached
       __syncwarp();
-      wgrad_tile<KQ0>(Hb, HS, Xw, c.XS, lane, a0);
-      __syncwarp();
-      if (!c.detach_input) {
-        const float* Wt0 = Ws + c.s_wt0;
-        for (int k = 0; k < c.IN; ++k) grow[k] += dgrad_dot(Wt0 + k * H, gz);
+      if constexpr (TC) {
+#ifndef HDPO_EMU
+        mma32::wgrad<NT0>(Hb, HS, Xw, c.XSb, lane, a0f);
+        float bs = 0.f;
+        for (int cidx = 0; cidx < 32; ++cidx) bs += Hb[cidx * HS + lane];
+        b0f += bs;
+        if (!c.detach_input) mma32::dgrad_accum_f32<NT0>(Ws + c.s_w0n, c.XSb, Hb, HS, Gx, c.XSb, lane);
+#endif
+      } else {
+        wgrad_tile<KQ0>(Hb, HS, Xw, c.XSb, lane, a0);
+        __syncwarp();
+        if (!c.detach_input) {
+          const float* Wt0 = Ws + c.s_wt0;
+          for (int k = 0; k < c.IN; ++k) grow[k] += dgrad_dot(Wt0 + k * H, gz);
+        }
       }
     }
   }
@@ -806,13 +823,24 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
   // ---- write this warp's partial gradient slab in state_dict layout
   float* out = partials + static_cast<int64_t>(gwarp) * p_stride;
   const int ni = lane >> 2, ki = lane & 3;
-  {  // layer 0: W0[n][k], n = 4*ni+i, k = ki*KQ0+q
+  if constexpr (TC) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < (TC ? NT0 : 1); ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = 16 * mt + ni + 8 * (i >> 1), k = 8 * nt + 2 * ki + (i & 1);
+          if (n < c.w[1] && k < c.IN) out[c.gw[0] + n * c.IN + k] = a0f[mt][nt][i];
+        }
+    if (lane < c.w[1]) out[c.gb[0] + lane] = b0f;
+  } else {  // layer 0: W0[n][k], n = 4*ni+i, k = ki*KQ0+q
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int n = 4 * ni + i;
       if (n < c.w[1]) {
 #pragma unroll
-        for (int q = 0; q < KQ0; ++q) {
+        for (int q = 0; q < (TC ? 1 : KQ0); ++q) {
           const int k = ki * KQ0 + q;
           if (k < c.IN) out[c.gw[0] + n * c.IN + k] = a0.at(i, q);
         }
@@ -884,7 +912,7 @@ int launch_bwd_nhh(const Cfg& c, const float* params, const float* demands, cons
 template <int ARCH, int KQ0, int NHH, bool TC>
 int launch_bwd_tc(const Cfg& c, const float* params, const float* demands, const HdpoStatics* st, const float* tape,
                   float g_total, float g_report, float* partials, int p_stride, int grid, int wpc, void* stream) {
-  const int per_warp = 32 * (2 * c.XS + (NHH + 1) * HS + kMaxOut);
+  const int per_warp = 32 * (2 * c.XSb + (NHH + 1) * HS + kMaxOut);
   const size_t wfl = static_cast<size_t>((c.s_total_bwd + 3) & ~3);
   const size_t smem = (wfl + static_cast<size_t>(wpc) * per_warp) * sizeof(float);
   auto k = small_bwd_kernel<ARCH, KQ0, NHH, TC>;
