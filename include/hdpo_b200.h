@@ -67,7 +67,9 @@ enum {
 /* matmul precision of the policy MLP */
 enum {
   HDPO_PREC_FP32 = 0,   /* FFMA, fp32 everywhere (parity mode) */
-  HDPO_PREC_TF32X3 = 1, /* tcgen05 kind::tf32, 3-pass split (hi*hi + hi*lo + lo*hi), fp32 accumulate */
+  HDPO_PREC_TF32X3 = 1, /* tensor cores with the 3-pass tf32 split (hi*hi + hi*lo + lo*hi), fp32 accumulate: tcgen05
+                           tile GEMMs for the wide policy MLPs; warp-level mma.sync for the 32-wide nets inside the
+                           adjoint kernels (small nets, SymmetryAware heads). fp32-grade: same parity bar as FP32 */
   HDPO_PREC_TF32 = 2    /* tcgen05 kind::tf32, single pass (throughput mode; NOT within the 1e-5 bar) */
 };
 

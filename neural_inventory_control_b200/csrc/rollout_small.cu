@@ -4,7 +4,9 @@
 //   forward : trainer.py:181-216 (simulate_batch loop) = neural_networks.py:200-214 / 319-355 + environment.py:110-299
 //   backward: autograd of the above (trainer.py:173)
 //
-// Design (B200): warp-centric SIMT fp32 (parity mode; true-fp32 like the reference's sgemm).
+// Design (B200): warp-centric; fp32 FFMA throughout in parity mode (true fp32 like the reference's sgemm), and in the
+// default tf32x3 mode the adjoint's 32-wide layers (recompute, dgrad, weight gradients) on warp-level tensor cores
+// (mma.sync 3xTF32, mma32.cuh) - see the TC template parameter of small_bwd_kernel.
 //   * one lane = one scenario (NS scenarios per lane in the forward); a warp owns tiles of 32*NS scenarios and
 //     loops over tiles persistently; the four warps of a CTA only share the read-only weight block in shared
 //     memory, so the period loop needs __syncwarp() only - never __syncthreads().
@@ -36,7 +38,7 @@ static int pad_in(int in) {
 
 bool supported(const HdpoRolloutDesc* d) {
   if (d->arch != HDPO_ARCH_VANILLA_ONE_STORE && d->arch != HDPO_ARCH_VANILLA_SERIAL) return false;
-  // any precision request is honoured with fp32 FFMA here (the small nets have no tensor-core variant yet)
+  // precision: fp32 = FFMA everywhere; tf32x3 / tf32 = the adjoint's 32-wide layers on mma.sync 3xTF32 (build_cfg: tc)
   const HdpoProblem& pb = d->pb;
   if (pb.S != 1) return false;
   const HdpoMlp& m = d->master;
