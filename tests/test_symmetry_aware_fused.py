@@ -148,7 +148,8 @@ def test_symmetry_aware_fused_problem_variants(be_name, precision, variant):
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 def test_symmetry_aware_fused_default_widths_many_scenarios(precision):
     """The shipped symmetry_aware.yml widths (context 153->256->256, store 263->32->32->1, warehouse 259->16->16->1)
-    on 50 stores, with enough scenarios for several concurrent chunks, ragged against the 128-row tiles."""
+    on 50 stores, thousands of scenarios (several scenarios per persistent warp, many row tiles in the trunk GEMMs),
+    ragged against the 128-row tiles."""
     be = backend("cuda")
     meta, params, data = sym_case("one_warehouse_s50", {"context": [256], "store": [32, 32], "warehouse": [16, 16]},
                                   256, seed=3)
