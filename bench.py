@@ -104,9 +104,6 @@ def time_dominant_gemm(lib, torch, dev, stream, M, N, K, n_pass, reps=64):
     its forward hidden-layer form (bias + ELU epilogue, (hi, lo) outputs) at the shape one scenario chunk launches.
     CUDA events on the launching stream; operands rotate through 16 buffer sets (> L2) so that no launch finds its
     inputs in L2 from the launch before."""
-    lib.hdpo_debug_gemm_tc_timeline.argtypes = ([C.c_void_p] * 3 + [C.c_int32] * 4 +
-                                                [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p])
-    lib.hdpo_debug_gemm_tc_timeline.restype = C.c_int
     nbuf = 16
     g = torch.Generator(device=dev).manual_seed(1)
     A = torch.randn(M, K, generator=g, device=dev)

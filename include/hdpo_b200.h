@@ -231,6 +231,16 @@ int hdpo_debug_gemm_tc(const float* A, const float* B, float* C, int32_t M, int3
 int hdpo_debug_gemm_tc_wgrad(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
                              int32_t k_per_split, int32_t n_pass, float* scratch, void* stream);
 
+/* The forward hidden-layer GEMM exactly as the wide rollout launches it, for timing it alone (bench.py `roofline`) and
+ * for per-CTA clock stamps (tools/gemm_timeline.py): C (+ C_lo) = epilogue(A[M,K] * B[N,K]^T) with A / B already split
+ * in `scratch` by a previous hdpo_debug_gemm_tc call on the same operands; epi = 0: bias + ELU + (hi, lo) outputs
+ * (C_lo and bias required), epi = 4: plain store. dbg_clock: device array of 8 * n_ctas int64 (clock64 stamps). */
+int hdpo_debug_gemm_tc_timeline(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
+                                int32_t n_pass, float* scratch, long long* dbg_clock, void* stream, int32_t epi,
+                                float* C_lo, const float* bias);
+/* Device-side trace buffer for tools/trace_step.py (one record per CTA of the wide path); NULL disables it. */
+int hdpo_debug_set_trace(unsigned long long* buf, int64_t capacity);
+
 /* misc */
 const char* hdpo_last_error(void);
 int hdpo_abi_version(void);

@@ -923,4 +923,10 @@ extern "C" int hdpo_debug_gemm_tc(const float*, const float*, float*, int32_t, i
   return HDPO_E_INVALID;
 }
 
+extern "C" int hdpo_debug_gemm_tc_timeline(const float*, const float*, float*, int32_t, int32_t, int32_t, int32_t, float*,
+                                           long long*, void*, int32_t, float*, const float*) {
+  hdpo::set_error("tcgen05 path is not available in the host-thread emulator");
+  return HDPO_E_INVALID;
+}
+
 #endif
