@@ -248,3 +248,35 @@ def test_device_resident_batches_match_dataloader_semantics():
         else:
             assert torch.equal(allt, torch.arange(n))
     assert len(DeviceBatches(DataLoader(ds, batch_size=256, shuffle=True, drop_last=True), "cuda:0")) == 3
+
+
+def test_main_run_cli_train_and_long_horizon_test(monkeypatch, capsys):
+    """`python main_run.py train|test one_store_lost vanilla_one_store` exactly as the reference wires it (main_run.py:
+    argv, YAML keys, datasets incl. the 32768 x 5000-period test set). `train` is capped at 2 epochs here; `test` runs
+    the long-horizon evaluation (trainer.py:121-141: 5000 periods, 3000 ignored, discrete allocation for Poisson demand)
+    on the fused forward-only rollout."""
+    import main_run
+    from neural_inventory_control_b200.trainer import Trainer
+    monkeypatch.chdir(ROOT)
+    paths = []
+    orig_train, orig_sim = Trainer.train, Trainer.simulate_batch
+
+    def capped_train(self, epochs, *a, **k):
+        return orig_train(self, min(epochs, 2), *a, **k)
+
+    def spy(self, *a, **k):
+        out = orig_sim(self, *a, **k)
+        paths.append(self.last_path)
+        return out
+
+    monkeypatch.setattr(Trainer, "train", capped_train)
+    monkeypatch.setattr(Trainer, "simulate_batch", spy)
+    torch.manual_seed(0)
+    main_run.main(["main_run.py", "train", "one_store_lost", "vanilla_one_store"])
+    assert paths and set(paths) == {"fused"}
+    n_train = len(paths)
+    main_run.main(["main_run.py", "test", "one_store_lost", "vanilla_one_store"])
+    assert set(paths[n_train:]) == {"fused"} and len(paths) == n_train + 1  # one batch of 32768 scenarios x 5000 periods
+    out = capsys.readouterr().out
+    loss = float(out.strip().splitlines()[-1].split(":")[1])
+    assert "Average per-period test loss" in out and np.isfinite(loss) and loss > 0
