@@ -136,7 +136,7 @@ static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255);
 size_t workspace_bytes(const HdpoRolloutDesc* d) {
   Cfg c;
   build_cfg(d, 0, &c);
-  size_t tape = align256(static_cast<size_t>(c.T) * c.B * c.tape_stride * sizeof(float));
+  size_t tape = d->save_for_backward ? align256(static_cast<size_t>(c.T) * c.B * c.tape_stride * sizeof(float)) : 0;
   size_t partial = align256(static_cast<size_t>(kMaxPartialRows) * ((c.P + 3) & ~3) * sizeof(float));
   return tape + partial + 256;
 }
@@ -187,7 +187,10 @@ int forward(const HdpoRolloutDesc* d, const float* params, const float* demands,
   }
   HdpoState fin = {nullptr, nullptr, nullptr};
   if (final_state) fin = *final_state;
-  const int rows = 32 * kFwdNS;
+  // two scenarios per lane amortise the weight loads when there are plenty of tiles; with few scenarios (training
+  // batches of a few thousand, the 32768-scenario evaluation sets) one per lane doubles the warps that share the work
+  const int ns = ceil_div(c.B, 32 * kFwdNS) < 4 * sm_count() ? 1 : kFwdNS;
+  const int rows = 32 * ns;
   const int n_tiles = ceil_div(c.B, rows);
   const int wpc = pick_warps_per_cta(n_tiles);
   const size_t smem_max = (static_cast<size_t>((c.s_total + 3) & ~3) + static_cast<size_t>(kWarpsPerCta) * rows * (c.XS + HS)) *
@@ -196,15 +199,21 @@ int forward(const HdpoRolloutDesc* d, const float* params, const float* demands,
   const int ctas_needed = ceil_div(n_tiles, wpc);
   const int max_ctas = sm_count() * 3;
   const int grid = ctas_needed < max_ctas ? ctas_needed : max_ctas;
+#define HDPO_FWD_LAUNCH(ARCH, NS)                                                                                      \
+  do {                                                                                                                \
+    auto k = small_fwd_kernel<ARCH, NS>;                                                                              \
+    HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)));   \
+    HDPO_LAUNCH(k, grid, wpc * 32, smem, stream, c, params, demands, *st, *init, cost_b, report_b, reward_tb, tape,   \
+                fin);                                                                                                 \
+  } while (0)
   if (c.arch == HDPO_ARCH_VANILLA_ONE_STORE) {
-    auto k = small_fwd_kernel<HDPO_ARCH_VANILLA_ONE_STORE, kFwdNS>;
-    HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)));
-    HDPO_LAUNCH(k, grid, wpc * 32, smem, stream, c, params, demands, *st, *init, cost_b, report_b, reward_tb, tape, fin);
+    if (ns == 1) HDPO_FWD_LAUNCH(HDPO_ARCH_VANILLA_ONE_STORE, 1);
+    else HDPO_FWD_LAUNCH(HDPO_ARCH_VANILLA_ONE_STORE, kFwdNS);
   } else {
-    auto k = small_fwd_kernel<HDPO_ARCH_VANILLA_SERIAL, kFwdNS>;
-    HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)));
-    HDPO_LAUNCH(k, grid, wpc * 32, smem, stream, c, params, demands, *st, *init, cost_b, report_b, reward_tb, tape, fin);
+    if (ns == 1) HDPO_FWD_LAUNCH(HDPO_ARCH_VANILLA_SERIAL, 1);
+    else HDPO_FWD_LAUNCH(HDPO_ARCH_VANILLA_SERIAL, kFwdNS);
   }
+#undef HDPO_FWD_LAUNCH
   HDPO_LAUNCH_OK();
   if (totals) {
     auto kt = totals_kernel;
@@ -219,7 +228,8 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
              float g_report, float* grad_params, void* workspace, size_t ws_bytes, void* stream) {
   Cfg c;
   build_cfg(d, 0, &c);
-  HDPO_REQUIRE(workspace != nullptr, "backward needs the workspace the forward filled");
+  HDPO_REQUIRE(workspace != nullptr && d->save_for_backward,
+               "backward needs the workspace of a forward run with save_for_backward = 1");
   if (ws_bytes < workspace_bytes(d)) {
     set_error("workspace too small: %zu < %zu", ws_bytes, workspace_bytes(d));
     return HDPO_E_WORKSPACE;
