@@ -65,3 +65,32 @@ def test_gemm_tc_weight_gradient_form(M, N, Kd, kps):
         err = np.abs(be.get(c).astype(np.float64) - want).max() / scale
         print(f"gemm_tc wgrad {M}x{N}x{Kd}/{kps} n_pass={n_pass}: max err/scale {err:.3e} (fp32 numpy: {fp32_err:.3e})")
         assert err < tol, (n_pass, err)
+
+
+@pytest.mark.parametrize("M,N,Kd", [(2048, 512, 512), (256, 128, 64), (384, 64, 96)])
+def test_gemm_tc_forward_hidden_epilogue_hook(M, N, Kd):
+    """hdpo_debug_gemm_tc_timeline with epi = 0 is the kernel bench.py times for `roofline`: the forward hidden-layer
+    form, (hi, lo) = split(ELU(A B^T + bias)). hi + lo must be the fp32-grade result and hi its tf32 rounding."""
+    be = D.CudaBackend()
+    rng = np.random.RandomState(7 + M + N + Kd)
+    A = rng.randn(M, Kd).astype(np.float32)
+    B = (rng.randn(N, Kd) / np.sqrt(Kd)).astype(np.float32)
+    bias = rng.randn(N).astype(np.float32)
+    z = A.astype(np.float64) @ B.astype(np.float64).T + bias.astype(np.float64)
+    want = np.where(z > 0, z, np.expm1(z))
+    a, b, bs = be.put(A), be.put(B), be.put(bias)
+    scratch = be.zeros(2 * (M * Kd + N * Kd))
+    c, c_lo = be.zeros((M, N)), be.zeros((M, N))
+    rc = be.lib.hdpo_debug_gemm_tc(be.ptr(a), be.ptr(b), be.ptr(c), M, N, Kd, 3, be.ptr(scratch), be.stream)  # splits
+    K.check(be.lib, rc, "hdpo_debug_gemm_tc")
+    dbg = be.zeros(8 * 4096, np.int64)
+    rc = be.lib.hdpo_debug_gemm_tc_timeline(be.ptr(a), be.ptr(b), be.ptr(c), M, N, Kd, 3, be.ptr(scratch), be.ptr(dbg),
+                                            be.stream, 0, be.ptr(c_lo), be.ptr(bs))
+    K.check(be.lib, rc, "hdpo_debug_gemm_tc_timeline")
+    be.sync()
+    hi, lo = be.get(c).astype(np.float64), be.get(c_lo).astype(np.float64)
+    err = np.abs(hi + lo - want).max() / np.abs(want).max()
+    assert err < 3e-6, err
+    assert np.abs(lo).max() <= 2.0 ** -10 * np.abs(hi).max()          # lo is the remainder of a tf32 rounding
+    assert np.all((be.get(c).view(np.uint32) & 0x1FFF) == 0)          # hi carries 10 mantissa bits
+    assert np.count_nonzero(be.get(dbg)) > 0                          # the per-CTA clock stamps were written
