@@ -200,3 +200,42 @@ def test_symmetry_aware_oracle_adjoint_matches_torch_autograd():
     flat = O.flatten_grads(pol, grads)
     for k, v in model.named_parameters():
         assert G.rel_l2(v.grad.numpy(), flat[k]) < 1e-10, k
+
+
+def test_torch_port_symmetry_aware_matches_oracle():
+    """The PyTorch-eager port of the SymmetryAware policy (what `bench.py --impl reference` / `cpu_baseline` time for the
+    symmetry-aware workload) against the numpy oracle: total cost and all gradients, float64."""
+    import torch
+    from oracle import torch_port as TP
+    meta, g = G.load("rollout", "one_warehouse_s5")
+    rng = np.random.default_rng(4)
+    S, L = g["data"]["initial_inventories"].shape[1:]
+    Lw, C = g["data"]["initial_warehouse_inventories"].shape[2], 12
+    widths = {"context": [S * L + Lw, 24, C], "store": [L + 4 + C, 16, 16, 1], "warehouse": [Lw + C, 8, 8, 1]}
+    acts = {"context": ("elu", "sigmoid"), "store": ("elu", "softplus"), "warehouse": ("elu", "sigmoid")}
+    sd, nets_t = {}, {}
+    for m, ws in widths.items():
+        layers = []
+        for i in range(len(ws) - 1):
+            w = rng.uniform(-1, 1, (ws[i + 1], ws[i])) / np.sqrt(ws[i])
+            b = rng.uniform(-1, 1, ws[i + 1]) / np.sqrt(ws[i])
+            sd[f"net.{m}.{2 * i}.weight"], sd[f"net.{m}.{2 * i}.bias"] = w, b
+            layers.append((torch.tensor(w, requires_grad=True), torch.tensor(b, requires_grad=True)))
+        nets_t[m] = (layers, *acts[m])
+    wub = float(meta["warehouse_upper_bound"])
+    pol_t = {"arch": "symmetry_aware", "nets": nets_t, "layers": [wb for m in nets_t for wb in nets_t[m][0]],
+             "wub": torch.tensor([wub], dtype=torch.float64), "prop_eps": 1e-15}
+    data = {k: torch.tensor(v[:12]).double() for k, v in g["data"].items()}
+    T = 8
+    pb = dict(meta["problem_params"], period_shift=0)
+    total, _, _ = TP.simulate(pol_t, pb, data, T)
+    (total / (12 * T * pb["n_stores"])).backward()
+    nets = {m: O.mlp_from_state_dict(sd, m, *acts[m]) for m in widths}
+    pol = O.Policy("symmetry_aware", nets, wub, prop_eps=1e-15)
+    fwd, grads = O.rollout_grad(pol, G.problem_from_meta(meta), {k: v.numpy() for k, v in data.items()}, T)
+    assert abs(float(total.detach()) / fwd["total"] - 1) < 1e-12
+    flat = O.flatten_grads(pol, grads)
+    for m in widths:
+        for i, (w, b) in enumerate(nets_t[m][0]):
+            assert G.rel_l2(w.grad.numpy(), flat[f"net.{m}.{2 * i}.weight"]) < 1e-10, (m, i)
+            assert G.rel_l2(b.grad.numpy(), flat[f"net.{m}.{2 * i}.bias"]) < 1e-10, (m, i)
