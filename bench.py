@@ -245,8 +245,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            # keep NCCL's version banner (printed at VERSION and WARN level) off stdout: rank 0 prints ONE JSON line
+            os.environ.pop("NCCL_DEBUG", None)
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/null")
         dist.init_process_group("nccl", device_id=dev)
 
     kw = {"T": args.periods}
