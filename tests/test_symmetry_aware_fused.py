@@ -164,3 +164,25 @@ def test_symmetry_aware_fused_default_widths_many_scenarios(precision):
     pol = oracle_policy(meta, params)
     fwd, grads = O.rollout_grad(pol, G.problem_from_meta(meta), G.cast(big, np.float64), T)
     check(out, fwd, grads, pol, ignore)
+
+
+@pytest.mark.parametrize("be_name,precision", MODES)
+def test_symmetry_aware_fused_more_than_64_stores(be_name, precision):
+    """70 stores (the 50-store scenario data with 20 stores repeated): three 32-store passes in the adjoint head, a
+    second two-stores-per-lane pass in the forward head, a state row that is not a multiple of the 64-float tile."""
+    be = backend(be_name)
+    meta0, g = G.load("rollout", "one_warehouse_s50")
+    S2 = 70
+    pick = np.concatenate([np.arange(50), np.arange(20)])
+    data = {k: (v[:5][:, pick] if v.ndim >= 2 and v.shape[1] == 50 else v[:5]) for k, v in g["data"].items()}
+    meta, params, _ = sym_case("one_warehouse_s50", {"context": [48], "store": [24, 24], "warehouse": [8]}, 16, seed=2)
+    meta["problem_params"] = dict(meta["problem_params"], n_stores=S2)
+    rng = np.random.default_rng(8)
+    L, Lw = data["initial_inventories"].shape[2], data["initial_warehouse_inventories"].shape[2]
+    w0 = params["net.context.0.weight"]
+    params["net.context.0.weight"] = (rng.uniform(-1, 1, (w0.shape[0], S2 * L + Lw)) / np.sqrt(S2 * L + Lw)).astype(np.float32)
+    T, ignore = 4, 1
+    out = D.rollout(be, meta, params, data, T=T, ignore=ignore, precision=precision)
+    pol = oracle_policy(meta, params)
+    fwd, grads = O.rollout_grad(pol, G.problem_from_meta(meta), G.cast(data, np.float64), T)
+    check(out, fwd, grads, pol, ignore)
