@@ -279,8 +279,10 @@ static int max_resident_ctas(size_t smem) {
 static void bwd_shape(const Cfg& c, int* grid, int* wpc) {
   const int per_warp = bwd_smem_floats_per_warp(c);
   *wpc = warps_per_cta(c, per_warp, c.Bp, true);
-  const int warps = ceil_div(c.Bp, 4);  // >= 4 scenarios per warp amortise the slab update
-  *grid = ceil_div(warps, *wpc);
+  // one scenario per warp until the machine is full, more beyond that (the per-launch slab update of a warp, ~4 k
+  // floats through L2, is ~10 % of one scenario's work; at 1024 scenarios four-per-warp left 116 SMs idle: adjoint
+  // sweep 8.75 ms per step)
+  *grid = ceil_div(c.Bp, *wpc);
   const int cap = max_resident_ctas(smem_bytes(c, *wpc, per_warp, true));
   if (*grid > cap) *grid = cap;
 }
@@ -1163,7 +1165,7 @@ int head_fwd(const Cfg& c, const PeriodArgs& a, const float* params, const float
   int wpc = warps_per_cta(c, per_warp, c.Bp, false);
   if (wpc > 4 && !getenv("HDPO_SYM_WPC")) wpc = 4;  // measured: 2 resident CTAs of 4 warps beat 1 of 8 (finer tail)
   const size_t smem = smem_bytes(c, wpc, per_warp, false);
-  int grid = ceil_div(ceil_div(c.Bp, 2), wpc);
+  int grid = ceil_div(c.Bp, wpc);
   const int cap = max_resident_ctas(smem);
   if (grid > cap) grid = cap;
   HDPO_REQUIRE(smem <= kSmemMax, "symmetry-aware head: %zu bytes of shared memory needed", smem);
