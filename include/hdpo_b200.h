@@ -240,6 +240,9 @@ int hdpo_debug_gemm_tc_timeline(const float* A, const float* B, float* C, int32_
                                 float* C_lo, const float* bias);
 /* Device-side trace buffer for tools/trace_step.py (one record per CTA of the wide path); NULL disables it. */
 int hdpo_debug_set_trace(unsigned long long* buf, int64_t capacity);
+/* Per-role event trace of the persistent wide sweeps (tools/wp_trace.py): buf = 74 pairs * 4 roles * cap_per_role
+ * records of {tag, globaltimer ns} (uint64 pairs); NULL disables it. */
+int hdpo_debug_set_wp_trace(unsigned long long* buf, int32_t cap_per_role);
 
 /* misc */
 const char* hdpo_last_error(void);

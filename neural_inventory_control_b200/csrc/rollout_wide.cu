@@ -19,6 +19,7 @@
 #include "rollout_wide.cuh"
 #include "rollout_sym.cuh"
 #include "gemm_tc.cuh"
+#include "wide_persist.cuh"
 
 #include <cstdlib>
 #ifndef HDPO_EMU
@@ -88,15 +89,27 @@ struct Plan {
   size_t o_X_hi, o_X_lo, o_act_lo[HDPO_MAX_LAYERS], o_gz_lo[HDPO_MAX_LAYERS];
   size_t x_stride, act_stride[HDPO_MAX_LAYERS];              // floats per period
   int max_wk;
+  int persist;                  // persistent one-launch sweeps (wide_persist.cu): rows padded to 256, one chunk
+  size_t o_extra, extra_bytes;  // their private scratch
 };
+
+static bool use_persist(const HdpoRolloutDesc* d) {
+#ifdef HDPO_EMU
+  (void)d;
+  return false;
+#else
+  return wp::enabled() && wp::eligible(d);
+#endif
+}
 
 static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
   Plan p;
+  p.persist = use_persist(d) ? 1 : 0;
   const HdpoMlp& m = d->master;
   p.sym = d->arch == HDPO_ARCH_SYMMETRY_AWARE;
   p.n = m.n_layers + (p.sym ? 1 : 0);
   p.B = Bc;
-  p.Bp = pad_to(p.B > 0 ? p.B : 1, kRowPad);
+  p.Bp = pad_to(p.B > 0 ? p.B : 1, p.persist ? 256 : kRowPad);
   p.T = d->T;
   p.save = d->save_for_backward;
   p.tc = d->precision != HDPO_PREC_FP32;
@@ -169,6 +182,15 @@ static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
   p.so_stride = p.sym ? static_cast<size_t>(p.Bp) * sc.ldo : 0;
   p.o_so = (p.sym && p.save) ? take(tslots * p.so_stride) : 0;
   p.o_slab = (p.sym && p.save) ? take(static_cast<size_t>(sym::bwd_warps(sc)) * sc.q_total) : 0;
+  p.o_extra = 0;
+  p.extra_bytes = 0;
+#ifndef HDPO_EMU
+  if (p.persist) {
+    p.extra_bytes = wp::extra_bytes(d, p.Bp, p.wp, p.n);
+    p.o_extra = o;
+    o += a256(p.extra_bytes);
+  }
+#endif
   p.total = o + 256;
   return p;
 }
@@ -1008,7 +1030,7 @@ static int requested_chunks(int B, bool sym) {
 static Chunking make_chunking(const HdpoRolloutDesc* d) {
   Chunking c;
   const int B = d->pb.B;
-  const int want = requested_chunks(B, d->arch == HDPO_ARCH_SYMMETRY_AWARE);
+  const int want = use_persist(d) ? 1 : requested_chunks(B, d->arch == HDPO_ARCH_SYMMETRY_AWARE);
   const int per = pad_to((B + want - 1) / want, kRowPad);
   c.n = 0;
   size_t o = 0;
@@ -1365,6 +1387,75 @@ static int fwd_end(ChunkCtx& c, const HdpoRolloutDesc* d) {
   return HDPO_OK;
 }
 
+#ifndef HDPO_EMU
+static bool persist_bwd_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HDPO_WIDE_PERSIST_BWD");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
+// hand the chunk's tapes to the persistent sweeps (wide_persist.cu)
+static void fill_persist_ctx(wp::Ctx* pc, const ChunkCtx& c, const HdpoRolloutDesc* d) {
+  const Plan& p = c.p;
+  void* ws = c.ws;
+  wp::Ctx& x = *pc;
+  x = wp::Ctx{};
+  x.B = p.B;
+  x.Bp = p.Bp;
+  x.T = p.T;
+  x.n = p.n;
+  for (int i = 0; i <= p.n; ++i) {
+    x.w[i] = p.w[i];
+    x.wp[i] = p.wp[i];
+  }
+  x.save = p.save;
+  x.n_pass = p.n_pass;
+  x.period_shift = d->period_shift;
+  x.ignore_periods = d->ignore_periods;
+  x.t_stride = d->t_stride;
+  x.demand_layout = d->demand_layout;
+  x.B_total = d->pb.B;
+  x.S = d->pb.S;
+  x.W = d->pb.W;
+  x.L = d->pb.L;
+  x.Lw = d->pb.Lw;
+  x.lost = d->pb.lost_demand;
+  x.profit = d->pb.maximize_profit;
+  x.has_edge = d->pb.has_edge_cost;
+  x.transshipment = d->transshipment;
+  x.discrete = d->discrete_allocation;
+  x.wub = d->warehouse_upper_bound;
+  x.adjacency = d->adjacency;
+  for (int l = 0; l < p.n; ++l) {
+    x.act[l] = p.act[l];
+    x.W_hi[l] = wsf(ws, p.o_W[l]);
+    x.W_lo[l] = wsf(ws, p.o_W_lo[l]);
+    x.bias[l] = wsf(ws, p.o_b[l]);
+    x.WT_hi[l] = wsf(ws, p.o_WT[l]);
+    x.WT_lo[l] = wsf(ws, p.o_WT_lo[l]);
+    x.act_hi[l] = wsf(ws, p.o_act[l]);
+    x.act_lo[l] = l + 1 < p.n ? wsf(ws, p.o_act_lo[l]) : nullptr;
+    x.gz_hi[l] = p.save ? wsf(ws, p.o_gz[l]) : nullptr;
+    x.gz_lo[l] = p.save ? wsf(ws, p.o_gz_lo[l]) : nullptr;
+    x.csum[l] = (p.save && l + 1 < p.n) ? wsf(ws, p.o_csum[l]) : nullptr;
+  }
+  x.gX = p.save ? wsf(ws, p.o_gx) : nullptr;
+  x.X = wsf(ws, p.o_X);
+  x.X_hi = wsf(ws, p.o_X_hi);
+  x.X_lo = wsf(ws, p.o_X_lo);
+  x.demands = c.demands;
+  x.st = c.st;
+  x.cost_b = c.cost_b;
+  x.report_b = c.report_b;
+  x.reward_tb = c.reward_tb;
+  x.extra = static_cast<char*>(ws) + p.o_extra;
+  x.stream = c.stream;
+}
+#endif
+
 // fork / join of the chunk streams around a region of `stream` (no-ops for a single chunk)
 struct StreamFork {
 #ifndef HDPO_EMU
@@ -1407,6 +1498,20 @@ struct StreamFork {
   }
 };
 
+}  // namespace wide
+}  // namespace hdpo
+#ifndef HDPO_EMU
+// Debug: per-role event trace of the persistent wide sweeps (tools/wp_trace.py): buf = 74 * 4 * cap * 2 uint64.
+extern "C" int hdpo_debug_set_wp_trace(unsigned long long* buf, int32_t cap_per_role) {
+  hdpo::wp::set_trace(buf, cap_per_role);
+  return HDPO_OK;
+}
+#else
+extern "C" int hdpo_debug_set_wp_trace(unsigned long long*, int32_t) { return HDPO_E_INVALID; }
+#endif
+namespace hdpo {
+namespace wide {
+
 int forward(const HdpoRolloutDesc* d, const float* params, const float* demands, const HdpoStatics* st,
             const HdpoState* init, float* cost_b, float* report_b, float* reward_tb, double* totals,
             HdpoState* final_state, void* ws, size_t ws_bytes, void* stream) {
@@ -1437,6 +1542,14 @@ int forward(const HdpoRolloutDesc* d, const float* params, const float* demands,
     c.reward_tb = shifted(reward_tb, b0);
     if ((rc = fwd_begin(c, d, params))) return rc;
   }
+#ifndef HDPO_EMU
+  if (ctx[0].p.persist) {
+    // ONE launch for all periods (wide_persist.cu); same tapes as the per-period chain below
+    wp::Ctx pc;
+    fill_persist_ctx(&pc, ctx[0], d);
+    if ((rc = wp::forward(pc))) return rc;
+  } else
+#endif
   // period-major issue order: the chunks advance together, so their kernels interleave on the device
   for (int t = 0; t < d->T; ++t)
     for (int i = 0; i < ck.n; ++i)
@@ -1698,6 +1811,13 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
     ctx[i].params = params;
     if ((rc = bwd_begin(ctx[i]))) return rc;
   }
+#ifndef HDPO_EMU
+  if (ctx[0].p.persist && persist_bwd_enabled()) {
+    wp::Ctx pc;
+    fill_persist_ctx(&pc, ctx[0], d);
+    if ((rc = wp::backward(pc, g_total, g_report))) return rc;
+  } else
+#endif
   for (int t = d->T - 1; t >= 0; --t) {
     const float rb = g_total + (t >= d->ignore_periods ? g_report : 0.f);
     for (int i = 0; i < ck.n; ++i)

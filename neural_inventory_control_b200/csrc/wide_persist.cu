@@ -1,0 +1,1572 @@
+// wide_persist.cu - persistent forward / adjoint sweeps of the wide-net rollout (see wide_persist.cuh).
+//
+// Replaces, for a whole direction of trainer.py:181-216 (+ its autograd), the chain of ~20 dependent launches per
+// period of rollout_wide.cu by ONE launch. Layout of a CTA (448 threads, one CTA per SM, clusters of 2 = CTA pairs):
+//
+//   warp 0      TMA producer: walks this pair's tile list, waits for the tile's input flag (release/acquire counters in
+//               global memory), streams K blocks of A (128 scenario rows of this CTA, hi + lo) and of B (this CTA's half
+//               of the tile's weight rows, hi + lo) into a 3-stage ring (cp.async.bulk.tensor, 128-byte swizzle).
+//   warp 1      MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::tf32, M = 256, N = 128 | 64, K = 8.
+//               3xTF32: hi*hi goes to a ROTATING accumulator that is closed every `kseg` K blocks (16 truncating
+//               adds at kseg = 4), lo*hi + hi*lo to a per-tile cross accumulator. TMEM: [cross 0 | cross 1 | hi 0 | hi 1]
+//               x 128 columns, so the MMAs of the next segment / next tile overlap the epilogue of this one.
+//   warps 2-9   epilogue: tcgen05.ld every closed segment and ADD it into registers with round-to-nearest (the tensor
+//               core's own accumulation truncates; short segments summed in registers keep the product fp32-grade),
+//               then bias + activation + (hi, lo) split -> swizzled staging -> TMA store; or x act'(saved output)
+//               (+ bias-gradient column sums) for the adjoint; finally a release-increment of the tile's output flag.
+//   warps 10-13 policy head + simulator period (forward: neural_networks.py:369-427 + environment.py:110-270; adjoint:
+//               their reverse), ONE THREAD per scenario over the transposed state X^T[column][scenario] so that every
+//               global access of a warp is one coalesced line; row-major tapes for the GEMMs are produced through a
+//               32 x 33 shared-memory transpose tile. Runs asynchronously to the GEMM pipeline of the same CTA.
+//
+// The tile lists are generated on the device (build_tasks_kernel) from a static schedule: pairs are grouped, a group
+// serves `k` row tiles ("chains", skewed against each other by `skew` layer steps so that one chain's serial
+// out-layer -> head -> first-layer section overlaps the other chain's hidden layers); all dependencies point backwards
+// in the common time order, so the in-order lists cannot deadlock as long as all CTAs are co-resident (grid <= SMs).
+#include "wide_persist.cuh"
+
+#ifndef HDPO_EMU
+#include <cstdlib>
+
+#include "gemm_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace hdpo {
+namespace wp {
+using namespace tc;
+
+constexpr int kStages = 3;
+constexpr int kBK = 32;
+constexpr int kABytes = 128 * kBK * 4;               // one half (hi or lo) of this CTA's A rows
+constexpr int kBBytesMax = 64 * kBK * 4;             // one half of this CTA's B rows (BN = 128: 64 rows)
+constexpr int kStageBytes = 2 * kABytes + 2 * kBBytesMax;
+constexpr int kRing = kStages * kStageBytes;
+constexpr int kEpiWarps = 8;
+constexpr int kWarps = 12;      // 384 threads: 168 registers per thread (448 threads would cap at 128)
+constexpr int kHeadWarps = kWarps;  // a head CTA is all head warps (GEMM CTAs: producer + MMA + 8 epilogue warps, 2 idle)
+constexpr int kBoxBytes = 32 * 128;
+constexpr int kEpiStage = kEpiWarps * 2 * kBoxBytes;
+constexpr int kBiasBytes = kEpiWarps * 64 * 4;  // per epilogue warp: the bias of its 64 tile columns
+constexpr int kBarBytes = 256;
+constexpr int kSmemTotal = kRing + kEpiStage + kBiasBytes + kBarBytes + 1024;
+constexpr int kHeadBytes = kSmemTotal - 1024;  // head CTAs use the whole allocation for the staged rows of their warps
+constexpr int kThreads = 32 * kWarps;
+constexpr int kTmemCols = 512;
+constexpr int kMaxPairs = 64;      // GEMM CTA pairs; the other SMs run the policy-head CTAs
+constexpr int kMinHeadPairs = 4;
+
+enum { EPI_FWD_HIDDEN = 0, EPI_FWD_OUT = 1, EPI_DGRAD_HIDDEN = 2, EPI_DGRAD_GX = 3 };
+
+// ------------------------------------------------------------------------------------------------------------
+// static schedule (shared by the device-side list builder and the host-side sizing)
+// ------------------------------------------------------------------------------------------------------------
+struct Sched {
+  int T, nsteps, R, k, g, groups, skew, bwd;
+  int C[HDPO_MAX_LAYERS];      // column tiles of step i
+  int bn[HDPO_MAX_LAYERS];     // tile width of step i
+  int nkb[HDPO_MAX_LAYERS];    // K blocks of step i
+  int layer[HDPO_MAX_LAYERS];  // layer descriptor index of step i
+  int epi[HDPO_MAX_LAYERS];
+  int max_tasks;               // list stride per pair (gemm list and head list)
+};
+__host__ __device__ inline int flag_index(const Sched& s, int tt, int i, int rt) { return (tt * (s.nsteps + 1) + i) * s.R + rt; }
+// pair (member q of its group) that runs column tile cc of chain c in step i of sweep position tt
+__host__ __device__ inline int tile_owner(const Sched& s, int c, int i, int cc, int tt) {
+  if (s.C[i] >= s.g) return (c * s.C[i] + cc) % s.g;
+  const int spread = s.g / s.k > 0 ? s.g / s.k : 1;
+  return (cc + c * spread + tt) % s.g;
+}
+
+struct Task {
+  int4 a, b;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------------------------
+struct LayerDesc {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo, c_hi, c_lo, x_hi, x_lo;
+  const float* bias;   // forward
+  float* colsum;       // adjoint, hidden: [rows / 32][ldc] column sums of 32-row blocks of the output
+  int act, bn, ldc;
+  int a_tmul, c_tmul, x_tmul;  // tape rows per period (Bp when the tape has one slot per period, else 0)
+};
+
+struct HeadP {
+  int B, Bp, S, W, L, Lw, ldx, ldy, nS, T;
+  int lost, profit, has_edge, transshipment, discrete, save, ignore_periods, B_total;
+  float wub, g_total, g_report;
+  const int32_t* adjacency;
+  const float* dTB;        // [T][Bp][S] demand of period t (period shift applied), scenario-major
+  HdpoStatics st;          // reference layouts
+  float *X, *X_hi, *X_lo;  // row-major state tapes
+  const float* Y;          // row-major output-layer tape (fp32)
+  float* gX;               // adjoint: [Bp][ldx] state adjoint
+  float *gY_hi, *gY_lo;    // adjoint: row-major tape of the output-layer adjoint (hi, lo)
+  float *cost_b, *report_b, *reward_tb;
+};
+
+struct Params {
+  LayerDesc L[HDPO_MAX_LAYERS];
+  HeadP head;
+  const Task* tasks;
+  const Task* head_tasks;
+  int* flags;
+  int max_tasks, n_pass, kseg;
+  int n_pairs;           // GEMM CTA pairs = blocks [0, 2 * n_pairs); the blocks after them are policy-head CTAs
+  unsigned long long* trace;  // optional: [pair][role 0..3][trace_cap] x {tag, globaltimer ns}
+  int trace_cap;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kTimeoutNs = 4000000000ull;  // a wait longer than this is a protocol bug: trap, do not hang
+
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __noinline__ void wait_timeout_trap(int what) {
+  printf("[hdpo wide_persist] wait timed out (what=%d block=%d thread=%d)\n", what, blockIdx.x, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity, int what) {
+  if (mbar_try(bar, parity)) return;
+  const unsigned long long t0 = gtime();
+  while (!mbar_try(bar, parity))
+    if (gtime() - t0 > kTimeoutNs) wait_timeout_trap(what);
+}
+__device__ __forceinline__ void bar_wait_cluster(uint64_t* bar, uint32_t parity, int what) {
+  if (mbar_try_cluster(bar, parity)) return;
+  const unsigned long long t0 = gtime();
+  while (!mbar_try_cluster(bar, parity))
+    if (gtime() - t0 > kTimeoutNs) wait_timeout_trap(what);
+}
+// arrive on a barrier of the pair's leader CTA (shared::cluster address)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// all lanes poll (one broadcast transaction), so every lane has acquire semantics for what follows
+__device__ __forceinline__ void wait_flag(const int* f, int count, int what) {
+  if (ld_acquire_gpu(f) >= count) return;
+  const unsigned long long t0 = gtime();
+  while (ld_acquire_gpu(f) < count) {
+    __nanosleep(40);
+    if (gtime() - t0 > kTimeoutNs) wait_timeout_trap(what);
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Activations other than ELU are cold paths: out of line, so that the six inlined variants (tanhf, log1pf, ...) times the
+// unrolled chunks do not bloat the epilogue loop (instruction cache).
+__device__ __noinline__ void act_cold_fwd(int act, float (&v)[16]) {
+  dispatch_act(act, [&](auto tag) {
+    constexpr int ACT = decltype(tag)::value;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = act_fwd_t<ACT>(v[i]);
+  });
+}
+__device__ __noinline__ void act_cold_bwd(int act, float (&v)[16], const float (&hv)[16]) {
+  dispatch_act(act, [&](auto tag) {
+    constexpr int ACT = decltype(tag)::value;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= act_grad_out_t<ACT>(hv[i]);
+  });
+}
+
+// 16 accumulator columns per call; `acc` indices are compile-time after unrolling
+template <int NC>
+__device__ __forceinline__ void tmem_accumulate(uint32_t taddr, float (&acc)[64]) {
+#pragma unroll
+  for (int c = 0; c < NC; c += 32) {
+    uint32_t r0[16], r1[16];
+    tmem_ld16_async(taddr + c, r0);
+    tmem_ld16_async(taddr + c + 16, r1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      acc[c + j] += __uint_as_float(r0[j]);
+      acc[c + 16 + j] += __uint_as_float(r1[j]);
+    }
+  }
+}
+
+// debug trace: role 0 producer, 1 MMA issuer, 2 first epilogue warp, 3 first head warp (leader CTA only)
+struct Tracer {
+  unsigned long long* at;
+  int n, cap;
+  __device__ __forceinline__ void init(const Params& p, int pair, int role) {
+    cap = p.trace ? p.trace_cap : 0;
+    at = p.trace ? p.trace + (static_cast<size_t>(pair) * 4 + role) * p.trace_cap * 2 : nullptr;
+    n = 0;
+  }
+  __device__ __forceinline__ void mark(unsigned tag) {
+    if (n < cap) {
+      at[2 * n] = tag;
+      at[2 * n + 1] = gtime();
+      ++n;
+    }
+  }
+};
+// ---- policy head + simulator period: lane = store (two passes cover S <= 64), one scenario row at a time ----------
+// Same arithmetic (and reduction order) as warehouse_head_fwd/bwd_kernel of rollout_wide.cu, but register-resident:
+// every per-store quantity is private to its lane, warehouse quantities live on lane w and are broadcast by shuffles.
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void store_split(float* x, float* hi, float* lo, size_t at, float v) {
+  if (x) x[at] = v;
+  if (hi) {
+    const float a = tf32_hi(v);
+    hi[at] = a;
+    lo[at] = tf32_hi(v - a);
+  }
+}
+
+// The SM's L2 return path is kept full by the TMA operand stream of the GEMM pipeline and the L1 is carved down to
+// nothing (227 KB of shared memory), so EVERY global or local-memory load of a head warp costs ~1.4 us. Hence:
+//  * a scenario row's inputs (state row, policy output row, demand, cost coefficients, lead times; adjoint: the
+//    state-adjoint row) are copied global -> shared memory with cp.async, double-buffered: row r + 1 is in flight while
+//    row r is computed from shared memory; results leave through stores / fire-and-forget reductions only;
+//  * no local memory: the head parameters are read from the constant bank (everything is inlined into the kernel, which
+//    takes them as a __grid_constant__), no register arrays with dynamic indices, no spills;
+//  * code size matters too (the role loops of one CTA share a 32 KB instruction cache): the loops over warehouses and
+//    pipeline slots are ROLLED, only the two stores of a lane are unrolled.
+struct RowLayout {  // float offsets inside one staged row
+  int oX, oY, oD, oH, oP, oLT, oWH, oG, total;
+};
+template <bool BWD>
+__host__ __device__ inline RowLayout row_layout(int S, int W, int L, int Lw) {
+  RowLayout r;
+  const int nX = S * L + W * Lw, SW = S * W;
+  int o = 0;
+  r.oX = o;
+  o += BWD ? S + W : nX;  // adjoint: only the on-hand slot of every store / warehouse
+  r.oY = o;
+  o += SW + W;
+  r.oD = o;
+  o += S;
+  r.oH = o;
+  o += S;
+  r.oP = o;
+  o += S;
+  r.oLT = o;
+  o += SW;
+  r.oWH = o;
+  o += 3 * W;
+  r.oG = o;
+  o += BWD ? nX : 0;
+  r.total = (o + 3) & ~3;
+  return r;
+}
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <bool BWD>
+__device__ __forceinline__ void head_stage(const HeadP& h, const RowLayout& rl, int t, int b, int lane, float* buf) {
+  if (b < h.B) {
+    const size_t xstride = static_cast<size_t>(h.Bp) * h.ldx, ystride = static_cast<size_t>(h.Bp) * h.ldy;
+    const int xs = (BWD || h.save) ? t : (t & 1);
+    const float* X = h.X + xs * xstride + static_cast<size_t>(b) * h.ldx;
+    const float* Y = h.Y + ((BWD || h.save) ? t : 0) * ystride + static_cast<size_t>(b) * h.ldy;
+    const int nX = h.nS + h.W * h.Lw, SW = h.S * h.W;
+    if (BWD) {
+      const float* G = h.gX + static_cast<size_t>(b) * h.ldx;
+      for (int e = lane; e < h.S; e += 32) cp_async4(buf + rl.oX + e, X + e * h.L);
+      if (lane < h.W) cp_async4(buf + rl.oX + h.S + lane, X + h.nS + lane * h.Lw);
+      for (int e = lane; e < nX; e += 32) cp_async4(buf + rl.oG + e, G + e);
+    } else {
+      for (int e = lane; e < nX; e += 32) cp_async4(buf + rl.oX + e, X + e);
+    }
+    for (int e = lane; e < SW + h.W; e += 32) cp_async4(buf + rl.oY + e, Y + e);
+    const float* dem = h.dTB + (static_cast<size_t>(t) * h.Bp + b) * h.S;
+    const float* hc = h.st.holding_costs + static_cast<size_t>(b) * h.S;
+    const float* pc = h.st.underage_costs + static_cast<size_t>(b) * h.S;
+    for (int e = lane; e < h.S; e += 32) {
+      cp_async4(buf + rl.oD + e, dem + e);
+      cp_async4(buf + rl.oH + e, hc + e);
+      cp_async4(buf + rl.oP + e, pc + e);
+    }
+    const float* ltrow = h.st.lead_times + static_cast<size_t>(b) * SW;
+    for (int e = lane; e < SW; e += 32) cp_async4(buf + rl.oLT + e, ltrow + e);
+    if (lane < h.W) {
+      const size_t bw = static_cast<size_t>(b) * h.W + lane;
+      cp_async4(buf + rl.oWH + lane, h.st.warehouse_holding_costs + bw);
+      cp_async4(buf + rl.oWH + h.W + lane, h.st.warehouse_lead_times + bw);
+      if (h.has_edge) cp_async4(buf + rl.oWH + 2 * h.W + lane, h.st.warehouse_edge_costs + bw);
+    }
+  }
+  cp_async_commit();
+}
+
+// Mapping: a HALF-warp per scenario row (two rows per warp at a time), lane hl = lane % 16 owns stores hl, hl + 16,
+// hl + 32, hl + 48 (S <= 64) and, for hl < W, warehouse hl. A single warp is latency-bound (dependent shuffles, LDS,
+// MUFU), so the per-row instruction count and the independent work per lane are what matter: 4 stores per lane give
+// the instruction-level parallelism, reductions are 4 shuffle steps inside the half-warp.
+constexpr int kSPL = 4;  // stores per lane
+
+__device__ __forceinline__ float half_sum(float v, unsigned mask) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+__device__ __forceinline__ float half_max(float v, unsigned mask) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o));
+  return v;
+}
+
+// softmax of warehouse w over its connected stores (+ the constant hold logit): shares p[i] of this lane's stores
+__device__ __forceinline__ void head_softmax(const HeadP& h, const RowLayout& rl, const float* buf, const int* adj, int w, int hl,
+                                             unsigned mask, float (&p)[kSPL]) {
+  float y[kSPL];
+  bool c[kSPL];
+  float mx = h.transshipment ? -INFINITY : 1.f;
+#pragma unroll
+  for (int i = 0; i < kSPL; ++i) {
+    const int s = hl + 16 * i;
+    c[i] = s < h.S && (!adj || adj[w * h.S + s] != 0);
+    y[i] = c[i] ? buf[rl.oY + s * h.W + w] : 0.f;
+    if (c[i]) mx = fmaxf(mx, y[i]);
+  }
+  mx = half_max(mx, mask);
+  float e[kSPL], sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSPL; ++i) {
+    e[i] = c[i] ? expf(y[i] - mx) : 0.f;
+    sum += e[i];
+  }
+  sum = half_sum(sum, mask);
+  if (!h.transshipment) sum += expf(1.f - mx);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < kSPL; ++i) p[i] = e[i] * inv;
+}
+
+// scr: per-row scratch in the warp's shared memory, [s * W + w]: values the later loops over (store, warehouse) need;
+// written and read by the owning lane only
+__device__ __forceinline__ void head_fwd_compute(const HeadP& h, const RowLayout& rl, int t, int b, int hl, unsigned mask,
+                                                 const float* buf, const int* adj, float* scr) {
+  const size_t xstride = static_cast<size_t>(h.Bp) * h.ldx;
+  const int xn = h.save ? t + 1 : ((t + 1) & 1);
+  float* __restrict__ Xn = h.X + xn * xstride + static_cast<size_t>(b) * h.ldx;
+  const bool split = t + 1 < h.T;
+  const size_t hs = h.save ? static_cast<size_t>(t + 1) : 0;
+  float* __restrict__ Xhi = split ? h.X_hi + hs * xstride + static_cast<size_t>(b) * h.ldx : nullptr;
+  float* __restrict__ Xlo = split ? h.X_lo + hs * xstride + static_cast<size_t>(b) * h.ldx : nullptr;
+  if (b >= h.B) {  // tile-padding rows stay exactly zero
+    for (int c = hl; c < h.ldx; c += 16) store_split(Xn, Xhi, Xlo, c, 0.f);
+    return;
+  }
+  // ---- masked softmax per warehouse x on-hand -> allocations (scr[s * W + w]); draw-down of warehouse w on lane w
+  float drawn = 0.f;
+#pragma unroll 1
+  for (int w = 0; w < h.W; ++w) {
+    const float W0 = buf[rl.oX + h.nS + w * h.Lw];
+    float p[kSPL];
+    head_softmax(h, rl, buf, adj, w, hl, mask, p);
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSPL; ++i) {
+      const int s = hl + 16 * i;
+      float a = p[i] * W0;
+      if (h.discrete) a = rintf(a);
+      part += a;
+      if (s < h.S) scr[s * h.W + w] = a;
+    }
+    part = half_sum(part, mask);
+    if (hl == w) drawn = part;
+  }
+  // ---- stores: cost, lost sales / backlog, pipeline shift, arrivals
+  float cost = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSPL; ++i) {
+    const int s = hl + 16 * i;
+    if (s < h.S) {
+      const float* xs = buf + rl.oX + s * h.L;
+      const float on_hand = xs[0], d = buf[rl.oD + s], hh = buf[rl.oH + s], pp = buf[rl.oP + s];
+      const float raw = on_hand - d;
+      cost += h.profit ? (-pp * fminf(on_hand, d) + hh * relu0(raw)) : (pp * relu0(-raw) + hh * relu0(raw));
+      const float post = h.lost ? relu0(raw) : raw;
+#pragma unroll 1
+      for (int k = 0; k < h.L; ++k) {
+        const float nx = k < h.L - 1 ? xs[k + 1] : 0.f;
+        float v = k == 0 ? post + nx : nx;
+#pragma unroll 1
+        for (int w = 0; w < h.W; ++w) {
+          const float al = scr[s * h.W + w];
+          if (al != 0.f && static_cast<int>(buf[rl.oLT + s * h.W + w]) - 1 == k) v += al;
+        }
+        store_split(Xn, Xhi, Xlo, s * h.L + k, v);
+      }
+    }
+  }
+  // ---- warehouses (lane w of the half-warp)
+  if (hl < h.W) {
+    const float* xw = buf + rl.oX + h.nS + hl * h.Lw;
+    const float raw = xw[0] - drawn;
+    float aw = sigmoid_f(buf[rl.oY + h.S * h.W + hl]) * h.wub;
+    if (h.discrete) aw = rintf(aw);
+    float cw = buf[rl.oWH + hl] * relu0(raw);
+    if (h.has_edge) cw += buf[rl.oWH + 2 * h.W + hl] * aw;
+    cost += cw;
+    const int slot = aw != 0.f ? static_cast<int>(buf[rl.oWH + h.W + hl]) - 1 : -1;
+#pragma unroll 1
+    for (int k = 0; k < h.Lw; ++k) {
+      const float nx = k < h.Lw - 1 ? xw[k + 1] : 0.f;
+      float v = k == 0 ? raw + nx : nx;
+      if (slot == k) v += aw;
+      store_split(Xn, Xhi, Xlo, h.nS + hl * h.Lw + k, v);
+    }
+  }
+  for (int c = h.nS + h.W * h.Lw + hl; c < h.ldx; c += 16) store_split(Xn, Xhi, Xlo, c, 0.f);
+  cost = half_sum(cost, mask);
+  if (hl == 0) {
+    // one addition per (scenario, period), periods ordered by the dependency chain: deterministic; RED = no round trip
+    atomicAdd(h.cost_b + b, cost);
+    if (h.report_b && t >= h.ignore_periods) atomicAdd(h.report_b + b, cost);
+    if (h.reward_tb) h.reward_tb[static_cast<size_t>(t) * h.B_total + b] = cost;
+  }
+}
+
+// Adjoint of head + period for scenario row b. gX row: adjoint wrt X_{t+1} on entry, direct part of the adjoint wrt X_t
+// on exit (the first-layer dgrad tiles add the rest); gy goes to the row-major (hi, lo) tape of the output layer.
+// scr: [2][S * W] floats (softmax shares, allocation adjoints).
+__device__ __forceinline__ void head_bwd_compute(const HeadP& h, const RowLayout& rl, int t, int b, int hl, unsigned mask,
+                                                 const float* buf, const int* adj, float* scr) {
+  const size_t ystride = static_cast<size_t>(h.Bp) * h.ldy;
+  float* __restrict__ G = h.gX + static_cast<size_t>(b) * h.ldx;
+  float* __restrict__ GYh = h.gY_hi + static_cast<size_t>(t) * ystride + static_cast<size_t>(b) * h.ldy;
+  float* __restrict__ GYl = h.gY_lo + static_cast<size_t>(t) * ystride + static_cast<size_t>(b) * h.ldy;
+  if (b >= h.B) {
+    for (int c = hl; c < h.ldy; c += 16) store_split(nullptr, GYh, GYl, c, 0.f);
+    return;
+  }
+  const float rb = h.g_total + (t >= h.ignore_periods ? h.g_report : 0.f);
+  const int SW = h.S * h.W;
+  const int src0 = (mask & 1u) ? 0 : 16;  // first lane of this half-warp (shuffle sources)
+  float* share = scr;        // [s * W + w]
+  float* galloc = scr + SW;  // [s * W + w]
+  const float* g = buf + rl.oG;  // adjoint wrt X_{t+1}, row layout of X
+  // ---- pass 1 over the warehouses: softmax shares + draw-down
+  float drawn = 0.f;
+#pragma unroll 1
+  for (int w = 0; w < h.W; ++w) {
+    const float W0 = buf[rl.oX + h.S + w];
+    float p[kSPL];
+    head_softmax(h, rl, buf, adj, w, hl, mask, p);
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSPL; ++i) {
+      const int s = hl + 16 * i;
+      part += p[i] * W0;
+      if (s < h.S) share[s * h.W + w] = p[i];
+    }
+    part = half_sum(part, mask);
+    if (hl == w) drawn = part;
+  }
+  // ---- warehouses (lane w): g_raw_w feeds the store-allocation adjoints
+  float g_raw_w = 0.f, gyw = 0.f;
+  if (hl < h.W) {
+    const float* gw = g + h.nS + hl * h.Lw;
+    float* gwo = G + h.nS + hl * h.Lw;
+    const float raw = buf[rl.oX + h.S + hl] - drawn;
+    const float sg = sigmoid_f(buf[rl.oY + SW + hl]);
+    const float aw = sg * h.wub;
+    const int slot = aw != 0.f ? static_cast<int>(buf[rl.oWH + h.W + hl]) - 1 : -1;
+    float gaw = (slot >= 0 && slot < h.Lw) ? gw[slot] : 0.f;
+    if (h.has_edge) gaw += rb * buf[rl.oWH + 2 * h.W + hl];
+    const float gn0 = gw[0];
+    g_raw_w = rb * buf[rl.oWH + hl] * ge0(raw) + gn0;
+#pragma unroll 1
+    for (int k = 1; k < h.Lw; ++k) gwo[k] = gw[k - 1];  // new gw[k] = old gw[k - 1]; gwo[0] is written below
+    gyw = gaw * h.wub * sg * (1.f - sg);
+  }
+  // ---- stores: dynamics adjoint
+#pragma unroll
+  for (int i = 0; i < kSPL; ++i) {
+    const int s = hl + 16 * i;
+    if (s < h.S) {
+      const float* gs = g + s * h.L;
+      float* gso = G + s * h.L;
+      const float on_hand = buf[rl.oX + s], d = buf[rl.oD + s], hh = buf[rl.oH + s], pp = buf[rl.oP + s];
+      const float raw = on_hand - d;
+      const float gn0 = gs[0];
+      float g0;
+      if (h.profit) {
+        const float tie = on_hand < d ? 1.f : (on_hand == d ? 0.5f : 0.f);
+        g0 = rb * (-pp * tie + hh * ge0(raw));
+      } else {
+        g0 = rb * (-pp * le0(raw) + hh * ge0(raw));
+      }
+      g0 += h.lost ? gn0 * ge0(raw) : gn0;
+      gso[0] = g0;
+#pragma unroll 1
+      for (int k = 1; k < h.L; ++k) gso[k] = gs[k - 1];
+    }
+  }
+  // ---- allocation adjoints galloc[s, w] = g_new[slot] - g_raw_w, softmax backward per warehouse: alloc = p * W0
+  float gw0_add = 0.f;
+#pragma unroll 1
+  for (int w = 0; w < h.W; ++w) {
+    const float W0 = buf[rl.oX + h.S + w];
+    const float graw = __shfl_sync(mask, g_raw_w, src0 + w);
+    float pr[kSPL], q[kSPL], dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSPL; ++i) {
+      const int s = hl + 16 * i;
+      pr[i] = q[i] = 0.f;
+      if (s < h.S) {
+        pr[i] = share[s * h.W + w];
+        float ga = 0.f;
+        if (pr[i] * W0 != 0.f) {
+          const int slot = static_cast<int>(buf[rl.oLT + s * h.W + w]) - 1;
+          if (slot >= 0 && slot < h.L) ga = g[s * h.L + slot];
+        }
+        q[i] = ga - graw;
+        dot += q[i] * pr[i];
+      }
+    }
+    dot = half_sum(dot, mask);  // sum_s g_alloc * p (= adjoint of W0, and with W0 the softmax inner product)
+    if (hl == w) gw0_add = dot;
+#pragma unroll
+    for (int i = 0; i < kSPL; ++i) {
+      const int s = hl + 16 * i;
+      if (s < h.S) store_split(nullptr, GYh, GYl, s * h.W + w, pr[i] * (q[i] * W0 - dot * W0));
+    }
+  }
+  (void)galloc;
+  if (hl < h.W) {
+    G[h.nS + hl * h.Lw] = g_raw_w + gw0_add;
+    store_split(nullptr, GYh, GYl, SW + hl, gyw);
+  }
+  for (int c = SW + h.W + hl; c < h.ldy; c += 16) store_split(nullptr, GYh, GYl, c, 0.f);
+}
+
+// floats of shared memory one head warp needs: adjacency + per-row scratch (2 rows) + 2 x 2 staged rows
+template <bool BWD>
+__host__ __device__ inline int head_warp_floats(int S, int W, int L, int Lw, bool adj) {
+  return (((adj ? S * W : 0) + 2 * S * W + 3) & ~3) + 4 * row_layout<BWD>(S, W, L, Lw).total;
+}
+
+// rows [row0, row0 + n), two at a time (one per half-warp): the inputs of the next row pair are in flight (cp.async)
+// while this pair is computed from shared memory
+template <bool BWD>
+__device__ __forceinline__ void head_block(const HeadP& h, int t, int row0, int n, int lane, float* wsm, Tracer* trc) {
+  const RowLayout rl = row_layout<BWD>(h.S, h.W, h.L, h.Lw);
+  const int SW = h.S * h.W;
+  const int hl = lane & 15, rp = lane >> 4;
+  const unsigned mask = rp ? 0xffff0000u : 0x0000ffffu;
+  const int* adj = h.adjacency ? reinterpret_cast<const int*>(wsm) : nullptr;  // staged once per kernel (see the head loop)
+  float* scr = wsm + (h.adjacency ? SW : 0) + rp * SW;
+  float* rows = wsm + (((h.adjacency ? SW : 0) + 2 * SW + 3) & ~3);
+  // buffer (pair parity, half) -> rows + (2 * parity + rp) * total
+  auto stage_pair = [&](int pr) {
+    float* dst = rows + (2 * (pr & 1)) * rl.total;
+    head_stage<BWD>(h, rl, t, row0 + 2 * pr, lane, dst);
+    head_stage<BWD>(h, rl, t, row0 + 2 * pr + 1, lane, dst + rl.total);
+  };
+  const int n_pairs = n / 2;
+  stage_pair(0);
+#pragma unroll 1
+  for (int pr = 0; pr < n_pairs; ++pr) {
+    if (trc) trc->mark(0x500 + pr);
+    if (pr + 1 < n_pairs) {
+      stage_pair(pr + 1);
+      if (trc) trc->mark(0x510 + pr);
+      cp_async_wait<2>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    if (trc) trc->mark(0x520 + pr);
+    const float* cur = rows + (2 * (pr & 1) + rp) * rl.total;
+    const int b = row0 + 2 * pr + rp;
+    if (BWD) head_bwd_compute(h, rl, t, b, hl, mask, cur, adj, scr);
+    else head_fwd_compute(h, rl, t, b, hl, mask, cur, adj, scr);
+    __syncwarp();  // every lane is done with this pair's buffers before the pair after next is staged into them
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the persistent kernel
+// ------------------------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads, 1) persist_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + ((1024 - (raw_addr & 1023)) & 1023);
+  unsigned char* ring = smem;
+  unsigned char* epi_stage = smem + kRing;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kRing + kEpiStage + kBiasBytes);
+  float* bias_all = reinterpret_cast<float*>(smem + kRing + kEpiStage);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* hi_full = empty_bar + kStages;
+  uint64_t* hi_empty = hi_full + 2;
+  uint64_t* cr_full = hi_empty + 2;
+  uint64_t* cr_empty = cr_full + 2;
+  uint64_t* aux_bar = cr_empty + 2;  // one per epilogue warp (adjoint: TMA loads of the saved-activation boxes)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + kEpiWarps);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const bool three = p.n_pass == 3;
+
+  if (pair >= p.n_pairs) {
+    // ===== policy head + simulator period CTAs: the 2 x 12 warps of a CTA pair share the rows of a head task =====
+    // (own SMs: their L2 return path and instruction cache are not competing with a GEMM pipeline)
+    const int hpair = pair - p.n_pairs;
+    const int hw_id = static_cast<int>(rank) * kHeadWarps + warp;
+    float* wsm = reinterpret_cast<float*>(smem) + warp * (kHeadBytes / 4 / kHeadWarps);
+    if (p.head.adjacency) {  // adjacency masks: staged once
+      for (int e = lane; e < p.head.S * p.head.W; e += 32) reinterpret_cast<int*>(wsm)[e] = __ldg(p.head.adjacency + e);
+      __syncwarp();
+    }
+    const Task* tp = p.head_tasks + static_cast<size_t>(hpair) * p.max_tasks;
+    Tracer tr;
+    tr.init(p, hpair, 3);
+    const bool tracing = rank == 0 && warp == 0 && lane == 0;
+    for (;; ++tp) {
+      const int4 a = __ldg(&tp->a), b = __ldg(&tp->b);
+      if ((a.x & 0xff) == 0) break;
+      if (tracing) tr.mark(0x100);
+      if (a.w >= 0) wait_flag(p.flags + a.w, b.x, 9);
+      if (tracing) tr.mark(0x200);
+      // 4-row blocks of the 256-row tile, round-robin over the pair's head warps
+      for (int blk = hw_id; blk < kRowTile / 4; blk += 2 * kHeadWarps) {
+        const int row0 = a.z * kRowTile + blk * 4;
+        head_block<BWD>(p.head, a.y, row0, 4, lane, wsm, nullptr);
+      }
+      if (tracing) tr.mark(0x300);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) red_release_gpu(p.flags + b.y, 1);
+      if (tracing) tr.mark(0x400);
+    }
+    return;
+  }
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&hi_full[i], 1);
+      mbar_init(&cr_full[i], 1);
+      mbar_init(&hi_empty[i], 2 * kEpiWarps);
+      mbar_init(&cr_empty[i], 2 * kEpiWarps);
+    }
+    for (int w = 0; w < kEpiWarps; ++w) mbar_init(&aux_bar[w], 1);
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 1) tmem_alloc_pair(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    const Task* tp = p.tasks + static_cast<size_t>(pair) * p.max_tasks;
+    uint32_t s = 0, ph = 0;
+    Tracer tr;
+    tr.init(p, pair, 0);
+    const bool tracing = rank == 0 && lane == 0;
+    for (;; ++tp) {
+      const int4 a = __ldg(&tp->a), b = __ldg(&tp->b);
+      if ((a.x & 0xff) == 0) break;
+      const LayerDesc& L = p.L[(a.x >> 8) & 0xff];
+      if (tracing) tr.mark(0x100 | ((a.x >> 8) & 0xff));  // reached the task
+      if (b.y >= 0) {
+        wait_flag(p.flags + b.y, b.z, 1);
+        fence_proxy_async_all();
+      }
+      if (tracing) tr.mark(0x200 | ((a.x >> 8) & 0xff));  // inputs ready
+      const int bn = L.bn;
+      const uint32_t tx = (three ? 2u : 1u) * static_cast<uint32_t>(kABytes + (bn / 2) * 128) * 2u;
+      const int arow = L.a_tmul * a.y + a.z * kRowTile + static_cast<int>(rank) * 128;
+      const int brow = a.w + static_cast<int>(rank) * (bn / 2);
+      for (int kb = 0; kb < b.x; ++kb) {
+        bar_wait(&empty_bar[s], ph ^ 1, 2);
+        unsigned char* st = ring + s * kStageBytes;
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(&full_bar[s], tx);
+          const uint32_t bar = mapa_u32(&full_bar[s], 0);
+          tma_load_2d_pair(st, &L.a_hi, bar, kb * kBK, arow);
+          tma_load_2d_pair(st + 2 * kABytes, &L.b_hi, bar, kb * kBK, brow);
+          if (three) {
+            tma_load_2d_pair(st + kABytes, &L.a_lo, bar, kb * kBK, arow);
+            tma_load_2d_pair(st + 2 * kABytes + kBBytesMax, &L.b_lo, bar, kb * kBK, brow);
+          }
+        }
+        __syncwarp();
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+      if (tracing) tr.mark(0x300 | ((a.x >> 8) & 0xff));  // all loads issued
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA of the pair) =====
+    if (rank == 0) {
+      const Task* tp = p.tasks + static_cast<size_t>(pair) * p.max_tasks;
+      uint32_t s = 0, ph = 0, hseg = 0, tcnt = 0;
+      Tracer tr;
+      tr.init(p, pair, 1);
+      for (;; ++tp) {
+        const int4 a = __ldg(&tp->a), b = __ldg(&tp->b);
+        if ((a.x & 0xff) == 0) break;
+        const LayerDesc& L = p.L[(a.x >> 8) & 0xff];
+        const int bn = L.bn, n_kb = b.x;
+        if (lane == 0) tr.mark(0x100 | ((a.x >> 8) & 0xff));
+        // D = f32 (bit 4), A = B = tf32 (2 << 7, 2 << 10), K-major both, N >> 3 at bit 17, M >> 4 at bit 24 (M = 256)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | ((256u >> 4) << 24);
+        const uint32_t cb = tcnt & 1;
+        const uint32_t d_cr = tmem + cb * 128;
+        if (three) {
+          bar_wait_cluster(&cr_empty[cb], ((tcnt >> 1) & 1) ^ 1, 3);
+          tc_fence_after();
+        }
+        int in_seg = 0;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          const uint32_t hb = hseg & 1;
+          if (in_seg == 0) {
+            bar_wait_cluster(&hi_empty[hb], ((hseg >> 1) & 1) ^ 1, 4);
+            tc_fence_after();
+          }
+          bar_wait(&full_bar[s], ph, 5);
+          tc_fence_after();
+          if (lane == 0 && kb == 0) tr.mark(0x200 | ((a.x >> 8) & 0xff));  // first operands landed
+          const bool seg_last = (in_seg == p.kseg - 1) || (kb == n_kb - 1);
+          if (elect_one()) {
+            const uint32_t st = smem_u32(ring + s * kStageBytes);
+            const uint64_t a_hi = make_kmajor_desc(st), a_lo = make_kmajor_desc(st + kABytes);
+            const uint64_t b_hi = make_kmajor_desc(st + 2 * kABytes), b_lo = make_kmajor_desc(st + 2 * kABytes + kBBytesMax);
+            const uint32_t d_hi = tmem + 256 + hb * 128;
+#pragma unroll
+            for (int k = 0; k < kBK / 8; ++k) {
+              const uint64_t adv = static_cast<uint64_t>((k * 8 * 4) >> 4);
+              umma_tf32_pair(d_hi, a_hi + adv, b_hi + adv, idesc, (in_seg == 0 && k == 0) ? 0u : 1u);
+              if (three) {
+                umma_tf32_pair(d_cr, a_lo + adv, b_hi + adv, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+                umma_tf32_pair(d_cr, a_hi + adv, b_lo + adv, idesc, 1u);
+              }
+            }
+            umma_commit_pair(&empty_bar[s]);
+            if (seg_last) umma_commit_pair(&hi_full[hb]);
+            if (three && kb == n_kb - 1) umma_commit_pair(&cr_full[cb]);
+          }
+          __syncwarp();
+          if (seg_last) {
+            ++hseg;
+            in_seg = 0;
+          } else {
+            ++in_seg;
+          }
+          if (++s == kStages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        ++tcnt;
+        if (lane == 0) tr.mark(0x300 | ((a.x >> 8) & 0xff));  // all MMAs issued
+      }
+    }
+  } else if (warp < 2 + kEpiWarps) {
+    // ===== epilogue: warp q = warp % 4 owns TMEM lanes [32q, 32q + 32) = rows of this CTA's half of the tile =====
+    const int q = warp & 3, we = warp - 2, half = we >> 2;
+    unsigned char* stg = epi_stage + we * (2 * kBoxBytes);
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t hi_empty_c = mapa_u32(&hi_empty[0], 0), cr_empty_c = mapa_u32(&cr_empty[0], 0);
+    const Task* tp = p.tasks + static_cast<size_t>(pair) * p.max_tasks;
+    uint32_t hseg = 0, tcnt = 0, aux_cnt = 0;
+    (void)aux_cnt;
+    Tracer tr;
+    tr.init(p, pair, 2);
+    const bool tracing = rank == 0 && warp == 2 && lane == 0;
+    // Deferred publish: the flag of a finished tile is incremented once its TMA stores have completed, but the warp
+    // does not sit on that wait - it moves on to the next tile's accumulators and publishes when it would block anyway
+    // (never later: the next tile of this pair may transitively depend on the pending flag).
+    int pending = -1;
+    auto publish_pending = [&]() {
+      if (pending >= 0) {
+        if (lane == 0) {
+          tma_store_wait_all();
+          fence_proxy_async_all();
+          red_release_gpu(p.flags + pending, 1);
+        }
+        pending = -1;
+      }
+    };
+    for (;; ++tp) {
+      const int4 a = __ldg(&tp->a), b = __ldg(&tp->b);
+      if ((a.x & 0xff) == 0) break;
+      const LayerDesc& L = p.L[(a.x >> 8) & 0xff];
+      const int epi = (a.x >> 16) & 0xff;
+      if (tracing) tr.mark(0x100 | ((a.x >> 8) & 0xff));
+      const int t = a.y, col0 = a.w, n_kb = b.x;
+      const bool wide = L.bn == 128;  // this warp drains 64 (wide) or 32 columns
+      const int cbase = half * (wide ? 64 : 32);
+      const int trow = a.z * kRowTile + static_cast<int>(rank) * 128 + q * 32;  // first scenario row of this warp
+      const int n0 = col0 + cbase;
+      float* bias_w = bias_all + we * 64;
+      // Global loads cost ~1.4 us here (the TMA operand stream keeps the SM's L2 return path full), so whatever the
+      // finalize step needs is requested NOW and arrives while the tile's MMAs run.
+      if (!BWD) {
+        __syncwarp();
+        bias_w[lane] = __ldg(L.bias + n0 + lane);
+        if (wide) bias_w[lane + 32] = __ldg(L.bias + n0 + 32 + lane);
+        __syncwarp();
+      }
+      auto issue_aux = [&](int j) {  // adjoint: box j of the tile this epilogue combines with -> staging
+        if (lane == 0) {
+          tma_store_wait_read();
+          fence_proxy_async_all();
+          if (epi == EPI_DGRAD_HIDDEN) {
+            mbar_expect_tx(&aux_bar[we], 2 * kBoxBytes);
+            tma_load_2d(stg, &L.x_hi, &aux_bar[we], n0 + 32 * j, L.x_tmul * t + trow);
+            tma_load_2d(stg + kBoxBytes, &L.x_lo, &aux_bar[we], n0 + 32 * j, L.x_tmul * t + trow);
+          } else {
+            mbar_expect_tx(&aux_bar[we], kBoxBytes);
+            tma_load_2d(stg, &L.x_hi, &aux_bar[we], n0 + 32 * j, trow);
+          }
+        }
+      };
+      if (BWD && epi == EPI_DGRAD_HIDDEN) {
+        publish_pending();  // the staging area is about to be overwritten: the pending tile's stores must have left it
+        issue_aux(0);       // saved activations: complete since the forward sweep
+      }
+      float acc[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+      for (int kb0 = 0; kb0 < n_kb; kb0 += p.kseg) {
+        const uint32_t hb = hseg & 1;
+        if (pending >= 0 && !__all_sync(0xffffffffu, mbar_try(&hi_full[hb], (hseg >> 1) & 1))) publish_pending();
+        bar_wait(&hi_full[hb], (hseg >> 1) & 1, 6);
+        tc_fence_after();
+        const uint32_t taddr = lane_base + 256 + hb * 128 + cbase;
+        if (BWD && epi == EPI_DGRAD_GX && kb0 == 0) {
+          // the state-adjoint rows are final only once this tile's operands exist (they depend on the period's head)
+          publish_pending();
+          issue_aux(0);
+        }
+        if (wide) tmem_accumulate<64>(taddr, acc);
+        else tmem_accumulate<32>(taddr, acc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(hi_empty_c + hb * 8);
+        ++hseg;
+      }
+      if (three) {
+        const uint32_t cb = tcnt & 1;
+        if (pending >= 0 && !__all_sync(0xffffffffu, mbar_try(&cr_full[cb], (tcnt >> 1) & 1))) publish_pending();
+        bar_wait(&cr_full[cb], (tcnt >> 1) & 1, 7);
+        tc_fence_after();
+        const uint32_t taddr = lane_base + cb * 128 + cbase;
+        if (wide) tmem_accumulate<64>(taddr, acc);
+        else tmem_accumulate<32>(taddr, acc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(cr_empty_c + cb * 8);
+      }
+      ++tcnt;
+      if (tracing) tr.mark(0x200 | ((a.x >> 8) & 0xff));  // accumulators drained
+      publish_pending();
+      // ---- finalize: this warp's 32 rows x (64 | 32) columns ----
+      if (!BWD && epi == EPI_FWD_HIDDEN) {
+        const int grow = L.c_tmul * t + trow;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (j == 0 || wide) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              float v[16];
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_w + 32 * j + 16 * hh + 4 * j4);
+                v[4 * j4 + 0] = acc[32 * j + 16 * hh + 4 * j4 + 0] + b4.x;
+                v[4 * j4 + 1] = acc[32 * j + 16 * hh + 4 * j4 + 1] + b4.y;
+                v[4 * j4 + 2] = acc[32 * j + 16 * hh + 4 * j4 + 2] + b4.z;
+                v[4 * j4 + 3] = acc[32 * j + 16 * hh + 4 * j4 + 3] + b4.w;
+              }
+              if (L.act == HDPO_ACT_ELU) {
+                elu_inplace(v);
+              } else {
+                act_cold_fwd(L.act, v);
+              }
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                float4 hi, lo;
+                hi.x = tf32_hi(v[4 * j4 + 0]);
+                hi.y = tf32_hi(v[4 * j4 + 1]);
+                hi.z = tf32_hi(v[4 * j4 + 2]);
+                hi.w = tf32_hi(v[4 * j4 + 3]);
+                lo.x = tf32_hi(v[4 * j4 + 0] - hi.x);
+                lo.y = tf32_hi(v[4 * j4 + 1] - hi.y);
+                lo.z = tf32_hi(v[4 * j4 + 2] - hi.z);
+                lo.w = tf32_hi(v[4 * j4 + 3] - hi.w);
+                const int chunk = ((4 * hh + j4) ^ (lane & 7)) << 4;
+                *reinterpret_cast<float4*>(stg + lane * 128 + chunk) = hi;
+                *reinterpret_cast<float4*>(stg + kBoxBytes + lane * 128 + chunk) = lo;
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&L.c_hi, stg, n0 + 32 * j, grow);
+              tma_store_2d(&L.c_lo, stg + kBoxBytes, n0 + 32 * j, grow);
+              tma_store_commit();
+            }
+          }
+        }
+      } else if (!BWD && epi == EPI_FWD_OUT) {
+        // output layer (64-column tiles: 32 columns per warp): fp32 row-major tape by TMA
+        const int grow = L.c_tmul * t + trow;
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_w + 4 * j4);
+          float4 v;
+          v.x = acc[4 * j4 + 0] + b4.x;
+          v.y = acc[4 * j4 + 1] + b4.y;
+          v.z = acc[4 * j4 + 2] + b4.z;
+          v.w = acc[4 * j4 + 3] + b4.w;
+          *reinterpret_cast<float4*>(stg + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = v;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&L.c_hi, stg, n0, grow);
+          tma_store_commit();
+        }
+      } else if (BWD && epi == EPI_DGRAD_HIDDEN) {
+        const int grow = L.c_tmul * t + trow;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (j == 0 || wide) {
+            if (j == 1) issue_aux(1);
+            bar_wait(&aux_bar[we], aux_cnt & 1, 8);
+            ++aux_cnt;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              float v[16], hv[16];
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const int chunk = ((4 * hh + j4) ^ (lane & 7)) << 4;
+                const float4 x0 = *reinterpret_cast<const float4*>(stg + lane * 128 + chunk);
+                const float4 x1 = *reinterpret_cast<const float4*>(stg + kBoxBytes + lane * 128 + chunk);
+                hv[4 * j4 + 0] = x0.x + x1.x;
+                hv[4 * j4 + 1] = x0.y + x1.y;
+                hv[4 * j4 + 2] = x0.z + x1.z;
+                hv[4 * j4 + 3] = x0.w + x1.w;
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = acc[32 * j + 16 * hh + i];
+              if (L.act == HDPO_ACT_ELU) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] *= elu_grad_from_out(hv[i]);
+              } else {
+                act_cold_bwd(L.act, v, hv);
+              }
+              if (L.colsum) {
+                // bias-gradient partials: column sums over this warp's 32 rows (reduce-scatter butterfly)
+                float w[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] = v[i];
+#pragma unroll
+                for (int hw = 8, o = 16; hw >= 1; hw >>= 1, o >>= 1) {
+                  const bool up = (lane & o) != 0;
+#pragma unroll
+                  for (int i = 0; i < hw; ++i) {
+                    const float send = up ? w[i] : w[i + hw];
+                    const float recv = __shfl_xor_sync(0xffffffffu, send, o);
+                    w[i] = (up ? w[i + hw] : w[i]) + recv;
+                  }
+                }
+                w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
+                if ((lane & 1) == 0) {
+                  const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                  L.colsum[(static_cast<size_t>(grow) >> 5) * L.ldc + n0 + 32 * j + 16 * hh + col] = w[0];
+                }
+              }
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                float4 hi, lo;
+                hi.x = tf32_hi(v[4 * j4 + 0]);
+                hi.y = tf32_hi(v[4 * j4 + 1]);
+                hi.z = tf32_hi(v[4 * j4 + 2]);
+                hi.w = tf32_hi(v[4 * j4 + 3]);
+                lo.x = tf32_hi(v[4 * j4 + 0] - hi.x);
+                lo.y = tf32_hi(v[4 * j4 + 1] - hi.y);
+                lo.z = tf32_hi(v[4 * j4 + 2] - hi.z);
+                lo.w = tf32_hi(v[4 * j4 + 3] - hi.w);
+                const int chunk = ((4 * hh + j4) ^ (lane & 7)) << 4;
+                *reinterpret_cast<float4*>(stg + lane * 128 + chunk) = hi;
+                *reinterpret_cast<float4*>(stg + kBoxBytes + lane * 128 + chunk) = lo;
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&L.c_hi, stg, n0 + 32 * j, grow);
+              tma_store_2d(&L.c_lo, stg + kBoxBytes, n0 + 32 * j, grow);
+              tma_store_commit();
+            }
+          }
+        }
+      } else if (BWD && epi == EPI_DGRAD_GX) {
+        // first-layer dgrad: add the product to the state adjoint (row-major [Bp][ldx]; box in, add, box out)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (j == 0 || wide) {
+            if (j == 1) issue_aux(1);
+            bar_wait(&aux_bar[we], aux_cnt & 1, 8);
+            ++aux_cnt;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float4* at = reinterpret_cast<float4*>(stg + lane * 128 + ((j4 ^ (lane & 7)) << 4));
+              float4 v = *at;
+              v.x += acc[32 * j + 4 * j4 + 0];
+              v.y += acc[32 * j + 4 * j4 + 1];
+              v.z += acc[32 * j + 4 * j4 + 2];
+              v.w += acc[32 * j + 4 * j4 + 3];
+              *at = v;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&L.c_hi, stg, n0 + 32 * j, trow);
+              tma_store_commit();
+            }
+          }
+        }
+      }
+      // publish: every store of this warp is complete and visible before the tile's flag is incremented
+      if (tracing) tr.mark(0x300 | ((a.x >> 8) & 0xff));  // tile staged, stores issued
+      pending = b.w;
+    }
+    publish_pending();
+  }
+  // (warps 10, 11 of a GEMM CTA are idle: the block size is what a policy-head CTA wants)
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA may release shared memory / TMEM the pair's MMAs and commits still use
+  if (warp == 1) tmem_dealloc_pair(tmem, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// device-side list builder: thread = pair
+// ------------------------------------------------------------------------------------------------------------
+__global__ void build_tasks_kernel(Sched s, Task* tasks, Task* head_tasks, int n_pairs, int n_hpairs) {
+  pdl_wait();
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_pairs + n_hpairs) return;
+  const int total = s.T * s.nsteps;
+  const int u_end = total + (s.k - 1) * s.skew;
+  Task end;
+  end.a = make_int4(0, 0, 0, 0);
+  end.b = make_int4(0, 0, 0, 0);
+  if (id >= n_pairs) {
+    // ---- list of a policy-head CTA pair: the head tasks of the row tiles it serves, in the common time order
+    const int hp = id - n_pairs;
+    Task* hout = head_tasks + static_cast<size_t>(hp) * s.max_tasks;
+    int nh = 0;
+    for (int u = 0; u < u_end; ++u) {
+      for (int c = 0; c < s.k; ++c) {
+        const int v = u - c * s.skew;
+        if (v < 0 || v >= total) continue;
+        const int tt = v / s.nsteps, i = v % s.nsteps;
+        if (i != (s.bwd ? 0 : s.nsteps - 1)) continue;
+        const int t = s.bwd ? s.T - 1 - tt : tt;
+        for (int gi = 0; gi < s.groups; ++gi) {
+          const int rt = gi * s.k + c;
+          if (rt >= s.R || rt % n_hpairs != hp) continue;
+          Task h;
+          if (s.bwd) {
+            // adjoint: the head opens the period (it needs the state adjoint completed by the previous sweep position)
+            h.a = make_int4(1, t, rt, tt == 0 ? -1 : flag_index(s, tt - 1, s.nsteps - 1, rt));
+          } else {
+            h.a = make_int4(1, t, rt, flag_index(s, tt, s.nsteps - 1, rt));
+          }
+          h.b = make_int4(16 * s.C[s.nsteps - 1], flag_index(s, tt, s.nsteps, rt), 0, 0);
+          hout[nh++] = h;
+        }
+      }
+    }
+    hout[nh] = end;
+    return;
+  }
+  const int pair = id;
+  const int gi = pair / s.g, q = pair % s.g;
+  Task* out = tasks + static_cast<size_t>(pair) * s.max_tasks;
+  int n = 0;
+  const int head_count = 2 * kHeadWarps;  // every warp of the head CTA pair arrives once
+  for (int u = 0; u < u_end && gi < s.groups; ++u) {
+    for (int c = 0; c < s.k; ++c) {
+      const int v = u - c * s.skew;
+      const int rt = gi * s.k + c;
+      if (v < 0 || v >= total || rt >= s.R) continue;
+      const int tt = v / s.nsteps, i = v % s.nsteps;
+      const int t = s.bwd ? s.T - 1 - tt : tt;
+      for (int cc = 0; cc < s.C[i]; ++cc) {
+        if (tile_owner(s, c, i, cc, tt) != q) continue;
+        Task k;
+        k.a = make_int4(1 | (s.layer[i] << 8) | (s.epi[i] << 16), t, rt, cc * s.bn[i]);
+        int wf, wc;
+        if (i > 0) {
+          wf = flag_index(s, tt, i - 1, rt);
+          wc = 16 * s.C[i - 1];
+        } else if (s.bwd) {
+          wf = flag_index(s, tt, s.nsteps, rt);
+          wc = head_count;
+        } else {
+          wf = tt == 0 ? -1 : flag_index(s, tt - 1, s.nsteps, rt);
+          wc = head_count;
+        }
+        k.b = make_int4(s.nkb[i], wf, wc, flag_index(s, tt, i, rt));
+        out[n++] = k;
+      }
+    }
+  }
+  out[n] = end;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pre-pass kernels: transposed copies the per-thread head reads coalesced
+// ------------------------------------------------------------------------------------------------------------
+// dTB[t][b][s] = demand of (b, s) in period t (column t + period_shift of the input), 0 for padding rows
+__global__ void __launch_bounds__(256) demand_tbs_kernel(const float* __restrict__ demands, int layout, int B, int Bp, int S, int T,
+                                                         int t_stride, int shift, int B_total, float* __restrict__ dTB) {
+  pdl_wait();
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (layout == HDPO_DEMAND_TSB) {
+    // per period: [S][B_total] -> [Bp][S]; block = 32 stores x 32 scenarios
+    const int nbs = (S + 31) / 32, nbb = Bp / 32;
+    const int sb = blockIdx.x % nbs, bb = (blockIdx.x / nbs) % nbb, t = blockIdx.x / (nbs * nbb);
+    const int s0 = sb * 32, b0 = bb * 32;
+    for (int r = ty; r < 32; r += 8) {
+      const int s = s0 + r, b = b0 + tx;
+      tile[r][tx] = (s < S && b < B) ? demands[(static_cast<size_t>(t + shift) * S + s) * B_total + b] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int b = b0 + r, s = s0 + tx;
+      if (s < S) dTB[(static_cast<size_t>(t) * Bp + b) * S + s] = tile[tx][r];
+    }
+    return;
+  }
+  // BST: per scenario [S][t_stride] -> column t of [T][.][S]; block = 32 stores x 32 periods of one scenario
+  const int nbs = (S + 31) / 32, nbt = (T + 31) / 32;
+  const int sb = blockIdx.x % nbs, tb = (blockIdx.x / nbs) % nbt, b = blockIdx.x / (nbs * nbt);
+  const int s0 = sb * 32, t0 = tb * 32;
+  for (int r = ty; r < 32; r += 8) {
+    const int s = s0 + r, t = t0 + tx;
+    tile[r][tx] = (b < B && s < S && t < T) ? demands[(static_cast<size_t>(b) * S + s) * t_stride + t + shift] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, s = s0 + tx;
+    if (t < T && s < S) dTB[(static_cast<size_t>(t) * Bp + b) * S + s] = tile[tx][r];
+  }
+}
+
+__global__ void __launch_bounds__(256) zero_ints_kernel(int* __restrict__ p, size_t n) {
+  pdl_wait();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0;
+}
+__global__ void __launch_bounds__(256) zero_floats_kernel(float* __restrict__ p, size_t n) {
+  pdl_wait();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+static unsigned long long* g_trace = nullptr;
+static int g_trace_cap = 0;
+void set_trace(unsigned long long* buf, int cap_per_role) {
+  g_trace = buf;
+  g_trace_cap = cap_per_role;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+bool enabled() {
+  static int v = -1;
+  if (v < 0) v = env_int("HDPO_WIDE_PERSIST", 1) != 0;
+  return v != 0;
+}
+bool eligible(const HdpoRolloutDesc* d) {
+  if (d->arch != HDPO_ARCH_VANILLA_WAREHOUSE || d->precision == HDPO_PREC_FP32) return false;
+  if (d->pb.W < 1 || d->pb.W > kMaxW || d->pb.E != 0) return false;
+  if (d->master.n_layers < 2 || d->master.n_layers > HDPO_MAX_LAYERS) return false;
+  if (d->T > 30000 || d->pb.S > 16 * kSPL || d->pb.L < 2 || d->pb.Lw < 2) return false;
+  const bool adj = d->pb.W > 1;
+  const int budget = kHeadBytes / 4 / kHeadWarps;  // floats of shared memory per head warp
+  if (head_warp_floats<false>(d->pb.S, d->pb.W, d->pb.L, d->pb.Lw, adj) > budget) return false;
+  if (head_warp_floats<true>(d->pb.S, d->pb.W, d->pb.L, d->pb.Lw, adj) > budget) return false;
+  return true;
+}
+
+static size_t a256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+static int tile_bn(int width) { return width % 128 == 0 ? 128 : 64; }
+
+// groups of `g` pairs, `k` row tiles (chains) per group
+static void choose_groups(Sched* s, int cmax) {
+  int g = cmax;
+  if (g > kMaxPairs) g = kMaxPairs;
+  if (g < 1) g = 1;
+  int groups = kMaxPairs / g;
+  if (groups > s->R) groups = s->R;
+  int k = (s->R + groups - 1) / groups;
+  groups = (s->R + k - 1) / k;
+  s->g = g;
+  s->k = k;
+  s->groups = groups;
+}
+
+// tile shapes of one direction: forward step l = layer l ([rows x wp[l]] x W_l^T -> wp[l+1] columns); adjoint step i =
+// dgrad of layer l = n-1-i ([rows x wp[l+1]] x WT_l^T -> wp[l] columns). Returns the list stride a pair needs.
+static void fill_sched(Sched* s, int T, int Bp, const int* wp, int n, int bwd) {
+  s->T = T;
+  s->nsteps = n;
+  s->R = Bp / kRowTile;
+  s->bwd = bwd;
+  int cmax = 1, csum = 0;
+  for (int i = 0; i < n; ++i) {
+    const int l = bwd ? n - 1 - i : i;
+    const int width = bwd ? wp[l] : wp[l + 1];
+    const bool narrow = bwd ? l == 0 : l + 1 == n;  // output layer / state adjoint: 64-column tiles
+    const int bn = narrow ? 64 : tile_bn(width);
+    s->C[i] = width / bn;
+    s->bn[i] = bn;
+    s->nkb[i] = (bwd ? wp[l + 1] : wp[l]) / kBK;
+    s->layer[i] = i;
+    s->epi[i] = bwd ? (l > 0 ? EPI_DGRAD_HIDDEN : EPI_DGRAD_GX) : (l + 1 < n ? EPI_FWD_HIDDEN : EPI_FWD_OUT);
+    if (s->C[i] > cmax) cmax = s->C[i];
+    csum += s->C[i];
+  }
+  choose_groups(s, cmax);
+  s->skew = env_int("HDPO_WP_SKEW", n / 2);
+  if (s->k < 2) s->skew = 0;
+  s->max_tasks = T * s->k * csum + 8;  // even if one pair of a group owned every tile of its chains
+  const int head_list = T * ((s->R + kMinHeadPairs - 1) / kMinHeadPairs) + 8;  // list of a policy-head CTA pair
+  if (head_list > s->max_tasks) s->max_tasks = head_list;
+}
+
+struct Extra {
+  size_t o_dTB, o_flags, o_tasks, o_htasks, total;
+  size_t n_flags;
+  int max_tasks;
+};
+static Extra plan_extra(int T, int S, int Bp, const int* wp, int n) {
+  Extra e;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = o;
+    o += a256(bytes);
+    return at;
+  };
+  e.o_dTB = take(static_cast<size_t>(T) * S * Bp * sizeof(float));
+  const int R = Bp / kRowTile;
+  e.n_flags = static_cast<size_t>(T) * (n + 1) * R;
+  e.o_flags = take(e.n_flags * sizeof(int));
+  Sched sf{}, sb{};
+  fill_sched(&sf, T, Bp, wp, n, 0);
+  fill_sched(&sb, T, Bp, wp, n, 1);
+  e.max_tasks = sf.max_tasks > sb.max_tasks ? sf.max_tasks : sb.max_tasks;
+  e.o_tasks = take(static_cast<size_t>(kMaxPairs) * e.max_tasks * sizeof(Task));
+  e.o_htasks = take(static_cast<size_t>(kMaxPairs) * e.max_tasks * sizeof(Task));
+  e.total = o + 256;
+  return e;
+}
+
+size_t extra_bytes(const HdpoRolloutDesc* d, int Bp, const int* wp, int n) {
+  return plan_extra(d->T, d->pb.S, Bp, wp, n).total;
+}
+
+static float* xf(const Ctx& c, size_t off) { return reinterpret_cast<float*>(static_cast<char*>(c.extra) + off); }
+
+static HeadP make_head(const Ctx& c, const Extra& e) {
+  HeadP h{};
+  h.B = c.B;
+  h.Bp = c.Bp;
+  h.S = c.S;
+  h.W = c.W;
+  h.L = c.L;
+  h.Lw = c.Lw;
+  h.ldx = c.wp[0];
+  h.ldy = c.wp[c.n];
+  h.nS = c.S * c.L;
+  h.T = c.T;
+  h.lost = c.lost;
+  h.profit = c.profit;
+  h.has_edge = c.has_edge;
+  h.transshipment = c.transshipment;
+  h.discrete = c.discrete;
+  h.save = c.save;
+  h.ignore_periods = c.ignore_periods;
+  h.B_total = c.B_total;
+  h.wub = c.wub;
+  h.adjacency = c.W > 1 ? c.adjacency : nullptr;
+  h.dTB = xf(c, e.o_dTB);
+  h.st = c.st;
+  h.X = c.X;
+  h.X_hi = c.X_hi;
+  h.X_lo = c.X_lo;
+  h.Y = c.act_hi[c.n - 1];
+  h.gX = c.gX;
+  h.gY_hi = c.gz_hi[c.n - 1];
+  h.gY_lo = c.gz_lo[c.n - 1];
+  h.cost_b = c.cost_b;
+  h.report_b = c.report_b;
+  h.reward_tb = c.reward_tb;
+  return h;
+}
+
+static int head_pairs_for(int n_pairs, int* out) {
+  int dev = 0, sms = 0;
+  HDPO_CUDA_OK(cudaGetDevice(&dev));
+  HDPO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int hp = (sms - 2 * n_pairs) / 2;  // one CTA per SM, all co-resident: the dependency flags need every CTA running
+  HDPO_REQUIRE(hp >= kMinHeadPairs, "persistent wide path: %d SMs leave no room for the policy-head CTAs next to %d GEMM pairs", sms,
+               n_pairs);
+  *out = hp;
+  return HDPO_OK;
+}
+
+template <bool BWD>
+static int launch_persist(const Params& p, int n_pairs, int n_hpairs, void* stream) {
+  auto k = persist_kernel<BWD>;
+  static bool configured = false;
+  if (!configured) {
+    HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * (n_pairs + n_hpairs));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemTotal;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  HDPO_CUDA_OK(cudaLaunchKernelEx(&cfg, k, p));
+  count_launch();
+  HDPO_LAUNCH_OK();
+  return HDPO_OK;
+}
+
+static int make_pair_maps(CUtensorMap* hi, CUtensorMap* lo, const float* phi, const float* plo, uint64_t rows, uint64_t cols,
+                          uint32_t box_rows) {
+  int rc = make_tensor_map(hi, phi, rows, cols, cols, box_rows);
+  if (rc) return rc;
+  return make_tensor_map(lo, plo ? plo : phi, rows, cols, cols, box_rows);
+}
+
+static int prepass(const Ctx& c, const Extra& e) {
+  auto dk = demand_tbs_kernel;
+  const int nbs = (c.S + 31) / 32;
+  const size_t blocks = c.demand_layout == HDPO_DEMAND_TSB ? static_cast<size_t>(nbs) * (c.Bp / 32) * c.T
+                                                           : static_cast<size_t>(nbs) * ((c.T + 31) / 32) * c.Bp;
+  HDPO_LAUNCH_PDL(dk, static_cast<unsigned>(blocks), 256, 0, c.stream, c.demands, c.demand_layout, c.B, c.Bp, c.S, c.T,
+                  c.t_stride, c.period_shift, c.B_total, xf(c, e.o_dTB));
+  HDPO_LAUNCH_OK();
+  return HDPO_OK;
+}
+
+static int zero_flags(const Ctx& c, const Extra& e) {
+  auto zk = zero_ints_kernel;
+  HDPO_LAUNCH_PDL(zk, static_cast<unsigned>(ceil_div64(static_cast<int64_t>(e.n_flags), 256)), 256, 0, c.stream,
+                  reinterpret_cast<int*>(static_cast<char*>(c.extra) + e.o_flags), e.n_flags);
+  HDPO_LAUNCH_OK();
+  return HDPO_OK;
+}
+
+static int build_lists(const Ctx& c, const Extra& e, const Sched& s, int n_pairs, int n_hpairs) {
+  auto bk = build_tasks_kernel;
+  HDPO_LAUNCH_PDL(bk, (n_pairs + n_hpairs + 31) / 32, 32, 0, c.stream, s,
+                  reinterpret_cast<Task*>(static_cast<char*>(c.extra) + e.o_tasks),
+                  reinterpret_cast<Task*>(static_cast<char*>(c.extra) + e.o_htasks), n_pairs, n_hpairs);
+  HDPO_LAUNCH_OK();
+  return HDPO_OK;
+}
+
+int forward(const Ctx& c) {
+  const Extra e = plan_extra(c.T, c.S, c.Bp, c.wp, c.n);
+  HDPO_REQUIRE(c.Bp % kRowTile == 0, "persistent wide path: rows must be padded to %d", kRowTile);
+  Params p{};
+  Sched s{};
+  fill_sched(&s, c.T, c.Bp, c.wp, c.n, 0);
+  s.max_tasks = e.max_tasks;
+  const uint64_t tslots = c.save ? static_cast<uint64_t>(c.T) : 1;
+  for (int l = 0; l < c.n; ++l) {
+    const bool hidden = l + 1 < c.n;
+    const int bn = s.bn[l];
+    LayerDesc& L = p.L[l];
+    const float* a_hi = l == 0 ? c.X_hi : c.act_hi[l - 1];
+    const float* a_lo = l == 0 ? c.X_lo : c.act_lo[l - 1];
+    int rc = make_pair_maps(&L.a_hi, &L.a_lo, a_hi, a_lo, tslots * c.Bp, c.wp[l], 128);
+    if (!rc) rc = make_pair_maps(&L.b_hi, &L.b_lo, c.W_hi[l], c.W_lo[l], c.wp[l + 1], c.wp[l], bn / 2);
+    if (!rc) rc = make_pair_maps(&L.c_hi, &L.c_lo, c.act_hi[l], hidden ? c.act_lo[l] : nullptr, tslots * c.Bp, c.wp[l + 1], 32);
+    if (rc) return rc;
+    L.x_hi = L.c_hi;
+    L.x_lo = L.c_lo;
+    L.bias = c.bias[l];
+    L.colsum = nullptr;
+    L.act = c.act[l];
+    L.bn = bn;
+    L.ldc = c.wp[l + 1];
+    L.a_tmul = L.c_tmul = L.x_tmul = c.save ? c.Bp : 0;
+  }
+  const int n_pairs = s.groups * s.g;
+  HDPO_REQUIRE(n_pairs <= kMaxPairs, "persistent wide path: %d pairs do not fit", n_pairs);
+  p.head = make_head(c, e);
+  p.tasks = reinterpret_cast<const Task*>(static_cast<char*>(c.extra) + e.o_tasks);
+  p.head_tasks = reinterpret_cast<const Task*>(static_cast<char*>(c.extra) + e.o_htasks);
+  p.flags = reinterpret_cast<int*>(static_cast<char*>(c.extra) + e.o_flags);
+  p.max_tasks = e.max_tasks;
+  p.n_pass = c.n_pass;
+  p.kseg = env_int("HDPO_WP_KSEG", 8);
+  if (p.kseg < 1) p.kseg = 1;
+  p.n_pairs = n_pairs;
+  p.trace = g_trace;
+  p.trace_cap = g_trace_cap;
+  int rc;
+  if ((rc = prepass(c, e))) return rc;
+  if ((rc = zero_flags(c, e))) return rc;
+  int n_hpairs = 0;
+  if ((rc = head_pairs_for(n_pairs, &n_hpairs))) return rc;
+  if ((rc = build_lists(c, e, s, n_pairs, n_hpairs))) return rc;
+  return launch_persist<false>(p, n_pairs, n_hpairs, c.stream);
+}
+
+int backward(const Ctx& c, float g_total, float g_report) {
+  const Extra e = plan_extra(c.T, c.S, c.Bp, c.wp, c.n);
+  HDPO_REQUIRE(c.save, "the adjoint sweep needs the tapes of a forward run with save_for_backward");
+  Params p{};
+  Sched s{};
+  fill_sched(&s, c.T, c.Bp, c.wp, c.n, 1);
+  s.max_tasks = e.max_tasks;
+  const uint64_t rows = static_cast<uint64_t>(c.T) * c.Bp;
+  for (int i = 0; i < c.n; ++i) {
+    const int l = c.n - 1 - i;  // step i = dgrad of layer l: [rows x wp[l+1]] x WT_l [wp[l] x wp[l+1]]^T -> [rows x wp[l]]
+    const int bn = s.bn[i];
+    LayerDesc& L = p.L[i];
+    int rc = make_pair_maps(&L.a_hi, &L.a_lo, c.gz_hi[l], c.gz_lo[l], rows, c.wp[l + 1], 128);
+    if (!rc) rc = make_pair_maps(&L.b_hi, &L.b_lo, c.WT_hi[l], c.WT_lo[l], c.wp[l], c.wp[l + 1], bn / 2);
+    if (!rc && l > 0) {
+      rc = make_pair_maps(&L.c_hi, &L.c_lo, c.gz_hi[l - 1], c.gz_lo[l - 1], rows, c.wp[l], 32);
+      if (!rc) rc = make_pair_maps(&L.x_hi, &L.x_lo, c.act_hi[l - 1], c.act_lo[l - 1], rows, c.wp[l], 32);
+    }
+    if (rc) return rc;
+    if (!rc && l == 0) {
+      rc = make_tensor_map(&L.c_hi, c.gX, c.Bp, c.wp[0], c.wp[0], 32);
+      L.c_lo = L.x_hi = L.x_lo = L.c_hi;
+    }
+    if (rc) return rc;
+    L.bias = nullptr;
+    L.colsum = l > 0 ? c.csum[l - 1] : nullptr;
+    L.act = l > 0 ? c.act[l - 1] : HDPO_ACT_NONE;
+    L.bn = bn;
+    L.ldc = c.wp[l];
+    L.a_tmul = c.Bp;
+    L.c_tmul = L.x_tmul = l > 0 ? c.Bp : 0;
+  }
+  const int n_pairs = s.groups * s.g;
+  HDPO_REQUIRE(n_pairs <= kMaxPairs, "persistent wide path: %d pairs do not fit", n_pairs);
+  p.head = make_head(c, e);
+  p.head.g_total = g_total;
+  p.head.g_report = g_report;
+  p.tasks = reinterpret_cast<const Task*>(static_cast<char*>(c.extra) + e.o_tasks);
+  p.head_tasks = reinterpret_cast<const Task*>(static_cast<char*>(c.extra) + e.o_htasks);
+  p.flags = reinterpret_cast<int*>(static_cast<char*>(c.extra) + e.o_flags);
+  p.max_tasks = e.max_tasks;
+  p.n_pass = c.n_pass;
+  p.kseg = env_int("HDPO_WP_KSEG", 8);
+  if (p.kseg < 1) p.kseg = 1;
+  p.n_pairs = n_pairs;
+  p.trace = g_trace;
+  p.trace_cap = g_trace_cap;
+  int rc;
+  {
+    auto zk = zero_floats_kernel;
+    const size_t n = static_cast<size_t>(c.wp[0]) * c.Bp;
+    HDPO_LAUNCH_PDL(zk, static_cast<unsigned>(ceil_div64(static_cast<int64_t>(n), 256)), 256, 0, c.stream, c.gX, n);
+    HDPO_LAUNCH_OK();
+  }
+  if ((rc = zero_flags(c, e))) return rc;
+  int n_hpairs = 0;
+  if ((rc = head_pairs_for(n_pairs, &n_hpairs))) return rc;
+  if ((rc = build_lists(c, e, s, n_pairs, n_hpairs))) return rc;
+  return launch_persist<true>(p, n_pairs, n_hpairs, c.stream);
+}
+
+}  // namespace wp
+}  // namespace hdpo
+#endif
