@@ -243,6 +243,9 @@ int hdpo_debug_set_trace(unsigned long long* buf, int64_t capacity);
 /* Per-role event trace of the persistent wide sweeps (tools/wp_trace.py): buf = 74 pairs * 4 roles * cap_per_role
  * records of {tag, globaltimer ns} (uint64 pairs); NULL disables it. */
 int hdpo_debug_set_wp_trace(unsigned long long* buf, int32_t cap_per_role);
+/* Opt-in persistent one-launch sweeps of the wide path (wide_persist.cu); default off (env HDPO_WIDE_PERSIST=1). The
+ * workspace size depends on it: query hdpo_rollout_workspace_bytes after switching. */
+int hdpo_debug_set_wide_persist(int32_t on);
 
 /* misc */
 const char* hdpo_last_error(void);

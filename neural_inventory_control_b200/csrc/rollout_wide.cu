@@ -1506,8 +1506,14 @@ extern "C" int hdpo_debug_set_wp_trace(unsigned long long* buf, int32_t cap_per_
   hdpo::wp::set_trace(buf, cap_per_role);
   return HDPO_OK;
 }
+// Switch the opt-in persistent one-launch sweeps of the wide path on / off (default: HDPO_WIDE_PERSIST, off).
+extern "C" int hdpo_debug_set_wide_persist(int32_t on) {
+  hdpo::wp::set_enabled(on);
+  return HDPO_OK;
+}
 #else
 extern "C" int hdpo_debug_set_wp_trace(unsigned long long*, int32_t) { return HDPO_E_INVALID; }
+extern "C" int hdpo_debug_set_wide_persist(int32_t) { return HDPO_E_INVALID; }
 #endif
 namespace hdpo {
 namespace wide {

@@ -54,9 +54,15 @@ constexpr int kThreads = 32 * kWarps;
 constexpr int kTmemCols = 512;
 constexpr int kMaxPairs = 64;      // GEMM CTA pairs; the other SMs run the policy-head CTAs
 constexpr int kMinHeadPairs = 4;
+constexpr int kServerWarps = 8;     // a head task = 256 rows = 8 warps x 32 rows: a head CTA pair hosts 3 independent servers
+constexpr int kServersPerPair = 2 * kWarps / kServerWarps;
 
 enum { EPI_FWD_HIDDEN = 0, EPI_FWD_OUT = 1, EPI_DGRAD_HIDDEN = 2, EPI_DGRAD_GX = 3 };
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 // ------------------------------------------------------------------------------------------------------------
 // static schedule (shared by the device-side list builder and the host-side sizing)
 // ------------------------------------------------------------------------------------------------------------
@@ -97,12 +103,11 @@ struct HeadP {
   int lost, profit, has_edge, transshipment, discrete, save, ignore_periods, B_total;
   float wub, g_total, g_report;
   const int32_t* adjacency;
-  const float* dTB;        // [T][Bp][S] demand of period t (period shift applied), scenario-major
-  HdpoStatics st;          // reference layouts
-  float *X, *X_hi, *X_lo;  // row-major state tapes
-  const float* Y;          // row-major output-layer tape (fp32)
-  float* gX;               // adjoint: [Bp][ldx] state adjoint
-  float *gY_hi, *gY_lo;    // adjoint: row-major tape of the output-layer adjoint (hi, lo)
+  const float *dT, *hT, *pT, *ltT, *whT;  // [T][S][Bp], [S][Bp], [S][Bp], [S*W][Bp], [3][W][Bp] (holding, lead, edge)
+  float *XT, *OUTT;                       // [slots][ldx][Bp], [slots][ldy][Bp] transposed state / policy output
+  float *X, *X_hi, *X_lo;                 // row-major state tapes (GEMM operands)
+  float *gXT, *gYT;                       // adjoint: [ldx][Bp] state adjoint, [ldy][Bp] scratch
+  float *gY_hi, *gY_lo;                   // adjoint: row-major tape of the output-layer adjoint (hi, lo)
   float *cost_b, *report_b, *reward_tb;
 };
 
@@ -241,20 +246,35 @@ struct Tracer {
     }
   }
 };
-// ---- policy head + simulator period: lane = store (two passes cover S <= 64), one scenario row at a time ----------
-// Same arithmetic (and reduction order) as warehouse_head_fwd/bwd_kernel of rollout_wide.cu, but register-resident:
-// every per-store quantity is private to its lane, warehouse quantities live on lane w and are broadcast by shuffles.
+// ---- policy head + simulator period: ONE THREAD PER SCENARIO (lane = row, 32 rows per warp task) -------------------
+// neural_networks.py:369-427 + environment.py:110-270 (forward) and their reverse (adjoint). Everything a thread
+// touches is a column of a TRANSPOSED array ([column][scenario]: state X^T, policy output Y^T, demand, cost
+// coefficients, lead times), so a warp access is one coalesced 128-byte line, there are no cross-lane reductions and
+// all 32 lanes do useful work (a lane = store mapping costs ~15x the instructions per scenario: shuffles, idle lanes).
+// Columns are staged global -> shared memory with cp.async in blocks of kSB stores, double-buffered, so no thread ever
+// waits on a global load in its dependent chain; results leave through coalesced column stores, and the row-major
+// tapes the GEMMs read (next state + its tf32 (hi, lo) split; adjoint: the output-layer adjoint) through a 32 x 33
+// shared-memory transpose tile. No local memory (parameters come from the constant bank, arrays are statically
+// indexed): with 227 KB of shared memory carved out there is no L1 behind it.
+constexpr int kSB = 2;  // stores per staged block
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// columns col0, col0 + stride, ... (ncols of them) of a [column][Bp] array, rows [row0, row0 + 32) -> dst[j * 32 + lane]
+__device__ __forceinline__ void stage_cols(float* dst, const float* src, int Bp, int row0, int col0, int stride, int ncols,
+                                           int lane) {
+  for (int c = lane; c < ncols * 8; c += 32) {
+    const int j = c >> 3, part = c & 7;
+    cp_async16(dst + j * 32 + part * 4, src + static_cast<size_t>(col0 + j * stride) * Bp + row0 + part * 4);
+  }
+}
+
 __device__ __forceinline__ void store_split(float* x, float* hi, float* lo, size_t at, float v) {
   if (x) x[at] = v;
   if (hi) {
@@ -264,212 +284,188 @@ __device__ __forceinline__ void store_split(float* x, float* hi, float* lo, size
   }
 }
 
-// The SM's L2 return path is kept full by the TMA operand stream of the GEMM pipeline and the L1 is carved down to
-// nothing (227 KB of shared memory), so EVERY global or local-memory load of a head warp costs ~1.4 us. Hence:
-//  * a scenario row's inputs (state row, policy output row, demand, cost coefficients, lead times; adjoint: the
-//    state-adjoint row) are copied global -> shared memory with cp.async, double-buffered: row r + 1 is in flight while
-//    row r is computed from shared memory; results leave through stores / fire-and-forget reductions only;
-//  * no local memory: the head parameters are read from the constant bank (everything is inlined into the kernel, which
-//    takes them as a __grid_constant__), no register arrays with dynamic indices, no spills;
-//  * code size matters too (the role loops of one CTA share a 32 KB instruction cache): the loops over warehouses and
-//    pipeline slots are ROLLED, only the two stores of a lane are unrolled.
-struct RowLayout {  // float offsets inside one staged row
-  int oX, oY, oD, oH, oP, oLT, oWH, oG, total;
+struct TileOut {  // row-major output of per-thread column streams through a 32 x 33 shared-memory transpose tile
+  float* tile;
+  float *d0, *d1, *d2;  // d0: fp32 (optional), d1 / d2: tf32 (hi, lo) split (optional); rows `ld` floats apart
+  int ld, lane, c;
+  __device__ __forceinline__ void flush() {
+    __syncwarp();
+    const int col = (c - 1) / 32 * 32 + lane;
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) store_split(d0, d1, d2, static_cast<size_t>(r) * ld + col, tile[r * 33 + lane]);
+    __syncwarp();
+  }
+  __device__ __forceinline__ void emit(float v) {
+    tile[lane * 33 + (c & 31)] = v;
+    ++c;
+    if ((c & 31) == 0) flush();
+  }
 };
+
+// shared memory of one head warp (floats): [ys: S columns][2 staged blocks][32 x 33 tile]
 template <bool BWD>
-__host__ __device__ inline RowLayout row_layout(int S, int W, int L, int Lw) {
-  RowLayout r;
-  const int nX = S * L + W * Lw, SW = S * W;
-  int o = 0;
-  r.oX = o;
-  o += BWD ? S + W : nX;  // adjoint: only the on-hand slot of every store / warehouse
-  r.oY = o;
-  o += SW + W;
-  r.oD = o;
-  o += S;
-  r.oH = o;
-  o += S;
-  r.oP = o;
-  o += S;
-  r.oLT = o;
-  o += SW;
-  r.oWH = o;
-  o += 3 * W;
-  r.oG = o;
-  o += BWD ? nX : 0;
-  r.total = (o + 3) & ~3;
-  return r;
+__host__ __device__ inline int block_cols(int W, int L) {  // columns of one staged block
+  return BWD ? kSB * (1 + 3 + 2 * W + L + W) : kSB * (L + 3 + 2 * W);
 }
-
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 template <bool BWD>
-__device__ __forceinline__ void head_stage(const HeadP& h, const RowLayout& rl, int t, int b, int lane, float* buf) {
-  if (b < h.B) {
-    const size_t xstride = static_cast<size_t>(h.Bp) * h.ldx, ystride = static_cast<size_t>(h.Bp) * h.ldy;
-    const int xs = (BWD || h.save) ? t : (t & 1);
-    const float* X = h.X + xs * xstride + static_cast<size_t>(b) * h.ldx;
-    const float* Y = h.Y + ((BWD || h.save) ? t : 0) * ystride + static_cast<size_t>(b) * h.ldy;
-    const int nX = h.nS + h.W * h.Lw, SW = h.S * h.W;
-    if (BWD) {
-      const float* G = h.gX + static_cast<size_t>(b) * h.ldx;
-      for (int e = lane; e < h.S; e += 32) cp_async4(buf + rl.oX + e, X + e * h.L);
-      if (lane < h.W) cp_async4(buf + rl.oX + h.S + lane, X + h.nS + lane * h.Lw);
-      for (int e = lane; e < nX; e += 32) cp_async4(buf + rl.oG + e, G + e);
-    } else {
-      for (int e = lane; e < nX; e += 32) cp_async4(buf + rl.oX + e, X + e);
-    }
-    for (int e = lane; e < SW + h.W; e += 32) cp_async4(buf + rl.oY + e, Y + e);
-    const float* dem = h.dTB + (static_cast<size_t>(t) * h.Bp + b) * h.S;
-    const float* hc = h.st.holding_costs + static_cast<size_t>(b) * h.S;
-    const float* pc = h.st.underage_costs + static_cast<size_t>(b) * h.S;
-    for (int e = lane; e < h.S; e += 32) {
-      cp_async4(buf + rl.oD + e, dem + e);
-      cp_async4(buf + rl.oH + e, hc + e);
-      cp_async4(buf + rl.oP + e, pc + e);
-    }
-    const float* ltrow = h.st.lead_times + static_cast<size_t>(b) * SW;
-    for (int e = lane; e < SW; e += 32) cp_async4(buf + rl.oLT + e, ltrow + e);
-    if (lane < h.W) {
-      const size_t bw = static_cast<size_t>(b) * h.W + lane;
-      cp_async4(buf + rl.oWH + lane, h.st.warehouse_holding_costs + bw);
-      cp_async4(buf + rl.oWH + h.W + lane, h.st.warehouse_lead_times + bw);
-      if (h.has_edge) cp_async4(buf + rl.oWH + 2 * h.W + lane, h.st.warehouse_edge_costs + bw);
-    }
-  }
-  cp_async_commit();
+__host__ __device__ inline int head_warp_floats(int S, int W, int L, int Lw) {
+  return 32 * (S + 4 * W + 2 * W * Lw) + 2 * 32 * block_cols<BWD>(W, L) + 32 * 33;
 }
 
-// Mapping: a HALF-warp per scenario row (two rows per warp at a time), lane hl = lane % 16 owns stores hl, hl + 16,
-// hl + 32, hl + 48 (S <= 64) and, for hl < W, warehouse hl. A single warp is latency-bound (dependent shuffles, LDS,
-// MUFU), so the per-row instruction count and the independent work per lane are what matter: 4 stores per lane give
-// the instruction-level parallelism, reductions are 4 shuffle steps inside the half-warp.
-constexpr int kSPL = 4;  // stores per lane
-
-__device__ __forceinline__ float half_sum(float v, unsigned mask) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
-  return v;
-}
-__device__ __forceinline__ float half_max(float v, unsigned mask) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o));
-  return v;
+// softmax statistics of warehouse w over its connected stores (+ the constant hold logit 1.0), from the staged
+// column block ys[s * 32 + lane]
+__device__ __forceinline__ void softmax_stats(const HeadP& h, const float* ys, const int* adj, int w, int lane, float& mx,
+                                              float& inv) {
+  float m = h.transshipment ? -INFINITY : 1.f;
+  for (int s = 0; s < h.S; ++s)
+    if (!adj || adj[w * h.S + s]) m = fmaxf(m, ys[s * 32 + lane]);
+  float sum = 0.f;
+  for (int s = 0; s < h.S; ++s)
+    if (!adj || adj[w * h.S + s]) sum += expf(ys[s * 32 + lane] - m);
+  if (!h.transshipment) sum += expf(1.f - m);
+  mx = m;
+  inv = 1.f / sum;
 }
 
-// softmax of warehouse w over its connected stores (+ the constant hold logit): shares p[i] of this lane's stores
-__device__ __forceinline__ void head_softmax(const HeadP& h, const RowLayout& rl, const float* buf, const int* adj, int w, int hl,
-                                             unsigned mask, float (&p)[kSPL]) {
-  float y[kSPL];
-  bool c[kSPL];
-  float mx = h.transshipment ? -INFINITY : 1.f;
-#pragma unroll
-  for (int i = 0; i < kSPL; ++i) {
-    const int s = hl + 16 * i;
-    c[i] = s < h.S && (!adj || adj[w * h.S + s] != 0);
-    y[i] = c[i] ? buf[rl.oY + s * h.W + w] : 0.f;
-    if (c[i]) mx = fmaxf(mx, y[i]);
-  }
-  mx = half_max(mx, mask);
-  float e[kSPL], sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < kSPL; ++i) {
-    e[i] = c[i] ? expf(y[i] - mx) : 0.f;
-    sum += e[i];
-  }
-  sum = half_sum(sum, mask);
-  if (!h.transshipment) sum += expf(1.f - mx);
-  const float inv = 1.f / sum;
-#pragma unroll
-  for (int i = 0; i < kSPL; ++i) p[i] = e[i] * inv;
-}
-
-// scr: per-row scratch in the warp's shared memory, [s * W + w]: values the later loops over (store, warehouse) need;
-// written and read by the owning lane only
-__device__ __forceinline__ void head_fwd_compute(const HeadP& h, const RowLayout& rl, int t, int b, int hl, unsigned mask,
-                                                 const float* buf, const int* adj, float* scr) {
-  const size_t xstride = static_cast<size_t>(h.Bp) * h.ldx;
-  const int xn = h.save ? t + 1 : ((t + 1) & 1);
-  float* __restrict__ Xn = h.X + xn * xstride + static_cast<size_t>(b) * h.ldx;
+__device__ __forceinline__ void head_fwd_rows(const HeadP& h, int t, int row0, int lane, float* wsm, const int* adj) {
+  const int b = row0 + lane;
+  const bool valid = b < h.B;
+  const int Bp = h.Bp, S = h.S, W = h.W, L = h.L, Lw = h.Lw;
+  const size_t Bps = static_cast<size_t>(Bp);
+  const int xs = h.save ? t : (t & 1), xn = h.save ? t + 1 : ((t + 1) & 1);
+  const float* XT = h.XT + static_cast<size_t>(xs) * h.ldx * Bps;
+  float* XTn = h.XT + static_cast<size_t>(xn) * h.ldx * Bps + b;
+  const float* YT = h.OUTT + static_cast<size_t>(h.save ? t : 0) * h.ldy * Bps;
+  const float* dT = h.dT + static_cast<size_t>(t) * S * Bps;
+  const size_t xstride = Bps * h.ldx;
+  float* ys = wsm;                            // [S] policy-output columns of one warehouse
+  float* whs = ys + 32 * S;                   // [W * Lw state | W outputs | 3 W statics] columns
+  float* blk = whs + 32 * (4 * W + 2 * W * Lw);
+  const int ncb = block_cols<false>(W, L);
+  TileOut out;
+  out.tile = blk + 2 * 32 * ncb;
+  out.ld = h.ldx;
+  out.lane = lane;
+  out.c = 0;
+  out.d0 = h.X + xn * xstride + static_cast<size_t>(row0) * h.ldx;
   const bool split = t + 1 < h.T;
   const size_t hs = h.save ? static_cast<size_t>(t + 1) : 0;
-  float* __restrict__ Xhi = split ? h.X_hi + hs * xstride + static_cast<size_t>(b) * h.ldx : nullptr;
-  float* __restrict__ Xlo = split ? h.X_lo + hs * xstride + static_cast<size_t>(b) * h.ldx : nullptr;
-  if (b >= h.B) {  // tile-padding rows stay exactly zero
-    for (int c = hl; c < h.ldx; c += 16) store_split(Xn, Xhi, Xlo, c, 0.f);
-    return;
-  }
-  // ---- masked softmax per warehouse x on-hand -> allocations (scr[s * W + w]); draw-down of warehouse w on lane w
-  float drawn = 0.f;
-#pragma unroll 1
-  for (int w = 0; w < h.W; ++w) {
-    const float W0 = buf[rl.oX + h.nS + w * h.Lw];
-    float p[kSPL];
-    head_softmax(h, rl, buf, adj, w, hl, mask, p);
-    float part = 0.f;
+  out.d1 = split ? h.X_hi + hs * xstride + static_cast<size_t>(row0) * h.ldx : nullptr;
+  out.d2 = split ? h.X_lo + hs * xstride + static_cast<size_t>(row0) * h.ldx : nullptr;
+
+  // block s0: [X: kSB * L][d][h][p: kSB each][y: kSB * W][lt: kSB * W]
+  auto stage_block = [&](int s0, float* dst) {
+    const int ns = S - s0 < kSB ? S - s0 : kSB;
+    stage_cols(dst, XT, Bp, row0, s0 * L, 1, ns * L, lane);
+    stage_cols(dst + 32 * kSB * L, dT, Bp, row0, s0, 1, ns, lane);
+    stage_cols(dst + 32 * kSB * (L + 1), h.hT, Bp, row0, s0, 1, ns, lane);
+    stage_cols(dst + 32 * kSB * (L + 2), h.pT, Bp, row0, s0, 1, ns, lane);
+    stage_cols(dst + 32 * kSB * (L + 3), YT, Bp, row0, s0 * W, 1, ns * W, lane);
+    stage_cols(dst + 32 * kSB * (L + 3 + W), h.ltT, Bp, row0, s0 * W, 1, ns * W, lane);
+    cp_async_commit();
+  };
+  // ---- warehouse columns, then per warehouse the policy-output columns of its stores -> softmax statistics
+  stage_cols(whs, XT, Bp, row0, h.nS, 1, W * Lw, lane);
+  stage_cols(whs + 32 * W * Lw, YT, Bp, row0, S * W, 1, W, lane);
+  stage_cols(whs + 32 * (W * Lw + W), h.whT, Bp, row0, 0, 1, 3 * W, lane);
+  float mx[kMaxW], inv[kMaxW], W0[kMaxW], drawn[kMaxW];
 #pragma unroll
-    for (int i = 0; i < kSPL; ++i) {
-      const int s = hl + 16 * i;
-      float a = p[i] * W0;
-      if (h.discrete) a = rintf(a);
-      part += a;
-      if (s < h.S) scr[s * h.W + w] = a;
+  for (int w = 0; w < kMaxW; ++w) {
+    mx[w] = inv[w] = W0[w] = drawn[w] = 0.f;
+    if (w < W) {
+      stage_cols(ys, YT, Bp, row0, w, W, S, lane);
+      cp_async_commit();
+      if (w + 1 == W) stage_block(0, blk);  // the first store block travels while the statistics are computed
+      if (w + 1 == W) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      __syncwarp();
+      softmax_stats(h, ys, adj, w, lane, mx[w], inv[w]);
+      W0[w] = whs[(w * Lw) * 32 + lane];
+      __syncwarp();
     }
-    part = half_sum(part, mask);
-    if (hl == w) drawn = part;
   }
-  // ---- stores: cost, lost sales / backlog, pipeline shift, arrivals
+  // ---- stores, kSB at a time
   float cost = 0.f;
+  const int n_blocks = (S + kSB - 1) / kSB;
+#pragma unroll 1
+  for (int ib = 0; ib < n_blocks; ++ib) {
+    const float* cur = blk + (ib & 1) * 32 * ncb;
+    if (ib + 1 < n_blocks) {
+      stage_block((ib + 1) * kSB, blk + ((ib + 1) & 1) * 32 * ncb);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
 #pragma unroll
-  for (int i = 0; i < kSPL; ++i) {
-    const int s = hl + 16 * i;
-    if (s < h.S) {
-      const float* xs = buf + rl.oX + s * h.L;
-      const float on_hand = xs[0], d = buf[rl.oD + s], hh = buf[rl.oH + s], pp = buf[rl.oP + s];
-      const float raw = on_hand - d;
-      cost += h.profit ? (-pp * fminf(on_hand, d) + hh * relu0(raw)) : (pp * relu0(-raw) + hh * relu0(raw));
-      const float post = h.lost ? relu0(raw) : raw;
-#pragma unroll 1
-      for (int k = 0; k < h.L; ++k) {
-        const float nx = k < h.L - 1 ? xs[k + 1] : 0.f;
-        float v = k == 0 ? post + nx : nx;
-#pragma unroll 1
-        for (int w = 0; w < h.W; ++w) {
-          const float al = scr[s * h.W + w];
-          if (al != 0.f && static_cast<int>(buf[rl.oLT + s * h.W + w]) - 1 == k) v += al;
+    for (int j = 0; j < kSB; ++j) {
+      const int s = ib * kSB + j;
+      if (s < S) {
+        const float* bx = cur + (j * L) * 32 + lane;
+        const float on_hand = bx[0];
+        const float d = cur[(kSB * L + j) * 32 + lane], hh = cur[(kSB * (L + 1) + j) * 32 + lane],
+                    pp = cur[(kSB * (L + 2) + j) * 32 + lane];
+        const float raw = on_hand - d;
+        cost += h.profit ? (-pp * fminf(on_hand, d) + hh * relu0(raw)) : (pp * relu0(-raw) + hh * relu0(raw));
+        const float post = h.lost ? relu0(raw) : raw;
+        float al[kMaxW];
+        int slot[kMaxW];
+#pragma unroll
+        for (int w = 0; w < kMaxW; ++w) {
+          al[w] = 0.f;
+          slot[w] = -1;
+          if (w < W && (!adj || adj[w * S + s])) {
+            float a = expf(cur[(kSB * (L + 3) + j * W + w) * 32 + lane] - mx[w]) * inv[w] * W0[w];
+            if (h.discrete) a = rintf(a);
+            drawn[w] += a;
+            al[w] = a;
+            if (a != 0.f) slot[w] = static_cast<int>(cur[(kSB * (L + 3 + W) + j * W + w) * 32 + lane]) - 1;
+          }
         }
-        store_split(Xn, Xhi, Xlo, s * h.L + k, v);
+#pragma unroll 1
+        for (int k = 0; k < L; ++k) {
+          const float nx = k < L - 1 ? bx[(k + 1) * 32] : 0.f;
+          float v = k == 0 ? post + nx : nx;
+#pragma unroll
+          for (int w = 0; w < kMaxW; ++w)
+            if (slot[w] == k) v += al[w];
+          v = valid ? v : 0.f;
+          __stcg(XTn + static_cast<size_t>(s * L + k) * Bps, v);
+          out.emit(v);
+        }
+      }
+    }
+    __syncwarp();  // every lane is done with `cur` before the block after next is staged into it
+  }
+  // ---- warehouses
+#pragma unroll
+  for (int w = 0; w < kMaxW; ++w) {
+    if (w < W) {
+      const float* xw = whs + (w * Lw) * 32 + lane;
+      const float raw = W0[w] - drawn[w];
+      float aw = sigmoid_f(whs[(W * Lw + w) * 32 + lane]) * h.wub;
+      if (h.discrete) aw = rintf(aw);
+      const float* st = whs + (W * Lw + W) * 32 + lane;  // [holding | lead | edge][W]
+      float cw = st[w * 32] * relu0(raw);
+      if (h.has_edge) cw += st[(2 * W + w) * 32] * aw;
+      cost += cw;
+      const int slotw = aw != 0.f ? static_cast<int>(st[(W + w) * 32]) - 1 : -1;
+#pragma unroll 1
+      for (int k = 0; k < Lw; ++k) {
+        const float nx = k < Lw - 1 ? xw[(k + 1) * 32] : 0.f;
+        float v = k == 0 ? raw + nx : nx;
+        if (slotw == k) v += aw;
+        v = valid ? v : 0.f;
+        __stcg(XTn + static_cast<size_t>(h.nS + w * Lw + k) * Bps, v);
+        out.emit(v);
       }
     }
   }
-  // ---- warehouses (lane w of the half-warp)
-  if (hl < h.W) {
-    const float* xw = buf + rl.oX + h.nS + hl * h.Lw;
-    const float raw = xw[0] - drawn;
-    float aw = sigmoid_f(buf[rl.oY + h.S * h.W + hl]) * h.wub;
-    if (h.discrete) aw = rintf(aw);
-    float cw = buf[rl.oWH + hl] * relu0(raw);
-    if (h.has_edge) cw += buf[rl.oWH + 2 * h.W + hl] * aw;
-    cost += cw;
-    const int slot = aw != 0.f ? static_cast<int>(buf[rl.oWH + h.W + hl]) - 1 : -1;
-#pragma unroll 1
-    for (int k = 0; k < h.Lw; ++k) {
-      const float nx = k < h.Lw - 1 ? xw[k + 1] : 0.f;
-      float v = k == 0 ? raw + nx : nx;
-      if (slot == k) v += aw;
-      store_split(Xn, Xhi, Xlo, h.nS + hl * h.Lw + k, v);
-    }
+  for (int c = h.nS + W * Lw; c < h.ldx; ++c) {
+    __stcg(XTn + static_cast<size_t>(c) * Bps, 0.f);
+    out.emit(0.f);
   }
-  for (int c = h.nS + h.W * h.Lw + hl; c < h.ldx; c += 16) store_split(Xn, Xhi, Xlo, c, 0.f);
-  cost = half_sum(cost, mask);
-  if (hl == 0) {
+  if (valid) {
     // one addition per (scenario, period), periods ordered by the dependency chain: deterministic; RED = no round trip
     atomicAdd(h.cost_b + b, cost);
     if (h.report_b && t >= h.ignore_periods) atomicAdd(h.report_b + b, cost);
@@ -477,163 +473,195 @@ __device__ __forceinline__ void head_fwd_compute(const HeadP& h, const RowLayout
   }
 }
 
-// Adjoint of head + period for scenario row b. gX row: adjoint wrt X_{t+1} on entry, direct part of the adjoint wrt X_t
-// on exit (the first-layer dgrad tiles add the rest); gy goes to the row-major (hi, lo) tape of the output layer.
-// scr: [2][S * W] floats (softmax shares, allocation adjoints).
-__device__ __forceinline__ void head_bwd_compute(const HeadP& h, const RowLayout& rl, int t, int b, int hl, unsigned mask,
-                                                 const float* buf, const int* adj, float* scr) {
-  const size_t ystride = static_cast<size_t>(h.Bp) * h.ldy;
-  float* __restrict__ G = h.gX + static_cast<size_t>(b) * h.ldx;
-  float* __restrict__ GYh = h.gY_hi + static_cast<size_t>(t) * ystride + static_cast<size_t>(b) * h.ldy;
-  float* __restrict__ GYl = h.gY_lo + static_cast<size_t>(t) * ystride + static_cast<size_t>(b) * h.ldy;
-  if (b >= h.B) {
-    for (int c = hl; c < h.ldy; c += 16) store_split(nullptr, GYh, GYl, c, 0.f);
-    return;
-  }
+// Adjoint of head + period. gX^T holds the adjoint wrt X_{t+1} on entry and the direct part of the adjoint wrt X_t on
+// exit (the first-layer dgrad tiles add the rest); gy goes to the row-major (hi, lo) tape of the output layer.
+__device__ __forceinline__ void head_bwd_rows(const HeadP& h, int t, int row0, int lane, float* wsm, const int* adj) {
+  const int b = row0 + lane;
+  const bool valid = b < h.B;
+  const int Bp = h.Bp, S = h.S, W = h.W, L = h.L, Lw = h.Lw;
+  const size_t Bps = static_cast<size_t>(Bp);
+  const float* XT = h.XT + static_cast<size_t>(t) * h.ldx * Bps;
+  const float* YT = h.OUTT + static_cast<size_t>(t) * h.ldy * Bps;
+  const float* dT = h.dT + static_cast<size_t>(t) * S * Bps;
+  float* G = h.gXT + b;
+  float* GY = h.gYT + b;
   const float rb = h.g_total + (t >= h.ignore_periods ? h.g_report : 0.f);
-  const int SW = h.S * h.W;
-  const int src0 = (mask & 1u) ? 0 : 16;  // first lane of this half-warp (shuffle sources)
-  float* share = scr;        // [s * W + w]
-  float* galloc = scr + SW;  // [s * W + w]
-  const float* g = buf + rl.oG;  // adjoint wrt X_{t+1}, row layout of X
-  // ---- pass 1 over the warehouses: softmax shares + draw-down
-  float drawn = 0.f;
-#pragma unroll 1
-  for (int w = 0; w < h.W; ++w) {
-    const float W0 = buf[rl.oX + h.S + w];
-    float p[kSPL];
-    head_softmax(h, rl, buf, adj, w, hl, mask, p);
-    float part = 0.f;
-#pragma unroll
-    for (int i = 0; i < kSPL; ++i) {
-      const int s = hl + 16 * i;
-      part += p[i] * W0;
-      if (s < h.S) share[s * h.W + w] = p[i];
-    }
-    part = half_sum(part, mask);
-    if (hl == w) drawn = part;
-  }
-  // ---- warehouses (lane w): g_raw_w feeds the store-allocation adjoints
-  float g_raw_w = 0.f, gyw = 0.f;
-  if (hl < h.W) {
-    const float* gw = g + h.nS + hl * h.Lw;
-    float* gwo = G + h.nS + hl * h.Lw;
-    const float raw = buf[rl.oX + h.S + hl] - drawn;
-    const float sg = sigmoid_f(buf[rl.oY + SW + hl]);
-    const float aw = sg * h.wub;
-    const int slot = aw != 0.f ? static_cast<int>(buf[rl.oWH + h.W + hl]) - 1 : -1;
-    float gaw = (slot >= 0 && slot < h.Lw) ? gw[slot] : 0.f;
-    if (h.has_edge) gaw += rb * buf[rl.oWH + 2 * h.W + hl];
-    const float gn0 = gw[0];
-    g_raw_w = rb * buf[rl.oWH + hl] * ge0(raw) + gn0;
-#pragma unroll 1
-    for (int k = 1; k < h.Lw; ++k) gwo[k] = gw[k - 1];  // new gw[k] = old gw[k - 1]; gwo[0] is written below
-    gyw = gaw * h.wub * sg * (1.f - sg);
-  }
-  // ---- stores: dynamics adjoint
-#pragma unroll
-  for (int i = 0; i < kSPL; ++i) {
-    const int s = hl + 16 * i;
-    if (s < h.S) {
-      const float* gs = g + s * h.L;
-      float* gso = G + s * h.L;
-      const float on_hand = buf[rl.oX + s], d = buf[rl.oD + s], hh = buf[rl.oH + s], pp = buf[rl.oP + s];
-      const float raw = on_hand - d;
-      const float gn0 = gs[0];
-      float g0;
-      if (h.profit) {
-        const float tie = on_hand < d ? 1.f : (on_hand == d ? 0.5f : 0.f);
-        g0 = rb * (-pp * tie + hh * ge0(raw));
-      } else {
-        g0 = rb * (-pp * le0(raw) + hh * ge0(raw));
-      }
-      g0 += h.lost ? gn0 * ge0(raw) : gn0;
-      gso[0] = g0;
-#pragma unroll 1
-      for (int k = 1; k < h.L; ++k) gso[k] = gs[k - 1];
-    }
-  }
-  // ---- allocation adjoints galloc[s, w] = g_new[slot] - g_raw_w, softmax backward per warehouse: alloc = p * W0
-  float gw0_add = 0.f;
-#pragma unroll 1
-  for (int w = 0; w < h.W; ++w) {
-    const float W0 = buf[rl.oX + h.S + w];
-    const float graw = __shfl_sync(mask, g_raw_w, src0 + w);
-    float pr[kSPL], q[kSPL], dot = 0.f;
-#pragma unroll
-    for (int i = 0; i < kSPL; ++i) {
-      const int s = hl + 16 * i;
-      pr[i] = q[i] = 0.f;
-      if (s < h.S) {
-        pr[i] = share[s * h.W + w];
-        float ga = 0.f;
-        if (pr[i] * W0 != 0.f) {
-          const int slot = static_cast<int>(buf[rl.oLT + s * h.W + w]) - 1;
-          if (slot >= 0 && slot < h.L) ga = g[s * h.L + slot];
-        }
-        q[i] = ga - graw;
-        dot += q[i] * pr[i];
-      }
-    }
-    dot = half_sum(dot, mask);  // sum_s g_alloc * p (= adjoint of W0, and with W0 the softmax inner product)
-    if (hl == w) gw0_add = dot;
-#pragma unroll
-    for (int i = 0; i < kSPL; ++i) {
-      const int s = hl + 16 * i;
-      if (s < h.S) store_split(nullptr, GYh, GYl, s * h.W + w, pr[i] * (q[i] * W0 - dot * W0));
-    }
-  }
-  (void)galloc;
-  if (hl < h.W) {
-    G[h.nS + hl * h.Lw] = g_raw_w + gw0_add;
-    store_split(nullptr, GYh, GYl, SW + hl, gyw);
-  }
-  for (int c = SW + h.W + hl; c < h.ldy; c += 16) store_split(nullptr, GYh, GYl, c, 0.f);
-}
+  const size_t ystride = Bps * h.ldy;
+  float* ys = wsm;
+  float* whs = ys + 32 * S;  // [W * Lw adjoint | W on-hand | W outputs | 3 W statics] columns
+  float* blk = whs + 32 * (4 * W + 2 * W * Lw);
+  const int ncb = block_cols<true>(W, L);
+  TileOut out;
+  out.tile = blk + 2 * 32 * ncb;
+  out.ld = h.ldy;
+  out.lane = lane;
+  out.c = 0;
+  out.d0 = nullptr;
+  out.d1 = h.gY_hi + static_cast<size_t>(t) * ystride + static_cast<size_t>(row0) * h.ldy;
+  out.d2 = h.gY_lo + static_cast<size_t>(t) * ystride + static_cast<size_t>(row0) * h.ldy;
+  const int SW = S * W;
 
-// floats of shared memory one head warp needs: adjacency + per-row scratch (2 rows) + 2 x 2 staged rows
-template <bool BWD>
-__host__ __device__ inline int head_warp_floats(int S, int W, int L, int Lw, bool adj) {
-  return (((adj ? S * W : 0) + 2 * S * W + 3) & ~3) + 4 * row_layout<BWD>(S, W, L, Lw).total;
-}
-
-// rows [row0, row0 + n), two at a time (one per half-warp): the inputs of the next row pair are in flight (cp.async)
-// while this pair is computed from shared memory
-template <bool BWD>
-__device__ __forceinline__ void head_block(const HeadP& h, int t, int row0, int n, int lane, float* wsm, Tracer* trc) {
-  const RowLayout rl = row_layout<BWD>(h.S, h.W, h.L, h.Lw);
-  const int SW = h.S * h.W;
-  const int hl = lane & 15, rp = lane >> 4;
-  const unsigned mask = rp ? 0xffff0000u : 0x0000ffffu;
-  const int* adj = h.adjacency ? reinterpret_cast<const int*>(wsm) : nullptr;  // staged once per kernel (see the head loop)
-  float* scr = wsm + (h.adjacency ? SW : 0) + rp * SW;
-  float* rows = wsm + (((h.adjacency ? SW : 0) + 2 * SW + 3) & ~3);
-  // buffer (pair parity, half) -> rows + (2 * parity + rp) * total
-  auto stage_pair = [&](int pr) {
-    float* dst = rows + (2 * (pr & 1)) * rl.total;
-    head_stage<BWD>(h, rl, t, row0 + 2 * pr, lane, dst);
-    head_stage<BWD>(h, rl, t, row0 + 2 * pr + 1, lane, dst + rl.total);
+  // pass-1 block s0: [x0: kSB][d][h][p: kSB each][y: kSB * W][lt: kSB * W][g: kSB * L]
+  auto stage_block1 = [&](int s0, float* dst) {
+    const int ns = S - s0 < kSB ? S - s0 : kSB;
+    stage_cols(dst, XT, Bp, row0, s0 * L, L, ns, lane);
+    stage_cols(dst + 32 * kSB, dT, Bp, row0, s0, 1, ns, lane);
+    stage_cols(dst + 32 * kSB * 2, h.hT, Bp, row0, s0, 1, ns, lane);
+    stage_cols(dst + 32 * kSB * 3, h.pT, Bp, row0, s0, 1, ns, lane);
+    stage_cols(dst + 32 * kSB * 4, YT, Bp, row0, s0 * W, 1, ns * W, lane);
+    stage_cols(dst + 32 * kSB * (4 + W), h.ltT, Bp, row0, s0 * W, 1, ns * W, lane);
+    stage_cols(dst + 32 * kSB * (4 + 2 * W), h.gXT, Bp, row0, s0 * L, 1, ns * L, lane);
+    cp_async_commit();
   };
-  const int n_pairs = n / 2;
-  stage_pair(0);
+  // pass-2 block s0: [y: kSB * W][galloc: kSB * W]
+  auto stage_block2 = [&](int s0, float* dst) {
+    const int ns = S - s0 < kSB ? S - s0 : kSB;
+    stage_cols(dst, YT, Bp, row0, s0 * W, 1, ns * W, lane);
+    stage_cols(dst + 32 * kSB * W, h.gYT, Bp, row0, s0 * W, 1, ns * W, lane);
+    cp_async_commit();
+  };
+  stage_cols(whs, h.gXT, Bp, row0, h.nS, 1, W * Lw, lane);
+  stage_cols(whs + 32 * W * Lw, XT, Bp, row0, h.nS, Lw, W, lane);
+  stage_cols(whs + 32 * (W * Lw + W), YT, Bp, row0, SW, 1, W, lane);
+  stage_cols(whs + 32 * (W * Lw + 2 * W), h.whT, Bp, row0, 0, 1, 3 * W, lane);
+  float mx[kMaxW], inv[kMaxW], W0[kMaxW], graw[kMaxW], dot[kMaxW], gyw[kMaxW];
+#pragma unroll
+  for (int w = 0; w < kMaxW; ++w) {
+    mx[w] = inv[w] = W0[w] = graw[w] = dot[w] = gyw[w] = 0.f;
+    if (w < W) {
+      stage_cols(ys, YT, Bp, row0, w, W, S, lane);
+      cp_async_commit();
+      if (w + 1 == W) stage_block1(0, blk);
+      if (w + 1 == W) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      __syncwarp();
+      softmax_stats(h, ys, adj, w, lane, mx[w], inv[w]);
+      W0[w] = whs[(W * Lw + w) * 32 + lane];
+      float drawn = 0.f;
+      for (int s = 0; s < S; ++s)
+        if (!adj || adj[w * S + s]) drawn += expf(ys[s * 32 + lane] - mx[w]) * inv[w] * W0[w];
+      // warehouse w: g_raw_w feeds the allocation adjoints of the stores
+      const float* st = whs + (W * Lw + 2 * W) * 32 + lane;  // [holding | lead | edge][W]
+      const float* gw = whs + (w * Lw) * 32 + lane;
+      float* gwo = G + static_cast<size_t>(h.nS + w * Lw) * Bps;
+      const float raw = W0[w] - drawn;
+      const float sg = sigmoid_f(whs[(W * Lw + W + w) * 32 + lane]);
+      const float aw = sg * h.wub;
+      const int slotw = aw != 0.f ? static_cast<int>(st[(W + w) * 32]) - 1 : -1;
+      float gaw = 0.f;
 #pragma unroll 1
-  for (int pr = 0; pr < n_pairs; ++pr) {
-    if (trc) trc->mark(0x500 + pr);
-    if (pr + 1 < n_pairs) {
-      stage_pair(pr + 1);
-      if (trc) trc->mark(0x510 + pr);
-      cp_async_wait<2>();
+      for (int k = 0; k < Lw; ++k) {
+        const float cur = gw[k * 32];
+        if (slotw == k) gaw = cur;
+        if (k + 1 < Lw) __stcg(gwo + static_cast<size_t>(k + 1) * Bps, valid ? cur : 0.f);  // new gw[k + 1] = old gw[k]
+      }
+      if (h.has_edge) gaw += rb * st[(2 * W + w) * 32];
+      graw[w] = rb * st[w * 32] * ge0(raw) + gw[0];
+      gyw[w] = gaw * h.wub * sg * (1.f - sg);
+      __syncwarp();
+    }
+  }
+  // ---- pass 1 over the stores: dynamics adjoint, allocation adjoints (parked in gY^T), softmax inner products
+  const int n_blocks = (S + kSB - 1) / kSB;
+#pragma unroll 1
+  for (int ib = 0; ib < n_blocks; ++ib) {
+    const float* cur = blk + (ib & 1) * 32 * ncb;
+    if (ib + 1 < n_blocks) {
+      stage_block1((ib + 1) * kSB, blk + ((ib + 1) & 1) * 32 * ncb);
+      cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncwarp();
-    if (trc) trc->mark(0x520 + pr);
-    const float* cur = rows + (2 * (pr & 1) + rp) * rl.total;
-    const int b = row0 + 2 * pr + rp;
-    if (BWD) head_bwd_compute(h, rl, t, b, hl, mask, cur, adj, scr);
-    else head_fwd_compute(h, rl, t, b, hl, mask, cur, adj, scr);
-    __syncwarp();  // every lane is done with this pair's buffers before the pair after next is staged into them
+#pragma unroll
+    for (int j = 0; j < kSB; ++j) {
+      const int s = ib * kSB + j;
+      if (s < S) {
+        const float on_hand = cur[j * 32 + lane];
+        const float d = cur[(kSB + j) * 32 + lane], hh = cur[(kSB * 2 + j) * 32 + lane], pp = cur[(kSB * 3 + j) * 32 + lane];
+        const float* gs = cur + (kSB * (4 + 2 * W) + j * L) * 32 + lane;
+        float* gso = G + static_cast<size_t>(s * L) * Bps;
+        const float raw = on_hand - d;
+        float share[kMaxW], ga[kMaxW];
+        int slot[kMaxW];
+#pragma unroll
+        for (int w = 0; w < kMaxW; ++w) {
+          share[w] = ga[w] = 0.f;
+          slot[w] = -1;
+          if (w < W && (!adj || adj[w * S + s])) {
+            share[w] = expf(cur[(kSB * 4 + j * W + w) * 32 + lane] - mx[w]) * inv[w];
+            if (share[w] * W0[w] != 0.f) slot[w] = static_cast<int>(cur[(kSB * (4 + W) + j * W + w) * 32 + lane]) - 1;
+          }
+        }
+        const float gn0 = gs[0];
+#pragma unroll 1
+        for (int k = 0; k < L; ++k) {
+          const float c = gs[k * 32];
+#pragma unroll
+          for (int w = 0; w < kMaxW; ++w)
+            if (slot[w] == k) ga[w] = c;
+          if (k + 1 < L) __stcg(gso + static_cast<size_t>(k + 1) * Bps, valid ? c : 0.f);  // new g[k + 1] = old g[k]
+        }
+        float g0;
+        if (h.profit) {
+          const float tie = on_hand < d ? 1.f : (on_hand == d ? 0.5f : 0.f);
+          g0 = rb * (-pp * tie + hh * ge0(raw));
+        } else {
+          g0 = rb * (-pp * le0(raw) + hh * ge0(raw));
+        }
+        g0 += h.lost ? gn0 * ge0(raw) : gn0;
+        __stcg(gso, valid ? g0 : 0.f);
+#pragma unroll
+        for (int w = 0; w < kMaxW; ++w) {
+          if (w < W) {
+            const float galloc = ga[w] - graw[w];
+            dot[w] += galloc * share[w];
+            __stcg(GY + static_cast<size_t>(s * W + w) * Bps, galloc);
+          }
+        }
+      }
+    }
+    __syncwarp();
   }
+#pragma unroll
+  for (int w = 0; w < kMaxW; ++w)
+    if (w < W) __stcg(G + static_cast<size_t>(h.nS + w * Lw) * Bps, valid ? graw[w] + dot[w] : 0.f);
+  // ---- pass 2: softmax backward -> gy in column order s * W + w, then the warehouse-order columns, then zero padding
+  __threadfence_block();  // this thread re-reads the allocation adjoints it parked in gY^T (through cp.async)
+  stage_block2(0, blk);
+#pragma unroll 1
+  for (int ib = 0; ib < n_blocks; ++ib) {
+    const float* cur = blk + (ib & 1) * 32 * ncb;
+    if (ib + 1 < n_blocks) {
+      stage_block2((ib + 1) * kSB, blk + ((ib + 1) & 1) * 32 * ncb);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kSB; ++j) {
+      const int s = ib * kSB + j;
+      if (s < S) {
+#pragma unroll
+        for (int w = 0; w < kMaxW; ++w) {
+          if (w < W) {
+            float v = 0.f;
+            if (!adj || adj[w * S + s]) {
+              const float pw = expf(cur[(j * W + w) * 32 + lane] - mx[w]) * inv[w];
+              v = pw * (cur[(kSB * W + j * W + w) * 32 + lane] * W0[w] - dot[w] * W0[w]);
+            }
+            out.emit(valid ? v : 0.f);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int w = 0; w < kMaxW; ++w)
+    if (w < W) out.emit(valid ? gyw[w] : 0.f);
+  for (int c = SW + W; c < h.ldy; ++c) out.emit(0.f);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -665,13 +693,18 @@ __global__ void __launch_bounds__(kThreads, 1) persist_kernel(const __grid_const
     // ===== policy head + simulator period CTAs: the 2 x 12 warps of a CTA pair share the rows of a head task =====
     // (own SMs: their L2 return path and instruction cache are not competing with a GEMM pipeline)
     const int hpair = pair - p.n_pairs;
-    const int hw_id = static_cast<int>(rank) * kHeadWarps + warp;
-    float* wsm = reinterpret_cast<float*>(smem) + warp * (kHeadBytes / 4 / kHeadWarps);
+    const int hw_id = static_cast<int>(rank) * kHeadWarps + warp;            // warp among the pair's 24
+    const int server = hpair * kServersPerPair + hw_id / kServerWarps;         // 8 warps = one head server
+    const int blk_id = hw_id % kServerWarps;                                   // its 32-row block of every task
+    int* adj_s = reinterpret_cast<int*>(smem);
+    const int adj_floats = p.head.adjacency ? ((p.head.S * p.head.W + 3) & ~3) : 0;
     if (p.head.adjacency) {  // adjacency masks: staged once
-      for (int e = lane; e < p.head.S * p.head.W; e += 32) reinterpret_cast<int*>(wsm)[e] = __ldg(p.head.adjacency + e);
-      __syncwarp();
+      for (int e = threadIdx.x; e < p.head.S * p.head.W; e += kThreads) adj_s[e] = __ldg(p.head.adjacency + e);
     }
-    const Task* tp = p.head_tasks + static_cast<size_t>(hpair) * p.max_tasks;
+    __syncthreads();
+    float* wsm = reinterpret_cast<float*>(smem) + adj_floats + warp * ((kHeadBytes / 4 - adj_floats) / kHeadWarps / 4 * 4);
+    const int* adj = p.head.adjacency ? adj_s : nullptr;
+    const Task* tp = p.head_tasks + static_cast<size_t>(server) * p.max_tasks;
     Tracer tr;
     tr.init(p, hpair, 3);
     const bool tracing = rank == 0 && warp == 0 && lane == 0;
@@ -681,11 +714,9 @@ __global__ void __launch_bounds__(kThreads, 1) persist_kernel(const __grid_const
       if (tracing) tr.mark(0x100);
       if (a.w >= 0) wait_flag(p.flags + a.w, b.x, 9);
       if (tracing) tr.mark(0x200);
-      // 4-row blocks of the 256-row tile, round-robin over the pair's head warps
-      for (int blk = hw_id; blk < kRowTile / 4; blk += 2 * kHeadWarps) {
-        const int row0 = a.z * kRowTile + blk * 4;
-        head_block<BWD>(p.head, a.y, row0, 4, lane, wsm, nullptr);
-      }
+      const int row0 = a.z * kRowTile + blk_id * 32;
+      if (BWD) head_bwd_rows(p.head, a.y, row0, lane, wsm, adj);
+      else head_fwd_rows(p.head, a.y, row0, lane, wsm, adj);
       if (tracing) tr.mark(0x300);
       __threadfence();
       __syncwarp();
@@ -874,14 +905,9 @@ __global__ void __launch_bounds__(kThreads, 1) persist_kernel(const __grid_const
         if (lane == 0) {
           tma_store_wait_read();
           fence_proxy_async_all();
-          if (epi == EPI_DGRAD_HIDDEN) {
-            mbar_expect_tx(&aux_bar[we], 2 * kBoxBytes);
-            tma_load_2d(stg, &L.x_hi, &aux_bar[we], n0 + 32 * j, L.x_tmul * t + trow);
-            tma_load_2d(stg + kBoxBytes, &L.x_lo, &aux_bar[we], n0 + 32 * j, L.x_tmul * t + trow);
-          } else {
-            mbar_expect_tx(&aux_bar[we], kBoxBytes);
-            tma_load_2d(stg, &L.x_hi, &aux_bar[we], n0 + 32 * j, trow);
-          }
+          mbar_expect_tx(&aux_bar[we], 2 * kBoxBytes);
+          tma_load_2d(stg, &L.x_hi, &aux_bar[we], n0 + 32 * j, L.x_tmul * t + trow);
+          tma_load_2d(stg + kBoxBytes, &L.x_lo, &aux_bar[we], n0 + 32 * j, L.x_tmul * t + trow);
         }
       };
       if (BWD && epi == EPI_DGRAD_HIDDEN) {
@@ -897,11 +923,6 @@ __global__ void __launch_bounds__(kThreads, 1) persist_kernel(const __grid_const
         bar_wait(&hi_full[hb], (hseg >> 1) & 1, 6);
         tc_fence_after();
         const uint32_t taddr = lane_base + 256 + hb * 128 + cbase;
-        if (BWD && epi == EPI_DGRAD_GX && kb0 == 0) {
-          // the state-adjoint rows are final only once this tile's operands exist (they depend on the period's head)
-          publish_pending();
-          issue_aux(0);
-        }
         if (wide) tmem_accumulate<64>(taddr, acc);
         else tmem_accumulate<32>(taddr, acc);
         tc_fence_before();
@@ -974,10 +995,12 @@ __global__ void __launch_bounds__(kThreads, 1) persist_kernel(const __grid_const
           }
         }
       } else if (!BWD && epi == EPI_FWD_OUT) {
-        // output layer (64-column tiles: 32 columns per warp): fp32 row-major tape by TMA
+        // output layer (64-column tiles: 32 columns per warp): fp32 row-major tape by TMA + transposed copy for the head
         const int grow = L.c_tmul * t + trow;
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
+        float* yt = p.head.OUTT + static_cast<size_t>(p.head.save ? t : 0) * p.head.ldy * p.head.Bp +
+                    static_cast<size_t>(n0) * p.head.Bp + trow + lane;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 b4 = *reinterpret_cast<const float4*>(bias_w + 4 * j4);
@@ -987,7 +1010,12 @@ __global__ void __launch_bounds__(kThreads, 1) persist_kernel(const __grid_const
           v.z = acc[4 * j4 + 2] + b4.z;
           v.w = acc[4 * j4 + 3] + b4.w;
           *reinterpret_cast<float4*>(stg + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = v;
+          __stcg(yt + static_cast<size_t>(4 * j4 + 0) * p.head.Bp, v.x);
+          __stcg(yt + static_cast<size_t>(4 * j4 + 1) * p.head.Bp, v.y);
+          __stcg(yt + static_cast<size_t>(4 * j4 + 2) * p.head.Bp, v.z);
+          __stcg(yt + static_cast<size_t>(4 * j4 + 3) * p.head.Bp, v.w);
         }
+        __threadfence();  // the transposed copy (plain stores) must be visible before the tile's flag is published
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -1070,31 +1098,17 @@ __global__ void __launch_bounds__(kThreads, 1) persist_kernel(const __grid_const
           }
         }
       } else if (BWD && epi == EPI_DGRAD_GX) {
-        // first-layer dgrad: add the product to the state adjoint (row-major [Bp][ldx]; box in, add, box out)
+        // first-layer dgrad: add the product to the (transposed) state adjoint, one coalesced line per column
+        float* g = p.head.gXT + static_cast<size_t>(n0) * p.head.Bp + trow + lane;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (j == 0 || wide) {
-            if (j == 1) issue_aux(1);
-            bar_wait(&aux_bar[we], aux_cnt & 1, 8);
-            ++aux_cnt;
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              float4* at = reinterpret_cast<float4*>(stg + lane * 128 + ((j4 ^ (lane & 7)) << 4));
-              float4 v = *at;
-              v.x += acc[32 * j + 4 * j4 + 0];
-              v.y += acc[32 * j + 4 * j4 + 1];
-              v.z += acc[32 * j + 4 * j4 + 2];
-              v.w += acc[32 * j + 4 * j4 + 3];
-              *at = v;
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&L.c_hi, stg, n0 + 32 * j, trow);
-              tma_store_commit();
-            }
+        for (int j = 0; j < 64; ++j) {
+          if (j < 32 || wide) {
+            float* at = g + static_cast<size_t>(j) * p.head.Bp;
+            __stcg(at, __ldcg(at) + acc[j]);
           }
         }
+        __threadfence();
+        __syncwarp();
       }
       // publish: every store of this warp is complete and visible before the tile's flag is incremented
       if (tracing) tr.mark(0x300 | ((a.x >> 8) & 0xff));  // tile staged, stores issued
@@ -1112,17 +1126,17 @@ __global__ void __launch_bounds__(kThreads, 1) persist_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------------------------
 // device-side list builder: thread = pair
 // ------------------------------------------------------------------------------------------------------------
-__global__ void build_tasks_kernel(Sched s, Task* tasks, Task* head_tasks, int n_pairs, int n_hpairs) {
+__global__ void build_tasks_kernel(Sched s, Task* tasks, Task* head_tasks, int n_pairs, int n_servers) {
   pdl_wait();
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= n_pairs + n_hpairs) return;
+  if (id >= n_pairs + n_servers) return;
   const int total = s.T * s.nsteps;
   const int u_end = total + (s.k - 1) * s.skew;
   Task end;
   end.a = make_int4(0, 0, 0, 0);
   end.b = make_int4(0, 0, 0, 0);
   if (id >= n_pairs) {
-    // ---- list of a policy-head CTA pair: the head tasks of the row tiles it serves, in the common time order
+    // ---- list of a head server (8 warps of a policy-head CTA pair): the head tasks of its row tiles, in time order
     const int hp = id - n_pairs;
     Task* hout = head_tasks + static_cast<size_t>(hp) * s.max_tasks;
     int nh = 0;
@@ -1135,7 +1149,7 @@ __global__ void build_tasks_kernel(Sched s, Task* tasks, Task* head_tasks, int n
         const int t = s.bwd ? s.T - 1 - tt : tt;
         for (int gi = 0; gi < s.groups; ++gi) {
           const int rt = gi * s.k + c;
-          if (rt >= s.R || rt % n_hpairs != hp) continue;
+          if (rt >= s.R || rt % n_servers != hp) continue;
           Task h;
           if (s.bwd) {
             // adjoint: the head opens the period (it needs the state adjoint completed by the previous sweep position)
@@ -1155,7 +1169,7 @@ __global__ void build_tasks_kernel(Sched s, Task* tasks, Task* head_tasks, int n
   const int gi = pair / s.g, q = pair % s.g;
   Task* out = tasks + static_cast<size_t>(pair) * s.max_tasks;
   int n = 0;
-  const int head_count = 2 * kHeadWarps;  // every warp of the head CTA pair arrives once
+  const int head_count = kServerWarps;  // every warp of the head server arrives once
   for (int u = 0; u < u_end && gi < s.groups; ++u) {
     for (int c = 0; c < s.k; ++c) {
       const int v = u - c * s.skew;
@@ -1189,40 +1203,53 @@ __global__ void build_tasks_kernel(Sched s, Task* tasks, Task* head_tasks, int n
 // ------------------------------------------------------------------------------------------------------------
 // pre-pass kernels: transposed copies the per-thread head reads coalesced
 // ------------------------------------------------------------------------------------------------------------
-// dTB[t][b][s] = demand of (b, s) in period t (column t + period_shift of the input), 0 for padding rows
-__global__ void __launch_bounds__(256) demand_tbs_kernel(const float* __restrict__ demands, int layout, int B, int Bp, int S, int T,
-                                                         int t_stride, int shift, int B_total, float* __restrict__ dTB) {
+// dst[c][b] = src[b][c] for b < rows_valid (else 0); src row-major with leading dimension ld_src, c < cols
+__global__ void __launch_bounds__(256) transpose_rows_kernel(const float* __restrict__ src, int rows_valid, int Bp, int cols,
+                                                             int ld_src, float* __restrict__ dst) {
   pdl_wait();
   __shared__ float tile[32][33];
+  const int b0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  if (layout == HDPO_DEMAND_TSB) {
-    // per period: [S][B_total] -> [Bp][S]; block = 32 stores x 32 scenarios
-    const int nbs = (S + 31) / 32, nbb = Bp / 32;
-    const int sb = blockIdx.x % nbs, bb = (blockIdx.x / nbs) % nbb, t = blockIdx.x / (nbs * nbb);
-    const int s0 = sb * 32, b0 = bb * 32;
-    for (int r = ty; r < 32; r += 8) {
-      const int s = s0 + r, b = b0 + tx;
-      tile[r][tx] = (s < S && b < B) ? demands[(static_cast<size_t>(t + shift) * S + s) * B_total + b] : 0.f;
-    }
-    __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-      const int b = b0 + r, s = s0 + tx;
-      if (s < S) dTB[(static_cast<size_t>(t) * Bp + b) * S + s] = tile[tx][r];
-    }
-    return;
-  }
-  // BST: per scenario [S][t_stride] -> column t of [T][.][S]; block = 32 stores x 32 periods of one scenario
-  const int nbs = (S + 31) / 32, nbt = (T + 31) / 32;
-  const int sb = blockIdx.x % nbs, tb = (blockIdx.x / nbs) % nbt, b = blockIdx.x / (nbs * nbt);
-  const int s0 = sb * 32, t0 = tb * 32;
   for (int r = ty; r < 32; r += 8) {
-    const int s = s0 + r, t = t0 + tx;
-    tile[r][tx] = (b < B && s < S && t < T) ? demands[(static_cast<size_t>(b) * S + s) * t_stride + t + shift] : 0.f;
+    const int b = b0 + r, c = c0 + tx;
+    tile[r][tx] = (src && b < rows_valid && c < cols) ? src[static_cast<size_t>(b) * ld_src + c] : 0.f;
   }
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
-    const int t = t0 + r, s = s0 + tx;
-    if (t < T && s < S) dTB[(static_cast<size_t>(t) * Bp + b) * S + s] = tile[tx][r];
+    const int c = c0 + r, b = b0 + tx;
+    if (c < cols && b < Bp) dst[static_cast<size_t>(c) * Bp + b] = tile[tx][r];
+  }
+}
+
+// dT[t][s][b] = demand of (b, s) in period t (column t + period_shift of the input), 0 for padding rows
+__global__ void __launch_bounds__(256) demand_t_kernel(const float* __restrict__ demands, int layout, int B, int Bp, int S, int T,
+                                                       int t_stride, int shift, int B_total, float* __restrict__ dT) {
+  pdl_wait();
+  if (layout == HDPO_DEMAND_TSB) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<size_t>(T) * S * Bp) return;
+    const int b = static_cast<int>(i % Bp);
+    const size_t ts = i / Bp;
+    const int s = static_cast<int>(ts % S), t = static_cast<int>(ts / S);
+    dT[i] = b < B ? demands[(static_cast<size_t>(t + shift) * S + s) * B_total + b] : 0.f;
+    return;
+  }
+  // BST: block = (32 scenarios) x (32 periods) of one store, transposed through shared memory
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int nbt = (T + 31) / 32;
+  const int bt = blockIdx.x % nbt;
+  const int rest = blockIdx.x / nbt;
+  const int s = rest % S, bb = rest / S;
+  const int b0 = bb * 32, t0 = bt * 32;
+  for (int r = ty; r < 32; r += 8) {
+    const int b = b0 + r, t = t0 + tx;
+    tile[r][tx] = (b < B && t < T) ? demands[(static_cast<size_t>(b) * S + s) * t_stride + t + shift] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, b = b0 + tx;
+    if (t < T && b < Bp) dT[(static_cast<size_t>(t) * S + s) * Bp + b] = tile[tx][r];
   }
 }
 
@@ -1247,24 +1274,23 @@ void set_trace(unsigned long long* buf, int cap_per_role) {
   g_trace_cap = cap_per_role;
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
+// Opt-in (HDPO_WIDE_PERSIST=1 or hdpo_debug_set_wide_persist): measured on B200 the one-launch sweeps are parity-green
+// but SLOWER than the per-period chain of rollout_wide.cu at 8192 scenarios (see DESIGN.md "persistent sweeps").
+static int g_enabled = -1;
 bool enabled() {
-  static int v = -1;
-  if (v < 0) v = env_int("HDPO_WIDE_PERSIST", 1) != 0;
-  return v != 0;
+  if (g_enabled < 0) g_enabled = env_int("HDPO_WIDE_PERSIST", 0) != 0;
+  return g_enabled != 0;
 }
+void set_enabled(int on) { g_enabled = on != 0; }
 bool eligible(const HdpoRolloutDesc* d) {
   if (d->arch != HDPO_ARCH_VANILLA_WAREHOUSE || d->precision == HDPO_PREC_FP32) return false;
   if (d->pb.W < 1 || d->pb.W > kMaxW || d->pb.E != 0) return false;
   if (d->master.n_layers < 2 || d->master.n_layers > HDPO_MAX_LAYERS) return false;
-  if (d->T > 30000 || d->pb.S > 16 * kSPL || d->pb.L < 2 || d->pb.Lw < 2) return false;
-  const bool adj = d->pb.W > 1;
-  const int budget = kHeadBytes / 4 / kHeadWarps;  // floats of shared memory per head warp
-  if (head_warp_floats<false>(d->pb.S, d->pb.W, d->pb.L, d->pb.Lw, adj) > budget) return false;
-  if (head_warp_floats<true>(d->pb.S, d->pb.W, d->pb.L, d->pb.Lw, adj) > budget) return false;
+  if (d->T > 30000 ||  d->pb.L < 2 || d->pb.Lw < 2) return false;
+  const int adj_floats = d->pb.W > 1 ? ((d->pb.S * d->pb.W + 3) & ~3) : 0;
+  const int budget = (kHeadBytes / 4 - adj_floats) / kHeadWarps / 4 * 4;  // floats of shared memory per head warp
+  if (head_warp_floats<false>(d->pb.S, d->pb.W, d->pb.L, d->pb.Lw) > budget) return false;
+  if (head_warp_floats<true>(d->pb.S, d->pb.W, d->pb.L, d->pb.Lw) > budget) return false;
   return true;
 }
 
@@ -1274,10 +1300,11 @@ static int tile_bn(int width) { return width % 128 == 0 ? 128 : 64; }
 
 // groups of `g` pairs, `k` row tiles (chains) per group
 static void choose_groups(Sched* s, int cmax) {
+  const int max_pairs = env_int("HDPO_WP_PAIRS", kMaxPairs) < kMaxPairs ? env_int("HDPO_WP_PAIRS", kMaxPairs) : kMaxPairs;
   int g = cmax;
-  if (g > kMaxPairs) g = kMaxPairs;
+  if (g > max_pairs) g = max_pairs;
   if (g < 1) g = 1;
-  int groups = kMaxPairs / g;
+  int groups = max_pairs / g;
   if (groups > s->R) groups = s->R;
   int k = (s->R + groups - 1) / groups;
   groups = (s->R + k - 1) / k;
@@ -1311,16 +1338,17 @@ static void fill_sched(Sched* s, int T, int Bp, const int* wp, int n, int bwd) {
   s->skew = env_int("HDPO_WP_SKEW", n / 2);
   if (s->k < 2) s->skew = 0;
   s->max_tasks = T * s->k * csum + 8;  // even if one pair of a group owned every tile of its chains
-  const int head_list = T * ((s->R + kMinHeadPairs - 1) / kMinHeadPairs) + 8;  // list of a policy-head CTA pair
+  const int min_servers = kMinHeadPairs * kServersPerPair;
+  const int head_list = T * ((s->R + min_servers - 1) / min_servers) + 8;  // list of a head server
   if (head_list > s->max_tasks) s->max_tasks = head_list;
 }
 
 struct Extra {
-  size_t o_dTB, o_flags, o_tasks, o_htasks, total;
+  size_t o_XT, o_OUTT, o_hT, o_pT, o_ltT, o_whT, o_dT, o_gXT, o_gYT, o_flags, o_tasks, o_htasks, total;
   size_t n_flags;
   int max_tasks;
 };
-static Extra plan_extra(int T, int S, int Bp, const int* wp, int n) {
+static Extra plan_extra(int T, int S, int W, int Bp, const int* wp, int n, int save) {
   Extra e;
   size_t o = 0;
   auto take = [&](size_t bytes) {
@@ -1328,7 +1356,17 @@ static Extra plan_extra(int T, int S, int Bp, const int* wp, int n) {
     o += a256(bytes);
     return at;
   };
-  e.o_dTB = take(static_cast<size_t>(T) * S * Bp * sizeof(float));
+  const size_t f = sizeof(float), B = static_cast<size_t>(Bp);
+  const int ldx = wp[0], ldy = wp[n];
+  e.o_XT = take(static_cast<size_t>(save ? T + 1 : 2) * ldx * B * f);
+  e.o_OUTT = take(static_cast<size_t>(save ? T : 1) * ldy * B * f);
+  e.o_hT = take(static_cast<size_t>(S) * B * f);
+  e.o_pT = take(static_cast<size_t>(S) * B * f);
+  e.o_ltT = take(static_cast<size_t>(S) * W * B * f);
+  e.o_whT = take(static_cast<size_t>(3) * W * B * f);
+  e.o_dT = take(static_cast<size_t>(T) * S * B * f);
+  e.o_gXT = take(save ? static_cast<size_t>(ldx) * B * f : 0);
+  e.o_gYT = take(save ? static_cast<size_t>(ldy) * B * f : 0);
   const int R = Bp / kRowTile;
   e.n_flags = static_cast<size_t>(T) * (n + 1) * R;
   e.o_flags = take(e.n_flags * sizeof(int));
@@ -1337,13 +1375,13 @@ static Extra plan_extra(int T, int S, int Bp, const int* wp, int n) {
   fill_sched(&sb, T, Bp, wp, n, 1);
   e.max_tasks = sf.max_tasks > sb.max_tasks ? sf.max_tasks : sb.max_tasks;
   e.o_tasks = take(static_cast<size_t>(kMaxPairs) * e.max_tasks * sizeof(Task));
-  e.o_htasks = take(static_cast<size_t>(kMaxPairs) * e.max_tasks * sizeof(Task));
+  e.o_htasks = take(static_cast<size_t>(74 * kServersPerPair) * e.max_tasks * sizeof(Task));
   e.total = o + 256;
   return e;
 }
 
 size_t extra_bytes(const HdpoRolloutDesc* d, int Bp, const int* wp, int n) {
-  return plan_extra(d->T, d->pb.S, Bp, wp, n).total;
+  return plan_extra(d->T, d->pb.S, d->pb.W, Bp, wp, n, d->save_for_backward).total;
 }
 
 static float* xf(const Ctx& c, size_t off) { return reinterpret_cast<float*>(static_cast<char*>(c.extra) + off); }
@@ -1370,13 +1408,18 @@ static HeadP make_head(const Ctx& c, const Extra& e) {
   h.B_total = c.B_total;
   h.wub = c.wub;
   h.adjacency = c.W > 1 ? c.adjacency : nullptr;
-  h.dTB = xf(c, e.o_dTB);
-  h.st = c.st;
+  h.dT = xf(c, e.o_dT);
+  h.hT = xf(c, e.o_hT);
+  h.pT = xf(c, e.o_pT);
+  h.ltT = xf(c, e.o_ltT);
+  h.whT = xf(c, e.o_whT);
+  h.XT = xf(c, e.o_XT);
+  h.OUTT = xf(c, e.o_OUTT);
   h.X = c.X;
   h.X_hi = c.X_hi;
   h.X_lo = c.X_lo;
-  h.Y = c.act_hi[c.n - 1];
-  h.gX = c.gX;
+  h.gXT = xf(c, e.o_gXT);
+  h.gYT = xf(c, e.o_gYT);
   h.gY_hi = c.gz_hi[c.n - 1];
   h.gY_lo = c.gz_lo[c.n - 1];
   h.cost_b = c.cost_b;
@@ -1430,12 +1473,25 @@ static int make_pair_maps(CUtensorMap* hi, CUtensorMap* lo, const float* phi, co
 }
 
 static int prepass(const Ctx& c, const Extra& e) {
-  auto dk = demand_tbs_kernel;
-  const int nbs = (c.S + 31) / 32;
-  const size_t blocks = c.demand_layout == HDPO_DEMAND_TSB ? static_cast<size_t>(nbs) * (c.Bp / 32) * c.T
-                                                           : static_cast<size_t>(nbs) * ((c.T + 31) / 32) * c.Bp;
-  HDPO_LAUNCH_PDL(dk, static_cast<unsigned>(blocks), 256, 0, c.stream, c.demands, c.demand_layout, c.B, c.Bp, c.S, c.T,
-                  c.t_stride, c.period_shift, c.B_total, xf(c, e.o_dTB));
+  void* stream = c.stream;
+  const int Bp = c.Bp;
+  auto tr = transpose_rows_kernel;
+  auto launch_t = [&](const float* src, int cols, int ld, float* dst) {
+    HDPO_LAUNCH_PDL(tr, dim3(Bp / 32, (cols + 31) / 32), 256, 0, stream, src, c.B, Bp, cols, ld, dst);
+  };
+  launch_t(c.st.holding_costs, c.S, c.S, xf(c, e.o_hT));
+  launch_t(c.st.underage_costs, c.S, c.S, xf(c, e.o_pT));
+  launch_t(c.st.lead_times, c.S * c.W, c.S * c.W, xf(c, e.o_ltT));
+  launch_t(c.st.warehouse_holding_costs, c.W, c.W, xf(c, e.o_whT));
+  launch_t(c.st.warehouse_lead_times, c.W, c.W, xf(c, e.o_whT) + static_cast<size_t>(c.W) * Bp);
+  launch_t(c.st.warehouse_edge_costs, c.W, c.W, xf(c, e.o_whT) + static_cast<size_t>(2) * c.W * Bp);
+  HDPO_LAUNCH_OK();
+  auto dk = demand_t_kernel;
+  unsigned blocks;
+  if (c.demand_layout == HDPO_DEMAND_TSB) blocks = static_cast<unsigned>(ceil_div64(static_cast<int64_t>(c.T) * c.S * Bp, 256));
+  else blocks = static_cast<unsigned>(static_cast<size_t>((c.T + 31) / 32) * c.S * (Bp / 32));
+  HDPO_LAUNCH_PDL(dk, blocks, 256, 0, stream, c.demands, c.demand_layout, c.B, Bp, c.S, c.T, c.t_stride, c.period_shift,
+                  c.B_total, xf(c, e.o_dT));
   HDPO_LAUNCH_OK();
   return HDPO_OK;
 }
@@ -1450,15 +1506,16 @@ static int zero_flags(const Ctx& c, const Extra& e) {
 
 static int build_lists(const Ctx& c, const Extra& e, const Sched& s, int n_pairs, int n_hpairs) {
   auto bk = build_tasks_kernel;
-  HDPO_LAUNCH_PDL(bk, (n_pairs + n_hpairs + 31) / 32, 32, 0, c.stream, s,
+  const int n_servers = n_hpairs * kServersPerPair;
+  HDPO_LAUNCH_PDL(bk, (n_pairs + n_servers + 31) / 32, 32, 0, c.stream, s,
                   reinterpret_cast<Task*>(static_cast<char*>(c.extra) + e.o_tasks),
-                  reinterpret_cast<Task*>(static_cast<char*>(c.extra) + e.o_htasks), n_pairs, n_hpairs);
+                  reinterpret_cast<Task*>(static_cast<char*>(c.extra) + e.o_htasks), n_pairs, n_servers);
   HDPO_LAUNCH_OK();
   return HDPO_OK;
 }
 
 int forward(const Ctx& c) {
-  const Extra e = plan_extra(c.T, c.S, c.Bp, c.wp, c.n);
+  const Extra e = plan_extra(c.T, c.S, c.W, c.Bp, c.wp, c.n, c.save);
   HDPO_REQUIRE(c.Bp % kRowTile == 0, "persistent wide path: rows must be padded to %d", kRowTile);
   Params p{};
   Sched s{};
@@ -1499,6 +1556,13 @@ int forward(const Ctx& c) {
   p.trace_cap = g_trace_cap;
   int rc;
   if ((rc = prepass(c, e))) return rc;
+  {
+    // transposed copy of the initial state (X[0] row-major was written by init_state_kernel)
+    auto tr = transpose_rows_kernel;
+    HDPO_LAUNCH_PDL(tr, dim3(c.Bp / 32, (c.wp[0] + 31) / 32), 256, 0, c.stream, static_cast<const float*>(c.X), c.Bp, c.Bp,
+                    c.wp[0], c.wp[0], xf(c, e.o_XT));
+    HDPO_LAUNCH_OK();
+  }
   if ((rc = zero_flags(c, e))) return rc;
   int n_hpairs = 0;
   if ((rc = head_pairs_for(n_pairs, &n_hpairs))) return rc;
@@ -1507,7 +1571,7 @@ int forward(const Ctx& c) {
 }
 
 int backward(const Ctx& c, float g_total, float g_report) {
-  const Extra e = plan_extra(c.T, c.S, c.Bp, c.wp, c.n);
+  const Extra e = plan_extra(c.T, c.S, c.W, c.Bp, c.wp, c.n, c.save);
   HDPO_REQUIRE(c.save, "the adjoint sweep needs the tapes of a forward run with save_for_backward");
   Params p{};
   Sched s{};
@@ -1525,11 +1589,7 @@ int backward(const Ctx& c, float g_total, float g_report) {
       if (!rc) rc = make_pair_maps(&L.x_hi, &L.x_lo, c.act_hi[l - 1], c.act_lo[l - 1], rows, c.wp[l], 32);
     }
     if (rc) return rc;
-    if (!rc && l == 0) {
-      rc = make_tensor_map(&L.c_hi, c.gX, c.Bp, c.wp[0], c.wp[0], 32);
-      L.c_lo = L.x_hi = L.x_lo = L.c_hi;
-    }
-    if (rc) return rc;
+    if (l == 0) L.c_hi = L.c_lo = L.x_hi = L.x_lo = L.a_hi;  // unused
     L.bias = nullptr;
     L.colsum = l > 0 ? c.csum[l - 1] : nullptr;
     L.act = l > 0 ? c.act[l - 1] : HDPO_ACT_NONE;
@@ -1557,7 +1617,7 @@ int backward(const Ctx& c, float g_total, float g_report) {
   {
     auto zk = zero_floats_kernel;
     const size_t n = static_cast<size_t>(c.wp[0]) * c.Bp;
-    HDPO_LAUNCH_PDL(zk, static_cast<unsigned>(ceil_div64(static_cast<int64_t>(n), 256)), 256, 0, c.stream, c.gX, n);
+    HDPO_LAUNCH_PDL(zk, static_cast<unsigned>(ceil_div64(static_cast<int64_t>(n), 256)), 256, 0, c.stream, xf(c, e.o_gXT), n);
     HDPO_LAUNCH_OK();
   }
   if ((rc = zero_flags(c, e))) return rc;

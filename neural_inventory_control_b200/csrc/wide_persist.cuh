@@ -49,7 +49,8 @@ struct Ctx {
   void* stream;
 };
 
-bool enabled();                                  // HDPO_WIDE_PERSIST != 0 (default on)
+bool enabled();                                  // HDPO_WIDE_PERSIST=1 (default off) or set_enabled()
+void set_enabled(int on);
 bool eligible(const HdpoRolloutDesc* d);         // shapes the persistent kernels handle
 size_t extra_bytes(const HdpoRolloutDesc* d, int Bp, const int* wp, int n);
 void set_trace(unsigned long long* buf, int cap_per_role);  // debug: [74 pairs][4 roles][cap] x {tag, ns}

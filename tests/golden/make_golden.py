@@ -116,8 +116,13 @@ def run_reference(s, obs_params, data, model, T, ignore, dtype):
     return out
 
 
+ONLY = None  # --only a,b: regenerate just these cases
+
+
 def rollout_case(name, setting, policy, B, T, T_total, ignore=30, setting_patch=None, nn_patch=None,
-                 torch_seed=0, state_dict_path=None, perturb=0.0):
+                 torch_seed=0, state_dict_path=None, perturb=0.0, compact=False):
+    if ONLY is not None and name not in ONLY:
+        return
     s, p, obs_params, scenario, data, model = build_case(setting, policy, B, T, T_total, setting_patch, nn_patch,
                                                          torch_seed)
     # materialise LazyLinear layers with one throw-away forward
@@ -151,7 +156,9 @@ def rollout_case(name, setting, policy, B, T, T_total, ignore=30, setting_patch=
     r64 = run_reference(s, obs_params, data, model64, T, ignore, torch.float64)
     for k, v in r64.items():
         if k.startswith("grad/") or k in ("reward_tb", "total", "report"):
-            arrays[f"ref64/{k}"] = v
+            # the 512-wide cases keep the float64 gradient as float32 (7 significant digits of the ground truth are
+            # plenty for a 1e-5 bar; halves the fixture)
+            arrays[f"ref64/{k}"] = v.astype(np.float32) if (compact and k.startswith("grad/")) else v
     pp = {k: v for k, v in scenario.problem_params.items()}
     meta = {
         "setting": setting, "policy": policy, "nn_name": p["nn_params"]["name"],
@@ -175,6 +182,8 @@ def rollout_case(name, setting, policy, B, T, T_total, ignore=30, setting_patch=
 
 def step_case(name, B, S, W, E, L, Lw, Le, lost, profit, edge_cost, seed):
     """One reference `Simulator.step` with random state / action / upstream adjoints (environment.py:110-169)."""
+    if ONLY is not None and f"step_{name}" not in ONLY:
+        return
     g = torch.Generator().manual_seed(seed)
     Wc = max(W, 1)
 
@@ -314,6 +323,11 @@ def main():
                  nn_patch=hidden([64, 64, 64]))
     rollout_case("many_warehouses_3x50", "many_warehouses_lost_demand", "vanilla_warehouse", B=16, T=50, T_total=50,
                  setting_patch=many3x50, nn_patch=hidden([64, 48]), perturb=0.02)
+    # the widths bench.py measures (BASELINE cfg 4 / cfg 5 with the shipped vanilla_warehouse.yml: three 512-wide layers)
+    rollout_case("one_warehouse_s50_w512", "one_warehouse_lost_demand", "vanilla_warehouse", B=16, T=50, T_total=50,
+                 setting_patch=stores50, compact=True)
+    rollout_case("many_warehouses_3x50_w512", "many_warehouses_lost_demand", "vanilla_warehouse", B=16, T=50,
+                 T_total=50, setting_patch=many3x50, compact=True)
 
     step_case("one_store_lost", B=16, S=1, W=0, E=0, L=4, Lw=0, Le=0, lost=True, profit=False, edge_cost=False, seed=1)
     step_case("one_store_backlog_profit", B=16, S=1, W=0, E=0, L=7, Lw=0, Le=0, lost=False, profit=True,
@@ -325,4 +339,6 @@ def main():
 
 
 if __name__ == "__main__":
+    if "--only" in sys.argv:
+        ONLY = set(sys.argv[sys.argv.index("--only") + 1].split(","))
     main()

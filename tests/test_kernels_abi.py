@@ -30,7 +30,9 @@ def backend(name):
 
 SMALL = ["one_store_lost", "one_store_lost_trained", "one_store_backlogged", "one_store_backlogged_lead20",
          "serial_system", "serial_system_perturbed"]
-WIDE = ["one_warehouse_s5", "one_warehouse_s50", "many_warehouses_2x10", "many_warehouses_3x50"]
+WIDE = ["one_warehouse_s5", "one_warehouse_s50", "many_warehouses_2x10", "many_warehouses_3x50",
+        # the widths bench.py measures: 153 -> 512^3 -> 51 and 309 -> 512^3 -> 153 (goldens of the unmodified reference)
+        "one_warehouse_s50_w512", "many_warehouses_3x50_w512"]
 
 
 def fused_cases():
@@ -235,9 +237,9 @@ def test_wide_rollout_costs_and_gradients_match_reference(name, precision):
     meta, g = G.load("rollout", name)
     out = D.rollout(be, meta, g["param"], g["data"], precision=precision)
     check_rollout_against_golden(out, meta, g, meta["T"], meta["ignore_periods"])
-    # the two 50-period goldens whose fp32 reference is itself 1e-3..1e-2 away from its float64 run are chaotic:
-    # any fp32-level perturbation (a different summation order is enough) lands within a few times that floor
-    _grad_check_vs_golden(out, g, floor_mult=3 if precision == "fp32" else 10)
+    # gradient against the float64 run of the reference: 1e-5, or 3x the fp32 reference's own distance to it where that
+    # is larger (50-period warehouse rollouts are chaotic) - the same bar for the fp32 and the 3xTF32 mode
+    _grad_check_vs_golden(out, g, floor_mult=3)
     names = {"store": "store_inventories", "wh": "warehouse_inventories"}
     for k, rk in names.items():
         rf = g["ref"][f"final/{rk}"]

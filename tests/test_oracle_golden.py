@@ -66,7 +66,9 @@ def test_rollout_fp64_matches_reference_fp64(name):
     assert abs(rep - ref["report"]) <= 1e-10 * abs(ref["report"])
     flat = O.flatten_grads(pol, grads)
     for k, v in flat.items():
-        assert G.rel_l2(v, ref[f"grad/{k}"]) < 1e-8, k
+        # the 512-wide fixtures store the float64 gradient rounded to float32 (half the file size): 2^-24 per element
+        tol = 1e-8 if ref[f"grad/{k}"].dtype == np.float64 else 1e-7
+        assert G.rel_l2(v, ref[f"grad/{k}"]) < tol, k
 
 
 @pytest.mark.parametrize("name", G.rollout_cases())
@@ -151,7 +153,8 @@ def test_torch_port_matches_reference_fp64(name):
     idxs = sorted({int(k.split(".")[2]) for k in g["param"] if k.endswith(".weight")})
     names = [f"net.master.{i}.{wb}" for i in idxs for wb in ("weight", "bias")]
     for n, gr in zip(names, grads):
-        assert G.rel_l2(gr.numpy(), ref[f"grad/{n}"]) < 1e-8, n
+        tol = 1e-8 if ref[f"grad/{n}"].dtype == np.float64 else 1e-7  # 512-wide fixtures: float32-rounded float64 truth
+        assert G.rel_l2(gr.numpy(), ref[f"grad/{n}"]) < tol, n
 
 
 def test_symmetry_aware_oracle_adjoint_matches_torch_autograd():
