@@ -6,8 +6,9 @@
 One "step" = one fused forward rollout + reverse-time adjoint over one batch of synthetic demand that is already
 resident in HBM (plus, for N > 1, the policy-gradient all-reduce over NCCL). Scenario batches are sharded across
 ranks with a fixed per-GPU batch (weak scaling). Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement").
-`--impl reference` times the CPU port of the reference's own path (oracle/torch_port.py, PyTorch eager on the
-host cores, all threads) on a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference (its own Trainer.simulate_batch + backward, imported from
+baseline/_ref, see baseline/ref_harness.py) on the host cores, all threads, on a bounded sample of the same workload
+(its PyTorch-eager port, oracle/torch_port.py, only where the reference snapshot has no such policy).
 """
 import argparse
 import ctypes as C
@@ -186,25 +187,46 @@ def time_cpu_port(workload, B, T, steps, warmup):
 
 
 def cpu_sample_size(workload):
-    return {"one_store_backlogged_lead20": 16384, "one_store_lost": 16384, "serial_system": 8192,
-            "one_warehouse_lost_demand": 512, "many_warehouses_lost_demand": 512,
+    """Scenarios per step of the CPU arm: the reference's own training batch where the host can afford it
+    (vanilla_warehouse.yml / one_store YAMLs: 1024 / 8192 per batch), a bounded sample of the 2^20 workloads."""
+    return {"one_store_backlogged_lead20": 16384, "one_store_lost": 8192, "serial_system": 8192,
+            "one_warehouse_lost_demand": 1024, "many_warehouses_lost_demand": 1024,
             "one_warehouse_lost_demand_symmetry_aware": 512}.get(workload, 1024)
 
 
+def time_reference(workload, B, T, steps, warmup, device="cpu"):
+    """(value, seconds per step, cores, kind, note): the unmodified reference when it can be imported and has the
+    policy, else its PyTorch-eager port."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    try:
+        from baseline import ref_harness as RH
+        run = RH.ReferenceRun(workload, B, T, device=device)
+        value, dt, _ = run.time(steps, warmup)
+        return value, dt, cores, "reference", f"unmodified reference from {os.path.relpath(run.where, ROOT)}"
+    except (ImportError, NotImplementedError) as e:
+        if device != "cpu":
+            raise
+        value, dt, cores = time_cpu_port(workload, B, T, steps, warmup)
+        return value, dt, cores, "port", f"PyTorch-eager port ({e})"
+
+
 def run_reference(args):
-    """Reference arm: the reference's CPU implementation of the path (PyTorch-eager port), rank 0 only."""
+    """Reference arm: the reference's own CPU implementation of the path, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    Bc, T = cpu_sample_size(args.workload), 50
-    value, dt, cores = time_cpu_port(args.workload, Bc, T, args.steps, args.warmup)
-    sample = f"{Bc} scenarios x {T} periods per step (bounded sample of the workload), PyTorch-eager port, {cores} threads"
+    Bc, T = args.batch or cpu_sample_size(args.workload), args.periods
+    value, dt, cores, kind, note = time_reference(args.workload, Bc, T, args.steps, args.warmup)
+    sample = (f"{Bc} scenarios x {T} periods per step (bounded sample of the workload: the reference's own training batch "
+              f"size where the host affords it), {note}, {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "periods": T, "scenarios_per_step": Bc, "device": "host cpu"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -421,8 +443,13 @@ def main():
         torch.cuda.empty_cache()
         others = {}
         for name in ("one_warehouse_lost_demand_symmetry_aware", "one_store_backlogged_lead20", "serial_system",
-                     "one_store_lost", "many_warehouses_lost_demand"):
-            ps2, pp2, data2, widths2 = WL.WORKLOADS[name](dev, seed=57, T=T)
+                     "one_store_lost", "many_warehouses_lost_demand", "many_warehouses_lost_demand_8192"):
+            kw2 = {}
+            if name.endswith("_8192"):  # BASELINE cfg 5 in full on ONE GPU: the strong-scaling reference point
+                name_wl, kw2 = "many_warehouses_lost_demand", {"B": 8192}
+            else:
+                name_wl = name
+            ps2, pp2, data2, widths2 = WL.WORKLOADS[name_wl](dev, seed=57, T=T, **kw2)
             B2, S2 = data2["demands"].shape[0], pp2["n_stores"]
             flat2 = WL.init_params(widths2, torch.Generator(device=dev).manual_seed(0), dev)
             prec2 = "tf32x3"
@@ -441,13 +468,77 @@ def main():
             del eng2, data2, flat2, grad2
             torch.cuda.empty_cache()
 
+    # ---- N > 1: data-parallel equivalence check and the strong-scaling configuration of BASELINE cfg 5
+    dp_check, strong = None, None
+    if world > 1:
+        del eng
+        torch.cuda.empty_cache()
+        # (a) gradient of ONE global batch sharded over the ranks, after the all-reduce, against the same batch on
+        #     rank 0 alone (same seed on every rank -> identical tensors; contiguous shards as parallel.shard_range)
+        from neural_inventory_control_b200 import parallel as PL
+        Bg = 256 * world
+        ps_c, pp_c, data_c, widths_c = WL.WORKLOADS[args.workload](dev, seed=1234, B=Bg, T=T)
+        a, b = PL.shard_range(Bg, rank, world)
+        shard = {k: v[a:b].contiguous() for k, v in data_c.items()}
+        gs = 1.0 / (Bg * T * S)
+        e_s = EN.FusedRollout(ps_c, pp_c, shard, T, ignore_periods=30, precision=precision)
+        e_s.forward(flat, shard)
+        g_sh = e_s.backward(gs, 0.0).clone()
+        dist.all_reduce(g_sh)
+        if rank == 0:
+            e_f = EN.FusedRollout(ps_c, pp_c, data_c, T, ignore_periods=30, precision=precision)
+            e_f.forward(flat, data_c)
+            g_full = e_f.backward(gs, 0.0)
+            rel = float((g_sh.double() - g_full.double()).norm() / g_full.double().norm())
+            dp_check = {"scenarios": Bg, "ranks": world, "grad_rel_l2_sharded_vs_single": rel, "bar": 1e-5,
+                        "ok": rel <= 1e-5}
+            del e_f
+        del e_s, data_c, shard
+        torch.cuda.empty_cache()
+        # (b) strong scaling: many_warehouses_lost_demand, 8192 scenarios GLOBAL (BASELINE cfg 5: "8192 over 8 GPUs")
+        Bs = 8192 // world
+        ps2, pp2, data2, widths2 = WL.WORKLOADS["many_warehouses_lost_demand"](dev, seed=57 + rank, B=Bs, T=T)
+        flat2 = WL.init_params(widths2, torch.Generator(device=dev).manual_seed(0), dev)
+        eng2 = EN.FusedRollout(ps2, pp2, data2, T, ignore_periods=30, precision=precision)
+        grad2 = torch.zeros_like(flat2)
+        S2 = pp2["n_stores"]
+
+        def step_s():
+            eng2.forward(flat2, data2)
+            eng2.backward(1.0 / (8192 * T * S2), 0.0, out=grad2)
+            dist.all_reduce(grad2)
+
+        for _ in range(3):
+            step_s()
+        dist.barrier()
+        ms_s = time_region(step_s, 8)
+        t = torch.tensor([ms_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_s = float(t.item())
+        strong = {"workload": "many_warehouses_lost_demand", "scaling": "strong", "scenarios_global": 8192,
+                  "scenarios_per_gpu": Bs, "ms_per_step": ms_s, "value": 8192 * T / (ms_s * 1e-3), "unit": UNIT,
+                  "note": "single-GPU time of the same 8192-scenario batch: other_workloads."
+                          "many_warehouses_lost_demand_8192 of the N = 1 line"}
+        del eng2, data2
+
     cpu_baseline = None
+    reference_cuda = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         Bc = cpu_sample_size(args.workload)
-        v, dt, cores = time_cpu_port(args.workload, Bc, T, 3, 1)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{Bc} scenarios x {T} periods, 1 warm-up + 3 timed steps, PyTorch-eager port of the "
-                                  f"reference path on {cores} host threads"}
+        n_cpu = 3 if Bc * S >= 16384 else 10
+        v, dt, cores, kind, note = time_reference(args.workload, Bc, T, n_cpu, 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "ms_per_step": dt * 1e3,
+                        "sample": f"{Bc} scenarios x {T} periods, 1 warm-up + {n_cpu} timed steps, {note}, {cores} host threads"}
+        # the same unmodified reference code with device='cuda:0' on this B200 (stock PyTorch eager kernels): the
+        # same-box number SURVEY.md 8d asks for, on the SAME scenarios-per-step as our arm where it fits
+        try:
+            torch.cuda.empty_cache()
+            Bg = min(B, 8192)
+            vg, dtg, _, kindg, noteg = time_reference(args.workload, Bg, T, 3, 1, device=f"cuda:{local}")
+            reference_cuda = {"value": vg, "unit": UNIT, "ms_per_step": dtg * 1e3, "scenarios": Bg, "kind": kindg,
+                              "note": f"{noteg}, device cuda:{local}, fp32 (allow_tf32 off), 1 warm-up + 3 timed steps"}
+        except Exception as e:  # noqa: BLE001  (no such policy in the reference snapshot, or out of memory)
+            reference_cuda = {"unavailable": str(e)[:200]}
 
     if rank == 0:
         line = {
@@ -461,7 +552,8 @@ def main():
                        if B * T * 4 * (1 + WL.net_list(widths)[0][1][0]) > 126e6 else "working set below L2 size; no flush",
                        "parallelism": f"dp{world} (scenario shards, gradient all-reduce)" if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "other_workloads": others,
+            "cpu_baseline": cpu_baseline, "reference_cuda": reference_cuda, "other_workloads": others,
+            "dp_check": dp_check, "strong_scaling": strong,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -59,7 +59,15 @@ def main(argv=None):
     observation_params = DefaultDict(lambda: None, cfg["observation_params"])
     problem_params, pbd = cfg["problem_params"], cfg["params_by_dataset"]
 
-    device = "cuda:0" if torch.cuda.is_available() else "cpu"
+    # one process per GPU under torchrun (WORLD_SIZE > 1): scenario shards of every batch, ONE gradient all-reduce per
+    # batch over NCCL (neural_inventory_control_b200/parallel.py); plain `python main_run.py ...` is rank 0 of 1
+    from neural_inventory_control_b200 import parallel as PL
+    rank, world, local_rank = PL.init_from_env()
+    device = f"cuda:{local_rank}" if torch.cuda.is_available() else "cpu"
+    if rank != 0:  # every rank trains; rank 0 alone talks and writes checkpoints
+        import builtins
+        builtins.print = lambda *a, **k: None
+        trainer_params["save_model"] = False
     scenario, train_set, dev_set, test_set = build_datasets(cfg, observation_params)
     data_loaders = {
         "train": DataLoader(train_set, batch_size=pbd["train"]["batch_size"], shuffle=True),

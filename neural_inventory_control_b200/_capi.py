@@ -48,10 +48,19 @@ class RolloutDesc(C.Structure):
                 ("warehouse_net", Mlp), ("adjacency", p)]
 
 
+class HdpoError(RuntimeError):
+    pass
+
+
 def make_mlp(widths, hidden_act, out_act):
+    """Nets the kernels do not cover (more than HDPO_MAX_LAYERS layers, activations outside ACT such as the
+    reference's 'softmax') raise the "no fused rollout" error that Trainer.simulate_batch turns into the generic
+    per-step path, exactly like an unsupported policy shape."""
     m = Mlp()
     if len(widths) - 1 > HDPO_MAX_LAYERS:
-        raise ValueError(f"MLP with {len(widths) - 1} linear layers exceeds HDPO_MAX_LAYERS={HDPO_MAX_LAYERS}")
+        raise HdpoError(f"no fused rollout: MLP with {len(widths) - 1} linear layers exceeds HDPO_MAX_LAYERS={HDPO_MAX_LAYERS}")
+    if hidden_act not in ACT or out_act not in ACT:
+        raise HdpoError(f"no fused rollout: activation {hidden_act!r} / {out_act!r} is not implemented in the kernels")
     m.n_layers = len(widths) - 1
     for i, w in enumerate(widths):
         m.widths[i] = int(w)
@@ -103,10 +112,6 @@ def bind(lib):
         if fn.restype is C.c_int:  # default restype: int status
             pass
     return lib
-
-
-class HdpoError(RuntimeError):
-    pass
 
 
 def check(lib, rc, what):

@@ -48,6 +48,9 @@ static int check_statics(const HdpoRolloutDesc* d, const HdpoStatics* st) {
     HDPO_REQUIRE(!d->pb.has_edge_cost || st->warehouse_edge_costs, "warehouse_edge_costs missing");
   }
   if (d->pb.E > 0) HDPO_REQUIRE(st->echelon_lead_times && st->echelon_holding_costs, "echelon statics missing");
+  // the SymmetryAware store net reads the per-store demand mean / std as input features
+  HDPO_REQUIRE(d->arch != HDPO_ARCH_SYMMETRY_AWARE || (st->mean && st->std),
+               "symmetry_aware needs the 'mean' and 'std' static features (observation_params.include_static_features)");
   return HDPO_OK;
 }
 

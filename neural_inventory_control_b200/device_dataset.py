@@ -35,8 +35,9 @@ class DeviceBatches:
         self.shuffle = isinstance(loader.sampler, RandomSampler)
         self.n = len(loader.dataset)
         self.lib = _lib.load()
-        # one H2D copy per tensor for the lifetime of the loader (expanded views are materialised)
-        self.data = {k: v.to(self.device, dtype=torch.float32).contiguous() for k, v in loader.dataset.data.items()}
+        # one H2D copy per tensor for the lifetime of the loader (expanded views are materialised); dtypes are kept
+        # (float32 rows go through the gather kernel, anything else through torch.index_select)
+        self.data = {k: v.to(self.device).contiguous() for k, v in loader.dataset.data.items()}
 
     def __len__(self):
         full, rem = divmod(self.n, self.batch_size)
@@ -46,6 +47,9 @@ class DeviceBatches:
         out = {}
         stream = current_stream_ptr(self.device)
         for k, src in self.data.items():
+            if src.dtype != torch.float32:
+                out[k] = src.index_select(0, index)
+                continue
             row = src[0].numel() if src.dim() > 1 else 1
             dst = torch.empty((index.numel(),) + tuple(src.shape[1:]), dtype=torch.float32, device=self.device)
             rc = self.lib.hdpo_gather_rows(dst.data_ptr(), src.data_ptr(), index.data_ptr(), index.numel(), row, stream)
@@ -53,16 +57,37 @@ class DeviceBatches:
             out[k] = dst
         return out
 
+    def _permutation(self):
+        """The permutation DataLoader + RandomSampler would draw, consuming the SAME host RNG draws in the same order
+        (torch/utils/data/dataloader.py: `_BaseDataLoaderIter.__init__` draws base_seed from loader.generator;
+        sampler.py: RandomSampler seeds a fresh generator from the global RNG when it has none), so that batch order
+        and every later draw from the global generator (e.g. LazyLinear initialisation) match the reference run.
+        Under torch.distributed rank 0's permutation is broadcast: all ranks must cut the same batches."""
+        torch.empty((), dtype=torch.int64).random_(generator=getattr(self.loader, "generator", None))  # base_seed
+        gen = getattr(self.loader.sampler, "generator", None)
+        if gen is None:
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
+            gen = torch.Generator()
+            gen.manual_seed(seed)
+        perm = torch.randperm(self.n, generator=gen)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            buf = perm.to(self.device) if dist.get_backend() == "nccl" else perm
+            dist.broadcast(buf, src=0)
+            perm = buf.cpu()
+        return perm
+
     def __iter__(self):
         if not self.shuffle:
+            # a DataLoader iterator draws its base_seed even when nothing is shuffled: keep the global RNG in step
+            torch.empty((), dtype=torch.int64).random_(generator=getattr(self.loader, "generator", None))
             for a in range(0, self.n, self.batch_size):
                 b = min(a + self.batch_size, self.n)
                 if b - a < self.batch_size and self.drop_last:
                     return
                 yield {k: v[a:b] for k, v in self.data.items()}  # contiguous views, no copy
             return
-        gen = getattr(self.loader.sampler, "generator", None)
-        perm = torch.randperm(self.n, generator=gen).to(self.device)  # host RNG stream, like RandomSampler
+        perm = self._permutation().to(self.device)
         for a in range(0, self.n, self.batch_size):
             b = min(a + self.batch_size, self.n)
             if b - a < self.batch_size and self.drop_last:

@@ -13,11 +13,13 @@ import torch.distributed as dist
 
 
 def init_from_env(backend=None):
-    """Initialise torch.distributed from torchrun's environment. Returns (rank, world, local_rank)."""
+    """Initialise torch.distributed from torchrun's environment. Returns (rank, world, local_rank).
+    HDPO_DIST_BACKEND overrides the backend (tests run two ranks on ONE GPU over gloo)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():
+        backend = backend or os.environ.get("HDPO_DIST_BACKEND")
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         kw = {}
@@ -65,6 +67,24 @@ def allreduce_sum_(tensors):
         t.copy_(flat[o:o + n].view_as(t))
         o += n
     return tensors
+
+
+def broadcast_parameters_(model, src=0):
+    """Rank `src`'s parameters to every rank as ONE flat bucket (replicas must start from identical weights; the
+    LazyLinear layers of the reference's nets materialise at the first batch, so this runs right after it)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    params = [p for p in model.parameters() if not isinstance(p, torch.nn.parameter.UninitializedParameter)]
+    if not params:
+        return
+    flat = torch.cat([p.detach().reshape(-1).to(torch.float32) for p in params])
+    dist.broadcast(flat, src=src)
+    o = 0
+    with torch.no_grad():
+        for p in params:
+            n = p.numel()
+            p.copy_(flat[o:o + n].view_as(p))
+            o += n
 
 
 def allreduce_gradients_and_losses(model, losses):

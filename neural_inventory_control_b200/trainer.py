@@ -10,6 +10,7 @@ clipping, best-model tracking, early stopping, checkpoints) is the reference's o
 import copy
 import datetime
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -41,6 +42,7 @@ class Trainer:
         self.use_device_dataset = os.environ.get("HDPO_DEVICE_DATASET", "1") != "0"
         self._device_loaders = {}
         self.last_path = None  # "fused" | "generic": which path the last simulate_batch took (for tests/logging)
+        self._replicas_synced = False  # multi-rank: parameters broadcast from rank 0 once they are materialised
 
     def reset(self):
         self.all_train_losses, self.all_dev_losses, self.all_test_losses = [], [], []
@@ -101,6 +103,11 @@ class Trainer:
                 data_batch = self.move_batch_to_device(PL.shard_batch(data_batch, rank, world))
                 if train:
                     optimizer.zero_grad()
+                if world > 1 and not self._replicas_synced:
+                    # replicas start from rank 0's weights (materialise the lazy layers first, as the first batch would)
+                    self._materialize(model, simulator, periods, problem_params, data_batch, observation_params)
+                    PL.broadcast_parameters_(model)
+                    self._replicas_synced = True
                 total_reward, reward_to_report = self.simulate_batch(
                     loss_function, simulator, model, periods, problem_params, data_batch, observation_params,
                     ignore_periods, discrete_allocation)
@@ -174,17 +181,39 @@ class Trainer:
             return None
         if not data_batch["initial_inventories"].is_cuda:
             return None
+        # the kernels implement the STOCK dynamics and the registered policies' own forward: a subclass that overrides
+        # either (custom simulator, custom forward) must not be silently bypassed - it runs on the generic path
+        from .environment import Simulator as _StockSimulator
+        from .neural_networks import NeuralNetworkCreator as _Creator
+        if type(simulator) is not _StockSimulator:
+            return None
+        registered = None
+        try:
+            registered = _Creator().get_architecture(model.nn_args["name"])
+        except Exception:  # noqa: BLE001
+            registered = None
+        if registered is None or type(model).forward is not registered.forward:
+            return None
         pspec = model.fusable_spec()
-        if pspec is None and any(isinstance(m, torch.nn.modules.lazy.LazyModuleMixin) for m in model.modules()):
-            # materialise the LazyLinear layers with one throw-away single-scenario forward (initialisation only)
-            one = {k: v[:1] for k, v in data_batch.items()}
-            with torch.no_grad():
-                obs, _ = simulator.reset(periods, problem_params, one, observation_params)
-                obs = dict(obs)
-                obs["internal_data"] = simulator._internal_data
-                model(obs)
+        if pspec is None and self._materialize(model, simulator, periods, problem_params, data_batch, observation_params):
             pspec = model.fusable_spec()
+        if pspec is not None and pspec.arch == "symmetry_aware" and not ("mean" in data_batch and "std" in data_batch):
+            return None  # the generic path raises the same KeyError the reference's forward would
         return pspec
+
+    def _materialize(self, model, simulator, periods, problem_params, data_batch, observation_params):
+        """Materialise LazyLinear layers with one throw-away single-scenario forward (initialisation only: the draws
+        from the global RNG are the ones the first real batch would make). Returns True when something was lazy."""
+        if not any(isinstance(m, torch.nn.modules.lazy.LazyModuleMixin) and m.has_uninitialized_params()
+                   for m in model.modules()):
+            return False
+        one = {k: v[:1] for k, v in data_batch.items()}
+        with torch.no_grad():
+            obs, _ = simulator.reset(periods, problem_params, one, observation_params)
+            obs = dict(obs)
+            obs["internal_data"] = simulator._internal_data
+            model(obs)
+        return True
 
     def _flat_params(self, model, pspec):
         names = [m for m in _FUSED_MODULE_ORDER if m in model.net]
@@ -198,15 +227,28 @@ class Trainer:
         need_grad = torch.is_grad_enabled() and model.trainable and not discrete_allocation
         shift = observation_params["demand"]["period_shift"]
         B = data_batch["initial_inventories"].shape[0]
+        # everything the cached descriptor bakes in: batch / state shapes, problem flags, adjacency, policy widths and
+        # activations, precision (the same model object may be reused with other problem_params)
+        shapes = tuple((k, tuple(v.shape[1:])) for k, v in sorted(data_batch.items()) if k.startswith("initial_"))
+        adj = pspec.adjacency
+        adj_key = None if adj is None else tuple(map(tuple, adj.tolist() if hasattr(adj, "tolist") else adj))
+        nets = tuple((tuple(n[0]), n[1], n[2]) if n is not None else None
+                     for n in (pspec.master, pspec.store_net, pspec.warehouse_net))
         key = (id(model), B, periods, data_batch["demands"].shape[2], ignore_periods, bool(discrete_allocation),
-               need_grad, shift, pspec.warehouse_upper_bound)
+               need_grad, shift, pspec.warehouse_upper_bound, shapes, adj_key, nets, pspec.transshipment, pspec.prop_eps,
+               self.precision, int(problem_params["n_stores"]), int(problem_params["n_warehouses"]),
+               int(problem_params["n_extra_echelons"]), bool(problem_params["lost_demand"]),
+               bool(problem_params["maximize_profit"]), "warehouse_edge_costs" in data_batch)
         eng = self._engines.get(key)
+        if eng is not None and eng.model_ref() is not model:  # id() of a collected model reused by a new object
+            eng = None
         if eng is None:
             if len(self._engines) > 8:
                 self._engines.clear()
             eng = EN.FusedRollout(pspec, problem_params, data_batch, periods, ignore_periods=ignore_periods,
                                   period_shift=shift, discrete_allocation=discrete_allocation,
                                   save_for_backward=need_grad, precision=self.precision)
+            eng.model_ref = weakref.ref(model)
             self._engines[key] = eng
         # keep the simulator's visible state coherent with what a per-period run would leave behind
         simulator.reset(periods, problem_params, data_batch, observation_params)
