@@ -3,8 +3,8 @@
 The reference (MatiasAlvo/Neural_inventory_control) is a flat directory of Python modules without setup.py /
 pyproject.toml, so `pip install --target baseline/_ref /root/reference` has nothing to build (outcome recorded in
 DESIGN.md). What a pip install would have produced - the importable modules - is produced here instead by
-BYTE-COMPILING the modules where they lie under /root/reference into baseline/_ref/*.pyc (sourceless, same
-interpreter image on the GPU box). No reference source enters the repository: baseline/_ref/ is git-ignored (and not
+BYTE-COMPILING the modules where they lie under /root/reference into baseline/_ref/<module>.bin (sourceless CPython
+bytecode, same interpreter image on the GPU box; not named *.pyc because snapshot tools drop those as caches). No reference source enters the repository: baseline/_ref/ is git-ignored (and not
 gpurun-ignored, so it travels). Run in the build container only (__graft_entry__.build() calls it).
 """
 import os
@@ -42,7 +42,7 @@ def build(verbose=True):
     for m in MODULES:
         src = os.path.join(REF, m + ".py")
         if os.path.exists(src):
-            py_compile.compile(src, cfile=os.path.join(OUT, m + ".pyc"), dfile=f"<reference>/{m}.py", doraise=True,
+            py_compile.compile(src, cfile=os.path.join(OUT, m + ".bin"), dfile=f"<reference>/{m}.py", doraise=True,
                                optimize=0)
     if verbose:
         print(f"[build_ref] {len(MODULES)} reference modules -> {OUT} (pip: {'ok' if ok else 'failed'}: {msg})")

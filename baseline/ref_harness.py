@@ -15,10 +15,17 @@ import types
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+REF_MODULES = ("shared_imports", "quantile_forecaster", "data_handling", "neural_networks", "environment",
+               "loss_functions", "trainer")  # dependency order of the reference's star-import chain
+
+
 def locate():
-    for cand in (os.path.join(ROOT, "baseline", "_ref"), os.environ.get("HDPO_REFERENCE_ROOT", "/root/reference")):
-        if cand and (os.path.exists(os.path.join(cand, "trainer.pyc")) or os.path.exists(os.path.join(cand, "trainer.py"))):
-            return cand
+    built = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.exists(os.path.join(built, "trainer.bin")):
+        return built
+    src = os.environ.get("HDPO_REFERENCE_ROOT", "/root/reference")
+    if os.path.exists(os.path.join(src, "trainer.py")):
+        return src
     return None
 
 
@@ -26,31 +33,40 @@ _REF = None
 
 
 def load_reference():
-    """Import the reference's `trainer` module (star-imports everything else)."""
+    """Import the reference's modules (byte-compiled .bin files of baseline/_ref, else the sources of /root/reference)
+    under their own names for the duration of the import, then restore this repo's same-named root shims. Returns
+    (the reference's `trainer` module - it star-imports everything else -, where it came from)."""
     global _REF
     if _REF is not None:
         return _REF
     where = locate()
     if where is None:
         raise ImportError("the reference is neither in baseline/_ref nor in /root/reference")
+    import importlib.machinery
+    import importlib.util
     sys.dont_write_bytecode = True
-    shadow = [m for m in ("trainer", "environment", "neural_networks", "data_handling", "loss_functions", "shared_imports")
-              if m in sys.modules]
-    saved = {m: sys.modules.pop(m) for m in shadow}  # this repo's root shims have the same module names
-    sys.path.insert(0, os.path.join(ROOT, "oracle", "refstubs"))
-    sys.path.insert(0, where)
+    saved = {m: sys.modules.pop(m) for m in REF_MODULES if m in sys.modules}
+    stubs = os.path.join(ROOT, "oracle", "refstubs")  # inert `gymnasium` / `matplotlib` (absent from the image)
+    sys.path.insert(0, stubs)
+    loaded = {}
     try:
-        import importlib
-        mod = importlib.import_module("trainer")
-        assert os.path.dirname(os.path.abspath(mod.__file__)) == os.path.abspath(where), mod.__file__
-        ref_mods = {m: sys.modules[m] for m in ("trainer", "environment", "neural_networks", "data_handling",
-                                                "loss_functions", "shared_imports") if m in sys.modules}
+        for name in REF_MODULES:
+            path_bin, path_py = os.path.join(where, name + ".bin"), os.path.join(where, name + ".py")
+            if os.path.exists(path_bin):
+                loader = importlib.machinery.SourcelessFileLoader(name, path_bin)
+            else:
+                loader = importlib.machinery.SourceFileLoader(name, path_py)
+            spec = importlib.util.spec_from_loader(name, loader)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            loader.exec_module(mod)
+            loaded[name] = mod
     finally:
-        sys.path.remove(where)
-        for m in list(ref_mods if "ref_mods" in dir() else []):
-            sys.modules.pop(m, None)
+        sys.path.remove(stubs)
+        for name in REF_MODULES:
+            sys.modules.pop(name, None)
         sys.modules.update(saved)
-    _REF = (mod, where)
+    _REF = (loaded["trainer"], where)
     return _REF
 
 

@@ -388,16 +388,18 @@ def main():
             "adjoint_group": group,
         })
 
-    # ---- end to end through the C ABI with HOST buffers (pinned): H2D of the batch + D2H of loss and gradient
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D of the batch + D2H of loss and gradient.
+    # Headline e2e: the synthetic demand is generated ON THE DEVICE inside the call (K4 Philox sampler wired into the
+    # path: demands = NULL + seed / offset in the descriptor), so what crosses the bus per step is parameters, initial
+    # inventories, cost coefficients and S means / standard deviations in, totals + gradient out. The variant that
+    # uploads a host-resident demand tensor every step stays reported beside it (e2e_host_demand).
     e2e = None
+    e2e_host_demand = None
     if not args.no_e2e:
         host = {k: v.cpu().pin_memory() for k, v in data.items()}
         h_flat = flat.cpu().pin_memory()
         h_grad = torch.empty_like(h_flat).pin_memory()
         h_tot = torch.zeros(2, dtype=torch.float64).pin_memory()
-        desc = eng.desc
-        ws_bytes = int(lib.hdpo_rollout_host_workspace_bytes(C.byref(desc)))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         hp = lambda k: host[k].data_ptr() if k in host else None  # noqa: E731
         h_st = K.Statics(hp("holding_costs"), hp("underage_costs"), hp("lead_times"), hp("warehouse_lead_times"),
                          hp("warehouse_holding_costs"), hp("warehouse_edge_costs"), hp("echelon_lead_times"),
@@ -408,33 +410,68 @@ def main():
         h_adj = None
         if pspec.adjacency is not None:
             h_adj = torch.tensor(pspec.adjacency, dtype=torch.int32).contiguous().pin_memory()
+        # demand model of the workload for the on-device sampler (workloads.py: per-store mean / std, rho = 0.5, clip)
+        if "mean" in host:
+            h_mean, h_std, dist_name, rho = host["mean"][0].clone().pin_memory(), host["std"][0].clone().pin_memory(), "normal", 0.5
+        elif args.workload == "one_store_lost":
+            h_mean, h_std, dist_name, rho = torch.full((1,), 5.0).pin_memory(), torch.ones(1).pin_memory(), "poisson", 0.0
+        else:
+            sd = 1.6 if args.workload == "one_store_backlogged_lead20" else 2.0
+            h_mean, h_std, dist_name, rho = torch.full((1,), 5.0).pin_memory(), torch.full((1,), sd).pin_memory(), "normal", 0.0
 
-        def host_step():
-            rc = lib.hdpo_rollout_train_host(C.byref(desc), h_flat.data_ptr(), host["demands"].data_ptr(),
-                                             C.byref(h_st), C.byref(h_init),
-                                             h_adj.data_ptr() if h_adj is not None else None, h_tot.data_ptr(),
-                                             h_grad.data_ptr(),
-                                             ws.data_ptr(), ws_bytes, stream)
-            K.check(lib, rc, "hdpo_rollout_train_host")
+        def run_host(generated):
+            desc = type(eng.desc).from_buffer_copy(eng.desc)
+            step_no = [0]
+            if generated:
+                desc.demand_source = K.DEMAND_PHILOX_NORMAL if dist_name == "normal" else K.DEMAND_PHILOX_POISSON
+                desc.demand_clip_at_zero = 1
+                desc.demand_rho = rho
+                desc.philox_seed = 57 + rank
+                desc.demand_mean = h_mean.data_ptr()
+                desc.demand_std = h_std.data_ptr()
+                desc.demand_layout = K.DEMAND_TSB
+                desc.t_stride = T
+            ws_bytes = int(lib.hdpo_rollout_host_workspace_bytes(C.byref(desc)))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            per_step_counters = (T * S * B + 3) // 4
 
-        for _ in range(2):
-            host_step()
-        n_e = max(3, min(args.steps, 5))
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e):
-            host_step()  # synchronises the stream before returning
-        dt = (time.perf_counter() - t0) / n_e
-        if world > 1:
-            t = torch.tensor([dt], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        h2d = sum(v.numel() * 4 for v in host.values()) + h_flat.numel() * 4
-        e2e = {"value": world * B * T / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 16 + h_grad.numel() * 4, "ms_per_step": dt * 1e3,
-               "api": "hdpo_rollout_train_host (C ABI, pinned host buffers)"}
-        del ws
+            def host_step():
+                if generated:
+                    desc.philox_offset = step_no[0] * per_step_counters  # fresh draws every step
+                    step_no[0] += 1
+                rc = lib.hdpo_rollout_train_host(C.byref(desc), h_flat.data_ptr(),
+                                                 None if generated else host["demands"].data_ptr(),
+                                                 C.byref(h_st), C.byref(h_init),
+                                                 h_adj.data_ptr() if h_adj is not None else None, h_tot.data_ptr(),
+                                                 h_grad.data_ptr(), ws.data_ptr(), ws_bytes, stream)
+                K.check(lib, rc, "hdpo_rollout_train_host")
+
+            for _ in range(2):
+                host_step()
+            n_e = max(3, min(args.steps, 5))
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e):
+                host_step()  # synchronises the stream before returning
+            dt = (time.perf_counter() - t0) / n_e
+            if world > 1:
+                t = torch.tensor([dt], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            h2d = sum(v.numel() * 4 for k, v in host.items() if not (generated and k == "demands")) + h_flat.numel() * 4
+            if generated:
+                h2d += 8 * S
+            del ws
+            torch.cuda.empty_cache()
+            return {"value": world * B * T / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 16 + h_grad.numel() * 4, "ms_per_step": dt * 1e3,
+                    "api": "hdpo_rollout_train_host (C ABI, pinned host buffers)",
+                    "demand": ("generated on the device inside the call (Philox4x32-10, " + dist_name + ", fresh draws per step)")
+                    if generated else "host tensor uploaded every step"}
+
+        e2e = run_host(True)
+        e2e_host_demand = run_host(False)
 
     # ---- the other BASELINE.json configs, device-timed the same way on a short run (context for the headline line)
     others = None
@@ -546,12 +583,13 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if precision == "fp32" else ("tf32x3 (fp32-grade split, fp32 accumulate)" if precision == "tf32x3"
                                                          else "tf32"),
-            "data": "synthetic",
+            "data": "synthetic (value: demand resident in HBM; e2e: demand generated on the device by the Philox sampler)",
             "config": {"workload": args.workload, "scenarios_per_gpu": B, "periods": T, "stores": S,
                        "policy_widths": widths, "l2": "inputs larger than L2 (demand + state tape per step)"
                        if B * T * 4 * (1 + WL.net_list(widths)[0][1][0]) > 126e6 else "working set below L2 size; no flush",
                        "parallelism": f"dp{world} (scenario shards, gradient all-reduce)" if world > 1 else "single GPU"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "clocks": clocks, "e2e": e2e, "e2e_host_demand": e2e_host_demand, "gpu_launches": int(launches),
+            "roofline": roofline,
             "cpu_baseline": cpu_baseline, "reference_cuda": reference_cuda, "other_workloads": others,
             "dp_check": dp_check, "strong_scaling": strong,
         }

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define HDPO_ABI_VERSION 1
+#define HDPO_ABI_VERSION 2
 #define HDPO_MAX_LAYERS 8 /* linear layers per MLP */
 
 enum {
@@ -62,6 +62,13 @@ enum { HDPO_ACT_NONE = 0, HDPO_ACT_ELU = 1, HDPO_ACT_RELU = 2, HDPO_ACT_TANH = 3
 enum {
   HDPO_DEMAND_BST = 0, /* [B, S, t_stride]  the reference layout (data_handling.py:59, environment.py:171-177) */
   HDPO_DEMAND_TSB = 1  /* [t_stride, S, B]  time-major, what hdpo_philox_* writes; fully coalesced */
+};
+
+/* where the demand of a rollout comes from (HdpoRolloutDesc.demand_source) */
+enum {
+  HDPO_DEMAND_FROM_ARGUMENT = 0,  /* the `demands` argument (device / host pointer) */
+  HDPO_DEMAND_PHILOX_NORMAL = 1,  /* generated on the device: hdpo_philox_normal(mean, std, rho, clip) */
+  HDPO_DEMAND_PHILOX_POISSON = 2  /* generated on the device: hdpo_philox_poisson(mean) */
 };
 
 /* matmul precision of the policy MLP */
@@ -172,6 +179,18 @@ typedef struct HdpoRolloutDesc {
   HdpoMlp store_net;          /* symmetry_aware only */
   HdpoMlp warehouse_net;      /* symmetry_aware only */
   const int32_t* adjacency;   /* device [W,S] 0/1, NULL = fully connected (neural_networks.py:383-390) */
+  /* K4 wired into the path (ABI 2): with demand_source != 0 the `demands` argument may be NULL - the [t_stride, S, B]
+   * trace is generated on the device by the Philox sampler (element (t, s, b) <-> counter philox_offset + index / 4,
+   * exactly what hdpo_philox_normal / _poisson write for layout HDPO_DEMAND_TSB) into the workspace, once per forward
+   * call, and read again by the adjoint. Replaces data_handling.py:178-211 + the per-batch H2D copy (trainer.py:156)
+   * for synthetic settings. demand_mean / demand_std: [S] (device pointers; HOST pointers for *_train_host). */
+  int32_t demand_source;      /* HDPO_DEMAND_* source */
+  int32_t demand_clip_at_zero;
+  float demand_rho;           /* one-factor correlation of the normal sampler */
+  int32_t reserved0;
+  uint64_t philox_seed, philox_offset;
+  const float* demand_mean;
+  const float* demand_std;
 } HdpoRolloutDesc;
 
 /* Number of float parameters the descriptor's nets hold, in state_dict order:

@@ -45,7 +45,14 @@ class RolloutDesc(C.Structure):
                                     ("arch", "T", "t_stride", "period_shift", "ignore_periods", "demand_layout",
                                      "discrete_allocation", "transshipment", "precision", "save_for_backward")] + \
                [("warehouse_upper_bound", C.c_float), ("prop_eps", C.c_float), ("master", Mlp), ("store_net", Mlp),
-                ("warehouse_net", Mlp), ("adjacency", p)]
+                ("warehouse_net", Mlp), ("adjacency", p),
+                # ABI 2: demand generated on the device by the Philox sampler (K4 in the path)
+                ("demand_source", C.c_int32), ("demand_clip_at_zero", C.c_int32), ("demand_rho", C.c_float),
+                ("reserved0", C.c_int32), ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
+                ("demand_mean", p), ("demand_std", p)]
+
+
+DEMAND_FROM_ARGUMENT, DEMAND_PHILOX_NORMAL, DEMAND_PHILOX_POISSON = 0, 1, 2
 
 
 class HdpoError(RuntimeError):

@@ -9,6 +9,7 @@ import os
 
 from . import _capi as K
 
+ABI_VERSION = 2  # include/hdpo_b200.h HDPO_ABI_VERSION
 _LIB = None
 _DEVICE_OK = False  # cudaGetDeviceProperties costs ~2.5 ms: check once, not per call
 
@@ -39,8 +40,8 @@ def load(require_device=True):
             _LIB = K.bind(ctypes.CDLL(path))
         except OSError as e:
             raise MissingExtension(f"cannot load {path}: {e}") from e
-        if _LIB.hdpo_abi_version() != 1:
-            raise MissingExtension(f"{path}: ABI version {_LIB.hdpo_abi_version()} != 1 (stale build?)")
+        if _LIB.hdpo_abi_version() != ABI_VERSION:
+            raise MissingExtension(f"{path}: ABI version {_LIB.hdpo_abi_version()} != {ABI_VERSION} (stale build?)")
     if require_device and not _DEVICE_OK:
         sm, major, minor = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         name = ctypes.create_string_buffer(128)

@@ -65,11 +65,50 @@ extern "C" int64_t hdpo_param_count(const HdpoRolloutDesc* d) {
   return n;
 }
 
-extern "C" size_t hdpo_rollout_workspace_bytes(const HdpoRolloutDesc* d) {
-  if (validate_desc(d)) return 0;
+// ---- K4 in the path: demand generated on the device into the tail of the workspace (HdpoRolloutDesc.demand_source) ----
+static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+static size_t generated_demand_bytes(const HdpoRolloutDesc* d) {
+  if (d->demand_source == HDPO_DEMAND_FROM_ARGUMENT) return 0;
+  return align256(static_cast<size_t>(d->t_stride) * d->pb.S * d->pb.B * sizeof(float));
+}
+static size_t inner_workspace_bytes(const HdpoRolloutDesc* d) {
   if (small::supported(d)) return small::workspace_bytes(d);
   if (wide::supported(d)) return wide::workspace_bytes(d);
   return 0;
+}
+// descriptor the kernels see (a plain time-major demand tensor) + where that tensor lives
+static int resolve_demand(const HdpoRolloutDesc* d, const float** demands, void* workspace, size_t* workspace_bytes,
+                          bool generate, void* stream, HdpoRolloutDesc* out) {
+  *out = *d;
+  if (d->demand_source == HDPO_DEMAND_FROM_ARGUMENT) return HDPO_OK;
+  HDPO_REQUIRE(d->demand_source == HDPO_DEMAND_PHILOX_NORMAL || d->demand_source == HDPO_DEMAND_PHILOX_POISSON,
+               "bad demand_source %d", d->demand_source);
+  HDPO_REQUIRE(d->demand_mean && (d->demand_source == HDPO_DEMAND_PHILOX_POISSON || d->demand_std),
+               "demand_source = Philox needs demand_mean (and demand_std for the normal sampler)");
+  const size_t gen = generated_demand_bytes(d);
+  HDPO_REQUIRE(workspace != nullptr, "the generated demand trace lives in the workspace");
+  if (*workspace_bytes < gen + inner_workspace_bytes(d)) {
+    set_error("workspace too small: %zu < %zu", *workspace_bytes, gen + inner_workspace_bytes(d));
+    return HDPO_E_WORKSPACE;
+  }
+  *workspace_bytes -= gen;
+  float* buf = reinterpret_cast<float*>(static_cast<char*>(workspace) + *workspace_bytes);
+  out->demand_source = HDPO_DEMAND_FROM_ARGUMENT;
+  out->demand_layout = HDPO_DEMAND_TSB;
+  *demands = buf;
+  if (!generate || d->pb.B == 0) return HDPO_OK;
+  if (d->demand_source == HDPO_DEMAND_PHILOX_NORMAL)
+    return hdpo_philox_normal(buf, d->pb.B, d->pb.S, d->t_stride, HDPO_DEMAND_TSB, d->demand_mean, d->demand_std, d->demand_rho,
+                              d->demand_clip_at_zero, d->philox_seed, d->philox_offset, stream);
+  return hdpo_philox_poisson(buf, d->pb.B, d->pb.S, d->t_stride, HDPO_DEMAND_TSB, d->demand_mean, d->philox_seed,
+                             d->philox_offset, stream);
+}
+
+extern "C" size_t hdpo_rollout_workspace_bytes(const HdpoRolloutDesc* d) {
+  if (validate_desc(d)) return 0;
+  const size_t inner = inner_workspace_bytes(d);
+  if (inner == 0) return 0;
+  return align256(inner) + generated_demand_bytes(d);
 }
 
 extern "C" int hdpo_rollout_fwd(const HdpoRolloutDesc* d, const float* params, const float* demands,
@@ -80,6 +119,9 @@ extern "C" int hdpo_rollout_fwd(const HdpoRolloutDesc* d, const float* params, c
   if (rc) return rc;
   rc = check_statics(d, st);
   if (rc) return rc;
+  HdpoRolloutDesc resolved;
+  if ((rc = resolve_demand(d, &demands, workspace, &workspace_bytes, true, stream, &resolved))) return rc;
+  d = &resolved;
   HDPO_REQUIRE(params && demands && init && init->store && cost_b, "null argument");
   HDPO_REQUIRE(d->pb.W == 0 || init->warehouse, "initial warehouse inventories missing");
   HDPO_REQUIRE(d->pb.E == 0 || init->echelon, "initial echelon inventories missing");
@@ -101,6 +143,9 @@ extern "C" int hdpo_rollout_bwd(const HdpoRolloutDesc* d, const float* params, c
   if (rc) return rc;
   rc = check_statics(d, st);
   if (rc) return rc;
+  HdpoRolloutDesc resolved;  // demand generated by the forward call: read it back from the workspace
+  if ((rc = resolve_demand(d, &demands, workspace, &workspace_bytes, false, stream, &resolved))) return rc;
+  d = &resolved;
   HDPO_REQUIRE(params && demands && grad_params, "null argument");
   HDPO_REQUIRE(!d->discrete_allocation, "discrete_allocation is forward-only (trainer.py:201-202 rounds under no_grad)");
   if (d->pb.B == 0) {
@@ -137,7 +182,7 @@ HostLayout host_layout(const HdpoRolloutDesc* d) {
   };
   l.params = take(P * f);
   l.grad = take(P * f);
-  l.demands = take(B * S * d->t_stride * f);
+  l.demands = take(d->demand_source == HDPO_DEMAND_FROM_ARGUMENT ? B * S * d->t_stride * f : 2 * S * f);  // or [mean | std]
   l.hold = take(B * S * f);
   l.under = take(B * S * f);
   l.lead = take(B * S * Wc * f);
@@ -174,8 +219,10 @@ extern "C" int hdpo_rollout_train_host(const HdpoRolloutDesc* d, const float* h_
   if (rc) return rc;
   rc = check_statics(d, h_st);
   if (rc) return rc;
-  HDPO_REQUIRE(h_params && h_demands && h_init && h_init->store && h_totals && h_grad_params && d_workspace,
+  const bool gen = d->demand_source != HDPO_DEMAND_FROM_ARGUMENT;
+  HDPO_REQUIRE(h_params && (h_demands || gen) && h_init && h_init->store && h_totals && h_grad_params && d_workspace,
                "null argument");
+  HDPO_REQUIRE(!gen || d->demand_mean, "demand_source = Philox needs demand_mean (host pointer for the host step)");
   const HostLayout l = host_layout(d);
   if (workspace_bytes < l.total) {
     set_error("host-step workspace too small: %zu < %zu", workspace_bytes, l.total);
@@ -191,7 +238,12 @@ extern "C" int hdpo_rollout_train_host(const HdpoRolloutDesc* d, const float* h_
     return cudaMemcpyAsync(base + off, src, bytes, cudaMemcpyHostToDevice, s);
   };
   HDPO_CUDA_OK(up(l.params, h_params, P * f));
-  HDPO_CUDA_OK(up(l.demands, h_demands, B * S * d->t_stride * f));
+  if (!gen) {
+    HDPO_CUDA_OK(up(l.demands, h_demands, B * S * d->t_stride * f));
+  } else {  // no demand crosses the bus: S means (+ S standard deviations) parameterise the on-device sampler
+    HDPO_CUDA_OK(up(l.demands, d->demand_mean, S * f));
+    HDPO_CUDA_OK(up(l.demands + S * f, d->demand_std, S * f));
+  }
   HDPO_CUDA_OK(up(l.hold, h_st->holding_costs, B * S * f));
   HDPO_CUDA_OK(up(l.under, h_st->underage_costs, B * S * f));
   HDPO_CUDA_OK(up(l.lead, h_st->lead_times, B * S * Wc * f));
@@ -215,6 +267,10 @@ extern "C" int hdpo_rollout_train_host(const HdpoRolloutDesc* d, const float* h_
   HdpoRolloutDesc dd = *d;
   dd.save_for_backward = 1;
   dd.adjacency = h_adjacency ? reinterpret_cast<const int32_t*>(base + l.adj) : nullptr;
+  if (gen) {
+    dd.demand_mean = reinterpret_cast<const float*>(base + l.demands);
+    dd.demand_std = d->demand_std ? reinterpret_cast<const float*>(base + l.demands) + S : nullptr;
+  }
   float* params = reinterpret_cast<float*>(base + l.params);
   float* grad = reinterpret_cast<float*>(base + l.grad);
   float* demands = reinterpret_cast<float*>(base + l.demands);

@@ -52,7 +52,11 @@ class FusedRollout:
     """One (policy, problem, batch-shape) instance of the fused forward rollout + reverse-time adjoint."""
 
     def __init__(self, pspec, problem_params, data, periods, ignore_periods=0, period_shift=0,
-                 discrete_allocation=False, demand_layout=K.DEMAND_BST, precision="fp32", save_for_backward=True):
+                 discrete_allocation=False, demand_layout=K.DEMAND_BST, precision="fp32", save_for_backward=True,
+                 philox=None):
+        """philox: None, or {dist: 'normal' | 'poisson', mean: [S] tensor, std: [S] tensor, rho, clip, seed, offset,
+        periods: time extent} - the demand trace is then generated on the device inside every forward call (the batch
+        dict needs no 'demands'); bump 'offset' per batch for fresh draws (set_philox_offset)."""
         self.lib = _lib.load()
         inv = data["initial_inventories"]
         self.device = inv.device
@@ -66,8 +70,15 @@ class FusedRollout:
         self.has_edge = W > 0 and data.get("warehouse_edge_costs") is not None
         self.pb = spec.problem(B, S, W, E, L, Lw, Le, problem_params["lost_demand"],
                                problem_params["maximize_profit"], self.has_edge)
-        dem = data["demands"]
-        t_stride = dem.shape[2] if demand_layout == K.DEMAND_BST else dem.shape[0]
+        self.philox = None
+        if philox is not None:
+            t_stride = int(philox.get("periods", periods + period_shift))
+            mean = _f32c(philox["mean"].to(self.device), "mean")
+            std = _f32c(philox["std"].to(self.device), "std") if philox.get("std") is not None else None
+            self.philox = dict(philox, mean_ptr=mean.data_ptr(), std_ptr=_ptr(std), _keep=(mean, std))
+        else:
+            dem = data["demands"]
+            t_stride = dem.shape[2] if demand_layout == K.DEMAND_BST else dem.shape[0]
         self.adj = None
         if pspec.adjacency is not None and W > 1:
             self.adj = torch.as_tensor(pspec.adjacency, dtype=torch.int32, device=self.device).contiguous()
@@ -78,7 +89,7 @@ class FusedRollout:
                                       save_for_backward=save_for_backward,
                                       warehouse_upper_bound=pspec.warehouse_upper_bound, prop_eps=pspec.prop_eps,
                                       store_net=pspec.store_net, warehouse_net=pspec.warehouse_net,
-                                      adjacency_ptr=_ptr(self.adj))
+                                      adjacency_ptr=_ptr(self.adj), philox=self.philox)
         self.n_params = int(self.lib.hdpo_param_count(C.byref(self.desc)))
         ws = int(self.lib.hdpo_rollout_workspace_bytes(C.byref(self.desc)))
         if ws == 0:
@@ -95,10 +106,14 @@ class FusedRollout:
         return (self.B, self.S, self.T, self.desc.t_stride, self.desc.ignore_periods, self.desc.discrete_allocation,
                 self.desc.save_for_backward)
 
+    def set_philox_offset(self, offset):
+        """Counter offset of the next forward call's demand draws (one batch consumes t_stride * S * B / 4 counters)."""
+        self.desc.philox_offset = int(offset)
+
     def bind(self, data):
         """Resolve the per-batch device pointers (reference layouts, fp32, contiguous)."""
         d = {k: _f32c(data.get(k), k) for k in _DATA_KEYS}
-        dem = _f32c(data["demands"], "demands")
+        dem = _f32c(data["demands"], "demands") if self.philox is None else None
         init = [_f32c(data["initial_inventories"], "initial_inventories"),
                 _f32c(data.get("initial_warehouse_inventories"), "initial_warehouse_inventories") if self.pb.W else None,
                 _f32c(data.get("initial_echelon_inventories"), "initial_echelon_inventories") if self.pb.E else None]
@@ -115,7 +130,7 @@ class FusedRollout:
         fin = None
         if final_state is not None:
             fin = K.State(*[_ptr(t) for t in final_state])
-        rc = self.lib.hdpo_rollout_fwd(C.byref(self.desc), flat_params.data_ptr(), dem.data_ptr(), C.byref(st),
+        rc = self.lib.hdpo_rollout_fwd(C.byref(self.desc), flat_params.data_ptr(), _ptr(dem), C.byref(st),
                                        C.byref(state), self.cost_b.data_ptr(), self.report_b.data_ptr(),
                                        _ptr(reward_tb), self.totals.data_ptr(),
                                        C.byref(fin) if fin is not None else None, self.workspace.data_ptr(),
@@ -126,7 +141,7 @@ class FusedRollout:
     def backward(self, g_total, g_report=0.0, out=None):
         d, dem, init, st, state = self._keep
         grad = out if out is not None else torch.empty(self.n_params, dtype=torch.float32, device=self.device)
-        rc = self.lib.hdpo_rollout_bwd(C.byref(self.desc), self._params.data_ptr(), dem.data_ptr(), C.byref(st),
+        rc = self.lib.hdpo_rollout_bwd(C.byref(self.desc), self._params.data_ptr(), _ptr(dem), C.byref(st),
                                        float(g_total), float(g_report), grad.data_ptr(), self.workspace.data_ptr(),
                                        self.ws_bytes, current_stream_ptr(self.device))
         K.check(self.lib, rc, "hdpo_rollout_bwd")

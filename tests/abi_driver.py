@@ -124,7 +124,8 @@ def slice_batch(data, n):
 
 
 def rollout(be, meta, params, data, T=None, ignore=None, demand_layout=K.DEMAND_BST, discrete=False, backward=True,
-            g_total=None, g_report=0.0, precision="fp32"):
+            g_total=None, g_report=0.0, precision="fp32", philox=None):
+    """philox: None, or {dist, mean, std, rho, clip, seed, offset, periods}: demands = NULL, generated inside the call."""
     L = be.lib
     pp = meta["problem_params"]
     bt = Batch(be, pp, data)
@@ -138,11 +139,18 @@ def rollout(be, meta, params, data, T=None, ignore=None, demand_layout=K.DEMAND_
         names += names_m
         nets[m] = (spec.mlp_widths(shapes), meta["inner_layer_activations"][m], meta["output_layer_activation"][m])
     flat = np.concatenate(flats)
-    dem = np.asarray(data["demands"], np.float32)
-    t_stride = dem.shape[2]
-    if demand_layout == K.DEMAND_TSB:
-        dem = np.ascontiguousarray(dem.transpose(2, 1, 0))
-    dem_h = be.put(dem)
+    ph = None
+    if philox is not None:
+        t_stride, dem_h = int(philox["periods"]), None
+        mean_h = be.put(np.asarray(philox["mean"], np.float32))
+        std_h = be.put(np.asarray(philox["std"], np.float32))
+        ph = dict(philox, mean_ptr=be.ptr(mean_h), std_ptr=be.ptr(std_h))
+    else:
+        dem = np.asarray(data["demands"], np.float32)
+        t_stride = dem.shape[2]
+        if demand_layout == K.DEMAND_TSB:
+            dem = np.ascontiguousarray(dem.transpose(2, 1, 0))
+        dem_h = be.put(dem)
     adj = pp.get("warehouse_store_adjacency")
     adj_h = None if adj is None else be.put(np.asarray(adj), np.int32)
     desc = spec.rollout_desc(meta["nn_name"], bt.pb, T, t_stride, nets[modules[0]],
@@ -152,7 +160,7 @@ def rollout(be, meta, params, data, T=None, ignore=None, demand_layout=K.DEMAND_
                              demand_layout=demand_layout, discrete_allocation=discrete,
                              transshipment=meta.get("transshipment", False), save_for_backward=backward,
                              warehouse_upper_bound=meta["warehouse_upper_bound"], adjacency_ptr=be.ptr(adj_h),
-                             precision=precision)
+                             precision=precision, philox=ph)
     assert L.hdpo_param_count(C.byref(desc)) == flat.size
     ws_bytes = L.hdpo_rollout_workspace_bytes(C.byref(desc))
     assert ws_bytes > 0, L.hdpo_last_error()

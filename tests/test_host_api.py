@@ -126,7 +126,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.lib_path())
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.hdpo_abi_version() == 1
+    assert lib.hdpo_abi_version() == 2
 
 
 def test_struct_layouts_match_header_sizes():
@@ -135,7 +135,8 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(K.Statics) == 10 * 8
     assert ctypes.sizeof(K.Mlp) == 4 * (1 + 9 + 2)
     # HdpoRolloutDesc: Problem (40) + 10 int32 + 2 float + 3 Mlp (48 each) + pointer (8-aligned)
-    assert ctypes.sizeof(K.RolloutDesc) == 40 + 40 + 8 + 3 * 48 + 8
+    # + ABI 2: 2 int32 + float + int32 + 2 uint64 + 2 pointers (Philox demand source)
+    assert ctypes.sizeof(K.RolloutDesc) == 40 + 40 + 8 + 3 * 48 + 8 + 16 + 16 + 16
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour WITHOUT a CUDA device")

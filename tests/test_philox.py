@@ -112,3 +112,44 @@ def test_poisson_demand_statistics(be_name):
         for k in range(0, 12):
             pk = exp(-lam[s]) * lam[s] ** k / factorial(k)
             assert abs((x == k).mean() - pk) < 5 * np.sqrt(pk * (1 - pk) / n) + 1e-4
+
+
+# ---- K4 wired into the rollout path: demands = NULL + Philox key (include/hdpo_b200.h, HdpoRolloutDesc.demand_source) ----
+@pytest.mark.parametrize("be_name", BACKENDS)
+@pytest.mark.parametrize("name,dist", [("one_store_lost", "poisson"), ("serial_system", "normal"),
+                                       pytest.param("one_warehouse_s5", "normal", marks=pytest.mark.gpu)])
+def test_rollout_with_device_generated_demand_equals_explicit_demand(be_name, name, dist):
+    """A rollout whose demand is generated inside the call (demands = NULL, Philox seed / offset in the descriptor) must
+    give bit-identical costs and gradients to the same rollout fed the trace hdpo_philox_* writes for that key."""
+    import golden_util as G
+    be = backend(be_name)
+    if be_name == "emu" and name == "one_warehouse_s5":
+        pytest.skip("wide path on the emulator is covered elsewhere (slow)")
+    meta, g = G.load("rollout", name)
+    data = dict(g["data"])
+    B, S, _ = data["demands"].shape
+    T, shift = 9, int(meta.get("period_shift", 0))
+    Tt = T + shift
+    rng = np.random.RandomState(3)
+    mean = rng.uniform(3.0, 6.0, S).astype(np.float32)
+    std = (mean * 0.3).astype(np.float32)
+    seed, offset = 0x1234ABCD, 77
+    if dist == "normal":
+        trace = _normal(be, B, S, Tt, K.DEMAND_TSB, mean, std, 0.5 if S > 1 else 0.0, True, seed, offset)
+    else:
+        out = be.zeros((Tt, S, B))
+        m = be.put(mean)
+        K.check(be.lib, be.lib.hdpo_philox_poisson(be.ptr(out), B, S, Tt, K.DEMAND_TSB, be.ptr(m), seed, offset, be.stream),
+                "hdpo_philox_poisson")
+        be.sync()
+        trace = be.get(out)
+    explicit = dict(data, demands=np.ascontiguousarray(trace.transpose(2, 1, 0)))  # [B, S, T]: the driver makes it TSB again
+    a = D.rollout(be, meta, g["param"], explicit, T=T, ignore=2, demand_layout=K.DEMAND_TSB)
+    philox = {"dist": dist, "mean": mean, "std": std, "rho": 0.5 if (S > 1 and dist == "normal") else 0.0, "clip": True,
+              "seed": seed, "offset": offset, "periods": Tt}
+    b = D.rollout(be, meta, g["param"], data, T=T, ignore=2, philox=philox)
+    assert np.array_equal(a["cost_b"], b["cost_b"]) and np.array_equal(a["reward_tb"], b["reward_tb"])
+    assert np.array_equal(a["grad_flat"], b["grad_flat"])
+    # another offset = other draws
+    c = D.rollout(be, meta, g["param"], data, T=T, ignore=2, philox=dict(philox, offset=offset + 10 ** 6))
+    assert not np.array_equal(a["cost_b"], c["cost_b"])
