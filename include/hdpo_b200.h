@@ -151,6 +151,12 @@ int hdpo_allocation_shift(int64_t* shift, int32_t B, int32_t n_nodes, int32_t le
 int hdpo_gather_rows(float* dst, const float* src, const int64_t* idx, int64_t n_rows, int64_t row_floats,
                      void* stream);
 
+/* One fused Adam step over a flat parameter vector (replaces optimizer.step() of trainer.py:177 for torch.optim.Adam
+ * without amsgrad; same arithmetic and operation order as torch/optim/adam.py::_single_tensor_adam). `step` is the
+ * 1-based step count AFTER this update; exp_avg / exp_avg_sq are the optimizer's moment vectors (updated in place). */
+int hdpo_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, int64_t step, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K1 / K2 - fused T-period rollout and its reverse-time adjoint.
  * ---------------------------------------------------------------------------------------------- */

@@ -77,7 +77,7 @@ def make_mlp(widths, hidden_act, out_act):
 
 
 EXPORTS = [
-    "hdpo_step_fwd", "hdpo_step_bwd", "hdpo_allocation_shift", "hdpo_gather_rows", "hdpo_param_count", "hdpo_rollout_workspace_bytes",
+    "hdpo_step_fwd", "hdpo_step_bwd", "hdpo_allocation_shift", "hdpo_gather_rows", "hdpo_adam_step", "hdpo_param_count", "hdpo_rollout_workspace_bytes",
     "hdpo_rollout_fwd", "hdpo_rollout_bwd", "hdpo_rollout_host_workspace_bytes", "hdpo_rollout_train_host",
     "hdpo_philox_normal", "hdpo_philox_poisson", "hdpo_philox_raw", "hdpo_debug_gemm_tc", "hdpo_debug_gemm_tc_wgrad", "hdpo_debug_gemm_tc_timeline", "hdpo_debug_set_trace", "hdpo_debug_set_wp_trace", "hdpo_debug_set_wide_persist", "hdpo_last_error", "hdpo_abi_version", "hdpo_kernel_launch_count",
     "hdpo_device_info",
@@ -91,6 +91,7 @@ def bind(lib):
                                   P(State), P(Action), p]
     lib.hdpo_allocation_shift.argtypes = [p, C.c_int32, C.c_int32, C.c_int32, p]
     lib.hdpo_gather_rows.argtypes = [p, p, p, C.c_int64, C.c_int64, p]
+    lib.hdpo_adam_step.argtypes = [p, p, p, p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, p]
     lib.hdpo_param_count.argtypes = [P(RolloutDesc)]
     lib.hdpo_param_count.restype = C.c_int64
     lib.hdpo_rollout_workspace_bytes.argtypes = [P(RolloutDesc)]

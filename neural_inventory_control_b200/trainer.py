@@ -43,6 +43,10 @@ class Trainer:
         self._device_loaders = {}
         self.last_path = None  # "fused" | "generic": which path the last simulate_batch took (for tests/logging)
         self._replicas_synced = False  # multi-rank: parameters broadcast from rank 0 once they are materialised
+        # fused training step: flat parameter / gradient / Adam-moment vectors, adjoint written straight
+        # into the flat gradient, ONE fused Adam kernel, no host synchronisation inside the batch loop
+        self.use_fused_step = os.environ.get("HDPO_FUSED_STEP", "1") != "0"
+        self._flat_ctx = {}
 
     def reset(self):
         self.all_train_losses, self.all_dev_losses, self.all_test_losses = [], [], []
@@ -90,8 +94,10 @@ class Trainer:
 
     def do_one_epoch(self, optimizer, data_loader, loss_function, simulator, model, periods, problem_params,
                      observation_params, train=True, ignore_periods=0, discrete_allocation=False):
-        epoch_loss = 0
-        epoch_loss_to_report = 0
+        # epoch sums live on the device: the reference's two .item() reads per batch (trainer.py:166-167) are host
+        # synchronisations that keep the CPU from running ahead of the GPU; they happen ONCE per epoch here
+        epoch_loss = None
+        epoch_loss_to_report = None
         total_samples = len(data_loader.dataset)
         n_stores = problem_params["n_stores"]
         rank, world = PL.world_info()  # (0, 1) unless launched under torchrun with an initialised process group
@@ -101,33 +107,140 @@ class Trainer:
                 n_global = len(data_batch["demands"])
                 # scenario-parallel: every rank sees the same batch order (same sampler seed) and keeps its shard
                 data_batch = self.move_batch_to_device(PL.shard_batch(data_batch, rank, world))
-                if train:
-                    optimizer.zero_grad()
                 if world > 1 and not self._replicas_synced:
                     # replicas start from rank 0's weights (materialise the lazy layers first, as the first batch would)
                     self._materialize(model, simulator, periods, problem_params, data_batch, observation_params)
                     PL.broadcast_parameters_(model)
                     self._replicas_synced = True
-                total_reward, reward_to_report = self.simulate_batch(
-                    loss_function, simulator, model, periods, problem_params, data_batch, observation_params,
-                    ignore_periods, discrete_allocation)
-                mean_loss = total_reward / (n_global * periods * n_stores)
-                do_step = train and model.trainable
-                if do_step:
-                    mean_loss.backward()
-                if world > 1:  # ONE collective per batch: flat gradient + the two loss scalars
-                    total_reward, reward_to_report = total_reward.detach().clone(), reward_to_report.detach().clone()
-                    PL.allreduce_sum_(([p.grad for p in model.parameters() if p.grad is not None] if do_step else [])
-                                      + [total_reward, reward_to_report])
-                epoch_loss += total_reward.item()
-                epoch_loss_to_report += reward_to_report.item()
-                if do_step:
-                    clip = getattr(model, "gradient_clipping_norm_value", None)
-                    if clip is not None:
-                        torch.nn.utils.clip_grad_norm_(model.parameters(), clip)
-                    optimizer.step()
+                fast = None
+                if train and model.trainable and not discrete_allocation:
+                    fast = self._fused_step_ctx(optimizer, loss_function, simulator, model, periods, problem_params,
+                                                data_batch, observation_params)
+                if fast is not None:
+                    total_reward, reward_to_report = self._train_batch_fused(
+                        fast, optimizer, simulator, model, periods, problem_params, data_batch, observation_params,
+                        ignore_periods, n_global, world)
+                else:
+                    if train:
+                        optimizer.zero_grad()
+                    total_reward, reward_to_report = self.simulate_batch(
+                        loss_function, simulator, model, periods, problem_params, data_batch, observation_params,
+                        ignore_periods, discrete_allocation)
+                    mean_loss = total_reward / (n_global * periods * n_stores)
+                    do_step = train and model.trainable
+                    if do_step:
+                        mean_loss.backward()
+                    if world > 1:  # ONE collective per batch: flat gradient + the two loss scalars
+                        total_reward, reward_to_report = total_reward.detach().clone(), reward_to_report.detach().clone()
+                        PL.allreduce_sum_(([p.grad for p in model.parameters() if p.grad is not None] if do_step else [])
+                                          + [total_reward, reward_to_report])
+                    if do_step:
+                        clip = getattr(model, "gradient_clipping_norm_value", None)
+                        if clip is not None:
+                            torch.nn.utils.clip_grad_norm_(model.parameters(), clip)
+                        optimizer.step()
+                tr_, rr_ = torch.as_tensor(total_reward).detach(), torch.as_tensor(reward_to_report).detach()
+                epoch_loss = tr_.double() if epoch_loss is None else epoch_loss + tr_.double()
+                epoch_loss_to_report = rr_.double() if epoch_loss_to_report is None else epoch_loss_to_report + rr_.double()
+        epoch_loss = 0.0 if epoch_loss is None else float(epoch_loss)
+        epoch_loss_to_report = 0.0 if epoch_loss_to_report is None else float(epoch_loss_to_report)
         return (epoch_loss / (total_samples * periods * n_stores),
                 epoch_loss_to_report / (total_samples * (periods - ignore_periods) * n_stores))
+
+    # ------------------------------------------------------------------ fused training step
+    def _fused_step_ctx(self, optimizer, loss_function, simulator, model, periods, problem_params, data_batch,
+                        observation_params):
+        """Flat-vector context when this (model, optimizer) pair can take the fused step: a fusable policy on the stock
+        simulator with PolicyLoss, and a plain torch.optim.Adam (one parameter group, no amsgrad / maximize /
+        capturable) over exactly the policy's parameters. Otherwise None (reference control flow)."""
+        if not self.use_fused_step:
+            return None
+        pspec = self._fusable_spec(loss_function, simulator, model, periods, problem_params, data_batch,
+                                   observation_params)
+        if pspec is None or type(optimizer) is not torch.optim.Adam or len(optimizer.param_groups) != 1:
+            return None
+        grp = optimizer.param_groups[0]
+        if grp.get("amsgrad") or grp.get("maximize") or grp.get("capturable") or grp.get("differentiable"):
+            return None
+        key = (id(model), id(optimizer))
+        ctx = self._flat_ctx.get(key)
+        if ctx is not None and ctx["model_ref"]() is model and ctx["opt_ref"]() is optimizer:
+            ctx["pspec"] = pspec
+            return ctx
+        names = [m for m in _FUSED_MODULE_ORDER if m in model.net]
+        params = [p for m in names for p in model.net[m].parameters()]
+        if {id(p) for p in params} != {id(p) for p in grp["params"]} or len(params) != len(list(model.parameters())):
+            return None
+        if any(p.dtype != torch.float32 or not p.is_cuda for p in params):
+            return None
+        n = sum(p.numel() for p in params)
+        dev = params[0].device
+        flat = torch.empty(n, dtype=torch.float32, device=dev)
+        grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        m1 = torch.zeros(n, dtype=torch.float32, device=dev)
+        m2 = torch.zeros(n, dtype=torch.float32, device=dev)
+        step, o = 0, 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                flat[o:o + k].copy_(p.detach().reshape(-1))
+                st = optimizer.state.get(p, {})
+                if "exp_avg" in st:  # resumed from a checkpoint (Trainer.load_model): keep the moments
+                    m1[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                    m2[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+                    step = int(st["step"])
+                # parameters, gradients and moments become VIEWS of the flat vectors: state_dict(), checkpoints,
+                # clip_grad_norm_ and any torch code keep working on the same memory
+                p.data = flat[o:o + k].view_as(p)
+                p.grad = grad[o:o + k].view_as(p)
+                optimizer.state[p] = {"step": torch.tensor(float(step)), "exp_avg": m1[o:o + k].view_as(p),
+                                      "exp_avg_sq": m2[o:o + k].view_as(p)}
+                o += k
+        ctx = {"flat": flat, "grad": grad, "m1": m1, "m2": m2, "step": step, "params": params, "pspec": pspec,
+               "model_ref": weakref.ref(model), "opt_ref": weakref.ref(optimizer)}
+        if len(self._flat_ctx) > 4:
+            self._flat_ctx.clear()
+        self._flat_ctx[key] = ctx
+        return ctx
+
+    def _train_batch_fused(self, ctx, optimizer, simulator, model, periods, problem_params, data_batch, observation_params,
+                           ignore_periods, n_global, world):
+        """forward rollout -> adjoint with dLoss/dtotal = 1 / (B_global T S) (trainer.py:169) into the flat gradient ->
+        [all-reduce] -> [clip] -> fused Adam; returns the two loss scalars as device tensors (nothing is read back)."""
+        eng = self._engine_for(ctx["pspec"], model, periods, problem_params, data_batch, observation_params,
+                               ignore_periods, False, True)
+        if simulator.observation is None or getattr(simulator, "batch_size", None) != len(data_batch["demands"]):
+            simulator.reset(periods, problem_params, data_batch, observation_params)  # attributes a caller may inspect
+        o = 0
+        for p in ctx["params"]:  # optimizer.zero_grad(set_to_none=True) elsewhere may have dropped the gradient views
+            k = p.numel()
+            if p.grad is None or p.grad.data_ptr() != ctx["grad"].data_ptr() + 4 * o:
+                p.grad = ctx["grad"][o:o + k].view_as(p)
+            o += k
+        totals = eng.forward(ctx["flat"], data_batch)
+        n_stores = problem_params["n_stores"]
+        eng.backward(1.0 / (n_global * periods * n_stores), 0.0, out=ctx["grad"])
+        totals32 = totals.to(torch.float32)
+        if world > 1:
+            totals32 = totals32.clone()
+            PL.allreduce_sum_([ctx["grad"], totals32])
+        clip = getattr(model, "gradient_clipping_norm_value", None)
+        if clip is not None:  # torch.nn.utils.clip_grad_norm_ on the flat vector, without its host read
+            coef = torch.clamp(float(clip) / (ctx["grad"].norm() + 1e-6), max=1.0)
+            ctx["grad"].mul_(coef)
+        grp = optimizer.param_groups[0]
+        # the step count lives in the optimizer's own (CPU) state tensors, so torch code that touches the optimizer in
+        # between (a generic-path batch, load_state_dict) stays consistent with this path
+        ctx["step"] = int(optimizer.state[ctx["params"][0]]["step"]) + 1
+        rc = eng.lib.hdpo_adam_step(ctx["flat"].data_ptr(), ctx["grad"].data_ptr(), ctx["m1"].data_ptr(),
+                                    ctx["m2"].data_ptr(), ctx["flat"].numel(), float(grp["lr"]), float(grp["betas"][0]),
+                                    float(grp["betas"][1]), float(grp["eps"]), float(grp["weight_decay"]), ctx["step"],
+                                    EN.current_stream_ptr(ctx["flat"].device))
+        EN.K.check(eng.lib, rc, "hdpo_adam_step")
+        for p in ctx["params"]:
+            optimizer.state[p]["step"].fill_(float(ctx["step"]))  # CPU scalar tensors: no device round trip
+        self.last_path = "fused"
+        return totals32[0], totals32[1]
 
     def _maybe_device_loader(self, data_loader):
         if not self.use_device_dataset or not str(self.device).startswith("cuda") or not DD.eligible(data_loader):
@@ -225,6 +338,22 @@ class Trainer:
     def _simulate_batch_fused(self, pspec, simulator, model, periods, problem_params, data_batch, observation_params,
                               ignore_periods, discrete_allocation):
         need_grad = torch.is_grad_enabled() and model.trainable and not discrete_allocation
+        eng = self._engine_for(pspec, model, periods, problem_params, data_batch, observation_params, ignore_periods,
+                               discrete_allocation, need_grad)
+        # keep the simulator's visible state coherent with what a per-period run would leave behind
+        simulator.reset(periods, problem_params, data_batch, observation_params)
+        flat = self._flat_params(model, pspec)
+        if need_grad:
+            total, report = EN.rollout(eng, data_batch, flat)
+        else:
+            totals = eng.forward(flat.detach(), data_batch).to(torch.float32)
+            total, report = totals[0], totals[1]
+        simulator.observation["current_period"] += periods
+        return total, report
+
+    def _engine_for(self, pspec, model, periods, problem_params, data_batch, observation_params, ignore_periods,
+                    discrete_allocation, need_grad):
+        """The cached FusedRollout (descriptor + workspace) of this (model, problem, batch shape)."""
         shift = observation_params["demand"]["period_shift"]
         B = data_batch["initial_inventories"].shape[0]
         # everything the cached descriptor bakes in: batch / state shapes, problem flags, adjacency, policy widths and
@@ -250,16 +379,7 @@ class Trainer:
                                   save_for_backward=need_grad, precision=self.precision)
             eng.model_ref = weakref.ref(model)
             self._engines[key] = eng
-        # keep the simulator's visible state coherent with what a per-period run would leave behind
-        simulator.reset(periods, problem_params, data_batch, observation_params)
-        flat = self._flat_params(model, pspec)
-        if need_grad:
-            total, report = EN.rollout(eng, data_batch, flat)
-        else:
-            totals = eng.forward(flat.detach(), data_batch).to(torch.float32)
-            total, report = totals[0], totals[1]
-        simulator.observation["current_period"] += periods
-        return total, report
+        return eng
 
     # ------------------------------------------------------------------ checkpoints / bookkeeping
     def save_model(self, epoch, model, optimizer, trainer_params):

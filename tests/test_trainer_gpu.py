@@ -312,3 +312,77 @@ def test_two_rank_trainer_matches_single_process(tmp_path):
     for k in a.files:
         if k.startswith("net_"):
             assert np.abs(b[k] - a[k]).max() <= 2e-4 * max(1.0, np.abs(a[k]).max()), k
+
+
+def test_fused_adam_kernel_matches_torch_adam():
+    """hdpo_adam_step (one launch over the flat vector) against torch.optim.Adam over 25 steps, incl. weight decay."""
+    from neural_inventory_control_b200 import _capi as K, _lib
+    from neural_inventory_control_b200.engine import current_stream_ptr
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(3)
+    for wd in (0.0, 0.01):
+        p_ref = torch.randn(10007, generator=g, device=dev).requires_grad_(True)
+        opt = torch.optim.Adam([p_ref], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+        p = p_ref.detach().clone()
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        for step in range(1, 26):
+            grad = torch.randn(p.shape, generator=g, device=dev) * (0.1 + 0.05 * step)
+            p_ref.grad = grad.clone()
+            opt.step()
+            rc = lib.hdpo_adam_step(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 3e-3, 0.9, 0.999,
+                                    1e-8, wd, step, current_stream_ptr(dev))
+            K.check(lib, rc, "hdpo_adam_step")
+        torch.cuda.synchronize()
+        assert float((p - p_ref.detach()).abs().max()) <= 2e-6 * float(p_ref.detach().abs().max())
+        st = opt.state[p_ref]
+        assert float((m - st["exp_avg"]).abs().max()) <= 1e-6 * float(st["exp_avg"].abs().max())
+        assert float((v - st["exp_avg_sq"]).abs().max()) <= 1e-6 * float(st["exp_avg_sq"].abs().max())
+
+
+def test_fused_training_step_matches_reference_control_flow(monkeypatch):
+    """`Trainer.train` with the fused step (flat vectors, adjoint straight into the flat gradient, hdpo_adam_step, no
+    per-batch host read) against the reference's control flow (autograd node + torch.optim.Adam.step) on the same
+    seeds: loss histories and trained weights agree; the optimizer's state_dict stays checkpoint-compatible."""
+    from torch.utils.data import DataLoader
+    from neural_inventory_control_b200.data_handling import DatasetCreator, Scenario
+    from neural_inventory_control_b200.environment import Simulator
+    from neural_inventory_control_b200.loss_functions import PolicyLoss
+    from neural_inventory_control_b200.neural_networks import NeuralNetworkCreator
+    from neural_inventory_control_b200.trainer import Trainer
+    dev = "cuda:0"
+    results = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("HDPO_FUSED_STEP", mode)
+        s = copy.deepcopy(_cfg("settings", "one_warehouse_lost_demand"))
+        p = copy.deepcopy(_cfg("policies_and_hyperparams", "vanilla_warehouse"))
+        p["nn_params"]["neurons_per_hidden_layer"]["master"] = [64, 64]
+        p["nn_params"]["gradient_clipping_norm_value"] = 5.0
+        obs_params = defaultdict(lambda: None, s["observation_params"])
+        pbd = s["params_by_dataset"]
+        pbd["train"].update(n_samples=600, batch_size=256)
+        pbd["dev"].update(n_samples=128, batch_size=128)
+        common = (s["problem_params"], s["store_params"], s["warehouse_params"], s["echelon_params"])
+        periods = max(pbd["train"]["periods"], pbd["dev"]["periods"])
+        sc = Scenario(periods, *common, 600 + 128, obs_params, copy.deepcopy(s["seeds"]))
+        train, devset = DatasetCreator().create_datasets(sc, split=True, by_sample_indexes=True, sample_index_for_split=128)
+        loaders = {"train": DataLoader(train, batch_size=256, shuffle=True),
+                   "dev": DataLoader(devset, batch_size=128, shuffle=False)}
+        torch.manual_seed(0)
+        model = NeuralNetworkCreator().create_neural_network(sc, p["nn_params"], device=dev)
+        opt = torch.optim.Adam(model.parameters(), lr=p["optimizer_params"]["learning_rate"])
+        tr, sim = Trainer(device=dev), Simulator(device=dev)
+        tp = p["trainer_params"]
+        tp.update(epochs=5, do_dev_every_n_epochs=2, print_results_every_n_epochs=100, save_model=False)
+        tr.train(5, PolicyLoss(), sim, model, loaders, opt, s["problem_params"], obs_params, pbd, tp)
+        assert tr.last_path == "fused"
+        sd = opt.state_dict()
+        assert len(sd["state"]) == len(list(model.parameters())) and all("exp_avg_sq" in v for v in sd["state"].values())
+        assert int(next(iter(sd["state"].values()))["step"]) == 5 * 3
+        results[mode] = (np.array(tr.all_train_losses), np.array(tr.all_dev_losses),
+                         {k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()})
+    a, b = results["1"], results["0"]
+    np.testing.assert_allclose(a[0], b[0], rtol=2e-5)
+    np.testing.assert_allclose(a[1], b[1], rtol=2e-5)
+    for k in a[2]:
+        assert np.abs(a[2][k] - b[2][k]).max() <= 1e-4 * max(1.0, np.abs(b[2][k]).max()), k
