@@ -218,6 +218,187 @@ class SymmetryAware(MyNeuralNetwork):
                           warehouse_net=nets[2], prop_eps=self.prop_eps)
 
 
+class GNN(MyNeuralNetwork):
+    """The reference's shipped weight-shared policy (neural_networks.py:742-1492): node / edge MLPs shared by all nodes
+    and edges of the supply graph, `num_message_passing` rounds (1 for warehouse-stores networks, E + 1 for the serial
+    system), softplus edge outputs, proportional allocation per supplying node. Same modules (`initial_node`,
+    `initial_edge`, `node_update`, `edge_update`, `output` => same state_dict keys) and the same arithmetic; the graph is
+    turned ONCE into index tensors (edge order: internal edges in row-major adjacency order, supplier edges, demand
+    edges, self-loops) and every per-edge Python loop of the reference becomes one gather / index_add. Runs on the
+    generic per-step path (torch policy + one K3 kernel per period)."""
+
+    def __init__(self, args, scenario, device="cpu"):
+        super().__init__(args, device)
+        self.scenario = scenario
+        self.transshipment = args.get("transshipment", False)
+        self._graph = {}
+
+    # ---- graph structure (neural_networks.py:757-845, 1015-1077), built once per device
+    def graph(self, device):
+        key = str(device)
+        if key in self._graph:
+            return self._graph[key]
+        pp = self.scenario.problem_params
+        S, W, E = pp.get("n_stores", 0), pp.get("n_warehouses", 0), pp.get("n_extra_echelons", 0)
+        n = E + W + S
+        adj = torch.zeros(n, n)
+        supplier, demand = torch.zeros(n), torch.zeros(n)
+        if E > 0:  # serial network: echelon_0 -> ... -> warehouse -> store
+            supplier[0] = 1
+            for i in range(E - 1):
+                adj[i, i + 1] = 1
+            adj[E - 1, E] = 1
+            adj[E, E + W] = 1
+            demand[E + W] = 1
+        else:  # warehouses -> stores
+            supplier[:W] = 1
+            demand[W:] = 1
+            if W == 1:
+                adj[0, W:] = 1
+            else:
+                wsa = pp.get("warehouse_store_adjacency", None)
+                if wsa is None:
+                    raise ValueError(f"Multiple warehouses ({W}) detected but no 'warehouse_store_adjacency' matrix found "
+                                     "in problem_params. Please specify which stores connect to which warehouses.")
+                adj[:W, W:] = torch.tensor(wsa, dtype=torch.float32)
+        internal = adj.nonzero(as_tuple=False)  # row-major: the reference's edge order
+        src, tgt = internal[:, 0], internal[:, 1]
+        sup_nodes = supplier.nonzero(as_tuple=False).squeeze(-1)
+        dem_nodes = demand.nonzero(as_tuple=False).squeeze(-1)
+        self_nodes = (adj.sum(dim=1) > 0).nonzero(as_tuple=False).squeeze(-1)
+        if self.transshipment:
+            self_nodes = self_nodes[:0]
+        n_int, n_sup, n_dem, n_self = len(src), len(sup_nodes), len(dem_nodes), len(self_nodes)
+        # per edge: source node (n = the virtual all-zero node), target node
+        e_src = torch.cat([src, torch.full((n_sup,), n), dem_nodes, self_nodes]).long()
+        e_tgt = torch.cat([tgt, sup_nodes, torch.full((n_dem,), n), self_nodes]).long()
+        # aggregation: which edges add into incoming[node] / outgoing[node] (neural_networks.py:1196-1268)
+        in_edges = torch.cat([torch.arange(n_int), n_int + torch.arange(n_sup), n_int + n_sup + n_dem + torch.arange(n_self)])
+        in_nodes = torch.cat([tgt, sup_nodes, self_nodes])
+        out_edges = torch.cat([torch.arange(n_int), n_int + n_sup + torch.arange(n_dem),
+                               n_int + n_sup + n_dem + torch.arange(n_self)])
+        out_nodes = torch.cat([src, dem_nodes, self_nodes])
+        in_deg = adj.sum(dim=0) + supplier
+        out_deg = adj.sum(dim=1) + demand
+        in_deg[self_nodes] += 1
+        out_deg[self_nodes] += 1
+        in_deg = torch.where(in_deg > 0, in_deg, torch.ones_like(in_deg))
+        out_deg = torch.where(out_deg > 0, out_deg, torch.ones_like(out_deg))
+        # proportional allocation: the constrained edges of every supplying node = its internal edges + its self-loop
+        alloc_edges = torch.cat([torch.arange(n_int), n_int + n_sup + n_dem + torch.arange(n_self)])
+        alloc_nodes = torch.cat([src, self_nodes])
+        # output mapping (neural_networks.py:1079-1138)
+        if E > 0:
+            maps = {"stores": [[n_int - 1]], "warehouses": [[n_int - 2]],
+                    "echelons": [[n_int]] + [[i - 1] for i in range(1, E)]}
+        else:
+            stores = [[] for _ in range(S)]
+            for i, (a, b) in enumerate(internal.tolist()):
+                if a < W <= b:
+                    stores[b - W].append(i)
+            maps = {"stores": stores, "warehouses": [[n_int + w] for w in range(W)]}
+        out_maps = {}
+        for k, rows in maps.items():
+            if not rows:
+                continue
+            cols = max(len(r) for r in rows)
+            idx = torch.full((len(rows), cols), -1, dtype=torch.long)
+            for i, r in enumerate(rows):
+                idx[i, :len(r)] = torch.tensor(r, dtype=torch.long)
+            out_maps[k] = idx
+        g = {"n": n, "S": S, "W": W, "E": E, "src": src, "tgt": tgt, "sup_nodes": sup_nodes, "e_src": e_src, "e_tgt": e_tgt,
+             "n_edges": n_int + n_sup + n_dem + n_self, "in_edges": in_edges, "in_nodes": in_nodes, "out_edges": out_edges,
+             "out_nodes": out_nodes, "in_scale": 1.0 / torch.sqrt(in_deg), "out_scale": 1.0 / torch.sqrt(out_deg),
+             "alloc_edges": alloc_edges, "alloc_nodes": alloc_nodes, "steps": E + 1 if E > 0 else 1, "out_maps": out_maps}
+        g = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in g.items()}
+        g["out_maps"] = {k: v.to(device) for k, v in out_maps.items()}
+        self._graph[key] = g
+        return g
+
+    # ---- node features, padded to a common [inventory | state] layout (neural_networks.py:847-911, 1170-1177)
+    def node_features(self, obs, g):
+        blocks, inv_lens = [], []
+        if g["E"] > 0:
+            blocks.append([obs["echelon_inventories"], obs["echelon_holding_costs"].unsqueeze(-1)])
+            inv_lens.append(obs["echelon_inventories"].size(-1))
+        wh = [obs["warehouse_inventories"], obs["warehouse_holding_costs"].unsqueeze(-1)]
+        if "warehouse_edge_costs" in obs and obs["warehouse_edge_costs"] is not None:
+            wh.append(obs["warehouse_edge_costs"].unsqueeze(-1))
+        blocks.append(wh)
+        inv_lens.append(obs["warehouse_inventories"].size(-1))
+        st = [obs["store_inventories"], obs["holding_costs"].unsqueeze(-1), obs["underage_costs"].unsqueeze(-1)]
+        if "past_demands" in obs:
+            st.append(obs["past_demands"])
+            if "days_from_christmas" in obs:
+                st.append(obs["days_from_christmas"].unsqueeze(-1))
+        else:
+            st += [obs["mean"].unsqueeze(-1), obs["std"].unsqueeze(-1)]
+        blocks.append(st)
+        inv_lens.append(obs["store_inventories"].size(-1))
+        max_inv = max(inv_lens)
+        max_state = max(sum(t.size(-1) for t in b[1:]) for b in blocks)
+        padded = []
+        for b, il in zip(blocks, inv_lens):
+            state = torch.cat(b[1:], dim=-1)
+            padded.append(torch.cat([F.pad(b[0], (0, max_inv - il)), F.pad(state, (0, max_state - state.size(-1)))], dim=2))
+        return torch.cat(padded, dim=1)
+
+    def edge_lead_times(self, obs, g):
+        """[n_edges] lead time feature of every edge, taken from scenario 0 like the reference (:949-1013)."""
+        n_int = len(g["src"])
+        lt = torch.zeros(g["n_edges"], device=g["src"].device)
+        if g["E"] > 0:
+            E = g["E"]
+            vals = [obs["echelon_lead_times"][0, i + 1] for i in range(E - 1)]
+            vals += [obs["warehouse_lead_times"][0, 0], obs["lead_times"][0, 0, 0]]
+            lt[:n_int] = torch.stack(vals)
+            lt[n_int] = obs["echelon_lead_times"][0, 0]
+        else:
+            W = g["W"]
+            lt[:n_int] = obs["lead_times"][0][g["tgt"] - W, g["src"]]
+            lt[n_int:n_int + len(g["sup_nodes"])] = obs["warehouse_lead_times"][0, g["sup_nodes"]]
+        return lt
+
+    def _gather_nodes(self, nodes, idx):
+        """nodes[:, idx] with index n = the virtual supplier / customer node (all zeros)."""
+        ext = torch.cat([nodes, torch.zeros_like(nodes[:, :1])], dim=1)
+        return ext[:, idx]
+
+    def forward(self, observation):
+        dev = observation["store_inventories"].device
+        g = self.graph(dev)
+        feats = self.node_features(observation, g)
+        nodes = self.net["initial_node"](feats)
+        B = nodes.size(0)
+        lt = self.edge_lead_times(observation, g).view(1, -1, 1).expand(B, -1, -1)
+        edges = self.net["initial_edge"](torch.cat([self._gather_nodes(nodes, g["e_src"]),
+                                                    self._gather_nodes(nodes, g["e_tgt"]), lt], dim=-1))
+        for _ in range(g["steps"]):
+            incoming = torch.zeros(B, g["n"], edges.size(-1), device=dev, dtype=edges.dtype)
+            outgoing = torch.zeros_like(incoming)
+            incoming = incoming.index_add(1, g["in_nodes"], edges[:, g["in_edges"]]) * g["in_scale"].view(1, -1, 1)
+            outgoing = outgoing.index_add(1, g["out_nodes"], edges[:, g["out_edges"]]) * g["out_scale"].view(1, -1, 1)
+            nodes = nodes + self.net["node_update"](torch.cat([nodes, incoming, outgoing], dim=-1))
+            edges = edges + self.net["edge_update"](torch.cat([edges, self._gather_nodes(nodes, g["e_src"]),
+                                                               self._gather_nodes(nodes, g["e_tgt"])], dim=-1))
+        out = self.net["output"](edges).squeeze(-1)  # [B, n_edges]
+        # proportional allocation per supplying node over its internal edges + self-loop (:1437-1492, :111-138)
+        inv = torch.cat([observation[k][:, :, 0] for k in ("echelon_inventories", "warehouse_inventories",
+                                                           "store_inventories") if k in observation and
+                         (k != "echelon_inventories" or g["E"] > 0)], dim=1)
+        want = torch.zeros(B, g["n"], device=dev, dtype=out.dtype).index_add(1, g["alloc_nodes"], out[:, g["alloc_edges"]])
+        scale = inv / (want + 1e-10)
+        if not self.transshipment:
+            scale = torch.clip(scale, max=1.0)
+        alloc = out.clone()
+        alloc[:, g["alloc_edges"]] = out[:, g["alloc_edges"]] * scale[:, g["alloc_nodes"]]
+        result = {}
+        for k, idx in g["out_maps"].items():
+            picked = alloc[:, idx.clamp(min=0).reshape(-1)].view(B, *idx.shape)
+            result[k] = picked * (idx >= 0).to(picked.dtype)
+        return result
+
+
 class BaseStock(MyNeuralNetwork):
     """order = max(base level - inventory position, 0) (neural_networks.py:216-229); generic path only."""
 
@@ -271,6 +452,7 @@ class NeuralNetworkCreator:
             "vanilla_serial": VanillaSerial,
             "vanilla_warehouse": VanillaWarehouse,
             "symmetry_aware": SymmetryAware,
+            "gnn": GNN,
         }[name]
 
     def get_warehouse_upper_bound(self, warehouse_upper_bound_mult, scenario, device="cpu"):
@@ -285,7 +467,7 @@ class NeuralNetworkCreator:
             if val is None:
                 params["output_sizes"][key] = self.set_default_output_size(key, scenario.problem_params)
         cls = self.get_architecture(params["name"])
-        if params["name"] in ("vanilla_warehouse",):
+        if params["name"] in ("vanilla_warehouse", "gnn"):
             model = cls(params, scenario, device=device)
         else:
             model = cls(params, device=device)

@@ -120,7 +120,7 @@ ONLY = None  # --only a,b: regenerate just these cases
 
 
 def rollout_case(name, setting, policy, B, T, T_total, ignore=30, setting_patch=None, nn_patch=None,
-                 torch_seed=0, state_dict_path=None, perturb=0.0, compact=False):
+                 torch_seed=0, state_dict_path=None, perturb=0.0, compact=False, kind="rollout"):
     if ONLY is not None and name not in ONLY:
         return
     s, p, obs_params, scenario, data, model = build_case(setting, policy, B, T, T_total, setting_patch, nn_patch,
@@ -173,7 +173,7 @@ def rollout_case(name, setting, policy, B, T, T_total, ignore=30, setting_patch=
         "torch": torch.__version__, "numpy": np.__version__,
     }
     arrays["meta"] = np.array(json.dumps(meta))
-    path = os.path.join(HERE, f"rollout_{name}.npz")
+    path = os.path.join(HERE, f"{kind}_{name}.npz")
     np.savez_compressed(path, **arrays)
     gn = float(np.sqrt(sum((v.astype(np.float64) ** 2).sum() for k, v in r32.items() if k.startswith("grad/"))))
     print(f"{name:34s} B={B:4d} total={r32['total']:.6e} report={r32['report']:.6e} |grad|={gn:.6e} "
@@ -328,6 +328,11 @@ def main():
                  setting_patch=stores50, compact=True)
     rollout_case("many_warehouses_3x50_w512", "many_warehouses_lost_demand", "vanilla_warehouse", B=16, T=50,
                  T_total=50, setting_patch=many3x50, compact=True)
+
+    # the reference's shipped weight-shared policy (GNN) on the generic per-step path: kind "gnn" keeps these fixtures
+    # out of the fused-kernel / numpy-oracle test matrices (the oracle restates the fused policies only)
+    rollout_case("one_warehouse", "one_warehouse_lost_demand", "gnn", B=32, T=50, T_total=60, kind="gnn")
+    rollout_case("many_warehouses", "many_warehouses_lost_demand", "gnn", B=32, T=50, T_total=60, kind="gnn")
 
     step_case("one_store_lost", B=16, S=1, W=0, E=0, L=4, Lw=0, Le=0, lost=True, profit=False, edge_cost=False, seed=1)
     step_case("one_store_backlog_profit", B=16, S=1, W=0, E=0, L=7, Lw=0, Le=0, lost=False, profit=True,
