@@ -129,8 +129,9 @@ typedef struct HdpoAction {
 
 /* demand[b*demand_stride_b + s*demand_stride_s] is the current demand of (b,s): pass the base pointer
  * already offset to column t+period_shift; strides are in elements.
- * Writes the next state into `next` (must not alias `cur`) and reward[B]. Precondition (as in the reference's
- * flat put, environment.py:422): every NON-ZERO allocation has 1 <= lead time <= pipeline length. */
+ * Writes the next state into `next` (must not alias `cur`) and reward[B]. A NON-ZERO order whose lead time is outside
+ * [1, pipeline length] lands where the reference's flat put (environment.py:422-432) puts it: in a neighbouring node's
+ * pipeline (lead 0 = last slot of the previous node); orders that would fall outside the tensor are dropped. */
 int hdpo_step_fwd(const HdpoProblem* pb, const HdpoStatics* st, const HdpoState* cur, const HdpoAction* act,
                   const float* demand, int64_t demand_stride_b, int64_t demand_stride_s, HdpoState* next,
                   float* reward, void* stream);

@@ -17,14 +17,58 @@ __device__ __forceinline__ void shift_pipeline(const float* __restrict__ src, fl
   dst[len - 1] = 0.f;
 }
 
-// the masked put(accumulate=True) of environment.py:422-432: exact zeros are skipped; slot = lead - 1
-__device__ __forceinline__ void land_order(float* __restrict__ dst, int len, float amount, float lead, int* bad) {
+// the masked put(accumulate=True) of environment.py:422-432: exact zeros are skipped; slot = lead - 1.
+// The reference's put works on the FLATTENED [B, nodes, len] tensor at index shift + lead - 1, so a non-zero order whose
+// lead time is outside [1, len] lands in a NEIGHBOURING node's pipeline (lead 0: the last slot of the previous node;
+// flat index -1 wraps to the tensor's last element). The shipped GNN policy does this on many_warehouses_lost_demand
+// (its ragged edge -> column mapping pairs allocations with the lead-time-0 entries of unconnected pairs), so the
+// behaviour is reproduced: in-range orders land here, out-of-range ones in stray_orders_kernel after this kernel.
+__device__ __forceinline__ void land_order(float* __restrict__ dst, int len, float amount, float lead, int* stray) {
   if (amount != 0.f) {
-    int slot = static_cast<int>(lead) - 1;
+    const int slot = static_cast<int>(lead) - 1;
     if (slot >= 0 && slot < len)
       dst[slot] += amount;
     else
-      *bad = 1;  // the reference would write into a neighbouring node's pipeline here; we refuse instead
+      *stray = 1;
+  }
+}
+// flat index of `slot` (possibly out of range) of node `node` in a [n_nodes_total, len] array, Python-style wrap of
+// negative indices; -1 when it falls outside the tensor (torch.put_ raises there)
+__device__ __forceinline__ int64_t flat_slot(int64_t node, int len, int slot, int64_t total) {
+  int64_t f = node * len + slot;
+  if (f < 0) f += total;
+  return (f >= 0 && f < total) ? f : -1;
+}
+
+// second pass of a period: orders with an out-of-range lead time -> the element the reference's flat put hits
+__global__ void __launch_bounds__(256) stray_orders_kernel(HdpoProblem pb, HdpoStatics st, HdpoAction act, HdpoState nxt) {
+  const int S = pb.S, W = pb.W, E = pb.E, Wc = W > 0 ? W : 1;
+  const int64_t n_store = static_cast<int64_t>(pb.B) * S * Wc, n_wh = static_cast<int64_t>(pb.B) * W,
+                n_ech = static_cast<int64_t>(pb.B) * E;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n_store) {
+    const float a = act.stores[i];
+    const int slot = static_cast<int>(st.lead_times[i]) - 1;
+    if (a != 0.f && (slot < 0 || slot >= pb.L)) {
+      const int64_t f = flat_slot(i / Wc, pb.L, slot, static_cast<int64_t>(pb.B) * S * pb.L);
+      if (f >= 0) atomicAdd(nxt.store + f, a);
+    }
+  } else if (i < n_store + n_wh) {
+    const int64_t j = i - n_store;
+    const float a = act.warehouses[j];
+    const int slot = static_cast<int>(st.warehouse_lead_times[j]) - 1;
+    if (a != 0.f && (slot < 0 || slot >= pb.Lw)) {
+      const int64_t f = flat_slot(j, pb.Lw, slot, static_cast<int64_t>(pb.B) * W * pb.Lw);
+      if (f >= 0) atomicAdd(nxt.warehouse + f, a);
+    }
+  } else if (i < n_store + n_wh + n_ech) {
+    const int64_t j = i - n_store - n_wh;
+    const float a = act.echelons[j];
+    const int slot = static_cast<int>(st.echelon_lead_times[j]) - 1;
+    if (a != 0.f && (slot < 0 || slot >= pb.Le)) {
+      const int64_t f = flat_slot(j, pb.Le, slot, static_cast<int64_t>(pb.B) * E * pb.Le);
+      if (f >= 0) atomicAdd(nxt.echelon + f, a);
+    }
   }
 }
 
@@ -121,8 +165,13 @@ __global__ void __launch_bounds__(128) step_bwd_kernel(HdpoProblem pb, HdpoStati
     const float a = act.echelons[i];
     float ga = 0.f;
     if (a != 0.f && gn) {
-      int slot = static_cast<int>(st.echelon_lead_times[i]) - 1;
-      if (slot >= 0 && slot < Le) ga = gn[slot];
+      const int slot = static_cast<int>(st.echelon_lead_times[i]) - 1;
+      if (slot >= 0 && slot < Le) {
+        ga = gn[slot];
+      } else {  // stray order: the adjoint of the element the flat put hit
+        const int64_t f = flat_slot(i, Le, slot, static_cast<int64_t>(pb.B) * E * Le);
+        if (f >= 0) ga = g_next.echelon[f];
+      }
     }
     if (e >= 1) ga -= g_raw_prev;  // this echelon's order drew down echelon e-1
     g_act.echelons[i] = ga;
@@ -147,8 +196,13 @@ __global__ void __launch_bounds__(128) step_bwd_kernel(HdpoProblem pb, HdpoStati
     const float a = act.warehouses[i];
     float ga = 0.f;
     if (a != 0.f && gn) {
-      int slot = static_cast<int>(st.warehouse_lead_times[i]) - 1;
-      if (slot >= 0 && slot < Lw) ga = gn[slot];
+      const int slot = static_cast<int>(st.warehouse_lead_times[i]) - 1;
+      if (slot >= 0 && slot < Lw) {
+        ga = gn[slot];
+      } else {
+        const int64_t f = flat_slot(i, Lw, slot, static_cast<int64_t>(pb.B) * W * Lw);
+        if (f >= 0) ga = g_next.warehouse[f];
+      }
     }
     if (pb.has_edge_cost) ga += rb * st.warehouse_edge_costs[i];
     if (E > 0) ga -= g_raw_last_echelon;
@@ -180,8 +234,13 @@ __global__ void __launch_bounds__(128) step_bwd_kernel(HdpoProblem pb, HdpoStati
       const float a = act.stores[j];
       float ga = 0.f;
       if (a != 0.f && gn) {
-        int slot = static_cast<int>(st.lead_times[j]) - 1;
-        if (slot >= 0 && slot < L) ga = gn[slot];
+        const int slot = static_cast<int>(st.lead_times[j]) - 1;
+        if (slot >= 0 && slot < L) {
+          ga = gn[slot];
+        } else {
+          const int64_t f = flat_slot(i, L, slot, static_cast<int64_t>(pb.B) * S * L);
+          if (f >= 0) ga = g_next.store[f];
+        }
       }
       if (W > 0) ga -= g_raw_w[w];
       g_act.stores[j] = ga;
@@ -260,6 +319,10 @@ extern "C" int hdpo_step_fwd(const HdpoProblem* pb, const HdpoStatics* st, const
   auto k = step_fwd_kernel;
   HDPO_LAUNCH(k, ceil_div(pb->B, 128), 128, 0, stream, *pb, *st, *cur, *act, demand, dsb, dss, *next, reward,
               static_cast<int*>(nullptr));
+  // orders whose lead time is outside [1, pipeline length]: the reference's flat put lands them in a neighbouring node
+  const int64_t n_orders = static_cast<int64_t>(pb->B) * (static_cast<int64_t>(pb->S) * (pb->W > 0 ? pb->W : 1) + pb->W + pb->E);
+  auto k2 = stray_orders_kernel;
+  HDPO_LAUNCH(k2, static_cast<unsigned>(ceil_div64(n_orders, 256)), 256, 0, stream, *pb, *st, *act, *next);
   HDPO_LAUNCH_OK();
   return HDPO_OK;
 }

@@ -353,8 +353,10 @@ def _pipeline_adjoint(g_new, g_raw, alloc, lead):
     g_inv[:, :, 0] = g_raw
     g_inv[:, :, 1] = g_new[:, :, 0]
     g_inv[:, :, 2:] = g_new[:, :, 1:L - 1]
-    slot = np.clip(lead.astype(np.int64) - 1, 0, L - 1)
-    g_alloc = np.take_along_axis(g_new, slot, axis=2) * (alloc != 0)
+    # gather at the SAME flat indices the put used: shift + lead - 1 over the flattened [B, n, L] tensor, so an order with
+    # a lead time outside [1, L] reads the adjoint of the neighbouring node's slot it landed in (index -1 wraps)
+    idx = allocation_shift(B, n, L)[:, :, None] + lead.astype(np.int64) - 1
+    g_alloc = g_new.reshape(-1)[idx] * (alloc != 0)
     return g_inv, g_alloc
 
 

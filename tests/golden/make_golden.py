@@ -180,7 +180,7 @@ def rollout_case(name, setting, policy, B, T, T_total, ignore=30, setting_patch=
           f"sha={meta['demands_sha256_12']} -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
-def step_case(name, B, S, W, E, L, Lw, Le, lost, profit, edge_cost, seed):
+def step_case(name, B, S, W, E, L, Lw, Le, lost, profit, edge_cost, seed, stray=False):
     """One reference `Simulator.step` with random state / action / upstream adjoints (environment.py:110-169)."""
     if ONLY is not None and f"step_{name}" not in ONLY:
         return
@@ -217,6 +217,13 @@ def step_case(name, B, S, W, E, L, Lw, Le, lost, profit, edge_cost, seed):
     if W > 1:
         data["lead_times"][:, 0, 0] = 0.0
         action["stores"][:, 0, 0] = 0.0
+    if stray:
+        # NON-zero orders on lead-time-0 pairs (what the shipped GNN policy does on many_warehouses_lost_demand): the
+        # reference's flat put lands them in the previous node's last slot; (b=0, s=0) wraps to the tensor's last element
+        data["lead_times"][:, 0, 0] = 0.0
+        action["stores"][:, 0, 0] = rnd(B, lo=0.5, hi=3.0)
+        data["lead_times"][:, 2, 1] = 0.0
+        action["stores"][:, 2, 1] = rnd(B, lo=0.5, hi=3.0)
     # some on-hand inventories exactly equal to demand -> clip kink at 0 (grad 1 at x==0)
     data["initial_inventories"][0, :, 0] = data["demands"][0, :, 1]
     if W > 0:
@@ -341,6 +348,8 @@ def main():
     step_case("one_warehouse", B=8, S=7, W=1, E=0, L=3, Lw=3, Le=0, lost=True, profit=False, edge_cost=False, seed=4)
     step_case("many_warehouses", B=8, S=6, W=3, E=0, L=6, Lw=3, Le=0, lost=True, profit=False, edge_cost=True,
               seed=5)
+    step_case("many_warehouses_stray", B=8, S=6, W=3, E=0, L=6, Lw=3, Le=0, lost=True, profit=False, edge_cost=True,
+              seed=6, stray=True)
 
 
 if __name__ == "__main__":
