@@ -480,17 +480,21 @@ def main():
         torch.cuda.empty_cache()
         others = {}
         for name in ("one_warehouse_lost_demand_symmetry_aware", "one_store_backlogged_lead20", "serial_system",
-                     "one_store_lost", "many_warehouses_lost_demand", "many_warehouses_lost_demand_8192"):
-            kw2 = {}
-            if name.endswith("_8192"):  # BASELINE cfg 5 in full on ONE GPU: the strong-scaling reference point
+                     "one_store_lost", "many_warehouses_lost_demand", "many_warehouses_lost_demand_8192",
+                     "one_store_backlogged_lead20_ckpt10", "one_warehouse_lost_demand_tf32"):
+            kw2, ckpt2, prec2 = {}, 0, "tf32x3"
+            if name.endswith("_ckpt10"):  # recomputation checkpoints: state of every 10th period taped, rest re-run
+                name_wl, ckpt2 = name[:-len("_ckpt10")], 10
+            elif name.endswith("_tf32"):  # the headline workload with single-pass TF32 GEMMs (NOT parity grade)
+                name_wl, prec2 = name[:-len("_tf32")], "tf32"
+            elif name.endswith("_8192"):  # BASELINE cfg 5 in full on ONE GPU: the strong-scaling reference point
                 name_wl, kw2 = "many_warehouses_lost_demand", {"B": 8192}
             else:
                 name_wl = name
             ps2, pp2, data2, widths2 = WL.WORKLOADS[name_wl](dev, seed=57, T=T, **kw2)
             B2, S2 = data2["demands"].shape[0], pp2["n_stores"]
             flat2 = WL.init_params(widths2, torch.Generator(device=dev).manual_seed(0), dev)
-            prec2 = "tf32x3"
-            eng2 = EN.FusedRollout(ps2, pp2, data2, T, ignore_periods=30, precision=prec2)
+            eng2 = EN.FusedRollout(ps2, pp2, data2, T, ignore_periods=30, precision=prec2, checkpoint_interval=ckpt2)
             grad2 = torch.zeros_like(flat2)
 
             def step2():
@@ -501,7 +505,9 @@ def main():
                 step2()
             ms2 = time_region(step2, 10)
             others[name] = {"value": B2 * T / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "scenarios": B2,
-                            "precision": prec2, "steps": 10, "warmup": 3}
+                            "precision": prec2, "steps": 10, "warmup": 3, "workspace_bytes": eng2.ws_bytes}
+            if ckpt2:
+                others[name]["checkpoint_interval"] = ckpt2
             del eng2, data2, flat2, grad2
             torch.cuda.empty_cache()
 

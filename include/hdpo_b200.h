@@ -194,7 +194,9 @@ typedef struct HdpoRolloutDesc {
   int32_t demand_source;      /* HDPO_DEMAND_* source */
   int32_t demand_clip_at_zero;
   float demand_rho;           /* one-factor correlation of the normal sampler */
-  int32_t reserved0;
+  int32_t checkpoint_interval;/* K > 1: the forward keeps the state of every K-th period only and the adjoint re-runs
+                                 the K - 1 periods in between (recomputation checkpointing: tape bytes / K for one
+                                 extra forward pass; small-net path). 0 / 1: the state of every period is taped */
   uint64_t philox_seed, philox_offset;
   const float* demand_mean;
   const float* demand_std;

@@ -48,7 +48,7 @@ class RolloutDesc(C.Structure):
                 ("warehouse_net", Mlp), ("adjacency", p),
                 # ABI 2: demand generated on the device by the Philox sampler (K4 in the path)
                 ("demand_source", C.c_int32), ("demand_clip_at_zero", C.c_int32), ("demand_rho", C.c_float),
-                ("reserved0", C.c_int32), ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
+                ("checkpoint_interval", C.c_int32), ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
                 ("demand_mean", p), ("demand_std", p)]
 
 

@@ -127,18 +127,34 @@ int build_cfg(const HdpoRolloutDesc* d, int, Cfg* c) {
   }
   c->s_total_bwd = c->tc ? s : c->s_total;
   c->tape_stride = c->IN4;
+  c->ckpt = d->checkpoint_interval > 1 ? d->checkpoint_interval : 1;
+  if (c->ckpt > c->T && c->T > 0) c->ckpt = c->T;
+  c->ring = nullptr;
   return HDPO_OK;
 }
 
 
 static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+// workspace = [state tape: ceil(T / K) checkpoints][per-warp gradient slabs][K > 1: per-warp segment rings]
+static size_t tape_bytes(const Cfg& c, int save) {
+  const size_t slots = (static_cast<size_t>(c.T) + c.ckpt - 1) / c.ckpt;
+  return save ? align256(slots * c.B * c.tape_stride * sizeof(float)) : 0;
+}
+static size_t partial_bytes(const Cfg& c) {
+  return align256(static_cast<size_t>(kMaxPartialRows) * ((c.P + 3) & ~3) * sizeof(float));
+}
+static size_t ring_bytes(const Cfg& c, int save) {
+  if (!save || c.ckpt <= 1) return 0;
+  // one ring per adjoint warp: the launch has at most ceil(B / 32) rounded up to a CTA, capped at kMaxPartialRows
+  size_t warps = static_cast<size_t>(ceil_div(c.B, 32)) + kWarpsPerCta;
+  if (warps > kMaxPartialRows) warps = kMaxPartialRows;
+  return align256(warps * c.ckpt * 32 * c.tape_stride * sizeof(float));
+}
 
 size_t workspace_bytes(const HdpoRolloutDesc* d) {
   Cfg c;
   build_cfg(d, 0, &c);
-  size_t tape = d->save_for_backward ? align256(static_cast<size_t>(c.T) * c.B * c.tape_stride * sizeof(float)) : 0;
-  size_t partial = align256(static_cast<size_t>(kMaxPartialRows) * ((c.P + 3) & ~3) * sizeof(float));
-  return tape + partial + 256;
+  return tape_bytes(c, d->save_for_backward) + partial_bytes(c) + ring_bytes(c, d->save_for_backward) + 256;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -235,8 +251,8 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
     return HDPO_E_WORKSPACE;
   }
   const float* tape = static_cast<const float*>(workspace);
-  const size_t tape_bytes = align256(static_cast<size_t>(c.T) * c.B * c.tape_stride * sizeof(float));
-  float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + tape_bytes);
+  float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + tape_bytes(c, 1));
+  if (c.ckpt > 1) c.ring = reinterpret_cast<float*>(static_cast<char*>(workspace) + tape_bytes(c, 1) + partial_bytes(c));
   const int p_stride = (c.P + 3) & ~3;
   const int n_tiles = ceil_div(c.B, 32);
   const int wpc = pick_warps_per_cta(n_tiles);

@@ -31,6 +31,8 @@ struct Cfg {
   // shared-memory weight block offsets (floats)
   int s_wt0, s_b0, s_wth[kMaxHH], s_bh[kMaxHH], s_wo, s_bo, s_total;
   int tape_stride;  // floats per (t, scenario) row in the tape
+  int ckpt;         // checkpoint interval K: the tape holds the state of periods 0, K, 2K, ... (K = 1: every period)
+  float* ring;      // adjoint, K > 1: per-warp scratch [warp][K][32][tape_stride] for the recomputed states of a segment
   // tensor-core adjoint (precision != fp32): fp32 copies W[n][k] (row stride HS) of the HxH layers for the mma.sync
   // fragments, staged by the adjoint kernel only (after the s_total block the forward kernel uses)
   int tc, s_wn[kMaxHH], s_total_bwd;

@@ -453,11 +453,12 @@ small_fwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
         d[j] = dnext[j];
         if (t + 1 < c.T) dnext[j] = demand_at(c, demands, b[j], t + 1);
       }
-      if (tape) {
+      if (tape && t % c.ckpt == 0) {  // checkpoint: the adjoint recomputes the c.ckpt - 1 states in between
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
           if (valid[j]) {
-            float4* dst = reinterpret_cast<float4*>(tape + (static_cast<int64_t>(t) * c.B + b[j]) * c.tape_stride);
+            float4* dst =
+                reinterpret_cast<float4*>(tape + (static_cast<int64_t>(t / c.ckpt) * c.B + b[j]) * c.tape_stride);
             for (int k4 = 0; k4 < c.IN4 / 4; ++k4) dst[k4] = reinterpret_cast<const float4*>(xrow[j])[k4];
           }
         }
@@ -681,10 +682,37 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
     Statics s;
     load_statics<ARCH>(c, st, b, s);
     for (int k = 0; k < c.XSb; ++k) grow[k] = 0.f;
-    for (int t = c.T - 1; t >= 0; --t) {
-      // A. state x_t from the tape, demand
+    // Recomputation checkpointing (c.ckpt = K > 1): the tape holds x_0, x_K, x_2K, ...; a segment [seg0, seg1) is
+    // re-run forward from its checkpoint (same device functions as the forward kernel: bit-identical states), the
+    // states x_{seg0+1 .. seg1-1} go to this warp's ring (a few KB per warp, L2-resident), then the reverse sweep of
+    // the segment reads them back. K = 1 degenerates to the plain tape.
+    float* ring = c.ring ? c.ring + static_cast<int64_t>(gwarp) * c.ckpt * 32 * c.tape_stride : nullptr;
+    for (int seg0 = ((c.T - 1) / c.ckpt) * c.ckpt; seg0 >= 0; seg0 -= c.ckpt) {
+    const int seg1 = seg0 + c.ckpt < c.T ? seg0 + c.ckpt : c.T;
+    if (seg1 - seg0 > 1) {
+      const float4* src =
+          reinterpret_cast<const float4*>(tape + (static_cast<int64_t>(seg0 / c.ckpt) * c.B + b) * c.tape_stride);
+      for (int k4 = 0; k4 < c.IN4 / 4; ++k4) reinterpret_cast<float4*>(xrow)[k4] = src[k4];
+      for (int t = seg0; t + 1 < seg1; ++t) {
+        float yf[1][kMaxOut];
+        const float* xin[1] = {xrow};
+        float* hr[1] = {hrow};
+        __syncwarp();
+        mlp_fwd<1>(c, Ws, xin, hr, HL, yf);
+        Head hf;
+        head_fwd<ARCH>(c, xrow, yf[0], hf);
+        env_fwd<ARCH>(c, xrow, demand_at(c, demands, b, t), hf, s);
+        float4* dst = reinterpret_cast<float4*>(ring + (static_cast<int64_t>(t + 1 - seg0) * 32 + lane) * c.tape_stride);
+        for (int k4 = 0; k4 < c.IN4 / 4; ++k4) dst[k4] = reinterpret_cast<const float4*>(xrow)[k4];
+      }
+      __syncwarp();
+    }
+    for (int t = seg1 - 1; t >= seg0; --t) {
+      // A. state x_t from the tape (checkpoint) or from the segment ring, demand
       {
-        const float4* src = reinterpret_cast<const float4*>(tape + (static_cast<int64_t>(t) * c.B + b) * c.tape_stride);
+        const float4* src =
+            t == seg0 ? reinterpret_cast<const float4*>(tape + (static_cast<int64_t>(seg0 / c.ckpt) * c.B + b) * c.tape_stride)
+                      : reinterpret_cast<const float4*>(ring + (static_cast<int64_t>(t - seg0) * 32 + lane) * c.tape_stride);
         for (int k4 = 0; k4 < c.IN4 / 4; ++k4) reinterpret_cast<float4*>(xrow)[k4] = src[k4];
       }
       const float d = demand_at(c, demands, b, t);
@@ -830,6 +858,7 @@ small_bwd_kernel(Cfg c, const float* __restrict__ params, const float* __restric
         }
       }
     }
+    }  // segments
   }
 
   // ---- write this warp's partial gradient slab in state_dict layout

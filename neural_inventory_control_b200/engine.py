@@ -53,8 +53,9 @@ class FusedRollout:
 
     def __init__(self, pspec, problem_params, data, periods, ignore_periods=0, period_shift=0,
                  discrete_allocation=False, demand_layout=K.DEMAND_BST, precision="fp32", save_for_backward=True,
-                 philox=None):
-        """philox: None, or {dist: 'normal' | 'poisson', mean: [S] tensor, std: [S] tensor, rho, clip, seed, offset,
+                 philox=None, checkpoint_interval=0):
+        """checkpoint_interval K > 1 (small-net path): tape the state of every K-th period only, the adjoint recomputes.
+        philox: None, or {dist: 'normal' | 'poisson', mean: [S] tensor, std: [S] tensor, rho, clip, seed, offset,
         periods: time extent} - the demand trace is then generated on the device inside every forward call (the batch
         dict needs no 'demands'); bump 'offset' per batch for fresh draws (set_philox_offset)."""
         self.lib = _lib.load()
@@ -89,7 +90,8 @@ class FusedRollout:
                                       save_for_backward=save_for_backward,
                                       warehouse_upper_bound=pspec.warehouse_upper_bound, prop_eps=pspec.prop_eps,
                                       store_net=pspec.store_net, warehouse_net=pspec.warehouse_net,
-                                      adjacency_ptr=_ptr(self.adj), philox=self.philox)
+                                      adjacency_ptr=_ptr(self.adj), philox=self.philox,
+                                      checkpoint_interval=checkpoint_interval)
         self.n_params = int(self.lib.hdpo_param_count(C.byref(self.desc)))
         ws = int(self.lib.hdpo_rollout_workspace_bytes(C.byref(self.desc)))
         if ws == 0:

@@ -28,7 +28,7 @@ def mlp_widths(state_shapes):
 def rollout_desc(arch, pb, T, t_stride, master, period_shift=0, ignore_periods=0, demand_layout=K.DEMAND_BST,
                  discrete_allocation=False, transshipment=False, precision="fp32", save_for_backward=True,
                  warehouse_upper_bound=0.0, prop_eps=1e-15, store_net=None, warehouse_net=None, adjacency_ptr=None,
-                 philox=None):
+                 philox=None, checkpoint_interval=0):
     """master / store_net / warehouse_net: (widths, hidden_act, out_act).
     philox: None (demand comes from the `demands` argument) or a dict {dist: 'normal' | 'poisson', mean_ptr, std_ptr,
     rho, clip, seed, offset}: the [t_stride, S, B] trace is generated on the device inside the forward call."""
@@ -49,6 +49,7 @@ def rollout_desc(arch, pb, T, t_stride, master, period_shift=0, ignore_periods=0
     if warehouse_net is not None:
         d.warehouse_net = K.make_mlp(*warehouse_net)
     d.adjacency = adjacency_ptr
+    d.checkpoint_interval = int(checkpoint_interval)
     if philox is not None:
         d.demand_source = K.DEMAND_PHILOX_NORMAL if philox["dist"] == "normal" else K.DEMAND_PHILOX_POISSON
         d.demand_clip_at_zero = int(bool(philox.get("clip", False)))

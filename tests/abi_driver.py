@@ -124,7 +124,7 @@ def slice_batch(data, n):
 
 
 def rollout(be, meta, params, data, T=None, ignore=None, demand_layout=K.DEMAND_BST, discrete=False, backward=True,
-            g_total=None, g_report=0.0, precision="fp32", philox=None):
+            g_total=None, g_report=0.0, precision="fp32", philox=None, checkpoint_interval=0):
     """philox: None, or {dist, mean, std, rho, clip, seed, offset, periods}: demands = NULL, generated inside the call."""
     L = be.lib
     pp = meta["problem_params"]
@@ -160,7 +160,7 @@ def rollout(be, meta, params, data, T=None, ignore=None, demand_layout=K.DEMAND_
                              demand_layout=demand_layout, discrete_allocation=discrete,
                              transshipment=meta.get("transshipment", False), save_for_backward=backward,
                              warehouse_upper_bound=meta["warehouse_upper_bound"], adjacency_ptr=be.ptr(adj_h),
-                             precision=precision, philox=ph)
+                             precision=precision, philox=ph, checkpoint_interval=checkpoint_interval)
     assert L.hdpo_param_count(C.byref(desc)) == flat.size
     ws_bytes = L.hdpo_rollout_workspace_bytes(C.byref(desc))
     assert ws_bytes > 0, L.hdpo_last_error()
@@ -181,7 +181,7 @@ def rollout(be, meta, params, data, T=None, ignore=None, demand_layout=K.DEMAND_
                             p(report_b), p(reward_tb), p(totals), C.byref(fin), p(ws), ws_bytes, be.stream)
     K.check(L, rc, "hdpo_rollout_fwd")
     be.sync()
-    out = {"cost_b": be.get(cost_b), "report_b": be.get(report_b), "reward_tb": be.get(reward_tb),
+    out = {"workspace_bytes": ws_bytes, "cost_b": be.get(cost_b), "report_b": be.get(report_b), "reward_tb": be.get(reward_tb),
            "totals": be.get(totals),
            "final": {"store": be.get(fin_store), "wh": be.get(fin_wh), "ech": be.get(fin_ech)}}
     if backward:

@@ -123,6 +123,44 @@ def test_rollout_costs_and_gradients_match_reference(be_name, precision, name):
 
 
 @pytest.mark.parametrize("be_name", BACKENDS)
+@pytest.mark.parametrize("K_ckpt", [4, 7, 50])
+@pytest.mark.parametrize("name", ["one_store_lost", "one_store_backlogged_lead20", "serial_system"])
+def test_rollout_recomputation_checkpoints_change_nothing(be_name, name, K_ckpt):
+    """checkpoint_interval K: the forward tapes the state of every K-th period, the adjoint re-runs the periods in
+    between with the forward's own device functions, so costs AND gradients equal the K = 1 run while the state tape
+    shrinks by ~K (T = 50 here: K = 7 leaves a ragged last segment, K = 50 a single checkpoint)."""
+    be = backend(be_name)
+    meta, g = G.load("rollout", name)
+    full = D.rollout(be, meta, g["param"], g["data"])
+    ck = D.rollout(be, meta, g["param"], g["data"], checkpoint_interval=K_ckpt)
+    np.testing.assert_array_equal(ck["reward_tb"], full["reward_tb"])
+    np.testing.assert_array_equal(ck["cost_b"], full["cost_b"])
+    scale = np.abs(full["grad_flat"]).max()
+    assert np.abs(ck["grad_flat"] - full["grad_flat"]).max() <= 1e-6 * scale
+
+
+def test_checkpointed_workspace_at_bench_size():
+    """Workspace of the small path at the bench size (2^20 scenarios x 50 periods), no compute: K = 1 tapes
+    50 state rows per scenario, K = 10 five, plus per-warp rings that do not grow with the batch."""
+    lib = backend("emu").lib
+    meta, g = G.load("rollout", "one_store_backlogged_lead20")
+    shapes = D.flat_params(g["param"])[1]
+    net = (D.spec.mlp_widths(shapes), meta["inner_layer_activations"]["master"], meta["output_layer_activation"]["master"])
+    B, T = 1 << 20, 50
+    S, L = g["data"]["initial_inventories"].shape[1:]
+    pb = D.spec.problem(B, S, 0, 0, L, 0, 0, meta["problem_params"]["lost_demand"], False, False)
+    size = {}
+    for k in (1, 10):
+        desc = D.spec.rollout_desc(meta["nn_name"], pb, T, T, net, save_for_backward=True, checkpoint_interval=k,
+                                   warehouse_upper_bound=meta["warehouse_upper_bound"])
+        size[k] = lib.hdpo_rollout_workspace_bytes(C.byref(desc))
+    row = 4 * 4 * (-(-(S * L) // 4))
+    assert size[1] >= T * B * row
+    assert size[10] <= 5 * B * row + (160 << 20), size  # + 4096 warp rings of 10 x 32 rows + gradient slabs
+    assert size[10] < (1 << 30)
+
+
+@pytest.mark.parametrize("be_name", BACKENDS)
 @pytest.mark.parametrize("name", ["one_store_lost", "serial_system"])
 def test_rollout_time_major_demand_layout_is_identical(be_name, name):
     be = backend(be_name)
