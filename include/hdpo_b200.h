@@ -274,6 +274,9 @@ int hdpo_debug_set_wp_trace(unsigned long long* buf, int32_t cap_per_role);
 /* Opt-in persistent one-launch sweeps of the wide path (wide_persist.cu); default off (env HDPO_WIDE_PERSIST=1). The
  * workspace size depends on it: query hdpo_rollout_workspace_bytes after switching. */
 int hdpo_debug_set_wide_persist(int32_t on);
+/* Routing threshold of the multi-tile CTA-pair GEMM of the wide path: min_tiles > 0 = fewest 256-row tiles of a layer
+ * launch that goes there (1 = every tensor-core GEMM), 0 = never, < 0 = default (off unless HDPO_TC_MULTI=1). */
+int hdpo_debug_set_tc_multi(int32_t min_tiles);
 
 /* misc */
 const char* hdpo_last_error(void);

@@ -1,6 +1,7 @@
 // gemm_tc.cu - tcgen05 / TMEM / TMA tile GEMM (see gemm_tc.cuh). Inline PTX only; no CUTLASS dependency.
 #include "gemm_tc.cuh"
 #include "tc_ptx.cuh"
+#include "wide_persist.cuh"
 
 #include <cstdlib>
 
@@ -546,6 +547,7 @@ static int launch_epi(const GemmTcMaps& tm, const GemmTcArgs& g, int epi, void* 
 }
 
 int gemm(const GemmTcMaps& tm, const GemmTcArgs& g, int epi, int bn, void* stream) {
+  if (bn > kBnMulti) return wp::gemm_multi(tm, g, epi, bn - kBnMulti, stream);
   const int bn_cols = bn == kBnPair ? 128 : bn;
   HDPO_REQUIRE(g.M % 128 == 0 && g.N % bn_cols == 0 && g.K % kBK == 0 && g.K > 0,
                "tcgen05 GEMM shape %dx%dx%d not tileable", g.M, g.N, g.K);
@@ -609,7 +611,8 @@ extern "C" int hdpo_debug_gemm_tc(const float* A, const float* B, float* C, int3
   count_launch();
   count_launch();
   HDPO_LAUNCH_OK();
-  const int bn = tc::pick_bn_pair(M, N);
+  const int bn_multi = wp::pick_bn_multi(M, N);  // hdpo_debug_set_tc_multi(1): the multi-tile CTA-pair form
+  const int bn = bn_multi ? bn_multi : tc::pick_bn_pair(M, N);
   tc::GemmTcMaps tm{};
   int rc;
   if ((rc = tc::make_tensor_map(&tm.a_hi, a_hi, M, K, K, 128))) return rc;
@@ -638,7 +641,8 @@ extern "C" int hdpo_debug_gemm_tc_timeline(const float* A, const float* B, float
   float* a_lo = a_hi + static_cast<size_t>(M) * K;
   float* b_hi = a_lo + static_cast<size_t>(M) * K;
   float* b_lo = b_hi + static_cast<size_t>(N) * K;
-  const int bn = tc::pick_bn_pair(M, N);
+  const int bn_multi = wp::pick_bn_multi(M, N);
+  const int bn = bn_multi ? bn_multi : tc::pick_bn_pair(M, N);
   tc::GemmTcMaps tm{};
   int rc;
   if ((rc = tc::make_tensor_map(&tm.a_hi, a_hi, M, K, K, 128))) return rc;

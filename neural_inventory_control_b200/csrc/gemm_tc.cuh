@@ -66,7 +66,9 @@ constexpr int kBoxRowsC = 32;
 inline int pick_bn(int N) { return (N % 128 == 0) ? 128 : 64; }
 // `bn` selector of gemm(): 64 / 128 = single-CTA tiles 128 x bn; kBnPair = CTA-pair (cta_group::2) tiles 256 x 128.
 constexpr int kBnPair = 1128;
-inline int b_box_rows(int bn) { return bn == kBnPair ? 64 : bn; }  // rows of the B operand's TMA box
+// kBnMulti + 64 | 128 = multi-tile CTA-pair form (wide_persist.cu, gemm_multi): 256 x 64 | 128 tiles, several per pair
+constexpr int kBnMulti = 2000;
+inline int b_box_rows(int bn) { return bn == kBnPair ? 64 : (bn > kBnMulti ? (bn - kBnMulti) / 2 : bn); }  // rows of the B operand's TMA box
 // the pair form needs 256-row and 128-column tiles; HDPO_TC_PAIR=0 disables it (A/B comparison on the GPU box)
 int pair_enabled();
 inline int pick_bn_pair(int M, int N) { return (pair_enabled() && M % 256 == 0 && N % 128 == 0) ? kBnPair : pick_bn(N); }

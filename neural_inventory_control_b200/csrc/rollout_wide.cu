@@ -102,6 +102,14 @@ static bool use_persist(const HdpoRolloutDesc* d) {
 #endif
 }
 
+static int multi_min_tiles() {
+#ifdef HDPO_EMU
+  return 1 << 30;
+#else
+  return wp::multi_min_tiles();
+#endif
+}
+
 static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
   Plan p;
   p.persist = use_persist(d) ? 1 : 0;
@@ -128,6 +136,13 @@ static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
     off += p.w[l + 1] * p.w[l];
     p.gb[l] = off;
     off += p.w[l + 1];
+  }
+  if (p.tc && !p.persist) {
+    // the multi-tile GEMM works on 256-row tiles: pad to them when any layer of this batch would be routed there
+    int widest = 0;
+    for (int i = 0; i <= p.n; ++i) widest = p.wp[i] > widest ? p.wp[i] : widest;
+    const int bp2 = pad_to(p.B > 0 ? p.B : 1, 256);
+    if ((bp2 / 256) * ((widest + 127) / 128) >= multi_min_tiles()) p.Bp = bp2;
   }
   p.P = off;  // sym: overwritten below with the parameter count of all three nets (the projection has no own block)
   sym::Cfg sc{};
@@ -1200,6 +1215,10 @@ static int forced_bn() {
 static int tile_bn(int rows, int cols, bool pair_ok) {
   const int f = forced_bn();
   if (f == 64 || (f == 128 && cols % 128 == 0)) return f;
+  if (f == 0) {
+    const int m = wp::pick_bn_multi(rows, cols);
+    if (m) return m;
+  }
   // few tiles (e.g. 1024 scenarios per GPU): 128 x 64 tiles double the CTAs of a launch that cannot fill the machine
   // anyway (measured on many_warehouses 3 x 50, 1024 scenarios: 7.77 -> 7.32 ms per step; 2048-row chunks lose 25 %)
   if (f == 0 && pair_ok && (rows / 128) * (cols / 128) <= 32 && cols % 128 == 0) return 64;
@@ -1511,7 +1530,14 @@ extern "C" int hdpo_debug_set_wide_persist(int32_t on) {
   hdpo::wp::set_enabled(on);
   return HDPO_OK;
 }
+// Routing threshold of the multi-tile CTA-pair GEMM: min_tiles > 0 = fewest tiles of a launch that goes there,
+// 0 = never, < 0 = back to the default (HDPO_TC_MULTI / HDPO_TC_MULTI_MIN).
+extern "C" int hdpo_debug_set_tc_multi(int32_t min_tiles) {
+  hdpo::wp::set_multi_min_tiles(min_tiles);
+  return HDPO_OK;
+}
 #else
+extern "C" int hdpo_debug_set_tc_multi(int32_t) { return HDPO_E_INVALID; }
 extern "C" int hdpo_debug_set_wp_trace(unsigned long long*, int32_t) { return HDPO_E_INVALID; }
 extern "C" int hdpo_debug_set_wide_persist(int32_t) { return HDPO_E_INVALID; }
 #endif

@@ -1124,6 +1124,425 @@ __global__ void __launch_bounds__(kThreads, 1) persist_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// multi-tile layer GEMM: the pipeline of the persistent kernel (TMA ring -> tcgen05 pair MMAs -> rotating TMEM
+// accumulators -> register-accumulating epilogue warps) behind the per-layer interface of gemm_tc.cuh. One launch =
+// one layer of one period; every CTA pair walks the tiles pair, pair + n_pairs, ... of the launch, so the epilogue of a
+// tile (tcgen05.ld, activation, (hi, lo) split, TMA stores: ~4 us) overlaps the MMAs of the pair's next tile and the
+// launch set-up (barriers, TMEM, cluster sync: ~3 us) is paid once per pair instead of once per tile.
+// ------------------------------------------------------------------------------------------------------------
+struct MultiArgs {
+  int M, N, K, bn, n_pass, kseg, n_pairs;
+  int a_row0, b_row0, c_row0, x_row0, ldc, act;
+  const float* bias;
+  float* colsum;
+};
+constexpr int kMultiThreads = 32 * (2 + kEpiWarps);
+constexpr int kMultiSmem = kSmemTotal;
+
+template <int EPI>
+__global__ void __launch_bounds__(kMultiThreads, 1) multi_kernel(const __grid_constant__ tc::GemmTcMaps tm, const MultiArgs g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + ((1024 - (raw_addr & 1023)) & 1023);
+  unsigned char* ring = smem;
+  unsigned char* epi_stage = smem + kRing;
+  float* bias_all = reinterpret_cast<float*>(smem + kRing + kEpiStage);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kRing + kEpiStage + kBiasBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* hi_full = empty_bar + kStages;
+  uint64_t* hi_empty = hi_full + 2;
+  uint64_t* cr_full = hi_empty + 2;
+  uint64_t* cr_empty = cr_full + 2;
+  uint64_t* aux_bar = cr_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + kEpiWarps);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const bool three = g.n_pass == 3;
+  const int bn = g.bn, n_kb = g.K / kBK;
+  const int tiles_n = g.N / bn;
+  const int n_tiles = (g.M / kRowTile) * tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm.a_hi);
+    prefetch_tmap(&tm.b_hi);
+    if (three) {
+      prefetch_tmap(&tm.a_lo);
+      prefetch_tmap(&tm.b_lo);
+    }
+    prefetch_tmap(&tm.c0);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&hi_full[i], 1);
+      mbar_init(&cr_full[i], 1);
+      mbar_init(&hi_empty[i], 2 * kEpiWarps);
+      mbar_init(&cr_empty[i], 2 * kEpiWarps);
+    }
+    for (int w = 0; w < kEpiWarps; ++w) mbar_init(&aux_bar[w], 1);
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 1) tmem_alloc_pair(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // everything above overlapped the tail of the previous kernel in the stream (PDL); from here on we read its output
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    uint32_t s = 0, ph = 0;
+    const uint32_t tx = (three ? 2u : 1u) * static_cast<uint32_t>(kABytes + (bn / 2) * 128) * 2u;
+    for (int tile = pair; tile < n_tiles; tile += g.n_pairs) {
+      const int mt = tile / tiles_n, nt = tile - mt * tiles_n;
+      const int arow = g.a_row0 + mt * kRowTile + static_cast<int>(rank) * 128;
+      const int brow = g.b_row0 + nt * bn + static_cast<int>(rank) * (bn / 2);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        bar_wait(&empty_bar[s], ph ^ 1, 2);
+        unsigned char* st = ring + s * kStageBytes;
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(&full_bar[s], tx);
+          const uint32_t bar = mapa_u32(&full_bar[s], 0);
+          tma_load_2d_pair(st, &tm.a_hi, bar, kb * kBK, arow);
+          tma_load_2d_pair(st + 2 * kABytes, &tm.b_hi, bar, kb * kBK, brow);
+          if (three) {
+            tma_load_2d_pair(st + kABytes, &tm.a_lo, bar, kb * kBK, arow);
+            tma_load_2d_pair(st + 2 * kABytes + kBBytesMax, &tm.b_lo, bar, kb * kBK, brow);
+          }
+        }
+        __syncwarp();
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA of the pair) =====
+    if (rank == 0) {
+      uint32_t s = 0, ph = 0, hseg = 0, tcnt = 0;
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | ((256u >> 4) << 24);
+      for (int tile = pair; tile < n_tiles; tile += g.n_pairs) {
+        const uint32_t cb = tcnt & 1;
+        const uint32_t d_cr = tmem + cb * 128;
+        if (three) {
+          bar_wait_cluster(&cr_empty[cb], ((tcnt >> 1) & 1) ^ 1, 3);
+          tc_fence_after();
+        }
+        int in_seg = 0;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          const uint32_t hb = hseg & 1;
+          if (in_seg == 0) {
+            bar_wait_cluster(&hi_empty[hb], ((hseg >> 1) & 1) ^ 1, 4);
+            tc_fence_after();
+          }
+          bar_wait(&full_bar[s], ph, 5);
+          tc_fence_after();
+          const bool seg_last = (in_seg == g.kseg - 1) || (kb == n_kb - 1);
+          if (elect_one()) {
+            const uint32_t st = smem_u32(ring + s * kStageBytes);
+            const uint64_t a_hi = make_kmajor_desc(st), a_lo = make_kmajor_desc(st + kABytes);
+            const uint64_t b_hi = make_kmajor_desc(st + 2 * kABytes), b_lo = make_kmajor_desc(st + 2 * kABytes + kBBytesMax);
+            const uint32_t d_hi = tmem + 256 + hb * 128;
+#pragma unroll
+            for (int k = 0; k < kBK / 8; ++k) {
+              const uint64_t adv = static_cast<uint64_t>((k * 8 * 4) >> 4);
+              umma_tf32_pair(d_hi, a_hi + adv, b_hi + adv, idesc, (in_seg == 0 && k == 0) ? 0u : 1u);
+              if (three) {
+                umma_tf32_pair(d_cr, a_lo + adv, b_hi + adv, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+                umma_tf32_pair(d_cr, a_hi + adv, b_lo + adv, idesc, 1u);
+              }
+            }
+            umma_commit_pair(&empty_bar[s]);
+            if (seg_last) umma_commit_pair(&hi_full[hb]);
+            if (three && kb == n_kb - 1) umma_commit_pair(&cr_full[cb]);
+          }
+          __syncwarp();
+          if (seg_last) {
+            ++hseg;
+            in_seg = 0;
+          } else {
+            ++in_seg;
+          }
+          if (++s == kStages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        ++tcnt;
+      }
+    }
+  } else {
+    // ===== epilogue: warp q = warp % 4 owns TMEM lanes [32q, 32q + 32) = rows of this CTA's half of the tile =====
+    const int q = warp & 3, we = warp - 2, half = we >> 2;
+    unsigned char* stg = epi_stage + we * (2 * kBoxBytes);
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t hi_empty_c = mapa_u32(&hi_empty[0], 0), cr_empty_c = mapa_u32(&cr_empty[0], 0);
+    const bool wide = bn == 128;  // this warp drains 64 (wide) or 32 columns
+    const int cbase = half * (wide ? 64 : 32);
+    float* bias_w = bias_all + we * 64;
+    uint32_t hseg = 0, tcnt = 0, aux_cnt = 0;
+    (void)aux_cnt;
+    (void)bias_w;
+    constexpr bool kAux = EPI == tc::EPI_DGRAD_HIDDEN || EPI == tc::EPI_DGRAD_ACCUM;
+    constexpr bool kSplit = EPI == tc::EPI_FWD_HIDDEN || EPI == tc::EPI_DGRAD_HIDDEN;
+    for (int tile = pair; tile < n_tiles; tile += g.n_pairs) {
+      const int mt = tile / tiles_n, nt = tile - mt * tiles_n;
+      const int trow = mt * kRowTile + static_cast<int>(rank) * 128 + q * 32;  // first row of this warp inside the GEMM
+      const int n0 = nt * bn + cbase;
+      const int grow = g.c_row0 + trow, xrow = g.x_row0 + trow;
+      if (EPI == tc::EPI_FWD_HIDDEN || EPI == tc::EPI_FWD_OUT) {
+        __syncwarp();
+        bias_w[lane] = __ldg(g.bias + n0 + lane);
+        if (wide) bias_w[lane + 32] = __ldg(g.bias + n0 + 32 + lane);
+        __syncwarp();
+      }
+      auto issue_aux = [&](int j) {  // box j of the tile this epilogue combines with -> staging
+        if (lane == 0) {
+          tma_store_wait_read();
+          fence_proxy_async_all();
+          mbar_expect_tx(&aux_bar[we], (EPI == tc::EPI_DGRAD_HIDDEN ? 2 : 1) * kBoxBytes);
+          tma_load_2d(stg, &tm.x0, &aux_bar[we], n0 + 32 * j, xrow);
+          if (EPI == tc::EPI_DGRAD_HIDDEN) tma_load_2d(stg + kBoxBytes, &tm.x1, &aux_bar[we], n0 + 32 * j, xrow);
+        }
+      };
+      if (kAux) issue_aux(0);
+      float acc[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+      for (int kb0 = 0; kb0 < n_kb; kb0 += g.kseg) {
+        const uint32_t hb = hseg & 1;
+        bar_wait(&hi_full[hb], (hseg >> 1) & 1, 6);
+        tc_fence_after();
+        const uint32_t taddr = lane_base + 256 + hb * 128 + cbase;
+        if (wide) tmem_accumulate<64>(taddr, acc);
+        else tmem_accumulate<32>(taddr, acc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(hi_empty_c + hb * 8);
+        ++hseg;
+      }
+      if (three) {
+        const uint32_t cb = tcnt & 1;
+        bar_wait(&cr_full[cb], (tcnt >> 1) & 1, 7);
+        tc_fence_after();
+        const uint32_t taddr = lane_base + cb * 128 + cbase;
+        if (wide) tmem_accumulate<64>(taddr, acc);
+        else tmem_accumulate<32>(taddr, acc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(cr_empty_c + cb * 8);
+      }
+      ++tcnt;
+      // ---- finalize: this warp's 32 rows x (64 | 32) columns, one 32-column box at a time ----
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (j == 0 || wide) {
+          if (kAux) {
+            if (j == 1) issue_aux(1);
+            bar_wait(&aux_bar[we], aux_cnt & 1, 8);
+            ++aux_cnt;
+          } else {
+            if (lane == 0) tma_store_wait_read();  // the previous box has left the staging area
+            __syncwarp();
+          }
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = acc[32 * j + 16 * hh + i];
+            if (EPI == tc::EPI_FWD_HIDDEN || EPI == tc::EPI_FWD_OUT) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_w + 32 * j + 16 * hh + 4 * j4);
+                v[4 * j4 + 0] += b4.x;
+                v[4 * j4 + 1] += b4.y;
+                v[4 * j4 + 2] += b4.z;
+                v[4 * j4 + 3] += b4.w;
+              }
+              if (g.act == HDPO_ACT_ELU) elu_inplace(v);
+              else if (g.act != HDPO_ACT_NONE) act_cold_fwd(g.act, v);
+            } else if (EPI == tc::EPI_DGRAD_HIDDEN) {
+              float hv[16];
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const int chunk = ((4 * hh + j4) ^ (lane & 7)) << 4;
+                const float4 x0 = *reinterpret_cast<const float4*>(stg + lane * 128 + chunk);
+                const float4 x1 = *reinterpret_cast<const float4*>(stg + kBoxBytes + lane * 128 + chunk);
+                hv[4 * j4 + 0] = x0.x + x1.x;
+                hv[4 * j4 + 1] = x0.y + x1.y;
+                hv[4 * j4 + 2] = x0.z + x1.z;
+                hv[4 * j4 + 3] = x0.w + x1.w;
+              }
+              if (g.act == HDPO_ACT_ELU) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] *= elu_grad_from_out(hv[i]);
+              } else if (g.act != HDPO_ACT_NONE) {
+                act_cold_bwd(g.act, v, hv);
+              }
+              if (g.colsum) {
+                // bias-gradient partials: column sums over this warp's 32 rows (reduce-scatter butterfly)
+                float w[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] = v[i];
+#pragma unroll
+                for (int hw = 8, o = 16; hw >= 1; hw >>= 1, o >>= 1) {
+                  const bool up = (lane & o) != 0;
+#pragma unroll
+                  for (int i = 0; i < hw; ++i) {
+                    const float send = up ? w[i] : w[i + hw];
+                    const float recv = __shfl_xor_sync(0xffffffffu, send, o);
+                    w[i] = (up ? w[i + hw] : w[i]) + recv;
+                  }
+                }
+                w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
+                if ((lane & 1) == 0) {
+                  const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                  g.colsum[(static_cast<size_t>(grow) >> 5) * g.ldc + n0 + 32 * j + 16 * hh + col] = w[0];
+                }
+              }
+            } else if (EPI == tc::EPI_DGRAD_ACCUM) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const int chunk = ((4 * hh + j4) ^ (lane & 7)) << 4;
+                const float4 x0 = *reinterpret_cast<const float4*>(stg + lane * 128 + chunk);
+                v[4 * j4 + 0] += x0.x;
+                v[4 * j4 + 1] += x0.y;
+                v[4 * j4 + 2] += x0.z;
+                v[4 * j4 + 3] += x0.w;
+              }
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const int chunk = ((4 * hh + j4) ^ (lane & 7)) << 4;
+              if (kSplit) {
+                float4 hi, lo;
+                hi.x = tf32_hi(v[4 * j4 + 0]);
+                hi.y = tf32_hi(v[4 * j4 + 1]);
+                hi.z = tf32_hi(v[4 * j4 + 2]);
+                hi.w = tf32_hi(v[4 * j4 + 3]);
+                lo.x = tf32_hi(v[4 * j4 + 0] - hi.x);
+                lo.y = tf32_hi(v[4 * j4 + 1] - hi.y);
+                lo.z = tf32_hi(v[4 * j4 + 2] - hi.z);
+                lo.w = tf32_hi(v[4 * j4 + 3] - hi.w);
+                *reinterpret_cast<float4*>(stg + lane * 128 + chunk) = hi;
+                *reinterpret_cast<float4*>(stg + kBoxBytes + lane * 128 + chunk) = lo;
+              } else {
+                *reinterpret_cast<float4*>(stg + lane * 128 + chunk) =
+                    make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+              }
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm.c0, stg, n0 + 32 * j, grow);
+            if (kSplit) tma_store_2d(&tm.c1, stg + kBoxBytes, n0 + 32 * j, grow);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_read();  // shared memory is released right after the final barrier
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA may release shared memory / TMEM the pair's MMAs and commits still use
+  if (warp == 1) tmem_dealloc_pair(tmem, kTmemCols);
+}
+
+template <int EPI>
+static int launch_multi(const tc::GemmTcMaps& tm, const MultiArgs& g, void* stream) {
+  auto k = multi_kernel<EPI>;
+  static bool configured = false;
+  if (!configured) {
+    HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMultiSmem));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * g.n_pairs);
+  cfg.blockDim = dim3(kMultiThreads);
+  cfg.dynamicSmemBytes = kMultiSmem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: set-up overlaps the previous kernel's tail
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  HDPO_CUDA_OK(cudaLaunchKernelEx(&cfg, k, tm, g));
+  count_launch();
+  HDPO_LAUNCH_OK();
+  return HDPO_OK;
+}
+
+static int g_multi_min = -1;
+int multi_min_tiles() {
+  if (g_multi_min < 0) {
+    const char* e = getenv("HDPO_TC_MULTI");
+    const char* m = getenv("HDPO_TC_MULTI_MIN");
+    // default OFF (measured on B200, 8192 x 512 x 512 3xTF32: 28.2 us vs 33.6 us for the single-tile pairs alone, but
+    // the step with four 2048-row chunks on concurrent streams stays ahead: 16.8 ms vs 17.9 ms)
+    g_multi_min = (e && atoi(e) != 0) ? (m ? atoi(m) : 48) : (1 << 30);
+  }
+  return g_multi_min;
+}
+void set_multi_min_tiles(int min_tiles) { g_multi_min = min_tiles == 0 ? (1 << 30) : min_tiles; }
+
+int gemm_multi(const tc::GemmTcMaps& tm, const tc::GemmTcArgs& a, int epi, int bn, void* stream) {
+  HDPO_REQUIRE(bn == 128 || bn == 64, "multi-tile GEMM: tile width %d", bn);
+  HDPO_REQUIRE(a.M % kRowTile == 0 && a.N % bn == 0 && a.K % kBK == 0 && a.K > 0 && a.M > 0,
+               "multi-tile GEMM shape %dx%dx%d not tileable", a.M, a.N, a.K);
+  HDPO_REQUIRE(a.n_pass == 1 || a.n_pass == 3, "n_pass must be 1 or 3");
+  static int kseg = 0, max_pairs = 0;
+  if (!kseg) {
+    kseg = env_int("HDPO_WP_KSEG", 8);
+    if (kseg < 1) kseg = 1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    max_pairs = env_int("HDPO_MULTI_PAIRS", sms / 2);
+    if (max_pairs < 1) max_pairs = 1;
+  }
+  MultiArgs g{};
+  g.M = a.M;
+  g.N = a.N;
+  g.K = a.K;
+  g.bn = bn;
+  g.n_pass = a.n_pass;
+  g.kseg = kseg;
+  const int n_tiles = (a.M / kRowTile) * (a.N / bn);
+  const int waves = (n_tiles + max_pairs - 1) / max_pairs;
+  g.n_pairs = (n_tiles + waves - 1) / waves;  // every pair walks `waves` tiles (the last ones one fewer)
+  g.a_row0 = a.a_row0;
+  g.b_row0 = a.b_row0;
+  g.c_row0 = a.c_row0;
+  g.x_row0 = a.x_row0;
+  g.ldc = a.ldc;
+  g.act = a.act;
+  g.bias = a.bias;
+  g.colsum = a.colsum_part;
+  switch (epi) {
+    case tc::EPI_FWD_HIDDEN: return launch_multi<tc::EPI_FWD_HIDDEN>(tm, g, stream);
+    case tc::EPI_FWD_OUT: return launch_multi<tc::EPI_FWD_OUT>(tm, g, stream);
+    case tc::EPI_DGRAD_HIDDEN: return launch_multi<tc::EPI_DGRAD_HIDDEN>(tm, g, stream);
+    case tc::EPI_DGRAD_ACCUM: return launch_multi<tc::EPI_DGRAD_ACCUM>(tm, g, stream);
+    case tc::EPI_STORE: return launch_multi<tc::EPI_STORE>(tm, g, stream);
+  }
+  set_error("bad epilogue %d", epi);
+  return HDPO_E_INVALID;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // device-side list builder: thread = pair
 // ------------------------------------------------------------------------------------------------------------
 __global__ void build_tasks_kernel(Sched s, Task* tasks, Task* head_tasks, int n_pairs, int n_servers) {

@@ -11,8 +11,26 @@
 #include "hdpo_internal.cuh"
 
 #ifndef HDPO_EMU
+#include "gemm_tc.cuh"
+
 namespace hdpo {
 namespace wp {
+
+// Multi-tile CTA-pair GEMM behind the interface of tc::gemm (same maps and arguments; the B map needs bn / 2-row
+// boxes): one launch per layer, every pair walks several 256 x bn tiles with the epilogue of one tile overlapping the
+// MMAs of the next (see wide_persist.cu). tc::gemm() routes the selectors tc::kBnMulti + 64 | 128 here.
+int gemm_multi(const tc::GemmTcMaps& tm, const tc::GemmTcArgs& g, int epi, int bn, void* stream);
+// Routing: fewest 256 x bn tiles of a launch that goes to gemm_multi (below that the single-tile forms spread the work
+// over more SMs). Opt-in: HDPO_TC_MULTI = 1 enables it, HDPO_TC_MULTI_MIN sets the threshold (default 48);
+// set_multi_min_tiles overrides both (> 0 threshold, 0 never, < 0 back to the default).
+int multi_min_tiles();
+void set_multi_min_tiles(int min_tiles);
+// tc::gemm selector (tc::kBnMulti + 64 | 128) when a rows x cols GEMM is routed to the multi-tile form, else 0
+inline int pick_bn_multi(int rows, int cols) {
+  if (rows % 256 != 0 || cols % 64 != 0) return 0;
+  const int bn = cols % 128 == 0 ? 128 : 64;
+  return (rows / 256) * (cols / bn) >= multi_min_tiles() ? tc::kBnMulti + bn : 0;
+}
 
 constexpr int kRowTile = 256;  // scenarios per row tile (one CTA pair, M = 256)
 constexpr int kMaxW = 4;       // warehouses the per-thread head handles
