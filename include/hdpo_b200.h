@@ -277,6 +277,10 @@ int hdpo_debug_set_wide_persist(int32_t on);
 /* Routing threshold of the multi-tile CTA-pair GEMM of the wide path: min_tiles > 0 = fewest 256-row tiles of a layer
  * launch that goes there (1 = every tensor-core GEMM), 0 = never, < 0 = default (off unless HDPO_TC_MULTI=1). */
 int hdpo_debug_set_tc_multi(int32_t min_tiles);
+/* Largest batch (scenarios) that the small-net rollout runs in its one-scenario-per-warp form (rollout_small_unit.cu);
+ * larger batches use the 32-scenarios-per-warp form. > 0 sets it, 0 = never, < 0 = default (HDPO_SMALL_UNIT_MAX, else
+ * 4096 one-store / 2048 serial). */
+int hdpo_debug_set_small_unit(int32_t max_batch);
 
 /* misc */
 const char* hdpo_last_error(void);

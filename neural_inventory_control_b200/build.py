@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libhdpo_b200.so")
 STAMP = os.path.join(PKG, ".libhdpo_b200.stamp")
 
-SOURCES = ["capi.cu", "step_kernels.cu", "rollout_small.cu", "rollout_small_bwd_kq1.cu", "rollout_small_bwd_kq2.cu", "rollout_small_bwd_kq4.cu",
+SOURCES = ["capi.cu", "step_kernels.cu", "rollout_small.cu", "rollout_small_unit.cu", "rollout_small_bwd_kq1.cu", "rollout_small_bwd_kq2.cu", "rollout_small_bwd_kq4.cu",
            "rollout_small_bwd_kq5.cu", "rollout_small_bwd_kq8.cu", "rollout_wide.cu", "rollout_sym.cu", "gemm_tc.cu", "wide_persist.cu", "rollout_api.cu", "philox.cu", "adam.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

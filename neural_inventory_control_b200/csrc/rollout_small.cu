@@ -203,6 +203,17 @@ int forward(const HdpoRolloutDesc* d, const float* params, const float* demands,
   }
   HdpoState fin = {nullptr, nullptr, nullptr};
   if (final_state) fin = *final_state;
+  if (use_unit(c)) {
+    int rc = forward_unit(c, params, demands, st, init, cost_b, report_b, reward_tb, tape, fin, stream);
+    if (rc) return rc;
+    if (totals) {
+      auto kt = totals_kernel;
+      HDPO_LAUNCH(kt, 1, 1024, 0, stream, static_cast<const float*>(cost_b), static_cast<const float*>(report_b), c.B,
+                  totals);
+      HDPO_LAUNCH_OK();
+    }
+    return HDPO_OK;
+  }
   // two scenarios per lane amortise the weight loads when there are plenty of tiles; with few scenarios (training
   // batches of a few thousand, the 32768-scenario evaluation sets) one per lane doubles the warps that share the work
   const int ns = ceil_div(c.B, 32 * kFwdNS) < 4 * sm_count() ? 1 : kFwdNS;
@@ -254,6 +265,16 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
   float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + tape_bytes(c, 1));
   if (c.ckpt > 1) c.ring = reinterpret_cast<float*>(static_cast<char*>(workspace) + tape_bytes(c, 1) + partial_bytes(c));
   const int p_stride = (c.P + 3) & ~3;
+  if (use_unit(c)) {
+    int n_rows = 0;
+    int rc = backward_unit(c, params, demands, st, tape, g_total, g_report, partials, p_stride, &n_rows, stream);
+    if (rc) return rc;
+    auto kr = reduce_partials_kernel;
+    HDPO_LAUNCH(kr, ceil_div(c.P, 256), 256, 0, stream, static_cast<const float*>(partials), n_rows, p_stride, c.P,
+                grad_params);
+    HDPO_LAUNCH_OK();
+    return HDPO_OK;
+  }
   const int n_tiles = ceil_div(c.B, 32);
   const int wpc = pick_warps_per_cta(n_tiles);
   const int ctas_needed = ceil_div(n_tiles, wpc);

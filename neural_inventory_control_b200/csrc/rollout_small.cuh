@@ -40,6 +40,14 @@ struct Cfg {
                        // (K0 + 4; = XS otherwise), fp32 copy W0[n][k] with row stride XSb
 };
 
+// lane = hidden unit / one scenario per warp form for training-size batches (rollout_small_unit.cu)
+bool use_unit(const Cfg& c);
+void set_unit_max_batch(int max_b);
+int forward_unit(const Cfg& c, const float* params, const float* demands, const HdpoStatics* st, const HdpoState* init,
+                 float* cost_b, float* report_b, float* reward_tb, float* tape, const HdpoState& fin, void* stream);
+int backward_unit(const Cfg& c, const float* params, const float* demands, const HdpoStatics* st, const float* tape,
+                  float g_total, float g_report, float* partials, int p_stride, int* n_rows, void* stream);
+
 bool supported(const HdpoRolloutDesc* d);
 int build_cfg(const HdpoRolloutDesc* d, int in_pad_quantum, Cfg* c);
 size_t workspace_bytes(const HdpoRolloutDesc* d);

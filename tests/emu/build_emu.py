@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "neural_inventory_control_b200", "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libhdpo_emu.so")
-SOURCES = ["capi.cu", "step_kernels.cu", "rollout_small.cu", "rollout_small_bwd_kq1.cu", "rollout_small_bwd_kq2.cu", "rollout_small_bwd_kq4.cu",
+SOURCES = ["capi.cu", "step_kernels.cu", "rollout_small.cu", "rollout_small_unit.cu", "rollout_small_bwd_kq1.cu", "rollout_small_bwd_kq2.cu", "rollout_small_bwd_kq4.cu",
            "rollout_small_bwd_kq5.cu", "rollout_small_bwd_kq8.cu", "rollout_wide.cu", "rollout_sym.cu", "gemm_tc.cu", "rollout_api.cu", "philox.cu", "adam.cu"]
 
 

@@ -94,17 +94,36 @@ def test_allocation_shift_bit_exact(be_name):
     assert np.array_equal(be.get(h), g["ref"]["allocation_shift"])  # the reference's own table
 
 
+MAPPINGS = ["unit", "scenario"]
+
+
+class small_mapping:
+    """Force one of the two thread mappings of the small-net rollout: "unit" = one scenario per warp, lane = hidden
+    unit (rollout_small_unit.cu; the default for batches of a few thousand scenarios), "scenario" = 32 per warp."""
+
+    def __init__(self, be, mapping):
+        self.be, self.mapping = be, mapping
+
+    def __enter__(self):
+        self.be.lib.hdpo_debug_set_small_unit((1 << 30) if self.mapping == "unit" else 0)
+
+    def __exit__(self, *exc):
+        self.be.lib.hdpo_debug_set_small_unit(-1)
+
+
 SMALL_MODES = [pytest.param("emu", "fp32", id="emu"), pytest.param("cuda", "fp32", id="cuda", marks=pytest.mark.gpu),
                # adjoint with the HxH layers on warp-level tensor cores (mma.sync 3xTF32, mma32.cuh)
                pytest.param("cuda", "tf32x3", id="cuda-tf32x3", marks=pytest.mark.gpu)]
 
 
+@pytest.mark.parametrize("mapping", MAPPINGS)
 @pytest.mark.parametrize("be_name,precision", SMALL_MODES)
 @pytest.mark.parametrize("name", SMALL)
-def test_rollout_costs_and_gradients_match_reference(be_name, precision, name):
+def test_rollout_costs_and_gradients_match_reference(be_name, precision, name, mapping):
     be = backend(be_name)
     meta, g = G.load("rollout", name)
-    out = D.rollout(be, meta, g["param"], g["data"], precision=precision)
+    with small_mapping(be, mapping):
+        out = D.rollout(be, meta, g["param"], g["data"], precision=precision)
     check_rollout_against_golden(out, meta, g, meta["T"], meta["ignore_periods"])
     ref, ref64 = g["ref"], g["ref64"]
     keys = sorted(out["grad"])
@@ -131,8 +150,9 @@ def test_rollout_recomputation_checkpoints_change_nothing(be_name, name, K_ckpt)
     shrinks by ~K (T = 50 here: K = 7 leaves a ragged last segment, K = 50 a single checkpoint)."""
     be = backend(be_name)
     meta, g = G.load("rollout", name)
-    full = D.rollout(be, meta, g["param"], g["data"])
-    ck = D.rollout(be, meta, g["param"], g["data"], checkpoint_interval=K_ckpt)
+    with small_mapping(be, "scenario"):  # checkpoints exist in the 32-scenarios-per-warp form only
+        full = D.rollout(be, meta, g["param"], g["data"])
+        ck = D.rollout(be, meta, g["param"], g["data"], checkpoint_interval=K_ckpt)
     np.testing.assert_array_equal(ck["reward_tb"], full["reward_tb"])
     np.testing.assert_array_equal(ck["cost_b"], full["cost_b"])
     scale = np.abs(full["grad_flat"]).max()
@@ -174,9 +194,13 @@ def test_rollout_time_major_demand_layout_is_identical(be_name, name):
 @pytest.mark.parametrize("be_name", BACKENDS)
 @pytest.mark.parametrize("name,n,T,ignore", [("one_store_lost", 45, 17, 5), ("serial_system", 33, 50, 49),
                                              ("one_store_backlogged_lead20", 1, 3, 0)])
-def test_rollout_ragged_batches_against_oracle(be_name, name, n, T, ignore):
+@pytest.mark.parametrize("mapping", MAPPINGS)
+def test_rollout_ragged_batches_against_oracle(be_name, name, n, T, ignore, mapping, request):
     """B not a multiple of the warp tile, short horizons, ignore near T: compare with the pinned oracle."""
     be = backend(be_name)
+    ctx = small_mapping(be, mapping)
+    ctx.__enter__()
+    request.addfinalizer(lambda: ctx.__exit__())
     meta, g = G.load("rollout", name)
     data = D.slice_batch(g["data"], n)
     out = D.rollout(be, meta, g["param"], data, T=T, ignore=ignore, g_total=0.37, g_report=-0.11)
@@ -206,10 +230,14 @@ def test_rollout_ragged_batches_against_oracle(be_name, name, n, T, ignore):
                                        pytest.param("cuda", 300, id="cuda-300", marks=pytest.mark.gpu),
                                        pytest.param("cuda", 100000, id="cuda-100000", marks=pytest.mark.gpu)])
 @pytest.mark.parametrize("name", ["one_store_backlogged", "serial_system"])
-def test_rollout_many_tiles_all_launch_shapes(be_name, n, name):
+@pytest.mark.parametrize("mapping", MAPPINGS)
+def test_rollout_many_tiles_all_launch_shapes(be_name, n, name, mapping, request):
     """Batches spanning many warp tiles (1, 2 and 4 warps per CTA, persistent tile loops, ragged last tile):
     per-scenario costs of replicated scenarios must repeat exactly and the gradient must equal the oracle's."""
     be = backend(be_name)
+    ctx = small_mapping(be, mapping)
+    ctx.__enter__()
+    request.addfinalizer(lambda: ctx.__exit__())
     meta, g = G.load("rollout", name)
     base = 50
     reps = -(-n // base)
