@@ -92,8 +92,8 @@ class ClockSampler:
 
 def load_traffic(workload):
     """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed ncu --set full
-    captures (profiles/r1_traffic.json names the capture each number comes from); None when there is none."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    captures (profiles/r2_traffic.json names the capture each number comes from); None when there is none."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f).get(workload)
