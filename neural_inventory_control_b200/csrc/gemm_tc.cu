@@ -29,9 +29,12 @@ constexpr int kHiChunks = kAccums - 1;
 // the single-CTA form) and the L2 traffic per flop drop by a quarter.
 // EARLY_AUX (CTA-pair dgrad epilogue): one stage less, and 64 KB after the ring receive half of the saved-activation
 // tile before the mainloop starts (the other half is fetched into the idle ring once the accumulators are ready).
-template <int BN, int CG = 1, bool EARLY_AUX = false>
+// OCC = 2: two CTAs per SM (BN = 64 only: 4 x 64 = 256 TMEM columns and a 2-stage ring each), so that the ramp, epilogue
+// and teardown of one tile overlap the MMAs of the tile that shares the SM - the hardware scheduler does the
+// interleaving across the concurrent chunk streams that a hand-written persistent loop could not.
+template <int BN, int CG = 1, bool EARLY_AUX = false, int OCC = 1>
 struct SmemPlan {
-  static constexpr int kStages = (BN == 128 && CG == 1) ? 3 : (EARLY_AUX ? 3 : 4);
+  static constexpr int kStages = OCC == 2 ? 2 : ((BN == 128 && CG == 1) ? 3 : (EARLY_AUX ? 3 : 4));
   static constexpr int kAuxBytes = EARLY_AUX ? kEpiWarps * 2 * 32 * 128 : 0;
   static constexpr int kABytes = 128 * kBK * 4;
   static constexpr int kBBytes = (BN / CG) * kBK * 4;
@@ -44,10 +47,11 @@ struct SmemPlan {
 // MN = true : D[M,N] = sum_k A[k][m] B[k][n], operands MN-major (rows = k, contiguous m / n): the weight-gradient
 //             form dW = gz^T h straight from the [row][feature] tapes; blockIdx.z selects a K range of k_per_split rows
 //             and writes its own partial slice (short ranges keep the truncating accumulation fp32-grade).
-template <int BN, int EPI, bool MN, int CG = 1>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int EPI, bool MN, int CG = 1, int OCC = 1>
+__global__ void __launch_bounds__(kThreads, OCC)
 gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
   static_assert(CG == 1 || !MN, "the CTA-pair form is K-major only");
+  static_assert(OCC == 1 || (OCC == 2 && BN == 64 && !MN), "two CTAs per SM: 64-column K-major tiles only");
   const CUtensorMap& tm_a_hi = tm.a_hi;
   const CUtensorMap& tm_a_lo = tm.a_lo;
   const CUtensorMap& tm_b_hi = tm.b_hi;
@@ -55,7 +59,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
   // Measured on B200 (cfg 4, in the pipeline): with the early half-tile the dgrad epilogue shrinks 4.25 -> 3.6 us but
   // the 3-stage ring lengthens the mainloop 6.6 -> 7.7 us, a net loss; the path is kept for A/B runs only.
   constexpr bool kEarlyAux = false && CG == 2 && EPI == EPI_DGRAD_HIDDEN;
-  using P = SmemPlan<BN, CG, kEarlyAux>;
+  using P = SmemPlan<BN, CG, kEarlyAux, OCC>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   unsigned char* smem = smem_raw + ((1024 - (raw_addr & 1023)) & 1023);  // SW128 needs 1024-byte aligned tiles
@@ -501,22 +505,24 @@ int make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t
   return HDPO_OK;
 }
 
-template <int BN, int EPI, bool MN = false, int CG = 1>
+template <int BN, int EPI, bool MN = false, int CG = 1, int OCC = 1>
 static int launch(const GemmTcMaps& tm, const GemmTcArgs& g_in, void* stream) {
   GemmTcArgs g = g_in;
   if (g.hi_chunks <= 0 || g.hi_chunks > kHiChunks) g.hi_chunks = kHiChunks;
   g.trace = trace_ref((g_in.trace.tag << 8) | (static_cast<unsigned>(EPI) << 4) | (MN ? 8u : 0u) | (BN == 128 ? 1u : 0u));
-  auto k = gemm_tc_kernel<BN, EPI, MN, CG>;
+  auto k = gemm_tc_kernel<BN, EPI, MN, CG, OCC>;
   static bool configured = false;
   if (!configured) {
-    HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlan<BN, CG, false>::kTotal));
+    HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlan<BN, CG, false, OCC>::kTotal));
+    if (OCC == 2)  // two CTAs of ~82 / ~98 KB each must fit next to each other
+      HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   const unsigned nz = MN ? static_cast<unsigned>(g.K / g.k_per_split) : 1u;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = CG == 2 ? dim3(2, g.M / 256, g.N / BN) : dim3(g.N / BN, g.M / 128, nz);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = SmemPlan<BN, CG, false>::kTotal;
+  cfg.dynamicSmemBytes = SmemPlan<BN, CG, false, OCC>::kTotal;
   cfg.stream = static_cast<cudaStream_t>(stream);
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: prologue overlaps the previous kernel's tail
@@ -548,7 +554,7 @@ static int launch_epi(const GemmTcMaps& tm, const GemmTcArgs& g, int epi, void* 
 
 int gemm(const GemmTcMaps& tm, const GemmTcArgs& g, int epi, int bn, void* stream) {
   if (bn > kBnMulti) return wp::gemm_multi(tm, g, epi, bn - kBnMulti, stream);
-  const int bn_cols = bn == kBnPair ? 128 : bn;
+  const int bn_cols = bn == kBnPair ? 128 : ((bn == kBnPair64 || bn == kBn64x2) ? 64 : bn);
   HDPO_REQUIRE(g.M % 128 == 0 && g.N % bn_cols == 0 && g.K % kBK == 0 && g.K > 0,
                "tcgen05 GEMM shape %dx%dx%d not tileable", g.M, g.N, g.K);
   HDPO_REQUIRE(g.n_pass == 1 || g.n_pass == 3, "n_pass must be 1 or 3");
@@ -560,6 +566,25 @@ int gemm(const GemmTcMaps& tm, const GemmTcArgs& g, int epi, int bn, void* strea
       case EPI_STORE: return launch<128, EPI_STORE, false, 2>(tm, g, stream);
     }
     set_error("the CTA-pair GEMM has no epilogue %d", epi);
+    return HDPO_E_INVALID;
+  }
+  if (bn == kBnPair64) {  // 256 x 64 pair tiles, two CTAs per SM (the B map must have 32-row boxes)
+    HDPO_REQUIRE(g.M % 256 == 0, "CTA-pair GEMM shape %dx%d not tileable", g.M, g.N);
+    switch (epi) {
+      case EPI_FWD_HIDDEN: return launch<64, EPI_FWD_HIDDEN, false, 2, 2>(tm, g, stream);
+      case EPI_DGRAD_HIDDEN: return launch<64, EPI_DGRAD_HIDDEN, false, 2, 2>(tm, g, stream);
+    }
+    set_error("the 256 x 64 CTA-pair GEMM has no epilogue %d", epi);
+    return HDPO_E_INVALID;
+  }
+  if (bn == kBn64x2) {  // 128 x 64 single-CTA tiles, two CTAs per SM
+    switch (epi) {
+      case EPI_FWD_HIDDEN: return launch<64, EPI_FWD_HIDDEN, false, 1, 2>(tm, g, stream);
+      case EPI_FWD_OUT: return launch<64, EPI_FWD_OUT, false, 1, 2>(tm, g, stream);
+      case EPI_DGRAD_HIDDEN: return launch<64, EPI_DGRAD_HIDDEN, false, 1, 2>(tm, g, stream);
+      case EPI_DGRAD_ACCUM: return launch<64, EPI_DGRAD_ACCUM, false, 1, 2>(tm, g, stream);
+    }
+    set_error("the two-per-SM GEMM has no epilogue %d", epi);
     return HDPO_E_INVALID;
   }
   if (bn == 128) return launch_epi<128>(tm, g, epi, stream);

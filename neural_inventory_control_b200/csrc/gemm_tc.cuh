@@ -68,7 +68,16 @@ inline int pick_bn(int N) { return (N % 128 == 0) ? 128 : 64; }
 constexpr int kBnPair = 1128;
 // kBnMulti + 64 | 128 = multi-tile CTA-pair form (wide_persist.cu, gemm_multi): 256 x 64 | 128 tiles, several per pair
 constexpr int kBnMulti = 2000;
-inline int b_box_rows(int bn) { return bn == kBnPair ? 64 : (bn > kBnMulti ? (bn - kBnMulti) / 2 : bn); }  // rows of the B operand's TMA box
+// two CTAs per SM (4 x 64 TMEM columns and a 2-stage ring each): kBnPair64 = CTA-pair tiles 256 x 64, kBn64x2 = single-CTA
+// tiles 128 x 64
+constexpr int kBnPair64 = 1064;
+constexpr int kBn64x2 = 1065;
+inline int b_box_rows(int bn) {  // rows of the B operand's TMA box
+  if (bn == kBnPair) return 64;
+  if (bn == kBnPair64) return 32;
+  if (bn == kBn64x2) return 64;
+  return bn > kBnMulti ? (bn - kBnMulti) / 2 : bn;
+}
 // the pair form needs 256-row and 128-column tiles; HDPO_TC_PAIR=0 disables it (A/B comparison on the GPU box)
 int pair_enabled();
 inline int pick_bn_pair(int M, int N) { return (pair_enabled() && M % 256 == 0 && N % 128 == 0) ? kBnPair : pick_bn(N); }

@@ -1212,9 +1212,23 @@ static int forced_bn() {
   }
   return v;
 }
+// HDPO_TC_OCC2 = 1: the per-period GEMMs run as 64-column tiles with TWO CTAs per SM (256 TMEM columns and a 2-stage
+// ring each; CTA pairs where the epilogue exists in that form), so that kernels of different chunk streams share SMs
+static int occ2_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HDPO_TC_OCC2");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
 static int tile_bn(int rows, int cols, bool pair_ok) {
   const int f = forced_bn();
   if (f == 64 || (f == 128 && cols % 128 == 0)) return f;
+  if (f == 0 && occ2_mode() && cols % 64 == 0) {
+    if (pair_ok && rows % 256 == 0 && tc::pair_enabled() && occ2_mode() != 2) return tc::kBnPair64;
+    return tc::kBn64x2;
+  }
   if (f == 0) {
     const int m = wp::pick_bn_multi(rows, cols);
     if (m) return m;

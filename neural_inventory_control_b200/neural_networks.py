@@ -435,6 +435,165 @@ class EchelonStock(MyNeuralNetwork):
                 "echelons": alloc[:, :E].unsqueeze(2)}
 
 
+class DataDrivenNet(MyNeuralNetwork):
+    """One MLP over inventories + real-data features (past demands, costs, days from Christmas, lead times)
+    (neural_networks.py:430-519). With warehouses the net emits W warehouse orders followed by S*W store orders,
+    masked by the adjacency and scaled down per warehouse when they exceed what the warehouse holds."""
+
+    def __init__(self, args, scenario=None, device="cpu"):
+        super().__init__(args, device)
+        self.scenario = scenario
+        self._edge_mask = None
+
+    def _mask(self, ref):
+        if self._edge_mask is None or self._edge_mask.device != ref.device:
+            adj = self.scenario.problem_params["warehouse_store_adjacency"]
+            self._edge_mask = torch.tensor(adj, dtype=torch.float32, device=ref.device).t().contiguous()  # [S, W]
+        return self._edge_mask.to(ref.dtype)
+
+    def forward(self, observation):
+        store_inv = observation["store_inventories"]
+        has_wh = "warehouse_inventories" in observation and observation["warehouse_inventories"].size(1) > 0
+        feats = [store_inv]
+        if has_wh:
+            feats.append(observation["warehouse_inventories"])
+        feats += [observation[k] for k in ("past_demands", "underage_costs", "holding_costs", "days_from_christmas",
+                                           "lead_times")]
+        out = self.net["master"](self.flatten_then_concatenate_tensors(feats))
+        if not has_wh:
+            return {"stores": out.unsqueeze(2)}
+        wh_inv = observation["warehouse_inventories"]
+        B, S, W = out.size(0), store_inv.size(1), wh_inv.size(1)
+        wanted = out[:, W:].reshape(B, S, W) * self._mask(out)
+        # per warehouse: scale the connected stores' orders by min(1, inventory / total wanted); "inventory" is the
+        # whole pipeline row of the warehouse, as in the reference (apply_proportional_allocation sums a 2-D argument)
+        scale = torch.clip(wh_inv.sum(dim=2) / (wanted.sum(dim=1) + 1e-10), max=1.0)
+        return {"stores": wanted * scale[:, None, :], "warehouses": out[:, :W].unsqueeze(2)}
+
+
+class QuantilePolicy(MyNeuralNetwork):
+    """Policies that choose a demand QUANTILE per store and turn it into a base-stock level with a frozen quantile
+    forecaster (neural_networks.py:521-591). Subclasses define compute_desired_quantiles."""
+
+    def __init__(self, args, device="cpu"):
+        super().__init__(args=args, device=device)
+        self.fixed_nets = {"quantile_forecaster": self.load_forecaster(args, requires_grad=False)}
+        self.allow_back_orders = False
+
+    def load_forecaster(self, nn_params, requires_grad=True):
+        from .quantile_forecaster import FullyConnectedForecaster
+        import numpy as np
+        net = FullyConnectedForecaster([128, 128], lead_times=nn_params["forecaster_lead_times"],
+                                       qs=np.arange(0.05, 1, 0.05))
+        # the shipped checkpoint was written from a CUDA process: map it to wherever this policy lives
+        net.load_state_dict(torch.load(f"{nn_params['forecaster_location']}", map_location="cpu"))
+        for p in net.parameters():
+            p.requires_grad_(requires_grad)
+        return net.to(self.device)
+
+    def _apply(self, fn, *a, **k):  # the forecaster is not a registered sub-module (it must stay out of state_dict)
+        out = super()._apply(fn, *a, **k)
+        for net in getattr(self, "fixed_nets", {}).values():
+            net._apply(fn)
+        return out
+
+    def forecast_base_stock_allocation(self, past_demands, days_from_christmas, store_inventories, lead_times,
+                                       quantiles, allow_back_orders=False):
+        feats = torch.cat((past_demands,
+                           days_from_christmas.unsqueeze(1).expand(past_demands.shape[0], past_demands.shape[1], 1)),
+                          dim=2)
+        level = self.fixed_nets["quantile_forecaster"].get_quantile(feats, quantiles, lead_times)
+        order = level - store_inventories.sum(dim=2)
+        if not allow_back_orders:
+            order = torch.clip(order, min=0)
+        return {"stores": order.unsqueeze(2)}
+
+    def compute_desired_quantiles(self, args):
+        raise NotImplementedError
+
+    def forward(self, observation):
+        quantiles = self.compute_desired_quantiles({k: observation[k] for k in ("underage_costs", "holding_costs")})
+        return self.forecast_base_stock_allocation(
+            observation["past_demands"], observation["days_from_christmas"], observation["store_inventories"],
+            observation["lead_times"][:, :, 0], quantiles, allow_back_orders=self.allow_back_orders)
+
+
+def _newsvendor_ratio(args):
+    return args["underage_costs"] / (args["underage_costs"] + args["holding_costs"])
+
+
+class TransformedNV(QuantilePolicy):
+    """Learned monotone-free map of the newsvendor ratio u/(u+h) to a quantile (neural_networks.py:593-600)."""
+
+    def compute_desired_quantiles(self, args):
+        return self.net["master"](_newsvendor_ratio(args))
+
+
+class QuantileNV(QuantilePolicy):
+    """Newsvendor quantile u/(u+h) itself; nothing to train (neural_networks.py:602-614)."""
+
+    def __init__(self, args, device="cpu"):
+        super().__init__(args=args, device=device)
+        self.trainable = False
+
+    def compute_desired_quantiles(self, args):
+        return _newsvendor_ratio(args)
+
+
+class ReturnsNV(QuantileNV):
+    """QuantileNV that may also return stock (negative orders): a non-admissible benchmark (neural_networks.py:616-625)."""
+
+    def __init__(self, args, device="cpu"):
+        super().__init__(args=args, device=device)
+        self.allow_back_orders = True
+
+
+class FixedQuantile(QuantilePolicy):
+    """One learned quantile for every store and period (neural_networks.py:627-634)."""
+
+    def compute_desired_quantiles(self, args):
+        q = self.net["master"](torch.tensor([0.0]).to(self.device))
+        return q.unsqueeze(1).expand(args["underage_costs"].shape[0], args["underage_costs"].shape[1])
+
+
+class JustInTime(MyNeuralNetwork):
+    """Clairvoyant benchmark: orders exactly the demand that will materialise when the order arrives
+    (neural_networks.py:637-740). With warehouses every store is served by its connected warehouse with the shortest
+    (batch-mean) lead time, and that warehouse orders the store's demand one warehouse lead time further out."""
+
+    def __init__(self, args, scenario=None, device="cpu"):
+        super().__init__(args=args, device=device)
+        self.scenario = scenario
+        self.trainable = False
+
+    @staticmethod
+    def _future(demands, when):
+        return torch.gather(demands, 2, when.unsqueeze(2)).squeeze(2)
+
+    def forward(self, observation):
+        demands, shift = self.unpack_args(observation["internal_data"], ["demands", "period_shift"])
+        now = int(observation["current_period"].reshape(-1)[0]) + shift
+        B, S, horizon = demands.shape
+        lead = observation["lead_times"]
+        n_wh = observation["warehouse_inventories"].size(1) if "warehouse_inventories" in observation else 0
+        if n_wh == 0:
+            when = torch.clip(now + lead[:, :, 0].long(), max=horizon - 1)
+            return {"stores": torch.clip(self._future(demands, when), min=0).unsqueeze(2)}
+        adj = torch.tensor(self.scenario.problem_params["warehouse_store_adjacency"], dtype=torch.float32,
+                           device=lead.device).t()  # [S, W]
+        served = adj.sum(dim=1) > 0
+        mean_lead = torch.where(adj > 0, lead.mean(dim=0), torch.full_like(adj, float("inf")))
+        pick = torch.argmin(mean_lead, dim=1)  # [S] supplying warehouse of each store
+        lead_sel = torch.gather(lead, 2, pick[None, :, None].expand(B, S, 1)).squeeze(2).long()
+        wh_lead_sel = observation["warehouse_lead_times"][:, pick].long()  # [B, S]
+        store_need = self._future(demands, torch.clip(now + lead_sel, max=horizon - 1)) * served
+        wh_need = self._future(demands, torch.clip(now + wh_lead_sel + lead_sel, max=horizon - 1)) * served
+        stores = torch.zeros(B, S, n_wh, device=lead.device, dtype=demands.dtype)
+        stores.scatter_(2, pick[None, :, None].expand(B, S, 1), store_need.unsqueeze(2))
+        orders = torch.zeros(B, n_wh, device=lead.device, dtype=demands.dtype).index_add_(1, pick, wh_need)
+        return {"stores": torch.clip(stores, min=0), "warehouses": torch.clip(orders, min=0).unsqueeze(2)}
+
+
 class NeuralNetworkCreator:
     """name -> class registry, default output sizes, warehouse upper bound (neural_networks.py:1495-1574)."""
 
@@ -452,6 +611,12 @@ class NeuralNetworkCreator:
             "vanilla_serial": VanillaSerial,
             "vanilla_warehouse": VanillaWarehouse,
             "symmetry_aware": SymmetryAware,
+            "data_driven": DataDrivenNet,
+            "transformed_nv": TransformedNV,
+            "fixed_quantile": FixedQuantile,
+            "quantile_nv": QuantileNV,
+            "returns_nv": ReturnsNV,
+            "just_in_time": JustInTime,
             "gnn": GNN,
         }[name]
 
@@ -467,7 +632,7 @@ class NeuralNetworkCreator:
             if val is None:
                 params["output_sizes"][key] = self.set_default_output_size(key, scenario.problem_params)
         cls = self.get_architecture(params["name"])
-        if params["name"] in ("vanilla_warehouse", "gnn"):
+        if params["name"] in ("vanilla_warehouse", "gnn", "just_in_time", "data_driven"):
             model = cls(params, scenario, device=device)
         else:
             model = cls(params, device=device)

@@ -43,6 +43,20 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import yaml  # noqa: E402
 
+# The shipped quantile-forecaster checkpoint was written from a CUDA process and the reference loads it with a bare
+# torch.load(path): on this CPU-only container that needs a default map_location. The wrapper lives HERE (generator
+# side); the reference's sources stay untouched.
+_torch_load = torch.load
+
+
+def _cpu_load(f, *a, **k):
+    k.setdefault("map_location", "cpu")
+    k.setdefault("weights_only", False)
+    return _torch_load(f, *a, **k)
+
+
+torch.load = _cpu_load
+
 import trainer as ref_trainer  # noqa: E402  (the reference's trainer.py)
 from collections import defaultdict  # noqa: E402
 
@@ -89,7 +103,7 @@ def build_case(setting, policy, B, T, T_total, setting_patch=None, nn_patch=None
     return s, p, obs_params, scenario, data, model
 
 
-def run_reference(s, obs_params, data, model, T, ignore, dtype):
+def run_reference(s, obs_params, data, model, T, ignore, dtype, backward=True):
     """Trainer.simulate_batch + backward, exactly as trainer.py:163-173 does for one batch."""
     sim = ref_trainer.Simulator(device="cpu")
     tr = ref_trainer.Trainer(device="cpu")
@@ -100,14 +114,16 @@ def run_reference(s, obs_params, data, model, T, ignore, dtype):
     total, report = tr.simulate_batch(loss, sim, model, T, s["problem_params"], d, obs_params, ignore, False)
     B = len(d["demands"])
     mean_loss = total / (B * T * s["problem_params"]["n_stores"])
-    mean_loss.backward()
+    if backward:
+        mean_loss.backward()
     out = {
         "reward_tb": torch.stack(loss.rewards, 0).numpy(),
         "total": np.array(total.item()),
         "report": np.array(report.item()),
     }
     for k, v in model.named_parameters():
-        out[f"grad/{k}"] = v.grad.detach().clone().numpy()
+        if backward and v.grad is not None:
+            out[f"grad/{k}"] = v.grad.detach().clone().numpy()
     for k in ("store_inventories", "warehouse_inventories", "echelon_inventories"):
         if k in sim.observation:
             out[f"final/{k}"] = sim.observation[k].detach().numpy()
@@ -120,9 +136,11 @@ ONLY = None  # --only a,b: regenerate just these cases
 
 
 def rollout_case(name, setting, policy, B, T, T_total, ignore=30, setting_patch=None, nn_patch=None,
-                 torch_seed=0, state_dict_path=None, perturb=0.0, compact=False, kind="rollout"):
+                 torch_seed=0, state_dict_path=None, perturb=0.0, compact=False, kind="rollout", backward=True):
     if ONLY is not None and name not in ONLY:
         return
+    if kind == "realdata":
+        os.chdir(REF)  # the real-data settings name their demand / calendar files relative to the reference root
     s, p, obs_params, scenario, data, model = build_case(setting, policy, B, T, T_total, setting_patch, nn_patch,
                                                          torch_seed)
     # materialise LazyLinear layers with one throw-away forward
@@ -145,15 +163,28 @@ def rollout_case(name, setting, policy, B, T, T_total, ignore=30, setting_patch=
     for k, v in data.items():
         arrays[f"data/{k}"] = v.numpy()
     for k, v in model.state_dict().items():
+        if isinstance(v, torch.nn.parameter.UninitializedTensorMixin):
+            continue  # benchmark policies that never call their (lazy) net
         arrays[f"param/{k}"] = v.detach().clone().numpy()
-    r32 = run_reference(s, obs_params, data, model, T, ignore, torch.float32)
+    if hasattr(model, "fixed_nets"):  # frozen quantile forecaster: not in the policy's state_dict
+        for k, v in model.fixed_nets["quantile_forecaster"].state_dict().items():
+            arrays[f"aux/forecaster/{k}"] = v.detach().clone().numpy()
+    r32 = run_reference(s, obs_params, data, model, T, ignore, torch.float32, backward)
     for k, v in r32.items():
         arrays[f"ref/{k}"] = v
     wub = model.warehouse_upper_bound
     model64 = copy.deepcopy(model).double()
     if torch.is_tensor(wub):
         model64.warehouse_upper_bound = wub.double()
-    r64 = run_reference(s, obs_params, data, model64, T, ignore, torch.float64)
+    if hasattr(model64, "fixed_nets"):  # deepcopy(...).double() does not reach the plain-dict forecaster
+        model64.fixed_nets["quantile_forecaster"].double()
+    if kind == "realdata":
+        # policies that build constants with torch.tensor([0.0]) (FixedQuantile) need the default dtype to follow
+        torch.set_default_dtype(torch.float64)
+    try:
+        r64 = run_reference(s, obs_params, data, model64, T, ignore, torch.float64, backward)
+    finally:
+        torch.set_default_dtype(torch.float32)
     for k, v in r64.items():
         if k.startswith("grad/") or k in ("reward_tb", "total", "report"):
             # the 512-wide cases keep the float64 gradient as float32 (7 significant digits of the ground truth are
@@ -340,6 +371,27 @@ def main():
     # out of the fused-kernel / numpy-oracle test matrices (the oracle restates the fused policies only)
     rollout_case("one_warehouse", "one_warehouse_lost_demand", "gnn", B=32, T=50, T_total=60, kind="gnn")
     rollout_case("many_warehouses", "many_warehouses_lost_demand", "gnn", B=32, T=50, T_total=60, kind="gnn")
+
+    # real-data observation features (past demands, days from Christmas, period shift, profit objective) with the
+    # policies that consume them: DataDrivenNet and the clairvoyant benchmark on the shipped 21-store / 3-warehouse
+    # Favorita setting; the quantile policies on one-store samples cut from the same file (the reference does not ship
+    # data_files/favorita/weekly_sales.pt, so the one-store setting gets its demand from a reshaped copy under /tmp)
+    def real_one_store(s):
+        tmp = "/tmp/hdpo_weekly_one_store.pt"
+        w = _torch_load(f"{REF}/data_files/favorita_21_stores/weekly_sales.pt")
+        torch.save(w.reshape(-1, 1, w.shape[2]).contiguous(), tmp)
+        s["store_params"]["demand"]["file_location"] = tmp
+
+    rollout_case("many_warehouses_data_driven", "many_warehouses_real_data_lost_demand", "data_driven_net", B=16, T=50,
+                 T_total=171, ignore=16, kind="realdata")
+    rollout_case("many_warehouses_just_in_time", "many_warehouses_real_data_lost_demand", "just_in_time", B=16, T=50,
+                 T_total=171, ignore=16, kind="realdata", backward=False)
+    for pol in ("transformed_nv", "fixed_quantile"):
+        rollout_case(f"one_store_{pol}", "one_store_real_data_lost_demand", pol, B=48, T=50, T_total=171, ignore=16,
+                     setting_patch=real_one_store, kind="realdata")
+    for pol in ("quantile_nv", "returns_nv", "just_in_time"):
+        rollout_case(f"one_store_{pol}", "one_store_real_data_lost_demand", pol, B=48, T=50, T_total=171, ignore=16,
+                     setting_patch=real_one_store, kind="realdata", backward=False)
 
     step_case("one_store_lost", B=16, S=1, W=0, E=0, L=4, Lw=0, Le=0, lost=True, profit=False, edge_cost=False, seed=1)
     step_case("one_store_backlog_profit", B=16, S=1, W=0, E=0, L=7, Lw=0, Le=0, lost=False, profit=True,
