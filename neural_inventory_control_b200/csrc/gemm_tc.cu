@@ -271,7 +271,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
     constexpr int kBoxes = BN / 64;         // 32-column boxes per warp and array
     constexpr int kBoxBytes = 32 * 128;
     const int cbase = half * (BN / 2);
-    const int grow = (MN ? static_cast<int>(blockIdx.z) * g.M : g.c_row0) + m0 + q * 32;  // first output row of this warp
+    // first output row of this warp (weight-gradient form: c_row0 = row of the first partial slice of this launch)
+    const int grow = g.c_row0 + (MN ? static_cast<int>(blockIdx.z) * g.M : 0) + m0 + q * 32;
     unsigned char* stg = smem + we * (2 * kBoxes * kBoxBytes);  // [array 0 | array 1][box][32 rows x 128 B]
     mbar_wait(accum_bar, 0);
     tc_fence_after();
@@ -419,20 +420,23 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
         for (int j4 = 0; j4 < 4; ++j4)
           *chunk_ptr(0, j4) = make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
       }
+      // staged box -> global as soon as its 32 columns are complete (one TMA store per 32 x 32 box and array): the
+      // store of box b drains while box b + 1 is still being computed
+      if ((cc & 31) == 16) {
+        const int b = cc >> 5;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tm.c0, stg + b * kBoxBytes, n0 + cbase + 32 * b, grow);
+          if (EPI == EPI_FWD_HIDDEN || EPI == EPI_DGRAD_HIDDEN)
+            tma_store_2d(&tm.c1, stg + (kBoxes + b) * kBoxBytes, n0 + cbase + 32 * b, grow);
+          tma_store_commit();
+        }
+      }
     }
-    // staged sub-tile -> global: one TMA store per 32 x 32 box
     if (dbg && warp == 2 && lane == 0) dbg[5] = clock64();
     if (g.trace.buf && warp == 2 && lane == 0) tmem_slot[2] = static_cast<uint32_t>(trace_now());  // tile staged
-    fence_proxy_async();
-    __syncwarp();
     if (lane == 0) {
-#pragma unroll
-      for (int b = 0; b < kBoxes; ++b) {
-        tma_store_2d(&tm.c0, stg + b * kBoxBytes, n0 + cbase + 32 * b, grow);
-        if (EPI == EPI_FWD_HIDDEN || EPI == EPI_DGRAD_HIDDEN)
-          tma_store_2d(&tm.c1, stg + (kBoxes + b) * kBoxBytes, n0 + cbase + 32 * b, grow);
-      }
-      tma_store_commit();
       tma_store_wait_read();  // shared memory (and TMEM) are released right after the final barrier
       if (dbg && warp == 2) dbg[6] = clock64();
       if (g.trace.buf && warp == 2) tmem_slot[3] = static_cast<uint32_t>(trace_now());  // staged tile read by TMA

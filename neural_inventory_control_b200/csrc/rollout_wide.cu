@@ -83,6 +83,9 @@ struct Plan {
   size_t o_W[HDPO_MAX_LAYERS], o_b[HDPO_MAX_LAYERS];       // packed weights / biases
   size_t o_X, o_act[HDPO_MAX_LAYERS], o_gz[HDPO_MAX_LAYERS];  // tapes
   size_t o_gx, o_part, o_bpart, total;                      // state adjoint, split-K partials
+  int wg_group;                    // > 0: the weight-gradient GEMMs run in groups of this many periods on a second
+                                   // (low-priority) stream WHILE the adjoint sweep is still going (wgrad overlap)
+  size_t o_part_l[HDPO_MAX_LAYERS];  // partial slices of layer l (= o_part for every layer unless wg_group > 0)
   size_t o_csum[HDPO_MAX_LAYERS];  // tensor-core mode: [T*Bp/32][wp] column sums of 32-row blocks of gz_l (hidden l)
   // tensor-core mode extras: lo halves, transposed weights (dgrad B operand), split state tape
   size_t o_W_lo[HDPO_MAX_LAYERS], o_WT[HDPO_MAX_LAYERS], o_WT_lo[HDPO_MAX_LAYERS];
@@ -102,6 +105,39 @@ static bool use_persist(const HdpoRolloutDesc* d) {
 #endif
 }
 
+// HDPO_WIDE_WG_GROUP = G: periods per weight-gradient group of the overlapped form (0 = all weight gradients after the
+// sweep, the round-1 form). The per-period chain leaves a quarter of the SMs idle (dependent 15 us launches, DESIGN
+// section 4); the weight gradients are independent of that chain once the gz rows of a period exist.
+static int wg_group_periods() {
+#ifdef HDPO_EMU
+  return 0;
+#else
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HDPO_WIDE_WG_GROUP");
+    v = e ? atoi(e) : 5;
+    if (v < 0) v = 0;
+  }
+  return v;
+#endif
+}
+// Measured on B200 (8192 x 50 x 50 stores, 3xTF32): with 3 - 4 concurrent chunk chains the overlapped form changes
+// nothing (adjoint 10.8 - 11.1 ms with groups of 2 / 5 / 10 / 25 periods against 10.8 - 11.0 without: the weight-gradient
+// CTAs take as many SM slots from the chains as they fill), so it is the default only for ONE chunk (<= 2048 scenarios per
+// GPU, e.g. BASELINE cfg 5 at 1024 per GPU: adjoint 4.10 -> 3.84 ms). HDPO_WIDE_WG_OVERLAP = 1 / 0 forces it on / off.
+static int wg_overlap_mode() {
+#ifdef HDPO_EMU
+  return 0;
+#else
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("HDPO_WIDE_WG_OVERLAP");
+    v = e ? (atoi(e) != 0) : -1;
+  }
+  return v;
+#endif
+}
+
 static int multi_min_tiles() {
 #ifdef HDPO_EMU
   return 1 << 30;
@@ -109,6 +145,8 @@ static int multi_min_tiles() {
   return wp::multi_min_tiles();
 #endif
 }
+
+static int requested_chunks(int B, bool sym);
 
 static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
   Plan p;
@@ -191,6 +229,21 @@ static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
     p.wg_splits = static_cast<int>(rows / p.wg_kps);
   }
   p.o_part = p.save ? take(static_cast<size_t>(p.tc ? (p.wg_splits > kSplitK ? p.wg_splits : kSplitK) : kSplitK) * p.max_wk) : 0;
+  // overlapped weight gradients: every layer keeps its own partial slices (groups of different layers are in flight
+  // at the same time); a group must cover whole K slices
+  p.wg_group = 0;
+  {
+    const int G = wg_group_periods();
+    const int mode = wg_overlap_mode();
+    const bool wanted = mode == 1 || (mode == -1 && requested_chunks(d->pb.B, p.sym) == 1);
+    if (wanted && p.save && p.tc && !p.sym && !p.persist && G > 0 && G < p.T &&
+        (static_cast<size_t>(G) * p.Bp) % static_cast<size_t>(p.wg_kps) == 0 &&
+        (p.T % G == 0 || p.Bp % p.wg_kps == 0))  // (the last, shorter group must cover whole slices too)
+      p.wg_group = G;
+  }
+  for (int l = 0; l < p.n; ++l)
+    p.o_part_l[l] = p.wg_group ? take(static_cast<size_t>(p.wg_splits > kSplitK ? p.wg_splits : kSplitK) * p.wp[l + 1] * p.wp[l])
+                               : p.o_part;  // (layers on the SIMT split-K path write kSplitK slices)
   int max_wp = 0;
   for (int i = 0; i <= p.n; ++i) max_wp = p.wp[i] > max_wp ? p.wp[i] : max_wp;
   p.o_bpart = p.save ? take(static_cast<size_t>(128) * max_wp) : 0;
@@ -1011,7 +1064,7 @@ __global__ void __launch_bounds__(1024) totals_kernel(const float* __restrict__ 
 // is short (15-45 us) and ends with a drained tail (partial second wave, un-overlapped epilogue, warp-per-scenario
 // heads), and consecutive kernels of one chain are strictly dependent; two or more independent chains keep every SM
 // fed. Chunks share nothing but the (read-only) parameters; the parameter gradient is their fixed-order sum.
-constexpr int kMaxChunks = 4;
+constexpr int kMaxChunks = 8;
 constexpr int kChunkMinRows = 2048;
 
 struct Chunking {
@@ -1075,6 +1128,11 @@ size_t workspace_bytes(const HdpoRolloutDesc* d) { return make_chunking(d).total
 struct SideStreams {
   cudaStream_t s[kMaxChunks - 1];
   cudaEvent_t fork, join[kMaxChunks - 1];
+  // overlapped weight gradients: one chain stream per chunk at the highest priority (chunk 0 leaves the caller's
+  // stream too, so that no chunk is scheduled behind the others) and one low-priority stream per chunk for the
+  // weight-gradient groups; ev_rows = "the gz rows of the group are written", ev_done = "all groups finished"
+  cudaStream_t hi[kMaxChunks], wg[kMaxChunks];
+  cudaEvent_t join_hi[kMaxChunks], ev_rows[kMaxChunks], ev_done[kMaxChunks];
   bool ready;
 };
 static std::mutex g_side_mutex;
@@ -1091,6 +1149,15 @@ static int get_side_streams(SideStreams** out) {
       HDPO_CUDA_OK(cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming));
     }
     HDPO_CUDA_OK(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+    int prio_low = 0, prio_high = 0;
+    HDPO_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+    for (int i = 0; i < kMaxChunks; ++i) {
+      HDPO_CUDA_OK(cudaStreamCreateWithPriority(&ss.hi[i], cudaStreamNonBlocking, prio_high));
+      HDPO_CUDA_OK(cudaStreamCreateWithPriority(&ss.wg[i], cudaStreamNonBlocking, prio_low));
+      HDPO_CUDA_OK(cudaEventCreateWithFlags(&ss.join_hi[i], cudaEventDisableTiming));
+      HDPO_CUDA_OK(cudaEventCreateWithFlags(&ss.ev_rows[i], cudaEventDisableTiming));
+      HDPO_CUDA_OK(cudaEventCreateWithFlags(&ss.ev_done[i], cudaEventDisableTiming));
+    }
     ss.ready = true;
   }
   *out = &ss;
@@ -1496,11 +1563,21 @@ struct StreamFork {
   std::unique_lock<std::mutex> lock;
 #endif
   int n = 1;
+  bool all_side = false;  // every chunk (also chunk 0) on its own high-priority stream + a weight-gradient stream each
   void* main = nullptr;
-  int begin(int n_chunks, void* stream) {
+  int begin(int n_chunks, void* stream, bool overlap = false) {
     n = n_chunks;
     main = stream;
+    all_side = overlap;
 #ifndef HDPO_EMU
+    if (all_side) {
+      lock = std::unique_lock<std::mutex>(g_side_mutex);
+      int rc = get_side_streams(&ss);
+      if (rc) return rc;
+      HDPO_CUDA_OK(cudaEventRecord(ss->fork, static_cast<cudaStream_t>(main)));
+      for (int i = 0; i < n; ++i) HDPO_CUDA_OK(cudaStreamWaitEvent(ss->hi[i], ss->fork, 0));
+      return HDPO_OK;
+    }
     if (n > 1) {
       lock = std::unique_lock<std::mutex>(g_side_mutex);
       int rc = get_side_streams(&ss);
@@ -1513,13 +1590,36 @@ struct StreamFork {
   }
   void* stream_of(int i) const {
 #ifndef HDPO_EMU
+    if (all_side) return ss->hi[i];
     if (i > 0) return ss->s[i - 1];
 #endif
     (void)i;
     return main;
   }
+#ifndef HDPO_EMU
+  // chunk i's weight-gradient stream may start on rows the chain stream has written so far
+  int rows_ready(int i) {
+    HDPO_CUDA_OK(cudaEventRecord(ss->ev_rows[i], ss->hi[i]));
+    HDPO_CUDA_OK(cudaStreamWaitEvent(ss->wg[i], ss->ev_rows[i], 0));
+    return HDPO_OK;
+  }
+  void* wg_stream_of(int i) const { return ss->wg[i]; }
+  // chunk i's chain stream continues after everything queued on its weight-gradient stream
+  int wg_join(int i) {
+    HDPO_CUDA_OK(cudaEventRecord(ss->ev_done[i], ss->wg[i]));
+    HDPO_CUDA_OK(cudaStreamWaitEvent(ss->hi[i], ss->ev_done[i], 0));
+    return HDPO_OK;
+  }
+#endif
   int end() {
 #ifndef HDPO_EMU
+    if (all_side) {
+      for (int i = 0; i < n; ++i) {
+        HDPO_CUDA_OK(cudaEventRecord(ss->join_hi[i], ss->hi[i]));
+        HDPO_CUDA_OK(cudaStreamWaitEvent(static_cast<cudaStream_t>(main), ss->join_hi[i], 0));
+      }
+      return HDPO_OK;
+    }
     if (n > 1) {
       for (int i = 1; i < n; ++i) {
         HDPO_CUDA_OK(cudaEventRecord(ss->join[i - 1], ss->s[i - 1]));
@@ -1720,6 +1820,61 @@ static int bwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t, float rb) {
 }
 
 // weight gradients: dW_l[n][k] = sum over all (t, b) rows of gz_l[row][n] * in_l[row][k], split-K over the rows
+#ifndef HDPO_EMU
+// does layer l take the tcgen05 MN-major form (straight from the tapes)?
+static bool wgrad_tc_layer(const Plan& p, int l) { return p.tc && (p.wp[l + 1] % 128 == 0 || p.wp[l] % 128 == 0); }
+
+// tcgen05 weight-gradient GEMM of layer l over the tape rows of periods [t_lo, t_hi]: partial slices
+// [t_lo * Bp / kps, (t_hi + 1) * Bp / kps) of o_part_l[l]. When the output width is not a multiple of the 128-row
+// MMA tile (e.g. the 64-padded last layer) dW^T = in^T gz is computed instead and transposed while unpacking.
+static int wgrad_tc_rows(ChunkCtx& c, int l, int t_lo, int t_hi, void* stream) {
+  const Plan& p = c.p;
+  void* ws = c.ws;
+  const size_t rows = static_cast<size_t>(p.T) * p.Bp;
+  const bool transposed = p.wp[l + 1] % 128 != 0;
+  const float* gz_hi = wsf(ws, p.o_gz[l]);
+  const float* gz_lo = wsf(ws, p.o_gz_lo[l]);
+  const float* in_hi = (l == 0) ? wsf(ws, p.o_X_hi) : wsf(ws, p.o_act[l - 1]);
+  const float* in_lo = (l == 0) ? wsf(ws, p.o_X_lo) : wsf(ws, p.o_act_lo[l - 1]);
+  MapPair mg, mi;
+  int rc = tc::make_tensor_map(&mg.hi, gz_hi, rows, p.wp[l + 1], p.wp[l + 1], 32, true);
+  if (!rc) rc = tc::make_tensor_map(&mg.lo, gz_lo, rows, p.wp[l + 1], p.wp[l + 1], 32, true);
+  if (!rc) rc = tc::make_tensor_map(&mi.hi, in_hi, rows, p.wp[l], p.wp[l], 32, true);
+  if (!rc) rc = tc::make_tensor_map(&mi.lo, in_lo, rows, p.wp[l], p.wp[l], 32, true);
+  if (rc) return rc;
+  tc::GemmTcArgs g{};
+  g.M = transposed ? p.wp[l] : p.wp[l + 1];
+  g.N = transposed ? p.wp[l + 1] : p.wp[l];
+  const size_t row0 = static_cast<size_t>(t_lo) * p.Bp;
+  g.K = static_cast<int>(static_cast<size_t>(t_hi - t_lo + 1) * p.Bp);
+  g.k_per_split = p.wg_kps;
+  g.a_row0 = g.b_row0 = static_cast<int>(row0);
+  g.c_row0 = static_cast<int>(row0 / p.wg_kps) * g.M;  // first partial slice of this row range
+  g.c_slice = static_cast<size_t>(p.wp[l + 1]) * p.wp[l];
+  g.n_pass = p.n_pass;
+  g.trace.tag = static_cast<unsigned>(c.index);
+  g.ldc = g.N;
+  CUtensorMap mpart;  // the partial slices as one [n_slices * M][N] array
+  rc = tc::make_tensor_map(&mpart, wsf(ws, p.o_part_l[l]), static_cast<uint64_t>(p.wg_splits) * g.M, g.N, g.N,
+                           tc::kBoxRowsC);
+  if (rc) return rc;
+  tc::GemmTcMaps tm = transposed ? tc::GemmTcMaps{mi.hi, mi.lo, mg.hi, mg.lo, mpart, mpart, mpart, mpart}
+                                 : tc::GemmTcMaps{mg.hi, mg.lo, mi.hi, mi.lo, mpart, mpart, mpart, mpart};
+  return tc::gemm_wgrad(tm, g, tc::pick_bn(g.N), stream);
+}
+
+// overlapped form: the weight gradients of periods [t_lo, t_hi] of every tcgen05 layer, on the chunk's second stream
+static int wgrad_group(ChunkCtx& c, int t_lo, int t_hi, void* wg_stream) {
+  for (int l = 0; l < c.p.n; ++l) {
+    if (!wgrad_tc_layer(c.p, l)) continue;
+    int rc = wgrad_tc_rows(c, l, t_lo, t_hi, wg_stream);
+    if (rc) return rc;
+  }
+  return HDPO_OK;
+}
+#endif
+
+// partial slices -> gradient (and, without the overlapped form, the weight-gradient GEMMs themselves)
 static int bwd_end(ChunkCtx& c) {
   const Plan& p = c.p;
   void* ws = c.ws;
@@ -1735,37 +1890,14 @@ static int bwd_end(ChunkCtx& c) {
     const size_t c_slice = static_cast<size_t>(p.wp[l + 1]) * p.wp[l];
     bool done = false;
 #ifndef HDPO_EMU
-    if (p.tc && (p.wp[l + 1] % 128 == 0 || p.wp[l] % 128 == 0)) {
-      // tcgen05 MN-major form straight from the tapes; when the output width is not a multiple of the 128-row MMA
-      // tile (e.g. the 64-padded last layer) compute dW^T = in^T gz instead and transpose while unpacking.
+    if (wgrad_tc_layer(p, l)) {
       transposed = p.wp[l + 1] % 128 != 0;
-      const float* in_hi = (l == 0) ? wsf(ws, p.o_X_hi) : wsf(ws, p.o_act[l - 1]);
-      const float* in_lo = (l == 0) ? wsf(ws, p.o_X_lo) : wsf(ws, p.o_act_lo[l - 1]);
-      MapPair mg, mi;
-      int rc = tc::make_tensor_map(&mg.hi, gz_hi, rows, p.wp[l + 1], p.wp[l + 1], 32, true);
-      if (!rc) rc = tc::make_tensor_map(&mg.lo, gz_lo, rows, p.wp[l + 1], p.wp[l + 1], 32, true);
-      if (!rc) rc = tc::make_tensor_map(&mi.hi, in_hi, rows, p.wp[l], p.wp[l], 32, true);
-      if (!rc) rc = tc::make_tensor_map(&mi.lo, in_lo, rows, p.wp[l], p.wp[l], 32, true);
-      if (rc) return rc;
-      tc::GemmTcArgs g{};
-      g.M = transposed ? p.wp[l] : p.wp[l + 1];
-      g.N = transposed ? p.wp[l + 1] : p.wp[l];
-      g.K = static_cast<int>(rows);
-      g.k_per_split = p.wg_kps;
-      g.c_slice = c_slice;
-      g.n_pass = p.n_pass;
-      g.trace.tag = static_cast<unsigned>(c.index);
-      g.ldc = g.N;
-      CUtensorMap mpart;  // the partial slices as one [n_slices * M][N] array
-      rc = tc::make_tensor_map(&mpart, wsf(ws, p.o_part), static_cast<uint64_t>(p.wg_splits) * g.M, g.N, g.N,
-                               tc::kBoxRowsC);
-      if (rc) return rc;
-      tc::GemmTcMaps tm = transposed ? tc::GemmTcMaps{mi.hi, mi.lo, mg.hi, mg.lo, mpart, mpart, mpart, mpart}
-                                     : tc::GemmTcMaps{mg.hi, mg.lo, mi.hi, mi.lo, mpart, mpart, mpart, mpart};
-      rc = tc::gemm_wgrad(tm, g, tc::pick_bn(g.N), stream);
-      if (rc) return rc;
+      if (!p.wg_group) {  // (overlapped form: the groups already ran on the second stream)
+        int rc = wgrad_tc_rows(c, l, 0, p.T - 1, stream);
+        if (rc) return rc;
+      }
       used_splits = p.wg_splits;
-      ldp = g.N;
+      ldp = transposed ? p.wp[l + 1] : p.wp[l];
       done = true;
     }
 #endif
@@ -1775,7 +1907,7 @@ static int bwd_end(ChunkCtx& c) {
       g.A2 = gz_lo;
       g.B = (l == 0) ? wsf(ws, p.o_X) : wsf(ws, p.o_act[l - 1]);  // [rows][wp[l]]  (X tape: first T blocks, full fp32)
       g.B2 = (p.tc && l > 0) ? wsf(ws, p.o_act_lo[l - 1]) : nullptr;
-      g.C = wsf(ws, p.o_part);
+      g.C = wsf(ws, p.o_part_l[l]);
       g.M = p.wp[l + 1];
       g.N = p.wp[l];
       g.K = static_cast<int>(rows_per);
@@ -1788,6 +1920,7 @@ static int bwd_end(ChunkCtx& c) {
       int rc = sgemm<true, false, EPI_SPLITK>(g, splits, stream);
       if (rc) return rc;
     }
+    const float* part = wsf(ws, p.o_part_l[l]);
     const int n_chunks = 128;
     auto k1 = colsum_stage1_kernel;
     if (p.tc && l + 1 < p.n) {  // the dgrad epilogue already reduced every 32-row block (full fp32 values)
@@ -1804,22 +1937,19 @@ static int bwd_end(ChunkCtx& c) {
       // projection layer: rows 0.. -> context columns of the store net's first layer (+ its bias), rows 32.. -> the
       // warehouse net's
       const sym::Cfg& sc = c.sc;
-      HDPO_LAUNCH_PDL(k2, ceil_div(sc.s_w[0] * sc.C, 256), 256, 0, stream,
-                      static_cast<const float*>(wsf(ws, p.o_part)), used_splits, c_slice, ldp, transposed, sc.s_w[0], sc.C,
-                      static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1], sc.g_s_w0 + sc.s_in,
-                      sc.g_s_b0, c.grad, 0, sc.s_ld0);
+      HDPO_LAUNCH_PDL(k2, ceil_div(sc.s_w[0] * sc.C, 256), 256, 0, stream, part, used_splits, c_slice, ldp, transposed,
+                      sc.s_w[0], sc.C, static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1],
+                      sc.g_s_w0 + sc.s_in, sc.g_s_b0, c.grad, 0, sc.s_ld0);
       HDPO_LAUNCH_OK();
-      HDPO_LAUNCH_PDL(k2, ceil_div(sc.w_w[0] * sc.C, 256), 256, 0, stream,
-                      static_cast<const float*>(wsf(ws, p.o_part)), used_splits, c_slice, ldp, transposed, sc.w_w[0], sc.C,
-                      static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1], sc.g_w_w0 + sc.Lw,
-                      sc.g_w_b0, c.grad, 32, sc.w_ld0);
+      HDPO_LAUNCH_PDL(k2, ceil_div(sc.w_w[0] * sc.C, 256), 256, 0, stream, part, used_splits, c_slice, ldp, transposed,
+                      sc.w_w[0], sc.C, static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1],
+                      sc.g_w_w0 + sc.Lw, sc.g_w_b0, c.grad, 32, sc.w_ld0);
       HDPO_LAUNCH_OK();
       continue;
     }
-    HDPO_LAUNCH_PDL(k2, ceil_div(p.w[l + 1] * p.w[l], 256), 256, 0, stream, static_cast<const float*>(wsf(ws, p.o_part)),
-                    used_splits, c_slice, ldp, transposed, p.w[l + 1], p.w[l],
-                    static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1], p.gw[l], p.gb[l], c.grad, 0,
-                    p.w[l]);
+    HDPO_LAUNCH_PDL(k2, ceil_div(p.w[l + 1] * p.w[l], 256), 256, 0, stream, part, used_splits, c_slice, ldp, transposed,
+                    p.w[l + 1], p.w[l], static_cast<const float*>(wsf(ws, p.o_bpart)), n_chunks, p.wp[l + 1], p.gw[l],
+                    p.gb[l], c.grad, 0, p.w[l]);
     HDPO_LAUNCH_OK();
   }
   if (p.sym) return sym::reduce_slabs(c.sc, wsf(ws, p.o_slab), c.grad, stream);
@@ -1847,7 +1977,11 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
     return HDPO_E_WORKSPACE;
   }
   StreamFork fork;
-  int rc = fork.begin(ck.n, stream);
+  // overlapped weight gradients: only when EVERY chunk can cut its rows into whole-slice groups (the chunks may differ
+  // in their padded row count), and by default only for a single chunk (see wg_overlap_mode)
+  bool overlap = true;
+  for (int i = 0; i < ck.n && overlap; ++i) overlap = make_plan(d, ck.rows[i]).wg_group > 0;
+  int rc = fork.begin(ck.n, stream, overlap);
   if (rc) return rc;
   ChunkCtx ctx[kMaxChunks];
   float* extra = reinterpret_cast<float*>(static_cast<char*>(ws) + ck.grad_off);
@@ -1855,6 +1989,7 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
     bind_chunk(&ctx[i], d, ck, i, demands, st, ws, fork.stream_of(i));
     ctx[i].grad = i == 0 ? grad_params : extra + static_cast<size_t>(i - 1) * ck.P;
     ctx[i].params = params;
+    if (!overlap) ctx[i].p.wg_group = 0;  // bwd_end then runs the weight-gradient GEMMs itself
     if ((rc = bwd_begin(ctx[i]))) return rc;
   }
 #ifndef HDPO_EMU
@@ -1868,7 +2003,27 @@ int backward(const HdpoRolloutDesc* d, const float* params, const float* demands
     const float rb = g_total + (t >= d->ignore_periods ? g_report : 0.f);
     for (int i = 0; i < ck.n; ++i)
       if ((rc = bwd_period(ctx[i], d, t, rb))) return rc;
+#ifndef HDPO_EMU
+    if (overlap) {
+      // the sweep runs backwards in time: once period t is done the gz rows of [t, t_hi] exist, and their weight
+      // gradients go to the chunk's low-priority stream, filling the SMs the dependent chain leaves idle
+      const int G = ctx[0].p.wg_group;
+      const int done = d->T - t;  // periods swept so far
+      if (done % G == 0 || t == 0) {
+        const int t_hi = t + ((done % G == 0) ? G : done % G) - 1;
+        for (int i = 0; i < ck.n; ++i) {
+          if ((rc = fork.rows_ready(i))) return rc;
+          if ((rc = wgrad_group(ctx[i], t, t_hi, fork.wg_stream_of(i)))) return rc;
+        }
+      }
+    }
+#endif
   }
+#ifndef HDPO_EMU
+  if (overlap)
+    for (int i = 0; i < ck.n; ++i)
+      if ((rc = fork.wg_join(i))) return rc;
+#endif
   for (int i = 0; i < ck.n; ++i)
     if ((rc = bwd_end(ctx[i]))) return rc;
   if ((rc = fork.end())) return rc;
