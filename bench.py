@@ -506,6 +506,14 @@ def main():
             ms2 = time_region(step2, 10)
             others[name] = {"value": B2 * T / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "scenarios": B2,
                             "precision": prec2, "steps": 10, "warmup": 3, "workspace_bytes": eng2.ws_bytes}
+            # its own roofline position: algorithmic FLOPs of the whole step (SymmetryAware: the factored
+            # count) against the measured tf32 peak (bf16 / 2; sustained figure: the kernels run inside a long step)
+            fl2 = WL.flops_per_scenario_period(widths2, first_layer_dgrad=ps2.arch != "vanilla_serial", n_stores=S2)
+            tf2 = fl2 * B2 * T / (ms2 * 1e-3) / 1e12
+            pk2 = load_peaks()
+            pk2 = pk2.get("bf16_tflops_sustained", pk2["bf16_tflops"]) / 2.0
+            others[name]["roofline"] = {"bound": "tensor", "flops_per_scenario_period": fl2, "achieved": tf2,
+                                        "peak": pk2, "unit": "TFLOP/s", "step_frac": tf2 / pk2}
             if ckpt2:
                 others[name]["checkpoint_interval"] = ckpt2
             del eng2, data2, flat2, grad2

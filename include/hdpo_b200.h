@@ -281,6 +281,9 @@ int hdpo_debug_set_tc_multi(int32_t min_tiles);
  * larger batches use the 32-scenarios-per-warp form. > 0 sets it, 0 = never, < 0 = default (HDPO_SMALL_UNIT_MAX, else
  * 4096 one-store / 2048 serial). */
 int hdpo_debug_set_small_unit(int32_t max_batch);
+/* Scenarios per warp of that form: 1, 2 or 4 (weights loaded once per warp for all of them, their policy heads on
+ * lanes 0..G-1); anything else = chosen by the batch size (HDPO_SMALL_UNIT_G). */
+int hdpo_debug_set_small_unit_group(int32_t g);
 
 /* misc */
 const char* hdpo_last_error(void);

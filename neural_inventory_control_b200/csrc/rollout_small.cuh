@@ -43,6 +43,7 @@ struct Cfg {
 // lane = hidden unit / one scenario per warp form for training-size batches (rollout_small_unit.cu)
 bool use_unit(const Cfg& c);
 void set_unit_max_batch(int max_b);
+void set_unit_group(int g);
 int forward_unit(const Cfg& c, const float* params, const float* demands, const HdpoStatics* st, const HdpoState* init,
                  float* cost_b, float* report_b, float* reward_tb, float* tape, const HdpoState& fin, void* stream);
 int backward_unit(const Cfg& c, const float* params, const float* demands, const HdpoStatics* st, const float* tape,

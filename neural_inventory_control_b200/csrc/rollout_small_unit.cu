@@ -17,11 +17,9 @@ namespace small {
 
 constexpr int kUnitWarpsFwd = 16;
 constexpr int kUnitWarpsBwd = 12;
-// dispatch thresholds (scenarios): largest batch of the lane = unit kernels per policy, and of 1 / 2 scenarios per warp
+// dispatch thresholds (scenarios): largest batch of the lane = unit kernels per policy
 constexpr int kUnitMaxOneStore = 4096;
 constexpr int kUnitMaxSerial = 2048;
-constexpr int kUnitG1Max = 2048;
-constexpr int kUnitG2Max = 4096;
 
 // shared-memory weight block of the unit kernels (float offsets). "n" = W[n][k] rows (forward, weight gradient),
 // "t" = W^T[k][n] rows (input gradient); all rows zero padded to 32 entries, stride HS (first layer: s0)
@@ -106,8 +104,12 @@ static __device__ void stage_weights_unit(const Cfg& c, const UnitLayout& u, con
 // G scenarios per warp (G = 1, 2, 4): the lane's weight row is loaded ONCE per float4 chunk and used for the G activation
 // vectors of the warp's scenarios (G independent FMA chains per lane), the G policy heads + simulator periods run on
 // lanes 0 .. G-1 at the same time, and the warp's weight-gradient rows are read-modified-written once for G scenarios.
-// G = 1 is the one-scenario-per-warp form (the cheapest in latency: 1024 - 2048 scenarios); G = 4 executes about half
-// the warp instructions per scenario (the lane-0 head section was a third of them) and is what 8192 scenarios want.
+// G = 1 is the one-scenario-per-warp form and the DEFAULT at every batch size: G = 2 / 4 execute fewer warp instructions
+// per scenario (the lane-0 head section was a third of them) but the period is a chain of dependent phases whose latency
+// grows with G, and at 12 - 16 warps per SM that is what bounds the kernels. Measured on B200 (fwd + adjoint of 50
+// periods, ms per step, G = 1 / 2 / 4 | lane = scenario form): one-store 1024: 0.53 / 0.68 / 1.10 | 1.06; 4096: 0.92 / 0.91 /
+// 1.12 | 1.11; 8192: 1.53 / 1.30 / 1.45 | 1.12; 32768: 5.3 / 4.1 / 3.5 | 1.76; serial 8192: 2.04 / 1.48 / 1.45 | 1.05. G > 1 stays
+// available for A/B runs (HDPO_SMALL_UNIT_G, hdpo_debug_set_small_unit_group) and is parity-tested like G = 1.
 constexpr int XR = kMaxIn + 4;          // floats of one scenario's state row (and of its adjoint row)
 constexpr int HSZ = (kMaxHH + 1) * H;   // floats of one scenario's activation vectors
 
@@ -462,7 +464,7 @@ void set_unit_group(int g) { g_unit_g = (g == 1 || g == 2 || g == 4) ? g : 0; }
 // scenario-period forward) but has 32x the independent warps, so it wins while the other form cannot fill the machine.
 // Measured on B200, fwd + adjoint of 50 periods, ms per step unit (G = 1) / scenario form:  one-store 1024: 0.49 / 1.06,
 // 2048: 0.62 / 1.08, 4096: 0.84 / 1.11, 6144: 1.12 / 1.12, 8192: 1.39 / 1.12;  serial 1024: 0.70 / 0.98,
-// 2048: 0.83 / 1.00, 4096: 1.11 / 1.04. Larger batches take 2 / 4 scenarios per warp (unit_group).
+// 2048: 0.83 / 1.00, 4096: 1.11 / 1.04.
 static int unit_max_batch(const Cfg& c) {
   if (g_unit_max < 0) {
     const char* e = getenv("HDPO_SMALL_UNIT_MAX");
@@ -477,7 +479,8 @@ static int unit_group(const Cfg& c) {
     set_unit_group(e ? atoi(e) : 0);
   }
   if (g_unit_g > 0) return g_unit_g;
-  return c.B <= kUnitG1Max ? 1 : (c.B <= kUnitG2Max ? 2 : 4);
+  (void)c;
+  return 1;
 }
 bool use_unit(const Cfg& c) { return c.ckpt == 1 && c.B <= unit_max_batch(c); }
 

@@ -94,21 +94,26 @@ def test_allocation_shift_bit_exact(be_name):
     assert np.array_equal(be.get(h), g["ref"]["allocation_shift"])  # the reference's own table
 
 
-MAPPINGS = ["unit", "scenario"]
+MAPPINGS = ["unit", "unit2", "unit4", "scenario"]
 
 
 class small_mapping:
-    """Force one of the two thread mappings of the small-net rollout: "unit" = one scenario per warp, lane = hidden
-    unit (rollout_small_unit.cu; the default for batches of a few thousand scenarios), "scenario" = 32 per warp."""
+    """Force one of the thread mappings of the small-net rollout: "unit" = lane = hidden unit, one scenario per warp
+    (rollout_small_unit.cu; the default for batches of a few thousand scenarios), "unit2" / "unit4" = the same with 2 / 4
+    scenarios per warp (weights loaded once for all of them, heads on lanes 0..G-1), "scenario" = 32 scenarios per warp,
+    lane = scenario."""
 
     def __init__(self, be, mapping):
         self.be, self.mapping = be, mapping
 
     def __enter__(self):
-        self.be.lib.hdpo_debug_set_small_unit((1 << 30) if self.mapping == "unit" else 0)
+        unit = self.mapping.startswith("unit")
+        self.be.lib.hdpo_debug_set_small_unit((1 << 30) if unit else 0)
+        self.be.lib.hdpo_debug_set_small_unit_group(int(self.mapping[4:] or 1) if unit else 0)
 
     def __exit__(self, *exc):
         self.be.lib.hdpo_debug_set_small_unit(-1)
+        self.be.lib.hdpo_debug_set_small_unit_group(0)
 
 
 SMALL_MODES = [pytest.param("emu", "fp32", id="emu"), pytest.param("cuda", "fp32", id="cuda", marks=pytest.mark.gpu),
