@@ -307,14 +307,35 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
       if (nch > 2) tmem_ld16_async(lane_base + 3 * BN + c0, r2);
       if (three) tmem_ld16_async(lane_base + c0, r3);  // cross terms
       tmem_ld_wait();
+      // (packed f32x2 adds: same order of additions as the scalar form, half the issued instructions)
+      unsigned long long a2[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float a = __uint_as_float(r0[j]);
-        if (nch > 1) a += __uint_as_float(r1[j]);
-        if (nch > 2) a += __uint_as_float(r2[j]);
-        if (three) a += __uint_as_float(r3[j]);
-        v[j] = a;
+      for (int jp = 0; jp < 8; ++jp) a2[jp] = pack2(__uint_as_float(r0[2 * jp]), __uint_as_float(r0[2 * jp + 1]));
+      if (nch > 1) {
+#pragma unroll
+        for (int jp = 0; jp < 8; ++jp)
+          a2[jp] = add2_rn(a2[jp], pack2(__uint_as_float(r1[2 * jp]), __uint_as_float(r1[2 * jp + 1])));
       }
+      if (nch > 2) {
+#pragma unroll
+        for (int jp = 0; jp < 8; ++jp)
+          a2[jp] = add2_rn(a2[jp], pack2(__uint_as_float(r2[2 * jp]), __uint_as_float(r2[2 * jp + 1])));
+      }
+      if (three) {
+#pragma unroll
+        for (int jp = 0; jp < 8; ++jp)
+          a2[jp] = add2_rn(a2[jp], pack2(__uint_as_float(r3[2 * jp]), __uint_as_float(r3[2 * jp + 1])));
+      }
+      if (EPI == EPI_FWD_HIDDEN || EPI == EPI_FWD_OUT) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cbase + cc + 4 * j4);
+          a2[2 * j4] = add2_rn(a2[2 * j4], pack2(b4.x, b4.y));
+          a2[2 * j4 + 1] = add2_rn(a2[2 * j4 + 1], pack2(b4.z, b4.w));
+        }
+      }
+#pragma unroll
+      for (int jp = 0; jp < 8; ++jp) unpack2(a2[jp], v[2 * jp], v[2 * jp + 1]);
       const int n = n0 + c0;
       if (kEarlyAux && cc == 32) mbar_wait(&epi_bar[we], 0);  // second box of the combined tile has landed by now
       // staging addresses of this lane's four 16-byte chunks (array 0; array 1 is kBoxes boxes further)
@@ -331,14 +352,6 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
         return reinterpret_cast<const float4*>(chunk_ptr(arr, j4));
       };
       if (EPI == EPI_FWD_HIDDEN || EPI == EPI_FWD_OUT) {
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j4);
-          v[4 * j4 + 0] += b4.x;
-          v[4 * j4 + 1] += b4.y;
-          v[4 * j4 + 2] += b4.z;
-          v[4 * j4 + 3] += b4.w;
-        }
         if (g.act == HDPO_ACT_ELU) {
           elu_inplace(v);  // branch-free, element chains overlap
         } else {
@@ -407,11 +420,16 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
           hi.y = tf32_hi(v[4 * j4 + 1]);
           hi.z = tf32_hi(v[4 * j4 + 2]);
           hi.w = tf32_hi(v[4 * j4 + 3]);
-          // the remainder is rounded (not left to the tensor core's truncation) so that its error is unbiased
-          lo.x = tf32_hi(v[4 * j4 + 0] - hi.x);
-          lo.y = tf32_hi(v[4 * j4 + 1] - hi.y);
-          lo.z = tf32_hi(v[4 * j4 + 2] - hi.z);
-          lo.w = tf32_hi(v[4 * j4 + 3] - hi.w);
+          // the remainder is rounded (not left to the tensor core's truncation) so that its error is unbiased;
+          // v - hi as one packed FMA per pair (hi * -1 + v: exact, like the subtraction)
+          const unsigned long long m1 = pack2(-1.f, -1.f);
+          float d0, d1, d2, d3;
+          unpack2(fma2_rn(pack2(hi.x, hi.y), m1, pack2(v[4 * j4 + 0], v[4 * j4 + 1])), d0, d1);
+          unpack2(fma2_rn(pack2(hi.z, hi.w), m1, pack2(v[4 * j4 + 2], v[4 * j4 + 3])), d2, d3);
+          lo.x = tf32_hi(d0);
+          lo.y = tf32_hi(d1);
+          lo.z = tf32_hi(d2);
+          lo.w = tf32_hi(d3);
           *chunk_ptr(0, j4) = hi;
           *chunk_ptr(1, j4) = lo;
         }

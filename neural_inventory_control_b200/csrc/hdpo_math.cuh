@@ -34,8 +34,79 @@ __device__ __forceinline__ float expm1_nonpos(float x) {
 // unrelated values: the per-element `x > 0 ? ... : ...` of elu_f compiles to one divergent region per element with a
 // serial 7-FMA Horner chain inside (measured: 5.8 us per 128 x 128 tile, as long as the tile's whole mainloop);
 // evaluating both branches for all elements lets the chains of different elements overlap.
+#ifndef HDPO_EMU
+// packed fp32 pairs (Blackwell f32x2 forms -> SASS FFMA2 / FADD2 / FMUL2): two independent round-to-nearest operations
+// per issued instruction, bit-identical to the scalar ones
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2_rn(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add2_rn(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul2_rn(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+#endif
+
 template <int N>
 __device__ __forceinline__ void elu_inplace(float (&v)[N]) {
+#ifndef HDPO_EMU
+  if constexpr (N % 2 == 0) {
+    // same arithmetic as the scalar form below, the Horner steps / products / the "- 1" on packed pairs
+    unsigned long long xm[N / 2], p[N / 2], e[N / 2];
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) xm[j] = pack2(fminf(v[2 * j], 0.f), fminf(v[2 * j + 1], 0.f));
+    const unsigned long long c7 = pack2(1.f / 5040.f, 1.f / 5040.f), c6 = pack2(1.f / 720.f, 1.f / 720.f),
+                             c5 = pack2(1.f / 120.f, 1.f / 120.f), c4 = pack2(1.f / 24.f, 1.f / 24.f),
+                             c3 = pack2(1.f / 6.f, 1.f / 6.f), c2 = pack2(0.5f, 0.5f), c1 = pack2(1.f, 1.f),
+                             m1 = pack2(-1.f, -1.f);
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) p[j] = fma2_rn(xm[j], c7, c6);
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) p[j] = fma2_rn(xm[j], p[j], c5);
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) p[j] = fma2_rn(xm[j], p[j], c4);
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) p[j] = fma2_rn(xm[j], p[j], c3);
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) p[j] = fma2_rn(xm[j], p[j], c2);
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) p[j] = fma2_rn(xm[j], p[j], c1);
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) p[j] = mul2_rn(xm[j], p[j]);
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+      float x0, x1;
+      unpack2(xm[j], x0, x1);
+      e[j] = add2_rn(pack2(__expf(x0), __expf(x1)), m1);
+    }
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+      float x0, x1, p0, p1, e0, e1;
+      unpack2(xm[j], x0, x1);
+      unpack2(p[j], p0, p1);
+      unpack2(e[j], e0, e1);
+      const float r0 = x0 > -0.35f ? p0 : e0, r1 = x1 > -0.35f ? p1 : e1;
+      v[2 * j] = v[2 * j] > 0.f ? v[2 * j] : r0;
+      v[2 * j + 1] = v[2 * j + 1] > 0.f ? v[2 * j + 1] : r1;
+    }
+  } else
+#endif
+  {
   float xm[N], p[N], e[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) xm[j] = fminf(v[j], 0.f);
@@ -65,6 +136,7 @@ __device__ __forceinline__ void elu_inplace(float (&v)[N]) {
   for (int j = 0; j < N; ++j) {
     const float r = xm[j] > -0.35f ? p[j] : e[j];
     v[j] = v[j] > 0.f ? v[j] : r;
+  }
   }
 }
 
