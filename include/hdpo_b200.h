@@ -277,6 +277,14 @@ int hdpo_debug_set_wide_persist(int32_t on);
 /* Routing threshold of the multi-tile CTA-pair GEMM of the wide path: min_tiles > 0 = fewest 256-row tiles of a layer
  * launch that goes there (1 = every tensor-core GEMM), 0 = never, < 0 = default (off unless HDPO_TC_MULTI=1). */
 int hdpo_debug_set_tc_multi(int32_t min_tiles);
+/* Two-CTAs-per-SM tile forms of the per-period tensor-core GEMMs (4 x 64 TMEM columns and a 2-stage ring per CTA):
+ * 0 = off (default), 1 = 256 x 64 CTA-pair tiles where the epilogue exists in that form, 2 = 128 x 64 single-CTA tiles,
+ * < 0 = back to HDPO_TC_OCC2. Opt-in: slower than the 256 x 128 pair tiles at 8192 scenarios. */
+int hdpo_debug_set_tc_occ2(int32_t mode);
+/* Weight-gradient GEMMs of the wide path cut into groups of `group` periods and run on a low-priority stream while the
+ * adjoint sweep is still going: mode 1 = on, 0 = off, < 0 = default (on when the batch is ONE chunk); group <= 0 keeps
+ * the current group size (HDPO_WIDE_WG_GROUP, 5). Changes hdpo_rollout_workspace_bytes. */
+int hdpo_debug_set_wide_wg_overlap(int32_t mode, int32_t group);
 /* Largest batch (scenarios) that the small-net rollout runs in its one-scenario-per-warp form (rollout_small_unit.cu);
  * larger batches use the 32-scenarios-per-warp form. > 0 sets it, 0 = never, < 0 = default (HDPO_SMALL_UNIT_MAX, else
  * 4096 one-store / 2048 serial). */

@@ -108,17 +108,18 @@ static bool use_persist(const HdpoRolloutDesc* d) {
 // HDPO_WIDE_WG_GROUP = G: periods per weight-gradient group of the overlapped form (0 = all weight gradients after the
 // sweep, the round-1 form). The per-period chain leaves a quarter of the SMs idle (dependent 15 us launches, DESIGN
 // section 4); the weight gradients are independent of that chain once the gz rows of a period exist.
+static int g_wg_group = -1;    // < 0: not read yet (HDPO_WIDE_WG_GROUP, default 5)
+static int g_wg_overlap = -2;  // -2: not read yet; -1 = by chunk count, 0 = off, 1 = on (HDPO_WIDE_WG_OVERLAP)
 static int wg_group_periods() {
 #ifdef HDPO_EMU
   return 0;
 #else
-  static int v = -1;
-  if (v < 0) {
+  if (g_wg_group < 0) {
     const char* e = getenv("HDPO_WIDE_WG_GROUP");
-    v = e ? atoi(e) : 5;
-    if (v < 0) v = 0;
+    g_wg_group = e ? atoi(e) : 5;
+    if (g_wg_group < 0) g_wg_group = 0;
   }
-  return v;
+  return g_wg_group;
 #endif
 }
 // Measured on B200 (8192 x 50 x 50 stores, 3xTF32): with 3 - 4 concurrent chunk chains the overlapped form changes
@@ -129,12 +130,11 @@ static int wg_overlap_mode() {
 #ifdef HDPO_EMU
   return 0;
 #else
-  static int v = -2;
-  if (v == -2) {
+  if (g_wg_overlap == -2) {
     const char* e = getenv("HDPO_WIDE_WG_OVERLAP");
-    v = e ? (atoi(e) != 0) : -1;
+    g_wg_overlap = e ? (atoi(e) != 0) : -1;
   }
-  return v;
+  return g_wg_overlap;
 #endif
 }
 
@@ -1281,13 +1281,14 @@ static int forced_bn() {
 }
 // HDPO_TC_OCC2 = 1: the per-period GEMMs run as 64-column tiles with TWO CTAs per SM (256 TMEM columns and a 2-stage
 // ring each; CTA pairs where the epilogue exists in that form), so that kernels of different chunk streams share SMs
+static int g_occ2 = -1;  // < 0: not read yet (HDPO_TC_OCC2, default 0)
 static int occ2_mode() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_occ2 < 0) {
     const char* e = getenv("HDPO_TC_OCC2");
-    v = e ? atoi(e) : 0;
+    g_occ2 = e ? atoi(e) : 0;
+    if (g_occ2 < 0) g_occ2 = 0;
   }
-  return v;
+  return g_occ2;
 }
 static int tile_bn(int rows, int cols, bool pair_ok) {
   const int f = forced_bn();
@@ -1650,7 +1651,22 @@ extern "C" int hdpo_debug_set_tc_multi(int32_t min_tiles) {
   hdpo::wp::set_multi_min_tiles(min_tiles);
   return HDPO_OK;
 }
+// Two-CTAs-per-SM tile forms of the per-period GEMMs: 0 = off (default), 1 = 256 x 64 CTA pairs where possible, 2 = 128 x 64
+// single-CTA tiles everywhere, < 0 = back to HDPO_TC_OCC2.
+extern "C" int hdpo_debug_set_tc_occ2(int32_t mode) {
+  hdpo::wide::g_occ2 = mode < 0 ? -1 : mode;
+  return HDPO_OK;
+}
+// Weight-gradient GEMMs overlapped with the adjoint sweep: mode 1 = on, 0 = off, < 0 = by chunk count (default);
+// group = periods per group (<= 0: keep). Changes the workspace size: query hdpo_rollout_workspace_bytes afterwards.
+extern "C" int hdpo_debug_set_wide_wg_overlap(int32_t mode, int32_t group) {
+  hdpo::wide::g_wg_overlap = mode < 0 ? -1 : (mode != 0);
+  if (group > 0) hdpo::wide::g_wg_group = group;
+  return HDPO_OK;
+}
 #else
+extern "C" int hdpo_debug_set_tc_occ2(int32_t) { return HDPO_E_INVALID; }
+extern "C" int hdpo_debug_set_wide_wg_overlap(int32_t, int32_t) { return HDPO_E_INVALID; }
 extern "C" int hdpo_debug_set_tc_multi(int32_t) { return HDPO_E_INVALID; }
 extern "C" int hdpo_debug_set_wp_trace(unsigned long long*, int32_t) { return HDPO_E_INVALID; }
 extern "C" int hdpo_debug_set_wide_persist(int32_t) { return HDPO_E_INVALID; }
