@@ -192,3 +192,62 @@ def test_rollout_costs_and_gradients_match_reference(name, tmp_path):
 @pytest.mark.parametrize("name", BENCHMARKS)
 def test_benchmark_policy_rollout_costs_match_reference(name, tmp_path):
     _rollout(name, tmp_path, need_grad=False)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# dataset pipeline on real-data FILES (data_handling.py:9-123, 162-168, 398-458): fixture files + hashes of what the
+# unmodified reference makes of them (tests/golden/make_realdata_pipeline_golden.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def _pipeline_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "make_realdata_pipeline_golden", os.path.join(ROOT, "tests", "golden", "make_realdata_pipeline_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_real_data_pipeline_matches_reference():
+    """Scenario reads the demand file + calendar file, DatasetCreator splits BY PERIOD: every tensor of the full data
+    and of the train / dev / test windows has the sha256 the unmodified reference produced from the same files."""
+    import json
+    from neural_inventory_control_b200.data_handling import DatasetCreator, Scenario
+    mod = _pipeline_module()
+    with open(os.path.join(ROOT, "tests", "golden", "realdata_pipeline_hashes.json")) as f:
+        want = json.load(f)
+    got = mod.run(Scenario, DatasetCreator)
+    for part in ("full", "train", "dev", "test"):
+        assert sorted(got[part]) == sorted(want[part]), part
+        for k, v in want[part].items():
+            assert got[part][k] == v, (part, k)
+    # the windows are slices of the full series, the per-sample tensors are shared
+    assert want["train"]["demands"][0] == [20, 3, 40] and want["dev"]["demands"][0] == [20, 3, 24]
+
+
+@pytest.mark.gpu
+def test_main_run_trains_data_driven_net_on_real_data_files(monkeypatch, capsys):
+    """`python main_run.py train <real-data setting> data_driven_net`: split by period, past-demand window + days from
+    Christmas in the observation, profit objective, DataDrivenNet on the generic per-step path - two epochs on the
+    fixture files."""
+    import copy as _copy
+    import main_run
+    mod = _pipeline_module()
+    real_load = main_run.load_yaml
+
+    def load(path):
+        if "settings" in path:
+            s = _copy.deepcopy(mod.setting_with_paths())
+            s["test_seeds"] = _copy.deepcopy(s["seeds"])
+            s["params_by_dataset"] = {
+                "train": {"n_samples": 24, "batch_size": 12, "periods": 32, "ignore_periods": 8},
+                "dev": {"n_samples": 24, "batch_size": 24, "periods": 16, "ignore_periods": 8},
+                "test": {"n_samples": 24, "batch_size": 24, "periods": 16, "ignore_periods": 8}}
+            return s
+        cfg = real_load(path)
+        cfg["trainer_params"].update(epochs=2, do_dev_every_n_epochs=1, save_model=False)
+        return cfg
+    monkeypatch.setattr(main_run, "load_yaml", load)
+    monkeypatch.chdir(ROOT)
+    main_run.main(["main_run.py", "train", "fixture_real_data", "data_driven_net"])
+    out = capsys.readouterr().out
+    assert "Average per-period train loss" in out
