@@ -371,6 +371,11 @@ def main():
     # out of the fused-kernel / numpy-oracle test matrices (the oracle restates the fused policies only)
     rollout_case("one_warehouse", "one_warehouse_lost_demand", "gnn", B=32, T=50, T_total=60, kind="gnn")
     rollout_case("many_warehouses", "many_warehouses_lost_demand", "gnn", B=32, T=50, T_total=60, kind="gnn")
+    def with_moments(s):  # the shipped transshipment setting omits the mean / std features the GNN reads (KeyError)
+        s["observation_params"]["include_static_features"].update(mean=True, std=True)
+
+    rollout_case("transshipment", "transshipment_backlogged", "gnn_transshipment", B=32, T=50, T_total=60, kind="gnn",
+                 setting_patch=with_moments)
 
     # real-data observation features (past demands, days from Christmas, period shift, profit objective) with the
     # policies that consume them: DataDrivenNet and the clairvoyant benchmark on the shipped 21-store / 3-warehouse

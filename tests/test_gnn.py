@@ -15,7 +15,7 @@ import yaml
 import golden_util as G
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CASES = ["one_warehouse", "many_warehouses"]
+CASES = ["one_warehouse", "many_warehouses", "transshipment"]  # the last one: gnn_transshipment.yml (no hold option)
 
 
 def _cfg(kind, name):
@@ -30,7 +30,7 @@ class _Scenario:
 
 def _model(meta, g, device, dtype=torch.float32):
     from neural_inventory_control_b200.neural_networks import NeuralNetworkCreator
-    nn_params = copy.deepcopy(_cfg("policies_and_hyperparams", "gnn"))["nn_params"]
+    nn_params = copy.deepcopy(_cfg("policies_and_hyperparams", meta["policy"]))["nn_params"]
     model = NeuralNetworkCreator().create_neural_network(_Scenario(meta["problem_params"]), nn_params, device=device)
     return model
 
@@ -83,7 +83,9 @@ def test_gnn_rollout_costs_and_gradients_match_reference(name):
     model = _model(meta, g, dev)
     data = {k: torch.tensor(v, device=dev) for k, v in g["data"].items()}
     pp = meta["problem_params"]
-    obs_params = defaultdict(lambda: None, _cfg("settings", meta["setting"])["observation_params"])
+    obs_params = defaultdict(lambda: None, copy.deepcopy(_cfg("settings", meta["setting"])["observation_params"]))
+    if "mean" in g["data"]:  # the transshipment fixture was generated with the demand moments switched on (the GNN reads them)
+        obs_params["include_static_features"].update(mean=True, std=True)
     tr, sim = Trainer(device=dev), Simulator(device=dev)
     with torch.no_grad():
         tr.simulate_batch(PolicyLoss(), sim, model, 1, pp, {k: v[:2] for k, v in data.items()}, obs_params)

@@ -7,6 +7,8 @@ from neural_inventory_control_b200 import engine as EN, workloads as WL
 dev = torch.device("cuda", 0)
 name = sys.argv[1] if len(sys.argv) > 1 else "one_warehouse_lost_demand"
 kw = {}
+if os.environ.get("HDPO_AB_BATCH"):
+    kw = {"B": int(os.environ["HDPO_AB_BATCH"])}
 if name.endswith("_8192"):
     name, kw = name[:-5], {"B": 8192}
 pspec, pp, data, widths = WL.WORKLOADS[name](dev, seed=57, T=50, **kw)
