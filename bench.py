@@ -527,6 +527,10 @@ def main():
             pk2 = pk2.get("bf16_tflops_sustained", pk2["bf16_tflops"]) / 2.0
             others[name]["roofline"] = {"bound": "tensor", "flops_per_scenario_period": fl2, "achieved": tf2,
                                         "peak": pk2, "unit": "TFLOP/s", "step_frac": tf2 / pk2}
+            tr2 = load_traffic(name_wl)  # dominant kernel + its dram bytes per launch from the committed ncu capture
+            if tr2:
+                others[name]["roofline"].update({"kernel": tr2["kernel"], "traffic": tr2["dram_bytes_per_launch"],
+                                                 "traffic_source": tr2["source"]})
             if ckpt2:
                 others[name]["checkpoint_interval"] = ckpt2
             del eng2, data2, flat2, grad2
