@@ -19,7 +19,8 @@ class MissingExtension(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhdpo_b200.so")
+    # HDPO_LIB_PATH: another build of the SAME library (A/B timing of compile-time variants, tools/epi_ab.sh)
+    return os.environ.get("HDPO_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhdpo_b200.so")
 
 
 def load(require_device=True):

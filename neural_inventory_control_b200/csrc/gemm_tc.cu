@@ -7,6 +7,18 @@
 
 #ifndef HDPO_EMU
 
+// A/B build switches (tools/epi_ab.sh): packed f32x2 accumulator sums / bias / split in the epilogue, packed ELU.
+// Measured on B200 (8192 x 50 x 50 stores, 3xTF32, three interleaved runs each): all scalar 16.18 - 16.20 ms per step, packed
+// ELU only 16.23 - 16.24, packed sums only 16.31 - 16.32, both 16.35 - 16.37: a quarter fewer issued instructions and a small
+// LOSS (the epilogue warps wait on TMEM loads, MUFU and the store drain; the pack / unpack moves lengthen the chains).
+// The scalar forms are the default here; the SIMT kernels (small nets, SymmetryAware heads) keep the packed ELU (+1 %).
+#ifndef HDPO_EPI_PACK_SUM
+#define HDPO_EPI_PACK_SUM 0
+#endif
+#ifndef HDPO_EPI_PACK_ELU
+#define HDPO_EPI_PACK_ELU 0
+#endif
+
 namespace hdpo {
 namespace tc {
 
@@ -307,6 +319,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
       if (nch > 2) tmem_ld16_async(lane_base + 3 * BN + c0, r2);
       if (three) tmem_ld16_async(lane_base + c0, r3);  // cross terms
       tmem_ld_wait();
+#if HDPO_EPI_PACK_SUM
       // (packed f32x2 adds: same order of additions as the scalar form, half the issued instructions)
       unsigned long long a2[8];
 #pragma unroll
@@ -336,6 +349,26 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
       }
 #pragma unroll
       for (int jp = 0; jp < 8; ++jp) unpack2(a2[jp], v[2 * jp], v[2 * jp + 1]);
+#else
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = __uint_as_float(r0[j]);
+        if (nch > 1) a += __uint_as_float(r1[j]);
+        if (nch > 2) a += __uint_as_float(r2[j]);
+        if (three) a += __uint_as_float(r3[j]);
+        v[j] = a;
+      }
+      if (EPI == EPI_FWD_HIDDEN || EPI == EPI_FWD_OUT) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cbase + cc + 4 * j4);
+          v[4 * j4 + 0] += b4.x;
+          v[4 * j4 + 1] += b4.y;
+          v[4 * j4 + 2] += b4.z;
+          v[4 * j4 + 3] += b4.w;
+        }
+      }
+#endif
       const int n = n0 + c0;
       if (kEarlyAux && cc == 32) mbar_wait(&epi_bar[we], 0);  // second box of the combined tile has landed by now
       // staging addresses of this lane's four 16-byte chunks (array 0; array 1 is kBoxes boxes further)
@@ -353,7 +386,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
       };
       if (EPI == EPI_FWD_HIDDEN || EPI == EPI_FWD_OUT) {
         if (g.act == HDPO_ACT_ELU) {
-          elu_inplace(v);  // branch-free, element chains overlap
+          elu_inplace<16, HDPO_EPI_PACK_ELU != 0>(v);  // branch-free, element chains overlap
         } else {
           dispatch_act(g.act, [&](auto tag) {
             constexpr int ACT = decltype(tag)::value;
@@ -422,10 +455,15 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
           hi.w = tf32_hi(v[4 * j4 + 3]);
           // the remainder is rounded (not left to the tensor core's truncation) so that its error is unbiased;
           // v - hi as one packed FMA per pair (hi * -1 + v: exact, like the subtraction)
+#if HDPO_EPI_PACK_SUM
           const unsigned long long m1 = pack2(-1.f, -1.f);
           float d0, d1, d2, d3;
           unpack2(fma2_rn(pack2(hi.x, hi.y), m1, pack2(v[4 * j4 + 0], v[4 * j4 + 1])), d0, d1);
           unpack2(fma2_rn(pack2(hi.z, hi.w), m1, pack2(v[4 * j4 + 2], v[4 * j4 + 3])), d2, d3);
+#else
+          const float d0 = v[4 * j4 + 0] - hi.x, d1 = v[4 * j4 + 1] - hi.y, d2 = v[4 * j4 + 2] - hi.z,
+                      d3 = v[4 * j4 + 3] - hi.w;
+#endif
           lo.x = tf32_hi(d0);
           lo.y = tf32_hi(d1);
           lo.z = tf32_hi(d2);

@@ -62,10 +62,10 @@ __device__ __forceinline__ unsigned long long mul2_rn(unsigned long long a, unsi
 }
 #endif
 
-template <int N>
+template <int N, bool PACKED = true>
 __device__ __forceinline__ void elu_inplace(float (&v)[N]) {
 #ifndef HDPO_EMU
-  if constexpr (N % 2 == 0) {
+  if constexpr (PACKED && N % 2 == 0) {
     // same arithmetic as the scalar form below, the Horner steps / products / the "- 1" on packed pairs
     unsigned long long xm[N / 2], p[N / 2], e[N / 2];
 #pragma unroll
