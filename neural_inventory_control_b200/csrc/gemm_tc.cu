@@ -18,6 +18,20 @@
 #ifndef HDPO_EPI_PACK_ELU
 #define HDPO_EPI_PACK_ELU 0
 #endif
+#ifndef HDPO_EPI_PIPE
+#define HDPO_EPI_PIPE 0
+#endif
+// where a CTA lets the dependent kernel of its stream start (griddepcontrol.launch_dependents): 0 = right after its own
+// dependency wait, 1 = once its accumulators are complete, 2 = after its epilogue, 3 = never (implicit at grid completion),
+// -1 (default) = 0 for the forward epilogues and GemmTcArgs::pdl_late for the adjoint ones (the wide rollout sets it when
+// several chunk streams compete for the SMs). Measured on B200 (8192 x 50 x 50 stores = 4 chunks, three interleaved runs, ms
+// per step / forward / adjoint): 0: 16.16 / 5.36 / 10.81; 1: 16.06 - 16.09 / 5.40 / 10.69; 2: 16.09 - 16.15 / 5.39 / 10.72 - 10.80;
+// 3: 16.19 - 16.24 / 5.43 / 10.76 (a dependent CTA that was launched early holds an SM - 198 KB of shared memory, all of
+// TMEM - while it waits, which the other chunk streams could have used). With ONE chunk (latency-bound chain, idle SMs)
+// the early trigger is better: many_warehouses 1024 scenarios adjoint 3.82 (early) vs 4.05 ms (late).
+#ifndef HDPO_PDL_TRIGGER
+#define HDPO_PDL_TRIGGER -1
+#endif
 
 namespace hdpo {
 namespace tc {
@@ -156,8 +170,12 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
     tma_load_2d(dst + 32 * 128, &tm.x1, &aux_bar[we0], n0 + half0 * (BN / 2), g.x_row0 + m0 + q0 * 32);
   }
   // everything above overlapped the tail of the previous kernel in the stream (PDL); from here on we read its output
+  // (-1: the caller decides per launch - g.pdl_late - and only the adjoint epilogues honour it)
+  const int kPdlTrigger = HDPO_PDL_TRIGGER >= 0
+                              ? HDPO_PDL_TRIGGER
+                              : (((EPI == EPI_DGRAD_HIDDEN || EPI == EPI_DGRAD_ACCUM) && g.pdl_late) ? 1 : 0);
   pdl_wait();
-  pdl_launch_dependents();
+  if (kPdlTrigger == 0) pdl_launch_dependents();
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
   // trace records start once the predecessor's data is visible (a PDL-launched CTA may have idled above for long)
   const unsigned long long trace_t0 = (g.trace.buf && threadIdx.x == 0) ? trace_now() : 0ull;
@@ -288,6 +306,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
     unsigned char* stg = smem + we * (2 * kBoxes * kBoxBytes);  // [array 0 | array 1][box][32 rows x 128 B]
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    if (kPdlTrigger == 1 && warp == 2 && lane == 0) pdl_launch_dependents();  // this CTA is past its mainloop
     if (dbg && warp == 2 && lane == 0) dbg[4] = clock64();
     if (g.trace.buf && warp == 2 && lane == 0) tmem_slot[1] = static_cast<uint32_t>(trace_now());  // accumulators ready
     if (EPI == EPI_DGRAD_HIDDEN || EPI == EPI_DGRAD_ACCUM) {
@@ -308,16 +327,25 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
     }
     const int nch = n_kb < g.hi_chunks ? n_kb : g.hi_chunks;
     const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t r0[16], r1[16], r2[16], r3[16];
+    // every accumulator's load for one 16-column chunk (results valid after tmem_ld_wait())
+    auto issue_loads = [&](int cc_) {
+      const int cl = cbase + cc_;
+      tmem_ld16_async(lane_base + BN + cl, r0);  // hi*hi, first K chunk
+      if (nch > 1) tmem_ld16_async(lane_base + 2 * BN + cl, r1);
+      if (nch > 2) tmem_ld16_async(lane_base + 3 * BN + cl, r2);
+      if (three) tmem_ld16_async(lane_base + cl, r3);  // cross terms
+    };
+#if HDPO_EPI_PIPE
+    issue_loads(0);
+#endif
 #pragma unroll 1
     for (int cc = 0; cc < BN / 2; cc += 16) {
       const int c0 = cbase + cc;
-      uint32_t r0[16], r1[16], r2[16], r3[16];
       float v[16];
-      // issue every accumulator's load for this column chunk, then wait once
-      tmem_ld16_async(lane_base + BN + c0, r0);  // hi*hi, first K chunk
-      if (nch > 1) tmem_ld16_async(lane_base + 2 * BN + c0, r1);
-      if (nch > 2) tmem_ld16_async(lane_base + 3 * BN + c0, r2);
-      if (three) tmem_ld16_async(lane_base + c0, r3);  // cross terms
+#if !HDPO_EPI_PIPE
+      issue_loads(cc);
+#endif
       tmem_ld_wait();
 #if HDPO_EPI_PACK_SUM
       // (packed f32x2 adds: same order of additions as the scalar form, half the issued instructions)
@@ -368,6 +396,11 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
           v[4 * j4 + 3] += b4.w;
         }
       }
+#endif
+#if HDPO_EPI_PIPE
+      // software pipeline: the accumulators of this chunk are summed into v; the next chunk's TMEM loads fly while the
+      // activation / split / staging of this one runs
+      if (cc + 16 < BN / 2) issue_loads(cc + 16);
 #endif
       const int n = n0 + c0;
       if (kEarlyAux && cc == 32) mbar_wait(&epi_bar[we], 0);  // second box of the combined tile has landed by now
@@ -498,6 +531,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
       if (g.trace.buf && warp == 2) tmem_slot[3] = static_cast<uint32_t>(trace_now());  // staged tile read by TMA
     }
   }
+  if (kPdlTrigger == 2 && threadIdx.x == 64) pdl_launch_dependents();  // first epilogue thread: its tile is on its way
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();  // neither CTA may release shared memory / TMEM the pair's MMAs and commits still use
@@ -554,7 +588,11 @@ int make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+#ifdef HDPO_TMA_L2_128  // (A/B: 256-byte promotion measured 0.3 % faster on the wide step, tools/epi_ab.sh)
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+#else
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+#endif
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box_rows=%u)", static_cast<int>(r),

@@ -33,6 +33,8 @@ struct GemmTcArgs {
   int c_row0, x_row0;   // row origin of the output tile inside maps c0/c1, of the combined tile inside x0/x1
   int ldc;              // leading dimension (floats) of the output (used by colsum_part only)
   int act;              // HDPO_ACT_* of the epilogue
+  int pdl_late;         // adjoint epilogues: let the dependent kernel start once this CTA's accumulators are complete
+                        // instead of right after its dependency wait (set when chunk streams compete for the SMs)
   const float* bias;    // EPI_FWD_*
   TraceRef trace;       // optional per-CTA trace records (hdpo_debug_set_trace); tag set by the caller
   long long* dbg_clock; // optional: 8 clock64 stamps per CTA (tools/gemm_timeline.py)
