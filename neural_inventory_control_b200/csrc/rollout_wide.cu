@@ -1163,15 +1163,24 @@ static int get_side_streams(SideStreams** out) {
   HDPO_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
   SideStreams& ss = g_side[dev];
   if (!ss.ready) {
+    int prio_low = 0, prio_high = 0;
+    HDPO_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+    // HDPO_WIDE_PRIO (A/B knob): 0 = every chunk stream at the default priority, 1 = chunk i at priority -(i) (chunk 0 is
+    // the caller's stream), 2 = every side stream one level above the caller's
+    const char* pe = getenv("HDPO_WIDE_PRIO");
+    const int prio_mode = pe ? atoi(pe) : 0;
     for (int i = 0; i < kMaxChunks - 1; ++i) {
-      HDPO_CUDA_OK(cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking));
+      int pr = prio_low;
+      if (prio_mode == 1) pr = prio_low - (i + 1);
+      if (prio_mode == 2) pr = prio_low - 1;
+      if (pr < prio_high) pr = prio_high;
+      HDPO_CUDA_OK(cudaStreamCreateWithPriority(&ss.s[i], cudaStreamNonBlocking, pr));
       HDPO_CUDA_OK(cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming));
     }
     HDPO_CUDA_OK(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
-    int prio_low = 0, prio_high = 0;
-    HDPO_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
     for (int i = 0; i < kMaxChunks; ++i) {
-      HDPO_CUDA_OK(cudaStreamCreateWithPriority(&ss.hi[i], cudaStreamNonBlocking, prio_high));
+      // (HDPO_WIDE_PRIO = 3: chains and weight-gradient groups at the SAME priority)
+      HDPO_CUDA_OK(cudaStreamCreateWithPriority(&ss.hi[i], cudaStreamNonBlocking, prio_mode == 3 ? prio_low : prio_high));
       HDPO_CUDA_OK(cudaStreamCreateWithPriority(&ss.wg[i], cudaStreamNonBlocking, prio_low));
       HDPO_CUDA_OK(cudaEventCreateWithFlags(&ss.join_hi[i], cudaEventDisableTiming));
       HDPO_CUDA_OK(cudaEventCreateWithFlags(&ss.ev_rows[i], cudaEventDisableTiming));
