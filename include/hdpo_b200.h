@@ -285,6 +285,11 @@ int hdpo_debug_set_tc_occ2(int32_t mode);
  * adjoint sweep is still going: mode 1 = on, 0 = off, < 0 = default (on when the batch is ONE chunk); group <= 0 keeps
  * the current group size (HDPO_WIDE_WG_GROUP, 5). Changes hdpo_rollout_workspace_bytes. */
 int hdpo_debug_set_wide_wg_overlap(int32_t mode, int32_t group);
+/* Split-K of the two thin GEMMs on the wide path's per-period chain (output layer: partial products summed by the forward
+ * head; first-layer dgrad: partials added by the next adjoint head): 1 = on, 0 = off, < 0 = default (on when the batch is
+ * ONE chunk, where the chain is latency-bound: 1024 scenarios 6.25 -> 5.71 ms per step). Changes the workspace size and the
+ * summation order of those two layers. */
+int hdpo_debug_set_wide_ksplit(int32_t mode);
 /* Largest batch (scenarios) that the small-net rollout runs in its one-scenario-per-warp form (rollout_small_unit.cu);
  * larger batches use the 32-scenarios-per-warp form. > 0 sets it, 0 = never, < 0 = default (HDPO_SMALL_UNIT_MAX, else
  * 4096 one-store / 2048 serial). */

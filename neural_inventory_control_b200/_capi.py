@@ -79,7 +79,7 @@ def make_mlp(widths, hidden_act, out_act):
 EXPORTS = [
     "hdpo_step_fwd", "hdpo_step_bwd", "hdpo_allocation_shift", "hdpo_gather_rows", "hdpo_adam_step", "hdpo_param_count", "hdpo_rollout_workspace_bytes",
     "hdpo_rollout_fwd", "hdpo_rollout_bwd", "hdpo_rollout_host_workspace_bytes", "hdpo_rollout_train_host",
-    "hdpo_philox_normal", "hdpo_philox_poisson", "hdpo_philox_raw", "hdpo_debug_gemm_tc", "hdpo_debug_gemm_tc_wgrad", "hdpo_debug_gemm_tc_timeline", "hdpo_debug_set_trace", "hdpo_debug_set_wp_trace", "hdpo_debug_set_wide_persist", "hdpo_debug_set_tc_multi", "hdpo_debug_set_tc_occ2", "hdpo_debug_set_wide_wg_overlap", "hdpo_debug_set_small_unit", "hdpo_debug_set_small_unit_group", "hdpo_last_error", "hdpo_abi_version", "hdpo_kernel_launch_count",
+    "hdpo_philox_normal", "hdpo_philox_poisson", "hdpo_philox_raw", "hdpo_debug_gemm_tc", "hdpo_debug_gemm_tc_wgrad", "hdpo_debug_gemm_tc_timeline", "hdpo_debug_set_trace", "hdpo_debug_set_wp_trace", "hdpo_debug_set_wide_persist", "hdpo_debug_set_tc_multi", "hdpo_debug_set_tc_occ2", "hdpo_debug_set_wide_wg_overlap", "hdpo_debug_set_wide_ksplit", "hdpo_debug_set_small_unit", "hdpo_debug_set_small_unit_group", "hdpo_last_error", "hdpo_abi_version", "hdpo_kernel_launch_count",
     "hdpo_device_info",
 ]
 
@@ -114,6 +114,7 @@ def bind(lib):
     lib.hdpo_debug_set_tc_multi.argtypes = [C.c_int32]
     lib.hdpo_debug_set_tc_occ2.argtypes = [C.c_int32]
     lib.hdpo_debug_set_wide_wg_overlap.argtypes = [C.c_int32, C.c_int32]
+    lib.hdpo_debug_set_wide_ksplit.argtypes = [C.c_int32]
     lib.hdpo_debug_set_small_unit.argtypes = [C.c_int32]
     lib.hdpo_debug_set_small_unit_group.argtypes = [C.c_int32]
     lib.hdpo_last_error.restype = C.c_char_p

@@ -105,8 +105,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
   const int n0 = CG == 2 ? blockIdx.z * BN : blockIdx.x * BN;
   long long* dbg = g.dbg_clock ? g.dbg_clock + 8 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
-  const int n_kb = (MN ? g.k_per_split : g.K) / kBK;
-  const int k_begin = MN ? static_cast<int>(blockIdx.z) * g.k_per_split : 0;
+  // K slices: rows of the MN-major operands (weight gradient) / columns of the K-major ones (split-K, single CTA only)
+  const bool ksplit = MN || (CG == 1 && g.k_per_split > 0);
+  const int n_kb = (ksplit ? g.k_per_split : g.K) / kBK;
+  const int k_begin = ksplit ? static_cast<int>(blockIdx.z) * g.k_per_split : 0;
   const bool three = g.n_pass == 3;
 
   if (warp == 0 && lane == 0) {
@@ -139,7 +141,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
     const int we0 = warp - 2, q0 = warp & 3, half0 = we0 >> 2;
     if (EPI == EPI_FWD_HIDDEN || EPI == EPI_FWD_OUT) {
       const int t = threadIdx.x - 64;
-      if (t < BN) bias_s[t] = g.bias[n0 + t];
+      if (t < BN) bias_s[t] = (CG == 1 && !MN && blockIdx.z > 0) ? 0.f : g.bias[n0 + t];  // split-K: slice 0 adds it
     }
     if (EPI == EPI_DGRAD_HIDDEN && lane == 0) {
       const int xrow = g.x_row0 + m0 + q0 * 32;
@@ -207,11 +209,12 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
         } else {
         mbar_expect_tx(&full_bar[s], tx);
         if (!MN) {
-          tma_load_2d(st, &tm_a_hi, &full_bar[s], kb * kBK, g.a_row0 + m0);
-          tma_load_2d(st + 2 * P::kABytes, &tm_b_hi, &full_bar[s], kb * kBK, g.b_row0 + n0);
+          const int kcol = k_begin + kb * kBK;
+          tma_load_2d(st, &tm_a_hi, &full_bar[s], kcol, g.a_row0 + m0);
+          tma_load_2d(st + 2 * P::kABytes, &tm_b_hi, &full_bar[s], kcol, g.b_row0 + n0);
           if (three) {
-            tma_load_2d(st + P::kABytes, &tm_a_lo, &full_bar[s], kb * kBK, g.a_row0 + m0);
-            tma_load_2d(st + 2 * P::kABytes + P::kBBytes, &tm_b_lo, &full_bar[s], kb * kBK, g.b_row0 + n0);
+            tma_load_2d(st + P::kABytes, &tm_a_lo, &full_bar[s], kcol, g.a_row0 + m0);
+            tma_load_2d(st + 2 * P::kABytes + P::kBBytes, &tm_b_lo, &full_bar[s], kcol, g.b_row0 + n0);
           }
         } else {
           constexpr int kBox = kBK * 128;  // bytes of one {32 mn, BK k} box
@@ -302,7 +305,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
     constexpr int kBoxBytes = 32 * 128;
     const int cbase = half * (BN / 2);
     // first output row of this warp (weight-gradient form: c_row0 = row of the first partial slice of this launch)
-    const int grow = g.c_row0 + (MN ? static_cast<int>(blockIdx.z) * g.M : 0) + m0 + q * 32;
+    const int grow = g.c_row0 + (MN ? static_cast<int>(blockIdx.z) * g.M
+                                    : (CG == 1 ? static_cast<int>(blockIdx.z) * g.c_zrows : 0)) + m0 + q * 32;
     unsigned char* stg = smem + we * (2 * kBoxes * kBoxBytes);  // [array 0 | array 1][box][32 rows x 128 B]
     mbar_wait(accum_bar, 0);
     tc_fence_after();
@@ -616,7 +620,7 @@ static int launch(const GemmTcMaps& tm, const GemmTcArgs& g_in, void* stream) {
       HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
-  const unsigned nz = MN ? static_cast<unsigned>(g.K / g.k_per_split) : 1u;
+  const unsigned nz = (MN || (CG == 1 && g.k_per_split > 0)) ? static_cast<unsigned>(g.K / g.k_per_split) : 1u;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = CG == 2 ? dim3(2, g.M / 256, g.N / BN) : dim3(g.N / BN, g.M / 128, nz);
   cfg.blockDim = dim3(kThreads);
@@ -656,6 +660,12 @@ int gemm(const GemmTcMaps& tm, const GemmTcArgs& g, int epi, int bn, void* strea
   HDPO_REQUIRE(g.M % 128 == 0 && g.N % bn_cols == 0 && g.K % kBK == 0 && g.K > 0,
                "tcgen05 GEMM shape %dx%dx%d not tileable", g.M, g.N, g.K);
   HDPO_REQUIRE(g.n_pass == 1 || g.n_pass == 3, "n_pass must be 1 or 3");
+  if (g.k_per_split > 0) {  // split-K of a K-major GEMM: single-CTA tiles, plain / bias epilogues (partials are summed later)
+    HDPO_REQUIRE((bn == 64 || bn == 128) && (epi == EPI_STORE || epi == EPI_FWD_OUT) && g.k_per_split % kBK == 0 &&
+                     g.K % g.k_per_split == 0 && g.c_zrows >= g.M,
+                 "split-K GEMM %dx%dx%d (k_per_split %d, bn %d, epilogue %d) not supported", g.M, g.N, g.K, g.k_per_split,
+                 bn, epi);
+  }
   if (bn == kBnPair) {  // CTA-pair form: 256 x 128 tiles (the B map must have BN / 2 = 64-row boxes)
     HDPO_REQUIRE(g.M % 256 == 0 && g.N % 128 == 0, "CTA-pair GEMM shape %dx%d not tileable", g.M, g.N);
     switch (epi) {

@@ -25,7 +25,10 @@ enum { EPI_FWD_HIDDEN = 0, EPI_FWD_OUT = 1, EPI_DGRAD_HIDDEN = 2, EPI_DGRAD_ACCU
 
 struct GemmTcArgs {
   int M, N, K;          // M % 128 == 0, N % BN == 0, K % 32 == 0
-  int k_per_split;      // weight-gradient form only: contraction rows handled by one blockIdx.z slice
+  int k_per_split;      // weight-gradient form: contraction rows handled by one blockIdx.z slice. K-major single-CTA
+                        // forms: > 0 = split-K, slice z takes columns [z, z + 1) * k_per_split of A / B and writes its
+                        // partial product c_zrows rows further down the c0 map (bias added by slice 0 only)
+  int c_zrows;          // K-major split-K: rows between the partial outputs of consecutive slices
   size_t c_slice;       // weight-gradient form only: floats between the partial outputs of consecutive slices
   int n_pass;           // 3 = 3xTF32, 1 = single-pass TF32
   int hi_chunks;        // accumulators the hi*hi term is spread over (0 = default, see gemm_tc.cu)

@@ -86,6 +86,11 @@ struct Plan {
   size_t o_W[HDPO_MAX_LAYERS], o_b[HDPO_MAX_LAYERS];       // packed weights / biases
   size_t o_X, o_act[HDPO_MAX_LAYERS], o_gz[HDPO_MAX_LAYERS];  // tapes
   size_t o_gx, o_part, o_bpart, total;                      // state adjoint, split-K partials
+  // split-K of the two THIN GEMMs on the per-period chain (few CTAs, K = the hidden width: their mainloop is a chain of
+  // TMA round trips): the output layer writes y_split partial products that the forward head sums (and writes to the Y
+  // tape), the first layer's dgrad writes gx_split partials that the next adjoint head adds to its gX row
+  int y_split, gx_split;
+  size_t o_ypart, o_gxpart;
   int wg_group;                    // > 0: the weight-gradient GEMMs run in groups of this many periods on a second
                                    // (low-priority) stream WHILE the adjoint sweep is still going (wgrad overlap)
   size_t o_part_l[HDPO_MAX_LAYERS];  // partial slices of layer l (= o_part for every layer unless wg_group > 0)
@@ -150,6 +155,19 @@ static int multi_min_tiles() {
 }
 
 static int requested_chunks(int B, bool sym);
+// Split-K of the thin chain GEMMs: HDPO_WIDE_KSPLIT = 1 / 0 forces it on / off; by default it is on for ONE chunk only.
+// Measured on B200 (3xTF32, ms per step off / on): one chunk - one_warehouse 1024 scenarios 6.25 / 5.71, many_warehouses
+// 1024 7.22 / 6.84 (the chain is latency-bound, the extra CTAs run on idle SMs); four chunks - one_warehouse 8192
+// 16.0 / 17.1, many_warehouses 8192 21.4 / 23.8 (four times the CTAs, each holding an SM's shared memory, compete with
+// the other chunk chains).
+static int g_ksplit = -2;  // -2: not read yet; -1 = by chunk count, 0 = off, 1 = on
+static bool thin_ksplit_enabled(int n_chunks) {
+  if (g_ksplit == -2) {
+    const char* e = getenv("HDPO_WIDE_KSPLIT");
+    g_ksplit = e ? (atoi(e) != 0) : -1;
+  }
+  return g_ksplit == 1 || (g_ksplit == -1 && n_chunks == 1);
+}
 
 static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
   Plan p;
@@ -250,6 +268,17 @@ static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
   int max_wp = 0;
   for (int i = 0; i <= p.n; ++i) max_wp = p.wp[i] > max_wp ? p.wp[i] : max_wp;
   p.o_bpart = p.save ? take(static_cast<size_t>(128) * max_wp) : 0;
+  p.y_split = p.gx_split = 1;
+  p.o_ypart = p.o_gxpart = 0;
+#ifndef HDPO_EMU
+  if (p.tc && !p.sym && !p.persist && thin_ksplit_enabled(requested_chunks(d->pb.B, p.sym))) {
+    auto splits = [](int K) { return (K >= 256 && K % 128 == 0) ? (K / 128 < 4 ? K / 128 : 4) : 1; };
+    if (p.act[p.n - 1] == HDPO_ACT_NONE) p.y_split = splits(p.wp[p.n - 1]);  // (an activation cannot act on partials)
+    if (p.save) p.gx_split = splits(p.wp[1]);
+    if (p.y_split > 1) p.o_ypart = take(static_cast<size_t>(p.y_split) * p.Bp * p.wp[p.n]);
+    if (p.gx_split > 1) p.o_gxpart = take(static_cast<size_t>(p.gx_split) * p.Bp * p.wp[0]);
+  }
+#endif
   p.so_stride = p.sym ? static_cast<size_t>(p.Bp) * sc.ldo : 0;
   p.o_so = (p.sym && p.save) ? take(tslots * p.so_stride) : 0;
   p.o_slab = (p.sym && p.save) ? take(static_cast<size_t>(sym::bwd_warps(sc)) * sc.q_total) : 0;
@@ -577,6 +606,12 @@ struct HeadArgs {
   const float* demands;
   HdpoStatics st;
   TraceRef trace;
+  // split-K partials of the thin chain GEMMs (n_part <= 1: none). Forward head: Y row = sum of y_nz partial rows
+  // (stride part_stride floats), written to y_out; adjoint head: entry gX row += sum of gx_nz partial rows.
+  const float* part;
+  size_t part_stride;
+  int n_part;
+  float* y_out;
 };
 
 
@@ -719,7 +754,22 @@ warehouse_head_fwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
   pdl_wait();
   head_pdl_trigger<0>();
   trace_scope.t0 = (a.trace.buf && threadIdx.x == 0) ? trace_now() : 0ull;  // records start after the dependency wait
-  {
+  if (a.n_part > 1) {
+    // split-K output layer: the policy outputs are the sum of the partial rows (fixed order); the row also goes to the
+    // Y tape, which the adjoint head reads
+    for (int k = lane * 4; k < a.ldy; k += 128) {
+      float4 v = *reinterpret_cast<const float4*>(a.part + static_cast<size_t>(b) * a.ldy + k);
+      for (int z = 1; z < a.n_part; ++z) {
+        const float4 u = *reinterpret_cast<const float4*>(a.part + z * a.part_stride + static_cast<size_t>(b) * a.ldy + k);
+        v.x += u.x;
+        v.y += u.y;
+        v.z += u.z;
+        v.w += u.w;
+      }
+      *reinterpret_cast<float4*>(r.y + k) = v;
+      *reinterpret_cast<float4*>(a.y_out + static_cast<size_t>(b) * a.ldy + k) = v;
+    }
+  } else {
     const float* yrow = Y + static_cast<size_t>(b) * a.ldy;
     for (int k = lane * 4; k < a.ldy; k += 128)
       *reinterpret_cast<float4*>(r.y + k) = *reinterpret_cast<const float4*>(yrow + k);
@@ -864,8 +914,18 @@ warehouse_head_bwd_kernel(HeadArgs a, const float* __restrict__ X, const float* 
   head_pdl_trigger<1>();
   trace_scope.t0 = (a.trace.buf && threadIdx.x == 0) ? trace_now() : 0ull;
   float* gx_row = gX + static_cast<size_t>(b) * a.ldx;
-  for (int k = lane * 4; k < a.ldx; k += 128)
-    *reinterpret_cast<float4*>(g + k) = *reinterpret_cast<const float4*>(gx_row + k);
+  for (int k = lane * 4; k < a.ldx; k += 128) {
+    float4 v = *reinterpret_cast<const float4*>(gx_row + k);
+    // split-K first-layer dgrad of the period before (t + 1): its partial products complete the adjoint wrt X_{t+1}
+    for (int z = 0; z < a.n_part; ++z) {
+      const float4 u = *reinterpret_cast<const float4*>(a.part + z * a.part_stride + static_cast<size_t>(b) * a.ldx + k);
+      v.x += u.x;
+      v.y += u.y;
+      v.z += u.z;
+      v.w += u.w;
+    }
+    *reinterpret_cast<float4*>(g + k) = v;
+  }
   __syncwarp();
   const float* x = r.xs;
   const float* y = r.y;
@@ -1230,6 +1290,7 @@ struct ChunkCtx {
   MapPair mAct[HDPO_MAX_LAYERS];                     // layer-output tapes as 32-row output boxes (lo unused for the last)
   MapPair mGz[HDPO_MAX_LAYERS];                      // pre-activation adjoint tapes as output boxes
   CUtensorMap mGx;                                   // state adjoint [Bp][wp0]
+  CUtensorMap mYpart, mGxPart;                       // split-K partial outputs [n_split * Bp][wp_out] / [.. * Bp][wp0]
 #endif
 };
 
@@ -1294,6 +1355,10 @@ static HeadArgs head_args(const HdpoRolloutDesc* d, const ChunkCtx& c, int t) {
   a.demands = c.demands;
   a.st = c.st;
   a.trace = trace_ref(0xF00u | static_cast<unsigned>(c.index));  // tag: head kernel of chunk index
+  a.part = nullptr;
+  a.part_stride = 0;
+  a.n_part = 0;
+  a.y_out = nullptr;
   return a;
 }
 
@@ -1354,10 +1419,40 @@ static int make_tape_maps(ChunkCtx& c) {
       if (rc) return rc;
     }
   }
+  if (p.y_split > 1) {
+    int rc = tc::make_tensor_map(&c.mYpart, wsf(ws, p.o_ypart), static_cast<uint64_t>(p.y_split) * p.Bp, p.wp[p.n], p.wp[p.n],
+                                 tc::kBoxRowsC);
+    if (rc) return rc;
+  }
+  if (p.save && p.gx_split > 1) {
+    int rc = tc::make_tensor_map(&c.mGxPart, wsf(ws, p.o_gxpart), static_cast<uint64_t>(p.gx_split) * p.Bp, p.wp[0],
+                                 p.wp[0], tc::kBoxRowsC);
+    if (rc) return rc;
+  }
   if (p.save) return tc::make_tensor_map(&c.mGx, wsf(ws, p.o_gx), p.Bp, p.wp[0], p.wp[0], tc::kBoxRowsC);
   return HDPO_OK;
 }
 #endif
+
+// tile selector of layer l's forward GEMM, 0 when there is no tensor-core path in this build
+static int fwd_bn_host(const Plan& p, int l) {
+#ifndef HDPO_EMU
+  return fwd_bn(p, l);
+#else
+  (void)p;
+  (void)l;
+  return 0;
+#endif
+}
+static int dgrad_bn_host(const Plan& p, int l) {
+#ifndef HDPO_EMU
+  return dgrad_bn(p, l);
+#else
+  (void)p;
+  (void)l;
+  return 0;
+#endif
+}
 
 // ---- forward: prologue (pack weights, initial state), one period, epilogue (final state) of one chunk ----
 static int fwd_begin(ChunkCtx& c, const HdpoRolloutDesc* d, const float* params) {
@@ -1465,7 +1560,15 @@ static int fwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t) {
       const bool hidden = l + 1 < p.n;
       tc::GemmTcMaps tm{c.mA[l].hi, c.mA[l].lo, c.mB[l].hi, c.mB[l].lo, c.mAct[l].hi, c.mAct[l].lo, c.mAct[l].hi,
                         c.mAct[l].lo};
-      rc = tc::gemm(tm, g, hidden ? tc::EPI_FWD_HIDDEN : tc::EPI_FWD_OUT, fwd_bn(p, l), stream);
+      const int bn_l = fwd_bn(p, l);
+      if (!hidden && p.y_split > 1 && (bn_l == 64 || bn_l == 128)) {
+        // thin output layer: split-K partial products into the chunk's partial buffer (the head sums them)
+        g.k_per_split = g.K / p.y_split;
+        g.c_zrows = p.Bp;
+        g.c_row0 = 0;
+        tm.c0 = tm.c1 = tm.x0 = tm.x1 = c.mYpart;
+      }
+      rc = tc::gemm(tm, g, hidden ? tc::EPI_FWD_HIDDEN : tc::EPI_FWD_OUT, bn_l, stream);
 #else
       rc = HDPO_E_INVALID;
 #endif
@@ -1490,6 +1593,12 @@ static int fwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t) {
                          stream);
   }
   HeadArgs a = head_args(d, c, t);
+  if (p.tc && p.y_split > 1 && (fwd_bn_host(p, p.n - 1) == 64 || fwd_bn_host(p, p.n - 1) == 128)) {
+    a.part = wsf(ws, p.o_ypart);
+    a.part_stride = static_cast<size_t>(p.Bp) * p.wp[p.n];
+    a.n_part = p.y_split;
+    a.y_out = const_cast<float*>(in);  // the Y tape slot of this period
+  }
   const size_t head_smem = static_cast<size_t>(HEAD_WARPS) * head_smem_floats(pb.S, pb.W, p.wp[0], p.wp[p.n], false) * sizeof(float);
   auto k = warehouse_head_fwd_kernel;
 #ifndef HDPO_EMU
@@ -1694,7 +1803,14 @@ extern "C" int hdpo_debug_set_wide_wg_overlap(int32_t mode, int32_t group) {
   if (group > 0) hdpo::wide::g_wg_group = group;
   return HDPO_OK;
 }
+// Split-K of the thin chain GEMMs (output layer, first-layer dgrad): 1 = on, 0 = off, < 0 = default (on for one chunk).
+// Changes the workspace size and the summation order of those two layers (results agree to fp32 rounding).
+extern "C" int hdpo_debug_set_wide_ksplit(int32_t mode) {
+  hdpo::wide::g_ksplit = mode < 0 ? -1 : (mode != 0);
+  return HDPO_OK;
+}
 #else
+extern "C" int hdpo_debug_set_wide_ksplit(int32_t) { return HDPO_E_INVALID; }
 extern "C" int hdpo_debug_set_tc_occ2(int32_t) { return HDPO_E_INVALID; }
 extern "C" int hdpo_debug_set_wide_wg_overlap(int32_t, int32_t) { return HDPO_E_INVALID; }
 extern "C" int hdpo_debug_set_tc_multi(int32_t) { return HDPO_E_INVALID; }
@@ -1767,6 +1883,11 @@ static int bwd_begin(ChunkCtx& c) {
     auto k = zero_kernel;
     HDPO_LAUNCH_PDL(k, static_cast<unsigned>(ceil_div64(p.x_stride, 256)), 256, 0, c.stream, gX, p.x_stride);
     HDPO_LAUNCH_OK();
+    if (p.gx_split > 1) {  // (the first adjoint head of the sweep adds them to its zero gX row)
+      const size_t n = static_cast<size_t>(p.gx_split) * p.x_stride;
+      HDPO_LAUNCH_PDL(k, static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, c.stream, wsf(ws, p.o_gxpart), n);
+      HDPO_LAUNCH_OK();
+    }
   }
 #ifndef HDPO_EMU
   if (p.tc) {
@@ -1804,6 +1925,12 @@ static int bwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t, float rb) {
     if (rc) return rc;
   } else {
     HeadArgs a = head_args(d, c, t);
+    const bool gx_parts = p.tc && p.gx_split > 1 && (dgrad_bn_host(p, 0) == 64 || dgrad_bn_host(p, 0) == 128);
+    if (gx_parts) {
+      a.part = wsf(ws, p.o_gxpart);
+      a.part_stride = p.x_stride;
+      a.n_part = p.gx_split;
+    }
     auto k = warehouse_head_bwd_kernel;
 #ifndef HDPO_EMU
     if (head_smem > 48 * 1024) HDPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHeadSmemMax)));
@@ -1854,8 +1981,17 @@ static int bwd_period(ChunkCtx& c, const HdpoRolloutDesc* d, int t, float rb) {
         rc = tc::gemm(tm, g, tc::EPI_DGRAD_HIDDEN, dgrad_bn(p, l), stream);
       } else {
         g.c_row0 = g.x_row0 = 0;
-        tc::GemmTcMaps tm{c.mA[l].hi, c.mA[l].lo, c.mB[l].hi, c.mB[l].lo, c.mGx, c.mGx, c.mGx, c.mGx};
-        rc = tc::gemm(tm, g, tc::EPI_DGRAD_ACCUM, dgrad_bn(p, l), stream);
+        const int bn0 = dgrad_bn(p, l);
+        if (p.gx_split > 1 && (bn0 == 64 || bn0 == 128)) {
+          // thin first-layer dgrad: split-K partial products; the adjoint head of period t - 1 adds them to its gX row
+          g.k_per_split = g.K / p.gx_split;
+          g.c_zrows = p.Bp;
+          tc::GemmTcMaps tm{c.mA[l].hi, c.mA[l].lo, c.mB[l].hi, c.mB[l].lo, c.mGxPart, c.mGxPart, c.mGxPart, c.mGxPart};
+          rc = tc::gemm(tm, g, tc::EPI_STORE, bn0, stream);
+        } else {
+          tc::GemmTcMaps tm{c.mA[l].hi, c.mA[l].lo, c.mB[l].hi, c.mB[l].lo, c.mGx, c.mGx, c.mGx, c.mGx};
+          rc = tc::gemm(tm, g, tc::EPI_DGRAD_ACCUM, bn0, stream);
+        }
       }
 #else
       rc = HDPO_E_INVALID;

@@ -115,11 +115,16 @@ def test_full_size_rollout_properties(workload, B, precision, n_oracle, tol):
     n = 300 if B >= 4096 else 100
     for start in (0, B // 2 - 37, B - n):
         idx = torch.arange(start, start + n, device=dev)
+        # (wide nets: a one-chunk batch takes the split-K form of the two thin chain GEMMs, whose partial products sum in a
+        # different order than in a multi-chunk batch: the small batch is put into the FULL batch's form for the
+        # bit-identity check in the same way; its own default form is the `other` run below)
         lib.hdpo_debug_set_small_unit(0)
+        lib.hdpo_debug_set_wide_ksplit(1 if B // 2048 <= 1 else 0)
         try:
             alone = _run(pspec, pp, _slice(data, idx), flat, T, precision, ignore=0, backward=False)
         finally:
             lib.hdpo_debug_set_small_unit(-1)
+            lib.hdpo_debug_set_wide_ksplit(-1)
         assert torch.equal(alone["cost_b"], full["cost_b"][idx]), (workload, start)
         other = _run(pspec, pp, _slice(data, idx), flat, T, precision, ignore=0, backward=False)
         rel = (other["cost_b"].double() / full["cost_b"][idx].double() - 1).abs().max().item()
@@ -159,7 +164,12 @@ def test_full_size_rollout_properties(workload, B, precision, n_oracle, tol):
         eng.forward(flat, _slice(data, pick), reward_tb=reward_tb)
         grad_alone = eng.backward(1.0 / (n_oracle * T * S), 0.0).double().cpu().numpy()
         mine_tb = reward_tb.double().cpu().numpy()
-        assert np.array_equal(eng.cost_b.cpu().numpy(), full["cost_b"][pick].cpu().numpy())  # independence again
+        # independence again (to rounding level for the wide nets: the picked scenarios alone are ONE chunk and take the
+        # split-K form of the two thin chain GEMMs, the full batch does not)
+        if pspec.arch in ("vanilla_warehouse", "symmetry_aware"):
+            assert np.abs(eng.cost_b.cpu().numpy() / full["cost_b"][pick].cpu().numpy() - 1).max() <= 1e-5
+        else:
+            assert np.array_equal(eng.cost_b.cpu().numpy(), full["cost_b"][pick].cpu().numpy())
         assert np.abs(mine_tb[:horizon] - true_tb[:horizon]).max() <= 1e-5 * scale, (workload, horizon)
         assert np.abs(got / true_b - 1).max() <= max(1e-5, 3 * floor_c), (workload, np.abs(got / true_b - 1).max(), floor_c)
         mine_g = _flat_like_oracle(pol, pspec, widths, grad_alone)
