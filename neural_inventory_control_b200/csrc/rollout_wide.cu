@@ -257,7 +257,13 @@ static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
     const int G = wg_group_periods();
     const int mode = wg_overlap_mode();
     const bool wanted = mode == 1 || (mode == -1 && requested_chunks(d->pb.B, p.sym) == 1);
-    if (wanted && p.save && p.tc && !p.sym && !p.persist && G > 0 && G < p.T &&
+    // HDPO_WIDE_WG_SYM = 0: not for the SymmetryAware trunk (one chunk by design; measured 23.35 -> 23.04 ms per step with it)
+    static int sym_ok = -1;
+    if (sym_ok < 0) {
+      const char* e = getenv("HDPO_WIDE_WG_SYM");
+      sym_ok = e ? (atoi(e) != 0) : 1;
+    }
+    if (wanted && p.save && p.tc && (!p.sym || sym_ok) && !p.persist && G > 0 && G < p.T &&
         (static_cast<size_t>(G) * p.Bp) % static_cast<size_t>(p.wg_kps) == 0 &&
         (p.T % G == 0 || p.Bp % p.wg_kps == 0))  // (the last, shorter group must cover whole slices too)
       p.wg_group = G;
