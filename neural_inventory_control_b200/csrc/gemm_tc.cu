@@ -76,7 +76,8 @@ struct SmemPlan {
 template <int BN, int EPI, bool MN, int CG = 1, int OCC = 1>
 __global__ void __launch_bounds__(kThreads, OCC)
 gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
-  static_assert(CG == 1 || !MN, "the CTA-pair form is K-major only");
+  // (MN && CG == 2: weight-gradient tiles of 256 x BN per CTA pair - each CTA stages its own 128 m-columns of A and HALF
+  // of the n-columns of B: a quarter fewer operand bytes per flop than the single-CTA form, which is L2-bound)
   static_assert(OCC == 1 || (OCC == 2 && BN == 64 && !MN), "two CTAs per SM: 64-column K-major tiles only");
   const CUtensorMap& tm_a_hi = tm.a_hi;
   const CUtensorMap& tm_a_lo = tm.a_lo;
@@ -101,8 +102,11 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // CG = 1: grid (N tiles, M tiles, K slices); CG = 2: grid (2 = CTA of the pair, 256-row tiles, N tiles)
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
-  const int m0 = CG == 2 ? blockIdx.y * 256 + static_cast<int>(rank) * 128 : blockIdx.y * 128;
-  const int n0 = CG == 2 ? blockIdx.z * BN : blockIdx.x * BN;
+  // MN && CG == 2: grid (2, row tiles x column tiles, K slices)
+  const int pair_tile_n = (MN && CG == 2) ? static_cast<int>(blockIdx.y) % (g.N / BN) : 0;
+  const int pair_tile_m = (MN && CG == 2) ? static_cast<int>(blockIdx.y) / (g.N / BN) : static_cast<int>(blockIdx.y);
+  const int m0 = CG == 2 ? pair_tile_m * 256 + static_cast<int>(rank) * 128 : blockIdx.y * 128;
+  const int n0 = CG == 2 ? (MN ? pair_tile_n : static_cast<int>(blockIdx.z)) * BN : blockIdx.x * BN;
   long long* dbg = g.dbg_clock ? g.dbg_clock + 8 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   // K slices: rows of the MN-major operands (weight gradient) / columns of the K-major ones (split-K, single CTA only)
@@ -199,12 +203,28 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps tm, GemmTcArgs g) {
           // both CTAs fill their own stage; all bytes are counted on the LEADER's full barrier (the MMA issuer's)
           if (rank == 0) mbar_expect_tx(&full_bar[s], tx);
           const uint32_t bar = mapa_u32(&full_bar[s], 0);
+          if (MN) {
+            constexpr int kBox = kBK * 128;  // bytes of one {32 mn, BK k} box
+            const int krow = k_begin + kb * kBK;
+            const int ncol = n0 + static_cast<int>(rank) * (BN / 2);
+            for (int i = 0; i < 128 / 32; ++i) {
+              tma_load_2d_pair(st + i * kBox, &tm_a_hi, bar, m0 + 32 * i, g.a_row0 + krow);
+              if (three) tma_load_2d_pair(st + P::kABytes + i * kBox, &tm_a_lo, bar, m0 + 32 * i, g.a_row0 + krow);
+            }
+            for (int i = 0; i < BN / 2 / 32; ++i) {
+              tma_load_2d_pair(st + 2 * P::kABytes + i * kBox, &tm_b_hi, bar, ncol + 32 * i, g.b_row0 + krow);
+              if (three)
+                tma_load_2d_pair(st + 2 * P::kABytes + P::kBBytes + i * kBox, &tm_b_lo, bar, ncol + 32 * i,
+                                 g.b_row0 + krow);
+            }
+          } else {
           const int brow = g.b_row0 + n0 + static_cast<int>(rank) * (BN / 2);
           tma_load_2d_pair(st, &tm_a_hi, bar, kb * kBK, g.a_row0 + m0);
           tma_load_2d_pair(st + 2 * P::kABytes, &tm_b_hi, bar, kb * kBK, brow);
           if (three) {
             tma_load_2d_pair(st + P::kABytes, &tm_a_lo, bar, kb * kBK, g.a_row0 + m0);
             tma_load_2d_pair(st + 2 * P::kABytes + P::kBBytes, &tm_b_lo, bar, kb * kBK, brow);
+          }
           }
         } else {
         mbar_expect_tx(&full_bar[s], tx);
@@ -622,7 +642,9 @@ static int launch(const GemmTcMaps& tm, const GemmTcArgs& g_in, void* stream) {
   }
   const unsigned nz = (MN || (CG == 1 && g.k_per_split > 0)) ? static_cast<unsigned>(g.K / g.k_per_split) : 1u;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = CG == 2 ? dim3(2, g.M / 256, g.N / BN) : dim3(g.N / BN, g.M / 128, nz);
+  cfg.gridDim = CG == 2 ? (MN ? dim3(2, (g.M / 256) * (g.N / BN), static_cast<unsigned>(g.K / g.k_per_split))
+                              : dim3(2, g.M / 256, g.N / BN))
+                        : dim3(g.N / BN, g.M / 128, nz);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = SmemPlan<BN, CG, false, OCC>::kTotal;
   cfg.stream = static_cast<cudaStream_t>(stream);
@@ -702,10 +724,19 @@ int gemm(const GemmTcMaps& tm, const GemmTcArgs& g, int epi, int bn, void* strea
 }
 
 int gemm_wgrad(const GemmTcMaps& tm, const GemmTcArgs& g, int bn, void* stream) {
-  HDPO_REQUIRE(g.M % 128 == 0 && g.N % bn == 0 && g.k_per_split % kBK == 0 && g.k_per_split > 0 &&
+  HDPO_REQUIRE(g.M % 128 == 0 && g.N % (bn == kBnPair ? 128 : (bn == kBnPair64 ? 64 : bn)) == 0 &&
+                   g.k_per_split % kBK == 0 && g.k_per_split > 0 &&
                    g.K % g.k_per_split == 0,
                "tcgen05 weight-gradient GEMM shape %dx%dx%d (k_per_split %d) not tileable", g.M, g.N, g.K, g.k_per_split);
   HDPO_REQUIRE(g.n_pass == 1 || g.n_pass == 3, "n_pass must be 1 or 3");
+  if (bn == kBnPair) {  // 256 x 128 CTA-pair tiles
+    HDPO_REQUIRE(g.M % 256 == 0 && g.N % 128 == 0, "CTA-pair weight-gradient shape %dx%d not tileable", g.M, g.N);
+    return launch<128, EPI_STORE, true, 2>(tm, g, stream);
+  }
+  if (bn == kBnPair64) {  // 256 x 64 CTA-pair tiles (one CTA per SM: the 4-stage ring of the single-CTA form)
+    HDPO_REQUIRE(g.M % 256 == 0 && g.N % 64 == 0, "CTA-pair weight-gradient shape %dx%d not tileable", g.M, g.N);
+    return launch<64, EPI_STORE, true, 2>(tm, g, stream);
+  }
   if (bn == 128) return launch<128, EPI_STORE, true>(tm, g, stream);
   if (bn == 64) return launch<64, EPI_STORE, true>(tm, g, stream);
   set_error("unsupported BN %d", bn);
@@ -831,7 +862,9 @@ extern "C" int hdpo_debug_gemm_tc_wgrad(const float* A, const float* B, float* C
   count_launch();
   count_launch();
   HDPO_LAUNCH_OK();
-  const int bn = tc::pick_bn(N);
+  const char* wg_pair = getenv("HDPO_WG_PAIR");
+  const bool wg_pair_on = !wg_pair || atoi(wg_pair) != 0;  // (same default as the rollout: pairs where the shape allows)
+  const int bn = (wg_pair_on && M % 256 == 0) ? (N % 128 == 0 ? tc::kBnPair : tc::kBnPair64) : tc::pick_bn(N);
   tc::GemmTcMaps tm{};
   int rc;
   if ((rc = tc::make_tensor_map(&tm.a_hi, a_hi, K, M, M, 32, true))) return rc;

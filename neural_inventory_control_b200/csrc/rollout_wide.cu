@@ -2049,7 +2049,21 @@ static int wgrad_tc_rows(ChunkCtx& c, int l, int t_lo, int t_hi, void* stream) {
   if (rc) return rc;
   tc::GemmTcMaps tm = transposed ? tc::GemmTcMaps{mi.hi, mi.lo, mg.hi, mg.lo, mpart, mpart, mpart, mpart}
                                  : tc::GemmTcMaps{mg.hi, mg.lo, mi.hi, mi.lo, mpart, mpart, mpart, mpart};
-  return tc::gemm_wgrad(tm, g, tc::pick_bn(g.N), stream);
+  // CTA-pair tiles (256 x 128 / 256 x 64) where the shape allows: each CTA stages its own 128 m-columns and HALF of the
+  // n-columns, a quarter fewer operand bytes per flop than the single-CTA 128 x 128 tiles, which ran at the L2 -> SM cap
+  // (1 MB per CTA in 12.7 us on 148 SMs). Measured on B200 (8192 x 50 x 50 stores): adjoint 10.73 -> 10.15 ms with the
+  // 256 x 128 form. HDPO_WG_PAIR = 0: single-CTA tiles (A/B), 2: pairs for the 128-multiple widths only.
+  static int wg_pair = -1;
+  if (wg_pair < 0) {
+    const char* e = getenv("HDPO_WG_PAIR");
+    wg_pair = e ? atoi(e) : 1;
+  }
+  int bn_w = tc::pick_bn(g.N);
+  if (wg_pair && g.M % 256 == 0) {
+    if (g.N % 128 == 0) bn_w = tc::kBnPair;
+    else if (wg_pair == 1 && g.N % 64 == 0) bn_w = tc::kBnPair64;
+  }
+  return tc::gemm_wgrad(tm, g, bn_w, stream);
 }
 
 // overlapped form: the weight gradients of periods [t_lo, t_hi] of every tcgen05 layer, on the chunk's second stream
