@@ -246,7 +246,20 @@ static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
   {
     // short K slices keep the tensor core's truncating accumulation fp32-grade (see gemm_tc.cu)
     const size_t rows = static_cast<size_t>(p.T) * p.Bp;
-    p.wg_kps = rows % 512 == 0 ? 512 : (rows % 256 == 0 ? 256 : 128);
+    // Slice length: the truncation error of a slice grows linearly with its length, the time falls with it (fewer CTA
+    // ramp-ups, fewer partial slices to write and reduce). Measured on B200 (8192 x 50 x 50 stores, 3xTF32; rel-L2 distance
+    // of the full-batch gradient to the 128-row-slice run | adjoint ms): 512: 6.9e-7 | 10.0; 1024: 1.8e-6 | 9.3; 2048:
+    // 4.2e-6 | 9.05; 4096: 8.4e-6. The true-fp32 SIMT path differs from all of them by 6.3e-6 (rounding-level differences of
+    // the chaotic 50-store rollouts), so 1024 rows stays well inside the workload's own fp32 floor.
+    p.wg_kps = rows % 1024 == 0 ? 1024 : (rows % 512 == 0 ? 512 : (rows % 256 == 0 ? 256 : 128));
+    {
+      static int kps_env = -1;  // HDPO_WG_KPS: other slice lengths (A/B of accuracy against time, tools/wg_accuracy.py)
+      if (kps_env < 0) {
+        const char* e = getenv("HDPO_WG_KPS");
+        kps_env = e ? atoi(e) : 0;
+      }
+      if (kps_env > 0 && kps_env % 32 == 0 && rows % static_cast<size_t>(kps_env) == 0) p.wg_kps = kps_env;
+    }
     p.wg_splits = static_cast<int>(rows / p.wg_kps);
   }
   p.o_part = p.save ? take(static_cast<size_t>(p.tc ? (p.wg_splits > kSplitK ? p.wg_splits : kSplitK) : kSplitK) * p.max_wk) : 0;
