@@ -291,7 +291,18 @@ static Plan make_plan(const HdpoRolloutDesc* d, int Bc) {
   p.o_ypart = p.o_gxpart = 0;
 #ifndef HDPO_EMU
   if (p.tc && !p.sym && !p.persist && thin_ksplit_enabled(requested_chunks(d->pb.B, p.sym))) {
-    auto splits = [](int K) { return (K >= 256 && K % 128 == 0) ? (K / 128 < 4 ? K / 128 : 4) : 1; };
+    static int max_splits = -1;  // HDPO_WIDE_KSPLIT_N: most K slices (default 4)
+    if (max_splits < 0) {
+      const char* e = getenv("HDPO_WIDE_KSPLIT_N");
+      max_splits = e ? atoi(e) : 4;
+      if (max_splits < 2) max_splits = 2;
+    }
+    auto splits = [](int K) {
+      if (K < 256 || K % 128 != 0) return 1;
+      int n = K / 128 < max_splits ? K / 128 : max_splits;
+      while (n > 1 && (K % n != 0 || (K / n) % 32 != 0)) --n;
+      return n;
+    };
     if (p.act[p.n - 1] == HDPO_ACT_NONE) p.y_split = splits(p.wp[p.n - 1]);  // (an activation cannot act on partials)
     if (p.save) p.gx_split = splits(p.wp[1]);
     if (p.y_split > 1) p.o_ypart = take(static_cast<size_t>(p.y_split) * p.Bp * p.wp[p.n]);
