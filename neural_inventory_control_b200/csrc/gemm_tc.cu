@@ -631,6 +631,16 @@ template <int BN, int EPI, bool MN = false, int CG = 1, int OCC = 1>
 static int launch(const GemmTcMaps& tm, const GemmTcArgs& g_in, void* stream) {
   GemmTcArgs g = g_in;
   if (g.hi_chunks <= 0 || g.hi_chunks > kHiChunks) g.hi_chunks = kHiChunks;
+  {
+    // HDPO_TC_HI_CHUNKS (accuracy experiments, tools/wg_accuracy.py): accumulators the hi*hi term of the K-major GEMMs is
+    // spread over (default 3; 1 = what a 256 x 256 pair tile could afford in TMEM)
+    static int env_chunks = -1;
+    if (env_chunks < 0) {
+      const char* e = getenv("HDPO_TC_HI_CHUNKS");
+      env_chunks = e ? atoi(e) : 0;
+    }
+    if (!MN && env_chunks >= 1 && env_chunks <= kHiChunks) g.hi_chunks = env_chunks;
+  }
   g.trace = trace_ref((g_in.trace.tag << 8) | (static_cast<unsigned>(EPI) << 4) | (MN ? 8u : 0u) | (BN == 128 ? 1u : 0u));
   auto k = gemm_tc_kernel<BN, EPI, MN, CG, OCC>;
   static bool configured = false;
