@@ -1,11 +1,11 @@
-out=gpurun_out/r3a_hichunks.log; rm -f $out
-for h in 1 2; do
-echo "HDPO_TC_HI_CHUNKS=$h parity:" >> $out
-HDPO_TC_HI_CHUNKS=$h timeout 900 python -m pytest tests/test_kernels_abi.py tests/test_full_size_properties.py -m gpu -q -k "wide or warehouse" 2>&1 | tail -6 >> $out
-done
-for h in 3 2 1; do HDPO_TC_HI_CHUNKS=$h python tools/wg_accuracy.py hc$h | tail -1 >> $out; done
-python tools/wg_accuracy.py fp32 | tail -1 >> $out
-python tools/wg_accuracy.py compare hc3 hc2 hc1 fp32 >> $out
-python tools/wg_accuracy.py compare fp32 hc3 hc2 hc1 >> $out
-rm -f gpurun_out/wg_grad_*.npy
+out=gpurun_out/r3f_chunks_small.log; rm -f $out
+run() { echo -n "$*: " >> $out; env "$@" timeout 200 python tools/wide_ab.py $WL 2>&1 | tail -1 | sed 's/\[.*\]//' >> $out; }
+for WL in one_warehouse_lost_demand many_warehouses_lost_demand; do
+for b in 2048 4096; do
+run HDPO_AB_BATCH=$b
+run HDPO_AB_BATCH=$b HDPO_WIDE_CHUNKS=2
+run HDPO_AB_BATCH=$b HDPO_WIDE_CHUNKS=2 HDPO_WIDE_KSPLIT=1 HDPO_WIDE_WG_OVERLAP=1
+run HDPO_AB_BATCH=$b HDPO_WIDE_CHUNKS=4
+run HDPO_AB_BATCH=$b HDPO_WIDE_CHUNKS=4 HDPO_WIDE_KSPLIT=1
+done; done
 cat $out
